@@ -1,0 +1,97 @@
+"""Varlen row layout of a batch of subject-object pairs in HBM.
+
+All activations are token-major matrices ``[rows, channels]`` (channels contiguous).  At pyramid level
+``l`` a pair with ``L`` valid frames owns ``L_l = ceil(L / 2**l)`` consecutive rows; a single all-zero
+*separator* row precedes the first pair and follows every pair, so that the three row-shifted K-slabs
+of a k=3 convolution-as-GEMM read zeros across sequence boundaries.  ``rows`` is rounded up to a
+multiple of 128 (the GEMM M tile); the tail rows are separators too.
+
+The reference pads instead (models/maskvrd.py:363-414): short pairs to ``max_seq_len``, long pairs to the
+longest pair of their 200-pair slice rounded up to ``max_div_factor``.  Padding is not neutral there
+(SURVEY.md section 7 hard-part 2 / appendix B): the first pad column of a level carries a per-channel constant that
+k=3 convolutions read.  ``haspad[l]`` records, per pair, whether such a column exists at level ``l``
+(``L_l < T_pad / 2**l``), and the kernels add the constant analytically.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+ROW_TILE = 128
+
+
+def max_div_factor(mc: dict) -> int:
+    """Largest fpn_stride * 2 * (win // 2) over the pyramid levels (reference maskvrd.py:57-63)."""
+    n_levels = mc["backbone_arch"][-1] + 1
+    w = mc["n_mha_win_size"]
+    best = 1
+    for l in range(mc["fpn_start_level"], n_levels):
+        s = mc["scale_factor"] ** l
+        best = max(best, s * (w // 2) * 2 if w > 1 else s)
+    return best
+
+
+def reference_padded_lengths(lengths: Sequence[int], mc: dict) -> List[int]:
+    """T_pad the reference would give each pair (it decides per slice of ``max_so_pair`` pairs)."""
+    msl, mdf, chunk = mc["max_seq_len"], max_div_factor(mc), mc["max_so_pair"]
+    out: List[int] = []
+    for s in range(0, len(lengths), chunk):
+        sl = lengths[s:s + chunk]
+        longest = max([msl] + [l for l in sl if l > msl])
+        t_long = (longest + mdf - 1) // mdf * mdf
+        out += [msl if l <= msl else t_long for l in sl]
+    return out
+
+
+class LevelLayout:
+    """Rows of one pyramid level.  ``seqinfo[i] = (row offset, valid length, haspad, 0)`` and ``row_seq[r]`` =
+    owning pair or -1 for a separator row; both live on the device as int32."""
+
+    def __init__(self, level: int, off: np.ndarray, length: np.ndarray, haspad: np.ndarray, rows: int):
+        self.level = level
+        self.off, self.len, self.haspad, self.R = off, length, haspad, rows
+        self.row_seq: torch.Tensor = None   # int32 [R]
+        self.seqinfo: torch.Tensor = None   # int32 [B, 4]
+
+    @property
+    def B(self) -> int:
+        return len(self.len)
+
+
+class PackLayout:
+    def __init__(self, lengths: Sequence[int], tpads: Sequence[int], n_levels: int, device):
+        lens = np.asarray(lengths, dtype=np.int64)
+        tp = np.asarray(tpads, dtype=np.int64)
+        assert lens.ndim == 1 and lens.shape == tp.shape and (lens >= 1).all() and (lens <= tp).all()
+        assert (tp % (1 << (n_levels - 1)) == 0).all()
+        self.lengths, self.tpads, self.n_levels = lens, tp, n_levels
+        self.B = len(lens)
+        self.levels: List[LevelLayout] = []
+        host = []
+        for l in range(n_levels):
+            ll = (lens + (1 << l) - 1) >> l
+            off = np.empty(self.B, dtype=np.int64)
+            off[0] = 1
+            np.cumsum(ll[:-1] + 1, out=off[1:])
+            off[1:] += 1
+            used = int(off[-1] + ll[-1] + 1)
+            rows = (used + ROW_TILE - 1) // ROW_TILE * ROW_TILE
+            haspad = (ll < (tp >> l)).astype(np.int32)
+            row_seq = np.full(rows, -1, dtype=np.int32)
+            row_seq[np.repeat(off, ll) + (np.arange(int(ll.sum())) - np.repeat(np.cumsum(ll) - ll, ll))] = \
+                np.repeat(np.arange(self.B, dtype=np.int32), ll)
+            info = np.stack([off.astype(np.int32), ll.astype(np.int32), haspad, np.zeros(self.B, np.int32)], 1)
+            lev = LevelLayout(l, off.astype(np.int32), ll.astype(np.int32), haspad, rows)
+            self.levels.append(lev)
+            host += [row_seq, info.reshape(-1)]
+        flat = torch.from_numpy(np.concatenate(host))
+        dev = flat.to(device, non_blocking=True) if torch.device(device).type == "cuda" else flat
+        pos = 0
+        for lev in self.levels:
+            lev.row_seq = dev[pos:pos + lev.R]
+            pos += lev.R
+            lev.seqinfo = dev[pos:pos + 4 * self.B].view(self.B, 4)
+            pos += 4 * self.B
+        self.total_frames = int(lens.sum())

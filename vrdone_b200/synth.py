@@ -1,0 +1,161 @@
+"""Seeded synthetic inputs and weight initialisations.
+
+Everything here is deterministic given a seed and runs on the CPU RNG, so the build container, the
+test fixtures and the GPU box produce identical tensors.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List
+
+import torch
+import yaml
+
+CONFIG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs")
+CONFIG_NAMES = ("vidvrd", "vidor", "vidor_local", "vidor_x")
+
+
+def load_config(name: str) -> dict:
+    """Return {'model_config', 'inference_config', 'dataset_config'}; ``with_clip_feature`` is copied from the
+    dataset section into the model section, as the reference CLI does (eval.py:53)."""
+    with open(os.path.join(CONFIG_DIR, name + ".yaml")) as f:
+        cfg = yaml.safe_load(f)
+    cfg["model_config"]["with_clip_feature"] = bool(cfg["dataset_config"].get("with_clip_feature", False))
+    return cfg
+
+
+def input_channels(mc: dict) -> int:
+    nc = mc["clip_dim"] if mc.get("with_clip_feature", False) else 0
+    return 2 * mc["visual_dim"] + 2 * nc + mc["bbox_so_dim"] + 2 * mc["bbox_entity_dim"]
+
+
+def stress_state_dict(sd: Dict[str, torch.Tensor], seed: int) -> Dict[str, torch.Tensor]:
+    """A seeded initialisation under which every branch of the network matters (the default init has
+    1e-4 path scales and constant class logits, SURVEY.md section 7 hard-part 1).  Keys are visited in
+    sorted order so the result depends only on (names, shapes, seed)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(sd.keys()):
+        v = sd[k]
+        shape = tuple(v.shape)
+        if k == "empty_weight":
+            out[k] = v.clone()
+        elif k.endswith(".scale"):
+            out[k] = 0.3 + 0.7 * torch.rand(shape, generator=g)
+        elif "norm" in k or ".ln" in k:
+            if k.endswith(".weight"):
+                out[k] = 0.5 + torch.rand(shape, generator=g)
+            else:
+                out[k] = 0.5 * torch.randn(shape, generator=g)
+        elif k.endswith("query_embed.weight"):
+            out[k] = torch.randn(shape, generator=g)
+        elif k.endswith(".bias"):
+            out[k] = 0.1 * torch.randn(shape, generator=g)
+        else:  # conv weights: uniform with the fan-in bound of the default Conv1d init
+            fan_in = shape[1] * shape[2]
+            bound = 1.0 / fan_in ** 0.5
+            out[k] = (2 * torch.rand(shape, generator=g) - 1) * bound
+    return out
+
+
+def pair_features(mc: dict, lengths: List[int], seed: int) -> List[torch.Tensor]:
+    """One (C, L) fp32 tensor per pair, N(0,1) visual/CLIP channels and O(1) geometry channels, delivered the way
+    the reference data loader does: a transposed view of an (L, C)-contiguous buffer (vidor.py:708-711)."""
+    g = torch.Generator().manual_seed(seed)
+    c = input_channels(mc)
+    return [torch.randn(l, c, generator=g).permute(1, 0) for l in lengths]
+
+
+def _geometry(sb, ob, w, h):
+    """5-d subject/object relative and 8-d per-entity box features (formulas of utils/misc.py:158-217)."""
+    def cwh(b):
+        return (b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+
+    sx, sy, sw, sh = cwh(sb)
+    ox, oy, ow, oh = cwh(ob)
+    rel = torch.stack([(sx - ox) / ox, (sy - oy) / oy, torch.log(sw / ow), torch.log(sh / oh),
+                       torch.log((sw * sh) / (ow * oh))], 1)
+
+    def ent(b):
+        n = b.clone()
+        n[:, 0::2] /= w
+        n[:, 1::2] /= h
+        cols = []
+        for v in cwh(n):
+            d = v[1:] - v[:-1]
+            first = d[:1] - (d[1:2] - d[:1]) if d.numel() > 1 else d[:1]
+            cols += [v, torch.cat([first, d])]
+        return torch.stack(cols, 1)
+
+    return rel, ent(sb), ent(ob)
+
+
+def synthetic_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None, name: str = None) -> dict:
+    """A synthetic ``input_data`` dict with the reference data loader's contract: every
+    ordered pair of tracklets with enough temporal overlap, features sub-sampled with ``feat_stride``."""
+    mc, dc, ic = cfg["model_config"], cfg["dataset_config"], cfg["inference_config"]
+    g = torch.Generator().manual_seed(seed)
+    stride = dc.get("feat_stride", 1)
+    clip = mc.get("with_clip_feature", False)
+    vid_w, vid_h = 1280.0, 720.0
+
+    def randint(lo, hi):
+        return int(torch.randint(lo, hi, (1,), generator=g))
+
+    if n_frames is None:
+        if stride == 1:
+            n_frames = 150
+        else:
+            n_frames = [900, 1200, 1800, 3600][int(torch.multinomial(torch.tensor([.3, .4, .2, .1]), 1, generator=g))]
+    if n_tracklets is None:
+        n_tracklets = 6 if stride == 1 else randint(20, 61)
+    n_cat = 35 if mc["num_classes"] > 100 else 80
+    durs, boxes, vis, clips = [], [], [], []
+    for _ in range(n_tracklets):
+        if stride == 1:
+            start = randint(0, 60)
+            length = min(randint(30, 150), n_frames - start)
+        else:
+            length = randint(60, n_frames + 1)
+            start = randint(0, n_frames - length + 1)
+        durs.append([start, start + length])
+        wh = 20 + 200 * torch.rand(length, 2, generator=g)
+        xy = torch.rand(length, 2, generator=g) * (torch.tensor([vid_w, vid_h]) - wh - 2) + 1
+        boxes.append(torch.cat([xy, xy + wh], 1))
+        vis.append(torch.randn(length, mc["visual_dim"], generator=g))
+        if clip:
+            clips.append(torch.randn(length, mc["clip_dim"], generator=g))
+    min_frames = 5 if stride > 1 else 2
+    sids, oids, feats, offs = [], [], [], []
+    for s in range(n_tracklets):
+        for o in range(n_tracklets):
+            if s == o:
+                continue
+            a, b = max(durs[s][0], durs[o][0]), min(durs[s][1], durs[o][1])
+            if b - a < min_frames:
+                continue
+            ss, os_ = a - durs[s][0], a - durs[o][0]
+            sl_s = slice(ss, ss + b - a, stride)
+            sl_o = slice(os_, os_ + b - a, stride)
+            if vis[s][sl_s].shape[0] < 2:
+                continue
+            rel, es, eo = _geometry(boxes[s][sl_s], boxes[o][sl_o], vid_w, vid_h)
+            parts = [vis[s][sl_s], vis[o][sl_o]]
+            if clip:
+                parts += [clips[s][sl_s], clips[o][sl_o]]
+            parts += [rel, es, eo]
+            feats.append(torch.cat(parts, -1).permute(1, 0))
+            sids.append(s)
+            oids.append(o)
+            offs.append(0)
+    return {
+        "video_name": name or f"synthetic_{seed}",
+        "sids": torch.tensor(sids, dtype=torch.int64),
+        "oids": torch.tensor(oids, dtype=torch.int64),
+        "cat_ids": torch.randint(1, n_cat + 1, (n_tracklets,), generator=g),
+        "cat_scores": 0.4 + 0.6 * torch.rand(n_tracklets, generator=g),
+        "traj_durations": torch.tensor(durs, dtype=torch.int64),
+        "bboxes_list": boxes,
+        "so_features_list": feats,
+        "so_offset": torch.tensor(offs, dtype=torch.int64),
+    }

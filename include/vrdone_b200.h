@@ -1,0 +1,118 @@
+/* vrdone_b200 -- C ABI of the B200-native MaskVRD inference kernels (libvrdone_b200.so).
+ *
+ * The reference (lucaspk512/vrdone) has no FFI layer: its "operator API" for this path is the Python class
+ * models/maskvrd.py:16 `MaskVRD` whose arithmetic is PyTorch library calls.  Each entry
+ * point below replaces one group of those library calls on the packed varlen layout of vrdone_b200/layout.py; the
+ * Python mirror `vrdone_b200.MaskVRD` binds them with ctypes (vrdone_b200/cuda_ops.py) and keeps the reference's
+ * constructor / config / checkpoint / forward contract.  INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated otherwise; matrices are row-major `[rows, cols]` with a
+ * leading dimension `ld*` in ELEMENTS; `*_dtype` is VRD_F32 or VRD_BF16; `stream` is a cudaStream_t; kernels are
+ * enqueued asynchronously.  Every function returns 0 on success and non-zero on error, with text in vrd_last_error().
+ *
+ * A pyramid level of the row layout is passed as (row_seq, seqinfo, R, B):
+ *   row_seq[r]  int32, owning pair of row r, -1 for a separator row        (R entries, R % 128 == 0)
+ *   seqinfo[i]  int32x4 (first row, valid rows, first-pad-column-exists, 0) (B entries, 16-byte aligned)
+ * Kernels that take `streams` operate on `streams` stacked copies of the level (subject rows then object rows).
+ */
+#ifndef VRDONE_B200_H
+#define VRDONE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRD_F32 0
+#define VRD_BF16 1
+#define VRD_ACT_NONE 0
+#define VRD_ACT_RELU 1
+#define VRD_ACT_GELU 2
+#define VRD_ABI_VERSION 1
+
+typedef void* vrd_stream_t; /* cudaStream_t */
+
+int vrd_abi_version(void);
+const char* vrd_last_error(void);
+/* compute capability major*10+minor of the current device (100 on B200); <0 on error */
+int vrd_device_arch(void);
+
+/* k9 -- replaces MaskVRD.preprocessing (maskvrd.py:363-414) + the channel split of backbones.py:161-166 / 329-341.
+ * pair_ptrs[i] -> fp32 (C, L_i) tensor with element strides pair_strides[2i] (channel), pair_strides[2i+1] (time).
+ * Writes vis [2R, nv], clip [2R, nc] (or NULL when nc == 0) in act_dtype, bbox_so [R, 8] and bbox_ent [2R, 8] in fp32. */
+int vrd_pack_pairs(const void* pair_ptrs, const int64_t* pair_strides, const int32_t* row_seq, const int32_t* seqinfo, int R,
+                   int B, int nv, int nc, int nbs, int nbe, void* vis, void* clip, int act_dtype, float* bbox_so,
+                   float* bbox_ent, vrd_stream_t stream);
+
+/* k1/k2 -- replaces nn.Conv1d (k=1, and dense k=3 as three row-shifted K-slabs; blocks.py:85, 46, 728-737, 1054-1060):
+ * out = act(A * W^T + bias [+ corr on the last valid row of pairs with a pad column]) + res1 + res2, separator rows = 0.
+ * a_dtype VRD_BF16 -> tcgen05/TMEM tensor-core kernel (W bf16); VRD_F32 -> fp32 CUDA-core kernel (W fp32).
+ * W is [N, taps*K]; row_seq may be NULL (no layout: all rows valid). */
+int vrd_gemm(const void* A, int a_dtype, int64_t lda, const void* W, const float* bias, void* out, int out_dtype, int64_t ldo,
+             int M, int N, int K, int taps, int act, const float* res1, int64_t ldr1, const float* res2, int64_t ldr2,
+             const float* corr, const int32_t* row_seq, const int32_t* seqinfo, int R, vrd_stream_t stream);
+
+/* k6 -- channel LayerNorm (blocks.py:143-158) [+ReLU]; C in {256, 512}; separator rows -> 0 when row_seq != NULL. */
+int vrd_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
+                  int64_t ldo, int rows, int C, int relu, const int32_t* row_seq, int R, vrd_stream_t stream);
+
+/* tiny-K k=3 conv of the box-geometry channels (backbones.py:199-202, 232): x [rows, 8] fp32, wt [3*cin, 512]. */
+int vrd_small_conv(const float* x, int cin, const float* wt, const float* bias, const float* gamma, const float* beta, int relu,
+                   void* out, int out_dtype, int64_t ldo, int rows, int N, const int32_t* row_seq, int R, vrd_stream_t stream);
+
+/* k3 -- [LN_pre] -> depthwise k=3 conv (stride 1|2) -> mask -> LN for up to 3 branches (q/k/v) sharing one read of x
+ * (blocks.py:927-933, local_transformer.py:150-156, 561-567).  w[b] is [3, C] tap-major. */
+int vrd_dwconv_ln(const void* x, int x_dtype, int64_t ldx, const int32_t* row_seq_in, const int32_t* seqinfo_in, int R_in,
+                  const int32_t* row_seq_out, const int32_t* seqinfo_out, int R_out, int B, int stride, const float* pre_gamma,
+                  const float* pre_beta, int n_branches, const float* const* w, const int32_t* use_pre,
+                  const float* const* gamma, const float* const* beta, void* const* out, const int64_t* ldo, int out_dtype,
+                  int C, int streams, vrd_stream_t stream);
+
+/* k4 -- windowed attention, softmax over keys |i-j| <= w inside each pair (blocks.py:950-986). C = 512. */
+int vrd_window_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, const int32_t* row_seq,
+                    const int32_t* seqinfo, int R, int B, int n_head, int C, int w, int streams, vrd_stream_t stream);
+
+/* k5 -- full attention inside each pair (local_transformer.py:170-183); max_len = longest pair of the level. */
+int vrd_full_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, const int32_t* row_seq,
+                  const int32_t* seqinfo, int R, int B, int n_head, int C, int max_len, vrd_stream_t stream);
+
+/* k7 -- MaxPool1d(3, 2, 1) skip path of the stride-2 blocks (blocks.py:1040-1046, 1074). fp32, C = 512. */
+int vrd_maxpool_skip(const float* x, int64_t ldx, const int32_t* row_seq_in, const int32_t* seqinfo_in, int R_in,
+                     const int32_t* row_seq_out, const int32_t* seqinfo_out, int R_out, int B, float* out, int64_t ldo, int C,
+                     vrd_stream_t stream);
+
+/* FPN (fpns.py:229-257): top level grouped conv; lower levels lateral-LN + nearest-up2 add + depthwise conv + LN;
+ * mask_features depthwise conv + bias.  fp32, fpn_dim = 256, input channels 512. */
+int vrd_fpn_top(const float* x, int64_t ldx, const int32_t* row_seq, const int32_t* seqinfo, int R, int B, const float* pre_gamma,
+                const float* pre_beta, const float* wt, const float* gamma, const float* beta, float* out, int64_t ldo,
+                vrd_stream_t stream);
+int vrd_fpn_level(const float* cur, int64_t ldc, const float* y_up, int64_t ldu, const int32_t* row_seq, const int32_t* seqinfo,
+                  int R, const int32_t* row_seq_up, const int32_t* seqinfo_up, int R_up, int B, const float* lat_gamma,
+                  const float* lat_beta, const float* beta_up, const float* w, const float* gamma, const float* beta,
+                  float* out, int64_t ldo, vrd_stream_t stream);
+int vrd_mask_features(const float* y, int64_t ldy, const int32_t* row_seq, const int32_t* seqinfo, int R, int B,
+                      const float* beta, const float* w, const float* bias, float* out, int64_t ldo, vrd_stream_t stream);
+
+/* predictor query rows (local_transformer.py:807-835, 956-976): out = LN2(dw * (LN(x) + pos[row % Q])), stages optional. */
+int vrd_query_ln(const float* x, int64_t ldx, const float* gamma, const float* beta, const float* pos, int Q, int nrows,
+                 int total_rows, const float* dw, const float* gamma2, const float* beta2, void* out, int out_dtype,
+                 int64_t ldo, int C, vrd_stream_t stream);
+int vrd_query_self_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, int B, int Q, int n_head,
+                        int C, vrd_stream_t stream);
+int vrd_query_cross_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, const int32_t* row_seq,
+                         const int32_t* seqinfo, int R, int B, int Q, int n_head, int C, vrd_stream_t stream);
+
+/* k10 -- heads epilogue (predictor.py:103-105, maskvrd.py:247-248, 287-295): mask logits <mask_embed, mask_features>,
+ * sigmoid(.) > 0.5 in fp32, first/last active frame per (pair, query) (-1, -1 if none); class softmax + top-k over
+ * classes 1..n_cls-1 (1-based ids; ties -> lower id).  masks may be NULL. */
+int vrd_mask_logits(const float* mask_embed, int64_t ldm, const float* mask_feat, int64_t ldf, const int32_t* row_seq,
+                    const int32_t* seqinfo, int R, int B, int Q, float* masks, int64_t ldk, int32_t* first_last,
+                    vrd_stream_t stream);
+int vrd_softmax_topk(const float* logits, int64_t ldl, int nrows, int n_cls, int topk, float* scores, int32_t* ids,
+                     vrd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRDONE_B200_H */

@@ -101,7 +101,7 @@ class EmuOps:
         xf = x[:, :cin].float()
         z = torch.zeros(1, cin)
         a = torch.cat([torch.cat([z, xf[:-1]]), xf, torch.cat([xf[1:], z])], 1)
-        y = a @ w.t() + bias
+        y = a @ w + bias          # w: [3*cin, N]
         if ln is not None:
             y = _ln_rows(y, ln[0], ln[1])
         if relu:
@@ -129,7 +129,7 @@ class EmuOps:
                     padv = torch.zeros(C)
                 ext = torch.cat([torch.zeros(1, C), src, padv[None], torch.zeros(1, C)])   # index t+1 <-> time t
                 t = torch.arange(L_out) * stride
-                y = ext[t] * w[:, 0] + ext[t + 1] * w[:, 1] + ext[t + 2] * w[:, 2]
+                y = ext[t] * w[0] + ext[t + 1] * w[1] + ext[t + 2] * w[2]      # w: [3, C]
                 out[r_out:r_out + L_out] = _ln_rows(y, g, b).to(out.dtype)
 
     def window_attn(self, q, k, v, out, lay, n_head, w, streams):
@@ -176,14 +176,13 @@ class EmuOps:
         """Grouped k=3 conv (F groups, 2 input channels each) over LN_pre(x), then LN."""
         self.calls.append("fpn_top")
         out.zero_()
-        Fd = w.shape[0]
-        wk = w.view(Fd, 2, 3)
+        Fd = w.shape[1] // 2          # w: [3, 2*F], indexed by input channel 2c + j
         for s, i, r0, L, hp in self._seqs(lay):
             src = _ln_rows(x[r0:r0 + L], pre[0], pre[1])
             C = src.shape[1]
             padv = pre[1] if hp else torch.zeros(C)
-            ext = torch.cat([torch.zeros(1, C), src, padv[None]]).view(L + 2, Fd, 2)
-            y = sum((ext[k:k + L] * wk[:, :, k]).sum(-1) for k in range(3))
+            ext = torch.cat([torch.zeros(1, C), src, padv[None]])
+            y = sum((ext[k:k + L] * w[k]).view(L, Fd, 2).sum(-1) for k in range(3))
             out[r0:r0 + L] = _ln_rows(y, ln[0], ln[1])
 
     def fpn_level(self, cur, y_up, lay, lay_up, ln_lat, beta_up, w, ln, out):
@@ -200,7 +199,7 @@ class EmuOps:
             else:
                 padv = torch.zeros(Fd)
             ext = torch.cat([torch.zeros(1, Fd), z, padv[None]])
-            y = ext[0:L] * w[:, 0] + ext[1:L + 1] * w[:, 1] + ext[2:L + 2] * w[:, 2]
+            y = ext[0:L] * w[0] + ext[1:L + 1] * w[1] + ext[2:L + 2] * w[2]
             out[r0:r0 + L] = _ln_rows(y, ln[0], ln[1])
 
     def mask_features(self, y, lay, beta, w, bias, out):
@@ -210,7 +209,7 @@ class EmuOps:
         for s, i, r0, L, hp in self._seqs(lay):
             padv = beta if hp else torch.zeros(Fd)
             ext = torch.cat([torch.zeros(1, Fd), y[r0:r0 + L].float(), padv[None]])
-            out[r0:r0 + L] = (ext[0:L] * w[:, 0] + ext[1:L + 1] * w[:, 1] + ext[2:L + 2] * w[:, 2] + bias).to(out.dtype)
+            out[r0:r0 + L] = (ext[0:L] * w[0] + ext[1:L + 1] * w[1] + ext[2:L + 2] * w[2] + bias).to(out.dtype)
 
     def query_ln(self, x, ln, pos, Q, nrows, dw, ln2, out):
         """out = LN2(dw * (LN(x) + pos[row % Q])) with every stage optional; rows >= nrows are zeroed."""

@@ -1,0 +1,93 @@
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference (imported read-only from
+/root/reference) on seeded inputs.  Run in the build container only:  python tests/golden/make_golden.py
+
+Weights and inputs are not stored: they are re-derived from the seeds with vrdone_b200.synth (CPU RNG, deterministic);
+a checksum of both is stored so that RNG drift is detected instead of silently invalidating the fixtures.
+"""
+import json
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from vrdone_b200 import MaskVRD, synth  # noqa: E402
+from vrdone_b200.layout import reference_padded_lengths  # noqa: E402
+
+CASES = {
+    "vidvrd": dict(lens=[96, 95, 49, 7, 2, 89, 97, 109], wseed=11, xseed=12),
+    "vidor": dict(lens=[512, 511, 505, 121, 127, 128, 64, 2, 3, 513, 640], wseed=21, xseed=22),
+    "vidor_local": dict(lens=[512, 509, 33, 200, 576], wseed=31, xseed=32),
+    "vidor_x": dict(lens=[512, 510, 17, 3, 130], wseed=41, xseed=42),
+}
+VIDEO_CASES = {"vidvrd": dict(wseed=11, vseed=0), "vidor": dict(wseed=21, vseed=3, n_tracklets=5, n_frames=700)}
+
+
+def load_reference():
+    sys.path.insert(0, "/root/reference")
+    for m in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+        del sys.modules[m]
+    from models.maskvrd import MaskVRD as Ref
+    sys.path.pop(0)
+    return Ref
+
+
+def checksum(tensors):
+    return float(sum(t.double().abs().sum() for t in tensors))
+
+
+def build_ref(Ref, name, wseed):
+    cfg = synth.load_config(name)
+    mc = cfg["model_config"]
+    ref = Ref(mc, "cpu").eval()
+    ref._config_eval(cfg["inference_config"])
+    ours = MaskVRD(mc, "cpu")
+    assert set(ours.state_dict().keys()) == set(ref.state_dict().keys())
+    sd = synth.stress_state_dict(ours.state_dict(), wseed)
+    ref.load_state_dict(sd, strict=True)
+    return cfg, ref, sd
+
+
+def main():
+    Ref = load_reference()
+    torch.manual_seed(0)
+    for name, case in CASES.items():
+        cfg, ref, sd = build_ref(Ref, name, case["wseed"])
+        mc = cfg["model_config"]
+        feats = synth.pair_features(mc, case["lens"], case["xseed"])
+        tpads = reference_padded_lengths(case["lens"], mc)
+        logits, masks = [], []
+        with torch.no_grad():
+            for f, t in zip(feats, tpads):   # one pair per reference call: outputs depend only on (pair, T_pad)
+                x = torch.zeros(1, f.shape[0], t)
+                x[0, :, : f.shape[1]] = f
+                m = (torch.arange(t) < f.shape[1])[None, None]
+                r = ref._mask_vrd(x, m)
+                logits.append(r["pred_logits"][0].clone())
+                masks.append(r["pred_masks"][0][:, : f.shape[1]].clone())
+        fix = {"config": name, "lens": case["lens"], "tpads": tpads, "wseed": case["wseed"], "xseed": case["xseed"],
+               "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(feats),
+               "pred_logits": torch.stack(logits), "pred_masks": masks,
+               "schema": {k: list(v.shape) for k, v in sd.items()}}
+        torch.save(fix, os.path.join(HERE, f"network_{name}.pt"))
+        print(name, "network fixture:", fix["pred_logits"].shape, "logit std", float(fix["pred_logits"].std()))
+    for name, case in VIDEO_CASES.items():
+        cfg, ref, sd = build_ref(Ref, name, case["wseed"])
+        kw = {k: v for k, v in case.items() if k in ("n_tracklets", "n_frames")}
+        video = synth.synthetic_video(cfg, case["vseed"], **kw)
+        with torch.no_grad():
+            out = ref(video)
+        lens = [int(f.shape[1]) for f in video["so_features_list"]]
+        if out is not None:   # keep the fixture small: trajectories are stored as (n_frames, checksum) per triplet
+            out["so_trajs"] = [[len(t[0]), float(torch.tensor(t).double().sum())] for t in out["so_trajs"]]
+        fix = {"config": name, **case, "n_pairs": len(lens), "lens": lens, "inputs_checksum": checksum(video["so_features_list"]),
+               "weights_checksum": checksum(sd.values()), "output": out}
+        with open(os.path.join(HERE, f"video_{name}.json"), "w") as f:
+            json.dump(fix, f)
+        print(name, "video fixture:", len(lens), "pairs ->", None if out is None else len(out["triplets"]), "triplets")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,328 @@
+// Attention kernels over the varlen row layout.
+// Reference semantics (under /root/reference/models/): windowed attention blocks.py:920-989 and
+// local_transformer.py:553-623 (softmax over keys with |i-j| <= w inside the pair; the -1e4 / -inf masking of the
+// padded batch reduces to "valid keys only" in the varlen layout); full attention local_transformer.py:144-187;
+// query self/cross attention of the predictor local_transformer.py:33-67, 144-187.
+// The 1/sqrt(head_dim) scale is folded into the query projection weights by the host.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vrd {
+
+constexpr int WARPS = 8;
+
+// ------------------------------------------------------------------------------------------------------------
+// window_attn: one warp per token row, all heads.  LPH = lanes per head (head_dim / 4).
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int NCH, int LPH>
+__global__ void window_attn_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                                   T* __restrict__ out, long long ld, Lay lay, int w, int streams) {
+    constexpr int MAXK = 9;
+    const int lane = threadIdx.x & 31;
+    const int grow = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (grow >= streams * lay.R) return;
+    const int s = grow / lay.R, r = grow - s * lay.R;
+    T* o = out + (long long)grow * ld;
+    const int seq = lay.row_seq[r];
+    if (seq < 0) { zero_row<T, NCH>(o, lane); return; }
+    const int4 si = lay.seqinfo[seq];
+    const int t = r - si.x;
+    const long long base = (long long)s * lay.R + si.x;
+    float qv[NCH][4];
+    load_row<T, NCH>(q + (long long)grow * ld, lane, qv);
+    float sc[MAXK][NCH];
+    float mx[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) mx[j] = -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < MAXK; ++kk) {
+        const int tt = t - w + kk;
+        const bool ok = (kk <= 2 * w) && tt >= 0 && tt < si.y;
+        if (ok) {
+            float kv[NCH][4];
+            load_row<T, NCH>(k + (base + tt) * ld, lane, kv);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                float d = qv[j][0] * kv[j][0] + qv[j][1] * kv[j][1] + qv[j][2] * kv[j][2] + qv[j][3] * kv[j][3];
+#pragma unroll
+                for (int off = LPH / 2; off > 0; off >>= 1) d += __shfl_xor_sync(FULL_MASK, d, off);
+                sc[kk][j] = d;
+                mx[j] = fmaxf(mx[j], d);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) sc[kk][j] = -INFINITY;
+        }
+    }
+    float sum[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) sum[j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < MAXK; ++kk)
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const float p = (sc[kk][j] == -INFINITY) ? 0.f : expf(sc[kk][j] - mx[j]);
+            sc[kk][j] = p;
+            sum[j] += p;
+        }
+    float acc[NCH][4];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < MAXK; ++kk) {
+        const int tt = t - w + kk;
+        const bool ok = (kk <= 2 * w) && tt >= 0 && tt < si.y;
+        if (ok) {
+            float vv[NCH][4];
+            load_row<T, NCH>(v + (base + tt) * ld, lane, vv);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(sc[kk][j], vv[j][i], acc[j][i]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const float inv = 1.0f / sum[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] *= inv;
+    }
+    store_row<T, NCH>(o, lane, acc);
+}
+
+int window_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int n_head, int C, int w,
+                int streams, cudaStream_t st) {
+    if (C != 512 || w > 4 || w < 1) return 1;
+    const int hs = C / n_head;
+    const int grid = (streams * lay.R + WARPS - 1) / WARPS;
+#define LAUNCH(T, LPH) \
+    window_attn_kernel<T, 4, LPH><<<grid, WARPS * 32, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay, w, streams)
+    if (hs == 64) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 16); else LAUNCH(float, 16); }
+    else if (hs == 128) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 32); else LAUNCH(float, 32); }
+    else return 1;
+#undef LAUNCH
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// full_attn: flash-style softmax(QK^T)V inside each pair, fp32 math on CUDA cores (round-1 baseline kernel).
+// A group of TPQ = HS/32 threads owns one query; thread `part` holds dims  d*TPQ + part.
+// grid = (query tiles, heads, pairs)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int HS>
+__global__ void __launch_bounds__(128) full_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                        const T* __restrict__ v, T* __restrict__ out, long long ld, Lay lay) {
+    constexpr int TPQ = HS / 32;
+    constexpr int QPB = 128 / TPQ;
+    constexpr int KT = 32;
+    __shared__ float Ks[KT][HS];
+    __shared__ float Vs[KT][HS];
+    const int seq = blockIdx.z, head = blockIdx.y;
+    const int4 si = lay.seqinfo[seq];
+    const int len = si.y;
+    const int q0 = blockIdx.x * QPB;
+    if (q0 >= len) return;
+    const int qi = q0 + threadIdx.x / TPQ;
+    const int part = threadIdx.x % TPQ;
+    const bool qok = qi < len;
+    const long long hoff = (long long)head * HS;
+    float qv[32], acc[32];
+    {
+        const T* qr = q + (long long)(si.x + (qok ? qi : 0)) * ld + hoff;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) { qv[d] = to_f(qr[d * TPQ + part]); acc[d] = 0.f; }
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int k0 = 0; k0 < len; k0 += KT) {
+        const int nk = min(KT, len - k0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < KT * HS; i += 128) {
+            const int kk = i / HS, d = i % HS;
+            float kvv = 0.f, vvv = 0.f;
+            if (kk < nk) {
+                const long long row = (long long)(si.x + k0 + kk) * ld + hoff + d;
+                kvv = to_f(k[row]);
+                vvv = to_f(v[row]);
+            }
+            Ks[kk][d] = kvv;
+            Vs[kk][d] = vvv;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < nk; ++kk) {
+            float sdot = 0.f;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) sdot = fmaf(qv[d], Ks[kk][d * TPQ + part], sdot);
+#pragma unroll
+            for (int off = TPQ / 2; off > 0; off >>= 1) sdot += __shfl_xor_sync(FULL_MASK, sdot, off);
+            const float mn = fmaxf(m, sdot);
+            const float corr = expf(m - mn);      // exp(-inf) = 0 on the first key
+            const float p = expf(sdot - mn);
+            l = l * corr + p;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) acc[d] = fmaf(p, Vs[kk][d * TPQ + part], acc[d] * corr);
+            m = mn;
+        }
+    }
+    if (qok) {
+        const float inv = 1.0f / l;
+        T* orow = out + (long long)(si.x + qi) * ld + hoff;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) orow[d * TPQ + part] = from_f<T>(acc[d] * inv);
+    }
+}
+
+// zero the separator rows of an attention output (full_attn only writes valid rows)
+template <typename T>
+__global__ void zero_separators_kernel(T* __restrict__ out, long long ld, int C, const int* __restrict__ row_seq, int R) {
+    const int r = blockIdx.x;
+    if (row_seq[r] >= 0) return;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) out[(long long)r * ld + c] = from_f<T>(0.f);
+}
+
+int full_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int n_head, int C,
+              int max_len, cudaStream_t st) {
+    const int hs = C / n_head;
+    if (lay.B > 65535 || max_len < 1) return 1;
+    const int max_rows = max_len;   // longest pair of the level bounds the number of query tiles (blocks past a pair's end exit)
+    if (dt == VRD_BF16) zero_separators_kernel<__nv_bfloat16><<<lay.R, 128, 0, st>>>((__nv_bfloat16*)out, ld, C, lay.row_seq, lay.R);
+    else zero_separators_kernel<float><<<lay.R, 128, 0, st>>>((float*)out, ld, C, lay.row_seq, lay.R);
+#define LAUNCH(T, HS) \
+    full_attn_kernel<T, HS><<<dim3((max_rows + (128 / (HS / 32)) - 1) / (128 / (HS / 32)), n_head, lay.B), 128, 0, st>>>( \
+        (const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay)
+    if (hs == 64) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 64); else LAUNCH(float, 64); }
+    else if (hs == 128) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 128); else LAUNCH(float, 128); }
+    else return 1;
+#undef LAUNCH
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// query_self_attn: attention among the Q (<= 12) queries of each pair.  One block per pair, D = 256.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) query_self_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                              const T* __restrict__ v, T* __restrict__ out, long long ld,
+                                                              int Q, int n_head) {
+    constexpr int D = 256, MAXQ = 12, MAXH = 8;
+    __shared__ float sq[MAXQ][D], sk[MAXQ][D], sv[MAXQ][D];
+    __shared__ float sp[MAXH][MAXQ][MAXQ];
+    const int pair = blockIdx.x;
+    const int hs = D / n_head;
+    const long long r0 = (long long)pair * Q;
+    for (int i = threadIdx.x; i < Q * D; i += 256) {
+        const int qi = i / D, d = i % D;
+        sq[qi][d] = to_f(q[(r0 + qi) * ld + d]);
+        sk[qi][d] = to_f(k[(r0 + qi) * ld + d]);
+        sv[qi][d] = to_f(v[(r0 + qi) * ld + d]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_head * Q * Q; i += 256) {
+        const int h = i / (Q * Q), qi = (i / Q) % Q, kj = i % Q;
+        float s = 0.f;
+        for (int d = 0; d < hs; ++d) s = fmaf(sq[qi][h * hs + d], sk[kj][h * hs + d], s);
+        sp[h][qi][kj] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_head * Q; i += 256) {
+        const int h = i / Q, qi = i % Q;
+        float mx = -INFINITY;
+        for (int j = 0; j < Q; ++j) mx = fmaxf(mx, sp[h][qi][j]);
+        float sum = 0.f;
+        for (int j = 0; j < Q; ++j) { const float p = expf(sp[h][qi][j] - mx); sp[h][qi][j] = p; sum += p; }
+        const float inv = 1.0f / sum;
+        for (int j = 0; j < Q; ++j) sp[h][qi][j] *= inv;
+    }
+    __syncthreads();
+    const int d = threadIdx.x, h = d / hs;
+    for (int qi = 0; qi < Q; ++qi) {
+        float acc = 0.f;
+        for (int j = 0; j < Q; ++j) acc = fmaf(sp[h][qi][j], sv[j][d], acc);
+        out[(r0 + qi) * ld + d] = from_f<T>(acc);
+    }
+}
+
+int query_self_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, int B, int Q, int n_head, int C,
+                    cudaStream_t st) {
+    if (C != 256 || Q > 12 || n_head > 8 || B < 1) return 1;
+    if (dt == VRD_BF16)
+        query_self_attn_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                                                                 (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ld, Q, n_head);
+    else
+        query_self_attn_kernel<float><<<B, 256, 0, st>>>((const float*)q, (const float*)k, (const float*)v, (float*)out, ld, Q, n_head);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// query_cross_attn: Q queries of a pair attend to the pair's rows of the coarsest level.  One block per pair; a warp
+// handles one (query, head) at a time: lanes = keys for the scores, lanes = head dims for P.V.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int HS>
+__global__ void __launch_bounds__(256) query_cross_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                               const T* __restrict__ v, T* __restrict__ out, long long ld,
+                                                               Lay lay, int Q, int n_head) {
+    constexpr int D = 256, MAXQ = 12, DPL = HS / 32;
+    __shared__ float sq[MAXQ][D];
+    const int pair = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int4 si = lay.seqinfo[pair];
+    const long long r0 = (long long)pair * Q;
+    for (int i = threadIdx.x; i < Q * D; i += 256) sq[i / D][i % D] = to_f(q[(r0 + i / D) * ld + (i % D)]);
+    __syncthreads();
+    for (int combo = warp; combo < Q * n_head; combo += 8) {
+        const int qi = combo / n_head, h = combo % n_head;
+        const float* qh = &sq[qi][h * HS];
+        float m = -INFINITY, l = 0.f;
+        float acc[DPL];
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+        for (int k0 = 0; k0 < si.y; k0 += 32) {
+            const int kj = k0 + lane;
+            float s = -INFINITY;
+            if (kj < si.y) {
+                const T* kr = k + (long long)(si.x + kj) * ld + h * HS;
+                float d = 0.f;
+#pragma unroll
+                for (int c = 0; c < HS; c += 4) {
+                    float kv[4];
+                    ld4(kr + c, kv);
+                    d += qh[c] * kv[0] + qh[c + 1] * kv[1] + qh[c + 2] * kv[2] + qh[c + 3] * kv[3];
+                }
+                s = d;
+            }
+            const float mn = fmaxf(m, warp_max(s));
+            const float corr = expf(m - mn);
+            const float p = (kj < si.y) ? expf(s - mn) : 0.f;
+            l = l * corr + warp_sum(p);
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) acc[i] *= corr;
+            const int nk = min(32, si.y - k0);
+            for (int jj = 0; jj < nk; ++jj) {
+                const float pj = __shfl_sync(FULL_MASK, p, jj);
+                const T* vr = v + (long long)(si.x + k0 + jj) * ld + h * HS;
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) acc[i] = fmaf(pj, to_f(vr[lane + 32 * i]), acc[i]);
+            }
+            m = mn;
+        }
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) out[(r0 + qi) * ld + h * HS + lane + 32 * i] = from_f<T>(acc[i] * inv);
+    }
+}
+
+int query_cross_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int Q, int n_head,
+                     int C, cudaStream_t st) {
+    if (C != 256 || Q > 12) return 1;
+    const int hs = C / n_head;
+#define LAUNCH(T, HS) \
+    query_cross_attn_kernel<T, HS><<<lay.B, 256, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay, Q, n_head)
+    if (hs == 32) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 32); else LAUNCH(float, 32); }
+    else if (hs == 64) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 64); else LAUNCH(float, 64); }
+    else return 1;
+#undef LAUNCH
+    return 0;
+}
+
+}  // namespace vrd

@@ -1,0 +1,195 @@
+// extern "C" boundary of libvrdone_b200.so: argument checking, error text, dispatch to the kernel launchers.
+#include <cstdio>
+#include <cstring>
+#include "../../include/vrdone_b200.h"
+#include "kernels.h"
+
+namespace {
+thread_local char t_err[512] = {0};
+
+int fail(const char* what) {
+    snprintf(t_err, sizeof t_err, "%s", what);
+    return 1;
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(t_err, sizeof t_err, "%s: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+Lay make_lay(const int32_t* row_seq, const int32_t* seqinfo, int R, int B) {
+    Lay l;
+    l.row_seq = row_seq;
+    l.seqinfo = reinterpret_cast<const int4*>(seqinfo);
+    l.R = R;
+    l.B = B;
+    return l;
+}
+}  // namespace
+
+extern "C" {
+
+int vrd_abi_version(void) { return VRD_ABI_VERSION; }
+const char* vrd_last_error(void) { return t_err; }
+
+int vrd_device_arch(void) {
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { fail("cudaGetDevice failed (no CUDA device?)"); return -1; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return major * 10 + minor;
+}
+
+int vrd_pack_pairs(const void* pair_ptrs, const int64_t* pair_strides, const int32_t* row_seq, const int32_t* seqinfo, int R,
+                   int B, int nv, int nc, int nbs, int nbe, void* vis, void* clip, int act_dtype, float* bbox_so,
+                   float* bbox_ent, vrd_stream_t stream) {
+    if (nbs > 8 || nbe > 8 || R <= 0 || B <= 0) return fail("vrd_pack_pairs: bad sizes");
+    if (nc > 0 && clip == nullptr) return fail("vrd_pack_pairs: clip output missing");
+    vrd::pack_pairs(pair_ptrs, (const long long*)pair_strides, make_lay(row_seq, seqinfo, R, B), nv, nc, nbs, nbe, vis, clip,
+                    act_dtype, bbox_so, bbox_ent, (cudaStream_t)stream);
+    return check_launch("vrd_pack_pairs");
+}
+
+int vrd_gemm(const void* A, int a_dtype, int64_t lda, const void* W, const float* bias, void* out, int out_dtype, int64_t ldo,
+             int M, int N, int K, int taps, int act, const float* res1, int64_t ldr1, const float* res2, int64_t ldr2,
+             const float* corr, const int32_t* row_seq, const int32_t* seqinfo, int R, vrd_stream_t stream) {
+    if (taps != 1 && taps != 3) return fail("vrd_gemm: taps must be 1 or 3");
+    if (corr != nullptr && row_seq == nullptr) return fail("vrd_gemm: corr needs a layout");
+    vrd::GemmArgs g;
+    g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.out = out; g.out_dtype = out_dtype; g.ldo = ldo;
+    g.M = M; g.N = N; g.K = K; g.taps = taps; g.act = act;
+    g.res1 = res1; g.ldr1 = ldr1; g.res2 = res2; g.ldr2 = ldr2; g.corr = corr;
+    g.row_seq = row_seq; g.seqinfo = reinterpret_cast<const int4*>(seqinfo); g.R = R;
+    if (a_dtype == VRD_BF16) {
+        if (vrd::gemm_tcgen05_bf16(g, (cudaStream_t)stream) != 0) return fail(vrd::gemm_tcgen05_error());
+    } else if (a_dtype == VRD_F32) {
+        if (vrd::gemm_simt_f32(g, (cudaStream_t)stream) != 0) return fail("vrd_gemm(fp32): K must be a multiple of 16 and lda of 4");
+    } else {
+        return fail("vrd_gemm: bad a_dtype");
+    }
+    return check_launch("vrd_gemm");
+}
+
+int vrd_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
+                  int64_t ldo, int rows, int C, int relu, const int32_t* row_seq, int R, vrd_stream_t stream) {
+    if (vrd::layernorm(x, x_dtype, ldx, gamma, beta, out, out_dtype, ldo, rows, C, relu, row_seq, R, (cudaStream_t)stream))
+        return fail("vrd_layernorm: unsupported C / dtype combination");
+    return check_launch("vrd_layernorm");
+}
+
+int vrd_small_conv(const float* x, int cin, const float* wt, const float* bias, const float* gamma, const float* beta, int relu,
+                   void* out, int out_dtype, int64_t ldo, int rows, int N, const int32_t* row_seq, int R, vrd_stream_t stream) {
+    if (row_seq == nullptr) return fail("vrd_small_conv: layout required");
+    if (vrd::small_conv(x, cin, wt, bias, gamma, beta, relu, out, out_dtype, ldo, rows, N, row_seq, R, (cudaStream_t)stream))
+        return fail("vrd_small_conv: N must be 512 and cin <= 8");
+    return check_launch("vrd_small_conv");
+}
+
+int vrd_dwconv_ln(const void* x, int x_dtype, int64_t ldx, const int32_t* row_seq_in, const int32_t* seqinfo_in, int R_in,
+                  const int32_t* row_seq_out, const int32_t* seqinfo_out, int R_out, int B, int stride, const float* pre_gamma,
+                  const float* pre_beta, int n_branches, const float* const* w, const int32_t* use_pre,
+                  const float* const* gamma, const float* const* beta, void* const* out, const int64_t* ldo, int out_dtype,
+                  int C, int streams, vrd_stream_t stream) {
+    if (n_branches < 1 || n_branches > 3) return fail("vrd_dwconv_ln: 1..3 branches");
+    if (stride != 1 && stride != 2) return fail("vrd_dwconv_ln: stride must be 1 or 2");
+    vrd::DwBranches br;
+    memset(&br, 0, sizeof br);
+    br.n = n_branches;
+    for (int i = 0; i < n_branches; ++i) {
+        br.w[i] = w[i]; br.use_pre[i] = use_pre[i]; br.g[i] = gamma[i]; br.b[i] = beta[i]; br.out[i] = out[i]; br.ldo[i] = ldo[i];
+        if (use_pre[i] && pre_gamma == nullptr) return fail("vrd_dwconv_ln: pre-LN branch without pre-LN parameters");
+    }
+    if (vrd::dwconv_ln(x, x_dtype, ldx, make_lay(row_seq_in, seqinfo_in, R_in, B), make_lay(row_seq_out, seqinfo_out, R_out, B),
+                       stride, pre_gamma, pre_beta, br, out_dtype, C, streams, (cudaStream_t)stream))
+        return fail("vrd_dwconv_ln: unsupported C / dtype combination");
+    return check_launch("vrd_dwconv_ln");
+}
+
+int vrd_window_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, const int32_t* row_seq,
+                    const int32_t* seqinfo, int R, int B, int n_head, int C, int w, int streams, vrd_stream_t stream) {
+    if (vrd::window_attn(q, k, v, out, dtype, ld, make_lay(row_seq, seqinfo, R, B), n_head, C, w, streams, (cudaStream_t)stream))
+        return fail("vrd_window_attn: needs C == 512, head_dim in {64, 128}, 1 <= w <= 4");
+    return check_launch("vrd_window_attn");
+}
+
+int vrd_full_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, const int32_t* row_seq,
+                  const int32_t* seqinfo, int R, int B, int n_head, int C, int max_len, vrd_stream_t stream) {
+    Lay l = make_lay(row_seq, seqinfo, R, B);
+    if (vrd::full_attn(q, k, v, out, dtype, ld, l, n_head, C, max_len, (cudaStream_t)stream))
+        return fail("vrd_full_attn: needs head_dim in {64, 128} and B <= 65535");
+    return check_launch("vrd_full_attn");
+}
+
+int vrd_maxpool_skip(const float* x, int64_t ldx, const int32_t* row_seq_in, const int32_t* seqinfo_in, int R_in,
+                     const int32_t* row_seq_out, const int32_t* seqinfo_out, int R_out, int B, float* out, int64_t ldo, int C,
+                     vrd_stream_t stream) {
+    if (vrd::maxpool_skip(x, ldx, make_lay(row_seq_in, seqinfo_in, R_in, B), make_lay(row_seq_out, seqinfo_out, R_out, B), out, ldo,
+                          C, (cudaStream_t)stream))
+        return fail("vrd_maxpool_skip: C must be 512");
+    return check_launch("vrd_maxpool_skip");
+}
+
+int vrd_fpn_top(const float* x, int64_t ldx, const int32_t* row_seq, const int32_t* seqinfo, int R, int B, const float* pre_gamma,
+                const float* pre_beta, const float* wt, const float* gamma, const float* beta, float* out, int64_t ldo,
+                vrd_stream_t stream) {
+    vrd::fpn_top(x, ldx, make_lay(row_seq, seqinfo, R, B), pre_gamma, pre_beta, wt, gamma, beta, out, ldo, (cudaStream_t)stream);
+    return check_launch("vrd_fpn_top");
+}
+
+int vrd_fpn_level(const float* cur, int64_t ldc, const float* y_up, int64_t ldu, const int32_t* row_seq, const int32_t* seqinfo,
+                  int R, const int32_t* row_seq_up, const int32_t* seqinfo_up, int R_up, int B, const float* lat_gamma,
+                  const float* lat_beta, const float* beta_up, const float* w, const float* gamma, const float* beta,
+                  float* out, int64_t ldo, vrd_stream_t stream) {
+    vrd::fpn_level(cur, ldc, y_up, ldu, make_lay(row_seq, seqinfo, R, B), make_lay(row_seq_up, seqinfo_up, R_up, B), lat_gamma,
+                   lat_beta, beta_up, w, gamma, beta, out, ldo, (cudaStream_t)stream);
+    return check_launch("vrd_fpn_level");
+}
+
+int vrd_mask_features(const float* y, int64_t ldy, const int32_t* row_seq, const int32_t* seqinfo, int R, int B,
+                      const float* beta, const float* w, const float* bias, float* out, int64_t ldo, vrd_stream_t stream) {
+    vrd::mask_features(y, ldy, make_lay(row_seq, seqinfo, R, B), beta, w, bias, out, ldo, (cudaStream_t)stream);
+    return check_launch("vrd_mask_features");
+}
+
+int vrd_query_ln(const float* x, int64_t ldx, const float* gamma, const float* beta, const float* pos, int Q, int nrows,
+                 int total_rows, const float* dw, const float* gamma2, const float* beta2, void* out, int out_dtype,
+                 int64_t ldo, int C, vrd_stream_t stream) {
+    if (vrd::query_ln(x, ldx, gamma, beta, pos, Q, nrows, total_rows, dw, gamma2, beta2, out, out_dtype, ldo, C,
+                      (cudaStream_t)stream))
+        return fail("vrd_query_ln: C must be 256");
+    return check_launch("vrd_query_ln");
+}
+
+int vrd_query_self_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, int B, int Q, int n_head,
+                        int C, vrd_stream_t stream) {
+    if (vrd::query_self_attn(q, k, v, out, dtype, ld, B, Q, n_head, C, (cudaStream_t)stream))
+        return fail("vrd_query_self_attn: needs C == 256, Q <= 12, n_head <= 8");
+    return check_launch("vrd_query_self_attn");
+}
+
+int vrd_query_cross_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, const int32_t* row_seq,
+                         const int32_t* seqinfo, int R, int B, int Q, int n_head, int C, vrd_stream_t stream) {
+    if (vrd::query_cross_attn(q, k, v, out, dtype, ld, make_lay(row_seq, seqinfo, R, B), Q, n_head, C, (cudaStream_t)stream))
+        return fail("vrd_query_cross_attn: needs C == 256, Q <= 12, head_dim in {32, 64}");
+    return check_launch("vrd_query_cross_attn");
+}
+
+int vrd_mask_logits(const float* mask_embed, int64_t ldm, const float* mask_feat, int64_t ldf, const int32_t* row_seq,
+                    const int32_t* seqinfo, int R, int B, int Q, float* masks, int64_t ldk, int32_t* first_last,
+                    vrd_stream_t stream) {
+    if (vrd::mask_logits(mask_embed, ldm, mask_feat, ldf, make_lay(row_seq, seqinfo, R, B), Q, masks, ldk, first_last,
+                         (cudaStream_t)stream))
+        return fail("vrd_mask_logits: Q must be <= 16");
+    return check_launch("vrd_mask_logits");
+}
+
+int vrd_softmax_topk(const float* logits, int64_t ldl, int nrows, int n_cls, int topk, float* scores, int32_t* ids,
+                     vrd_stream_t stream) {
+    if (vrd::softmax_topk(logits, ldl, nrows, n_cls, topk, scores, ids, (cudaStream_t)stream))
+        return fail("vrd_softmax_topk: needs n_cls <= 256 and topk < n_cls");
+    return check_launch("vrd_softmax_topk");
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// Shared device helpers for the vrdone_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define VRD_F32 0
+#define VRD_BF16 1
+
+#define VRD_EPS 1e-5f
+#define FULL_MASK 0xffffffffu
+
+// One pyramid level of the varlen row layout (see vrdone_b200/layout.py).
+// seqinfo[i] = (first row, valid rows, first-pad-column-exists, 0); row_seq[r] = owning pair or -1.
+struct Lay {
+    const int* __restrict__ row_seq;
+    const int4* __restrict__ seqinfo;
+    int R;   // rows per stream (multiple of 128)
+    int B;   // pairs
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- 4-element chunk loads/stores (a lane owns chunks  c = j*32 + lane,  elements 4c .. 4c+3) ----
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+}
+
+// A full row of C = 128*NCH channels distributed over a warp: v[j][i] = row[(j*32 + lane)*4 + i].
+template <typename T, int NCH>
+__device__ __forceinline__ void load_row(const T* row, int lane, float (&v)[NCH][4]) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) ld4(row + (j * 32 + lane) * 4, v[j]);
+}
+template <typename T, int NCH>
+__device__ __forceinline__ void store_row(T* row, int lane, const float (&v)[NCH][4]) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) st4(row + (j * 32 + lane) * 4, v[j]);
+}
+template <typename T, int NCH>
+__device__ __forceinline__ void zero_row(T* row, int lane) {
+    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) st4(row + (j * 32 + lane) * 4, z);
+}
+
+// Channel LayerNorm statistics of a warp-distributed row (biased variance, two-pass as the reference).
+template <int NCH>
+__device__ __forceinline__ void row_stats(const float (&v)[NCH][4], float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) s += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+    mean = warp_sum(s) * (1.0f / (NCH * 128));
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float d = v[j][i] - mean; q += d * d; }
+    }
+    float var = warp_sum(q) * (1.0f / (NCH * 128));
+    rstd = 1.0f / sqrtf(var + VRD_EPS);
+}
+
+// v <- (v - mean) * rstd * gamma + beta
+template <int NCH>
+__device__ __forceinline__ void row_normalize(float (&v)[NCH][4], int lane, const float* __restrict__ gamma,
+                                              const float* __restrict__ beta) {
+    float mean, rstd;
+    row_stats<NCH>(v, mean, rstd);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        float g[4], b[4];
+        ld4(gamma + (j * 32 + lane) * 4, g);
+        ld4(beta + (j * 32 + lane) * 4, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[j][i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+    }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

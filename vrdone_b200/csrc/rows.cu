@@ -1,0 +1,646 @@
+// Memory-bound row kernels: one warp owns one token row of C = 128*NCH channels, lanes own 16-byte chunks so
+// every warp load/store instruction touches one contiguous 512 B (fp32) / 256 B (bf16) span.
+// Reference semantics (file:line under /root/reference/models/): channel LayerNorm blocks.py:143-158,
+// masked depthwise conv blocks.py:91-113 + 706-724, max-pool skip blocks.py:1040-1046 + 1074,
+// FPN fpns.py:229-257, input contract maskvrd.py:363-414 (padding, re-derived analytically per SURVEY appendix B).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vrd {
+
+constexpr int WARPS = 8;   // warps per block for the row kernels
+
+// ------------------------------------------------------------------------------------------------------------
+// pack_pairs: ragged (C, L) fp32 pair tensors with arbitrary (channel, time) strides -> token-major operand rows
+// ------------------------------------------------------------------------------------------------------------
+template <typename TA>
+__global__ void pack_pairs_kernel(const float* const* __restrict__ ptrs, const long long* __restrict__ strides, Lay lay,
+                                  int nv, int nc, int nbs, int nbe, TA* __restrict__ vis, TA* __restrict__ clip,
+                                  float* __restrict__ bso, float* __restrict__ bent) {
+    const int r = blockIdx.x;
+    const int seq = lay.row_seq[r];
+    const long long R = lay.R;
+    const int c0 = 2 * nv + 2 * nc;
+    const int C = c0 + nbs + 2 * nbe;
+    if (seq < 0) {
+        for (int c = threadIdx.x; c < nv; c += blockDim.x) {
+            vis[(long long)r * nv + c] = from_f<TA>(0.f);
+            vis[(R + r) * nv + c] = from_f<TA>(0.f);
+        }
+        for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+            clip[(long long)r * nc + c] = from_f<TA>(0.f);
+            clip[(R + r) * nc + c] = from_f<TA>(0.f);
+        }
+        if (threadIdx.x < 8) {
+            bso[(long long)r * 8 + threadIdx.x] = 0.f;
+            bent[(long long)r * 8 + threadIdx.x] = 0.f;
+            bent[(R + r) * 8 + threadIdx.x] = 0.f;
+        }
+        return;
+    }
+    const int4 si = lay.seqinfo[seq];
+    const int t = r - si.x;
+    const float* src = ptrs[seq];
+    const long long sc = strides[2 * seq], st = strides[2 * seq + 1];
+    src += (long long)t * st;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = __ldg(src + (long long)c * sc);
+        if (c < nv) vis[(long long)r * nv + c] = from_f<TA>(v);
+        else if (c < 2 * nv) vis[(R + r) * nv + (c - nv)] = from_f<TA>(v);
+        else if (c < 2 * nv + nc) clip[(long long)r * nc + (c - 2 * nv)] = from_f<TA>(v);
+        else if (c < c0) clip[(R + r) * nc + (c - 2 * nv - nc)] = from_f<TA>(v);
+        else if (c < c0 + nbs) bso[(long long)r * 8 + (c - c0)] = v;
+        else if (c < c0 + nbs + nbe) bent[(long long)r * 8 + (c - c0 - nbs)] = v;
+        else bent[(R + r) * 8 + (c - c0 - nbs - nbe)] = v;
+    }
+    // unused tail columns of the 8-wide geometry rows
+    if (threadIdx.x < 8) {
+        if ((int)threadIdx.x >= nbs) bso[(long long)r * 8 + threadIdx.x] = 0.f;
+        if ((int)threadIdx.x >= nbe) {
+            bent[(long long)r * 8 + threadIdx.x] = 0.f;
+            bent[(R + r) * 8 + threadIdx.x] = 0.f;
+        }
+    }
+}
+
+void pack_pairs(const void* ptrs, const long long* strides, Lay lay, int nv, int nc, int nbs, int nbe, void* vis,
+                void* clip, int adt, float* bso, float* bent, cudaStream_t st) {
+    if (adt == VRD_BF16)
+        pack_pairs_kernel<__nv_bfloat16><<<lay.R, 256, 0, st>>>((const float* const*)ptrs, strides, lay, nv, nc, nbs, nbe,
+                                                                (__nv_bfloat16*)vis, (__nv_bfloat16*)clip, bso, bent);
+    else
+        pack_pairs_kernel<float><<<lay.R, 256, 0, st>>>((const float* const*)ptrs, strides, lay, nv, nc, nbs, nbe,
+                                                        (float*)vis, (float*)clip, bso, bent);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// layernorm (+ReLU): out = [relu](LN(x)), separator rows -> 0
+// ------------------------------------------------------------------------------------------------------------
+template <typename TI, typename TO, int NCH>
+__global__ void layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, TO* __restrict__ out, long long ldo, int rows, int relu,
+                                 const int* __restrict__ row_seq, int R) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    TO* o = out + (long long)row * ldo;
+    if (row_seq != nullptr && row_seq[row % R] < 0) { zero_row<TO, NCH>(o, lane); return; }
+    float v[NCH][4];
+    load_row<TI, NCH>(x + (long long)row * ldx, lane, v);
+    row_normalize<NCH>(v, lane, gamma, beta);
+    if (relu) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[j][i] = fmaxf(v[j][i], 0.f);
+    }
+    store_row<TO, NCH>(o, lane, v);
+}
+
+template <typename TI, typename TO>
+static int layernorm_t(const void* x, long long ldx, const float* g, const float* b, void* out, long long ldo, int rows,
+                       int C, int relu, const int* row_seq, int R, cudaStream_t st) {
+    const int grid = (rows + WARPS - 1) / WARPS;
+    if (C == 512)
+        layernorm_kernel<TI, TO, 4><<<grid, WARPS * 32, 0, st>>>((const TI*)x, ldx, g, b, (TO*)out, ldo, rows, relu, row_seq, R);
+    else if (C == 256)
+        layernorm_kernel<TI, TO, 2><<<grid, WARPS * 32, 0, st>>>((const TI*)x, ldx, g, b, (TO*)out, ldo, rows, relu, row_seq, R);
+    else
+        return 1;
+    return 0;
+}
+
+int layernorm(const void* x, int xdt, long long ldx, const float* g, const float* b, void* out, int odt, long long ldo,
+              int rows, int C, int relu, const int* row_seq, int R, cudaStream_t st) {
+    if (xdt == VRD_F32 && odt == VRD_F32) return layernorm_t<float, float>(x, ldx, g, b, out, ldo, rows, C, relu, row_seq, R, st);
+    if (xdt == VRD_F32 && odt == VRD_BF16) return layernorm_t<float, __nv_bfloat16>(x, ldx, g, b, out, ldo, rows, C, relu, row_seq, R, st);
+    if (xdt == VRD_BF16 && odt == VRD_BF16) return layernorm_t<__nv_bfloat16, __nv_bfloat16>(x, ldx, g, b, out, ldo, rows, C, relu, row_seq, R, st);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small_conv: k=3 conv with cin <= 8 input channels on 8-wide fp32 rows (+bias [+LN] [+ReLU]); N = 512 outputs
+// wt is [3*cin, N] (tap-major rows) so that lanes read contiguous output channels.
+// ------------------------------------------------------------------------------------------------------------
+template <typename TO, int NCH>
+__global__ void small_conv_kernel(const float* __restrict__ x, int cin, const float* __restrict__ wt,
+                                  const float* __restrict__ bias, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, int relu, TO* __restrict__ out, long long ldo, int rows,
+                                  const int* __restrict__ row_seq, int R) {
+    constexpr int N = NCH * 128;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    TO* o = out + (long long)row * ldo;
+    if (row_seq[row % R] < 0) { zero_row<TO, NCH>(o, lane); return; }
+    float v[NCH][4];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) ld4(bias + (j * 32 + lane) * 4, v[j]);
+    for (int tap = 0; tap < 3; ++tap) {
+        const int rr = row + tap - 1;
+        if (rr < 0 || rr >= rows) continue;
+        const float* xr = x + (long long)rr * 8;
+        for (int c = 0; c < cin; ++c) {
+            const float xv = __ldg(xr + c);
+            const float* w = wt + (long long)(tap * cin + c) * N;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                float wv[4];
+                ld4(w + (j * 32 + lane) * 4, wv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[j][i] = fmaf(xv, wv[i], v[j][i]);
+            }
+        }
+    }
+    if (gamma != nullptr) row_normalize<NCH>(v, lane, gamma, beta);
+    if (relu) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[j][i] = fmaxf(v[j][i], 0.f);
+    }
+    store_row<TO, NCH>(o, lane, v);
+}
+
+int small_conv(const float* x, int cin, const float* wt, const float* bias, const float* g, const float* b, int relu,
+               void* out, int odt, long long ldo, int rows, int N, const int* row_seq, int R, cudaStream_t st) {
+    if (N != 512 || cin > 8) return 1;
+    const int grid = (rows + WARPS - 1) / WARPS;
+    if (odt == VRD_BF16)
+        small_conv_kernel<__nv_bfloat16, 4><<<grid, WARPS * 32, 0, st>>>(x, cin, wt, bias, g, b, relu, (__nv_bfloat16*)out, ldo, rows, row_seq, R);
+    else
+        small_conv_kernel<float, 4><<<grid, WARPS * 32, 0, st>>>(x, cin, wt, bias, g, b, relu, (float*)out, ldo, rows, row_seq, R);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dwconv_ln: [LN_pre] -> depthwise k=3 (stride 1|2) -> LN, for up to 3 branches sharing one read of the input rows
+// ------------------------------------------------------------------------------------------------------------
+template <typename TI, typename TO, int NCH>
+__global__ void dwconv_ln_kernel(const TI* __restrict__ x, long long ldx, Lay lin, Lay lout, int stride,
+                                 const float* __restrict__ pre_g, const float* __restrict__ pre_b, DwBranches br,
+                                 int streams) {
+    const int lane = threadIdx.x & 31;
+    const int grow = blockIdx.x * WARPS + (threadIdx.x >> 5);   // row over all streams
+    if (grow >= streams * lout.R) return;
+    const int s = grow / lout.R, r = grow - s * lout.R;
+    const int seq = lout.row_seq[r];
+    if (seq < 0) {
+        for (int b = 0; b < br.n; ++b) zero_row<TO, NCH>((TO*)br.out[b] + (long long)grow * br.ldo[b], lane);
+        return;
+    }
+    const int4 so = lout.seqinfo[seq], si = lin.seqinfo[seq];
+    const int t = (r - so.x) * stride;            // centre time index at the input level
+    const int len = si.y;
+    const TI* base = x + ((long long)s * lin.R + si.x) * ldx;
+    // raw rows t-1, t, t+1 (zero when outside [0, len))
+    float raw[3][NCH][4];
+    bool inside[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int tt = t + d - 1;
+        inside[d] = (tt >= 0 && tt < len);
+        if (inside[d]) load_row<TI, NCH>(base + (long long)tt * ldx, lane, raw[d]);
+        else {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) raw[d][j][i] = 0.f;
+        }
+    }
+    // first pad column (time index == len) exists?  stride-2 reads it only for odd len, where it always exists.
+    const bool right_is_pad = (t + 1 == len) && (si.z != 0 || stride == 2);
+    bool any_pre = false;
+    for (int b = 0; b < br.n; ++b) any_pre |= (br.use_pre[b] != 0);
+    float nrm[3][NCH][4];
+    if (any_pre) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nrm[d][j][i] = raw[d][j][i];
+            if (inside[d]) row_normalize<NCH>(nrm[d], lane, pre_g, pre_b);
+        }
+        if (right_is_pad) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) ld4(pre_b + (j * 32 + lane) * 4, nrm[2][j]);
+        }
+    }
+    for (int b = 0; b < br.n; ++b) {
+        const float* w = br.w[b];   // [3, C] tap-major
+        float y[NCH][4];
+        const bool pre = br.use_pre[b] != 0;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float w0[4], w1[4], w2[4];
+            const int c = (j * 32 + lane) * 4;
+            ld4(w + c, w0); ld4(w + NCH * 128 + c, w1); ld4(w + 2 * NCH * 128 + c, w2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float a0 = pre ? nrm[0][j][i] : raw[0][j][i];
+                const float a1 = pre ? nrm[1][j][i] : raw[1][j][i];
+                const float a2 = pre ? nrm[2][j][i] : raw[2][j][i];
+                y[j][i] = a0 * w0[i] + a1 * w1[i] + a2 * w2[i];
+            }
+        }
+        row_normalize<NCH>(y, lane, br.g[b], br.b[b]);
+        store_row<TO, NCH>((TO*)br.out[b] + (long long)grow * br.ldo[b], lane, y);
+    }
+}
+
+int dwconv_ln(const void* x, int xdt, long long ldx, Lay lin, Lay lout, int stride, const float* pre_g, const float* pre_b,
+              const DwBranches& br, int odt, int C, int streams, cudaStream_t st) {
+    const int grid = (streams * lout.R + WARPS - 1) / WARPS;
+#define LAUNCH(TI, TO, NCH) \
+    dwconv_ln_kernel<TI, TO, NCH><<<grid, WARPS * 32, 0, st>>>((const TI*)x, ldx, lin, lout, stride, pre_g, pre_b, br, streams)
+    if (C == 512) {
+        if (xdt == VRD_F32 && odt == VRD_F32) LAUNCH(float, float, 4);
+        else if (xdt == VRD_F32 && odt == VRD_BF16) LAUNCH(float, __nv_bfloat16, 4);
+        else return 1;
+    } else if (C == 256) {
+        if (xdt == VRD_F32 && odt == VRD_F32) LAUNCH(float, float, 2);
+        else if (xdt == VRD_F32 && odt == VRD_BF16) LAUNCH(float, __nv_bfloat16, 2);
+        else return 1;
+    } else return 1;
+#undef LAUNCH
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// maxpool_skip: out[i] = max(x[2i-1], x[2i], x[2i+1]) (left edge ignored, first pad column counts as 0)
+// ------------------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void maxpool_skip_kernel(const float* __restrict__ x, long long ldx, Lay lin, Lay lout, float* __restrict__ out,
+                                    long long ldo) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= lout.R) return;
+    float* o = out + (long long)r * ldo;
+    const int seq = lout.row_seq[r];
+    if (seq < 0) { zero_row<float, NCH>(o, lane); return; }
+    const int4 so = lout.seqinfo[seq], si = lin.seqinfo[seq];
+    const int t = (r - so.x) * 2;
+    const float* base = x + (long long)si.x * ldx;
+    float m[NCH][4];
+    load_row<float, NCH>(base + (long long)t * ldx, lane, m);
+    if (t - 1 >= 0) {
+        float v[NCH][4];
+        load_row<float, NCH>(base + (long long)(t - 1) * ldx, lane, v);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[j][i] = fmaxf(m[j][i], v[j][i]);
+    }
+    if (t + 1 < si.y) {
+        float v[NCH][4];
+        load_row<float, NCH>(base + (long long)(t + 1) * ldx, lane, v);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[j][i] = fmaxf(m[j][i], v[j][i]);
+    } else {   // t + 1 == len: a zero pad column
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[j][i] = fmaxf(m[j][i], 0.f);
+    }
+    store_row<float, NCH>(o, lane, m);
+}
+
+int maxpool_skip(const float* x, long long ldx, Lay lin, Lay lout, float* out, long long ldo, int C, cudaStream_t st) {
+    if (C != 512) return 1;
+    maxpool_skip_kernel<4><<<(lout.R + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(x, ldx, lin, lout, out, ldo);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FPN kernels (fpn_dim = 256 = 2 chunks per lane; top level reads 512 input channels)
+// ------------------------------------------------------------------------------------------------------------
+// fpn_top: grouped k=3 conv, out[c] = sum_{j<2,k<3} W[c,j,k] * LN_pre(x)[t+k-1, 2c+j]; wt[k][e] = W[e/2, e%2, k].
+__global__ void fpn_top_kernel(const float* __restrict__ x, long long ldx, Lay lay, const float* __restrict__ pre_g,
+                               const float* __restrict__ pre_b, const float* __restrict__ wt, const float* __restrict__ g,
+                               const float* __restrict__ b, float* __restrict__ out, long long ldo) {
+    constexpr int NCH = 4;
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= lay.R) return;
+    float* o = out + (long long)r * ldo;
+    const int seq = lay.row_seq[r];
+    if (seq < 0) {
+        for (int j = 0; j < NCH; ++j) *reinterpret_cast<float2*>(o + (j * 32 + lane) * 2) = make_float2(0.f, 0.f);
+        return;
+    }
+    const int4 si = lay.seqinfo[seq];
+    const int t = r - si.x;
+    float acc[NCH][2];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) acc[j][0] = acc[j][1] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int tt = t + d - 1;
+        float v[NCH][4];
+        if (tt >= 0 && tt < si.y) {
+            load_row<float, NCH>(x + (long long)(si.x + tt) * ldx, lane, v);
+            row_normalize<NCH>(v, lane, pre_g, pre_b);
+        } else if (tt == si.y && si.z != 0) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) ld4(pre_b + (j * 32 + lane) * 4, v[j]);
+        } else {
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float w[4];
+            ld4(wt + d * 512 + (j * 32 + lane) * 4, w);
+            acc[j][0] += v[j][0] * w[0] + v[j][1] * w[1];
+            acc[j][1] += v[j][2] * w[2] + v[j][3] * w[3];
+        }
+    }
+    // LayerNorm over the 256 outputs: lane owns channels (j*32+lane)*2 + {0,1}
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) s += acc[j][0] + acc[j][1];
+    const float mean = warp_sum(s) * (1.0f / 256);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) { float d0 = acc[j][0] - mean, d1 = acc[j][1] - mean; q += d0 * d0 + d1 * d1; }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 256) + VRD_EPS);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int c = (j * 32 + lane) * 2;
+        const float2 gg = *reinterpret_cast<const float2*>(g + c), bb = *reinterpret_cast<const float2*>(b + c);
+        *reinterpret_cast<float2*>(o + c) =
+            make_float2((acc[j][0] - mean) * rstd * gg.x + bb.x, (acc[j][1] - mean) * rstd * gg.y + bb.y);
+    }
+}
+
+int fpn_top(const float* x, long long ldx, Lay lay, const float* pre_g, const float* pre_b, const float* wt, const float* g,
+            const float* b, float* out, long long ldo, cudaStream_t st) {
+    fpn_top_kernel<<<(lay.R + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(x, ldx, lay, pre_g, pre_b, wt, g, b, out, ldo);
+    return 0;
+}
+
+// fpn_level: z[u] = LN_lat(cur[u]) + y_up[u/2]; out[t] = LN(w0 z[t-1] + w1 z[t] + w2 z[t+1]).
+__global__ void fpn_level_kernel(const float* __restrict__ cur, long long ldc, const float* __restrict__ yup, long long ldu,
+                                 Lay lay, Lay lup, const float* __restrict__ lat_g, const float* __restrict__ lat_b,
+                                 const float* __restrict__ beta_up, const float* __restrict__ w, const float* __restrict__ g,
+                                 const float* __restrict__ b, float* __restrict__ out, long long ldo) {
+    constexpr int NCH = 2;
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= lay.R) return;
+    float* o = out + (long long)r * ldo;
+    const int seq = lay.row_seq[r];
+    if (seq < 0) { zero_row<float, NCH>(o, lane); return; }
+    const int4 si = lay.seqinfo[seq], su = lup.seqinfo[seq];
+    const int t = r - si.x;
+    float y[NCH][4];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[j][i] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int u = t + d - 1;
+        float z[NCH][4];
+        if (u >= 0 && u < si.y) {
+            load_row<float, NCH>(cur + (long long)(si.x + u) * ldc, lane, z);
+            row_normalize<NCH>(z, lane, lat_g, lat_b);
+        } else if (u == si.y && si.z != 0) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) ld4(lat_b + (j * 32 + lane) * 4, z[j]);
+        } else {
+            continue;
+        }
+        const int uu = u >> 1;
+        float up[NCH][4];
+        if (uu < su.y) load_row<float, NCH>(yup + (long long)(su.x + uu) * ldu, lane, up);
+        else {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) ld4(beta_up + (j * 32 + lane) * 4, up[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float wv[4];
+            ld4(w + d * 256 + (j * 32 + lane) * 4, wv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[j][i] += (z[j][i] + up[j][i]) * wv[i];
+        }
+    }
+    row_normalize<NCH>(y, lane, g, b);
+    store_row<float, NCH>(o, lane, y);
+}
+
+int fpn_level(const float* cur, long long ldc, const float* yup, long long ldu, Lay lay, Lay lup, const float* lat_g,
+              const float* lat_b, const float* beta_up, const float* w, const float* g, const float* b, float* out,
+              long long ldo, cudaStream_t st) {
+    fpn_level_kernel<<<(lay.R + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(cur, ldc, yup, ldu, lay, lup, lat_g, lat_b, beta_up, w,
+                                                                           g, b, out, ldo);
+    return 0;
+}
+
+// mask_features: depthwise k=3 + bias over the level-0 FPN output (whose first pad column is beta of its LayerNorm)
+__global__ void mask_features_kernel(const float* __restrict__ y, long long ldy, Lay lay, const float* __restrict__ beta,
+                                     const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                                     long long ldo) {
+    constexpr int NCH = 2;
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= lay.R) return;
+    float* o = out + (long long)r * ldo;
+    const int seq = lay.row_seq[r];
+    if (seq < 0) { zero_row<float, NCH>(o, lane); return; }
+    const int4 si = lay.seqinfo[seq];
+    const int t = r - si.x;
+    float acc[NCH][4];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) ld4(bias + (j * 32 + lane) * 4, acc[j]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int u = t + d - 1;
+        float z[NCH][4];
+        if (u >= 0 && u < si.y) load_row<float, NCH>(y + (long long)(si.x + u) * ldy, lane, z);
+        else if (u == si.y && si.z != 0) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) ld4(beta + (j * 32 + lane) * 4, z[j]);
+        } else continue;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float wv[4];
+            ld4(w + d * 256 + (j * 32 + lane) * 4, wv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] += z[j][i] * wv[i];
+        }
+    }
+    store_row<float, NCH>(o, lane, acc);
+}
+
+int mask_features(const float* y, long long ldy, Lay lay, const float* beta, const float* w, const float* bias, float* out,
+                  long long ldo, cudaStream_t st) {
+    mask_features_kernel<<<(lay.R + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(y, ldy, lay, beta, w, bias, out, ldo);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// query_ln: out = LN2(dw * (LN(x) + pos[row % Q])) with each stage optional (256 channels); rows >= nrows -> 0
+// ------------------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void query_ln_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ g,
+                                const float* __restrict__ b, const float* __restrict__ pos, int Q, int nrows, int total_rows,
+                                const float* __restrict__ dw, const float* __restrict__ g2, const float* __restrict__ b2,
+                                TO* __restrict__ out, long long ldo) {
+    constexpr int NCH = 2;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    TO* o = out + (long long)row * ldo;
+    if (row >= nrows) { zero_row<TO, NCH>(o, lane); return; }
+    float v[NCH][4];
+    load_row<float, NCH>(x + (long long)row * ldx, lane, v);
+    if (g != nullptr) row_normalize<NCH>(v, lane, g, b);
+    if (pos != nullptr) {
+        const float* p = pos + (long long)(row % Q) * 256;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float pv[4];
+            ld4(p + (j * 32 + lane) * 4, pv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[j][i] += pv[i];
+        }
+    }
+    if (dw != nullptr) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float wv[4];
+            ld4(dw + (j * 32 + lane) * 4, wv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[j][i] *= wv[i];
+        }
+    }
+    if (g2 != nullptr) row_normalize<NCH>(v, lane, g2, b2);
+    store_row<TO, NCH>(o, lane, v);
+}
+
+int query_ln(const float* x, long long ldx, const float* g, const float* b, const float* pos, int Q, int nrows,
+             int total_rows, const float* dw, const float* g2, const float* b2, void* out, int odt, long long ldo, int C,
+             cudaStream_t st) {
+    if (C != 256) return 1;
+    const int grid = (total_rows + WARPS - 1) / WARPS;
+    if (odt == VRD_BF16)
+        query_ln_kernel<__nv_bfloat16><<<grid, WARPS * 32, 0, st>>>(x, ldx, g, b, pos, Q, nrows, total_rows, dw, g2, b2, (__nv_bfloat16*)out, ldo);
+    else
+        query_ln_kernel<float><<<grid, WARPS * 32, 0, st>>>(x, ldx, g, b, pos, Q, nrows, total_rows, dw, g2, b2, (float*)out, ldo);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// heads: mask logits + binarisation + first/last active frame; class softmax + top-k
+// ------------------------------------------------------------------------------------------------------------
+// One block per pair.  masks[row, q] = <me[pair*Q+q, :], mf[row, :]> (256 channels); a frame is active iff
+// sigmoid(logit) > 0.5 evaluated in fp32 exactly as the reference does (maskvrd.py:287), NOT logit > 0.
+__global__ void mask_logits_kernel(const float* __restrict__ me, long long ldm, const float* __restrict__ mf, long long ldf,
+                                   Lay lay, int Q, float* __restrict__ masks, long long ldk, int* __restrict__ first_last) {
+    constexpr int NCH = 2;
+    constexpr int MAXQ = 16;
+    __shared__ int s_first[MAXQ], s_last[MAXQ];
+    __shared__ float s_me[MAXQ * 256];
+    const int pair = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int4 si = lay.seqinfo[pair];
+    if (threadIdx.x < MAXQ) { s_first[threadIdx.x] = 0x7fffffff; s_last[threadIdx.x] = -1; }
+    for (int i = threadIdx.x; i < Q * 256; i += blockDim.x)
+        s_me[i] = me[(long long)(pair * Q + i / 256) * ldm + (i % 256)];
+    __syncthreads();
+    for (int t = warp; t < si.y; t += WARPS) {
+        const long long row = si.x + t;
+        float v[NCH][4];
+        load_row<float, NCH>(mf + row * ldf, lane, v);
+        for (int q = 0; q < Q; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                const float* m = s_me + q * 256 + (j * 32 + lane) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc = fmaf(v[j][i], m[i], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                if (masks != nullptr) masks[row * ldk + q] = acc;
+                const float sg = 1.0f / (1.0f + expf(-acc));
+                if (sg > 0.5f) { atomicMin(&s_first[q], t); atomicMax(&s_last[q], t); }
+            }
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < Q) {
+        const int l = s_last[threadIdx.x];
+        first_last[(pair * Q + threadIdx.x) * 2 + 0] = (l < 0) ? -1 : s_first[threadIdx.x];
+        first_last[(pair * Q + threadIdx.x) * 2 + 1] = l;
+    }
+}
+
+int mask_logits(const float* me, long long ldm, const float* mf, long long ldf, Lay lay, int Q, float* masks, long long ldk,
+                int* first_last, cudaStream_t st) {
+    if (Q > 16) return 1;
+    mask_logits_kernel<<<lay.B, WARPS * 32, 0, st>>>(me, ldm, mf, ldf, lay, Q, masks, ldk, first_last);
+    return 0;
+}
+
+// One warp per (pair, query): softmax over n_cls logits, then top-k of classes 1..n_cls-1 (ties -> lower class id).
+__global__ void softmax_topk_kernel(const float* __restrict__ logits, long long ldl, int nrows, int n_cls, int topk,
+                                    float* __restrict__ scores, int* __restrict__ ids) {
+    constexpr int PER = 8;   // up to 256 classes
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    float p[PER];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = i * 32 + lane;
+        p[i] = (c < n_cls) ? logits[(long long)row * ldl + c] : -INFINITY;
+        mx = fmaxf(mx, p[i]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = i * 32 + lane;
+        p[i] = (c < n_cls) ? expf(p[i] - mx) : 0.f;
+        sum += p[i];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = i * 32 + lane;
+        p[i] = (c < n_cls && c > 0) ? p[i] / sum : -1.f;   // background (class 0) and out-of-range are excluded
+    }
+    for (int k = 0; k < topk; ++k) {
+        float best = -1.f;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int c = i * 32 + lane;
+            if (p[i] > best) { best = p[i]; bi = c; }   // ascending c within a lane: strict > keeps the lower id
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(FULL_MASK, best, o);
+            const int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) { scores[(long long)row * topk + k] = best; ids[(long long)row * topk + k] = bi; }
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (i * 32 + lane == bi) p[i] = -1.f;
+    }
+}
+
+int softmax_topk(const float* logits, long long ldl, int nrows, int n_cls, int topk, float* scores, int* ids, cudaStream_t st) {
+    if (n_cls > 256 || topk >= n_cls) return 1;
+    softmax_topk_kernel<<<(nrows + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(logits, ldl, nrows, n_cls, topk, scores, ids);
+    return 0;
+}
+
+}  // namespace vrd

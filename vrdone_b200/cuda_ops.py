@@ -1,0 +1,259 @@
+"""ctypes binding of libvrdone_b200.so (the C ABI declared in include/vrdone_b200.h).
+
+``CudaOps`` is the only kernel provider of the product: there is no CPU or PyTorch fallback.  Loading fails loudly
+when the shared library has not been built, and every op raises if the kernel launcher reports an error.
+PyTorch is used for device memory and the current CUDA stream only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvrdone_b200.so")
+_lib = None
+
+F32, BF16 = 0, 1
+_vp, _i32, _i64, _f32p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p
+
+# name -> argtypes, in the order of include/vrdone_b200.h
+_SIGNATURES = {
+    "vrd_abi_version": [],
+    "vrd_device_arch": [],
+    "vrd_pack_pairs": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
+    "vrd_gemm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp,
+                 _vp, _i32, _vp],
+    "vrd_layernorm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _vp],
+    "vrd_small_conv": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp],
+    "vrd_dwconv_ln": [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
+                      _vp, _i32, _i32, _i32, _vp],
+    "vrd_window_attn": [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "vrd_full_attn": [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "vrd_maxpool_skip": [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp],
+    "vrd_fpn_top": [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "vrd_fpn_level": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "vrd_mask_features": [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp],
+    "vrd_query_ln": [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
+    "vrd_query_self_attn": [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _vp],
+    "vrd_query_cross_attn": [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "vrd_mask_logits": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp],
+    "vrd_softmax_topk": [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp],
+}
+
+
+def exported_symbols():
+    return list(_SIGNATURES) + ["vrd_last_error"]
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree shared library; raises if it is missing (build it with ``python -m vrdone_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(f"{_LIB_PATH} not found: the CUDA extension is not built (run `python -m vrdone_b200.build`); "
+                           "vrdone_b200 has no CPU fallback")
+    lib = C.CDLL(_LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.vrd_last_error.argtypes = []
+    lib.vrd_last_error.restype = C.c_char_p
+    if lib.vrd_abi_version() != 1:
+        raise RuntimeError("libvrdone_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _mat(t: torch.Tensor):
+    assert t.dim() == 2 and t.stride(1) == 1 and t.is_cuda, "row-major 2-D CUDA tensor expected"
+    return t.data_ptr(), t.stride(0)
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous()
+    return t.data_ptr()
+
+
+def _f32(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.dtype == torch.float32
+    return _p(t)
+
+
+class CudaOps:
+    """Kernel provider used by ``engine.Engine``; every method enqueues one kernel on torch's current stream."""
+
+    def __init__(self):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("vrdone_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        arch = self.lib.vrd_device_arch()
+        if arch < 100:
+            raise RuntimeError(f"vrdone_b200 kernels are built for sm_100a only; current device is sm_{arch}")
+        self.launches = 0
+        self._keep = []   # host-side argument arrays that must outlive the asynchronous launch call (ctypes temporaries)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _check(self, rc, name):
+        self.launches += 1
+        if rc != 0:
+            raise RuntimeError(f"{name} failed: {self.lib.vrd_last_error().decode()}")
+
+    @staticmethod
+    def _lay(lay):
+        return lay.row_seq.data_ptr(), lay.seqinfo.data_ptr(), lay.R
+
+    # -- ops ------------------------------------------------------------------------------------------------------
+    def pack_pairs(self, ptrs, strides, lay, nv, nc, nbs, nbe, vis, clp, bso, bent):
+        rs, si, R = self._lay(lay)
+        self._check(self.lib.vrd_pack_pairs(_p(ptrs), _p(strides), rs, si, R, lay.B, nv, nc, nbs, nbe, _p(vis), _p(clp),
+                                            _dt(vis), _f32(bso), _f32(bent), self._stream()), "vrd_pack_pairs")
+
+    def gemm(self, a, w, out, bias=None, taps=1, act=0, res1=None, res2=None, corr=None, lay=None, streams=1):
+        ap, lda = _mat(a)
+        op, ldo = _mat(out)
+        M, K = a.shape
+        N = w.shape[0]
+        assert w.dtype == a.dtype and w.is_contiguous() and w.shape[1] == taps * K and out.shape == (M, N)
+        r1, ld1 = _mat(res1) if res1 is not None else (None, 0)
+        r2, ld2 = _mat(res2) if res2 is not None else (None, 0)
+        if lay is not None:
+            assert M == streams * lay.R
+            rs, si, R = self._lay(lay)
+        else:
+            rs, si, R = None, None, 0
+        self._check(self.lib.vrd_gemm(ap, _dt(a), lda, _p(w), _f32(bias), op, _dt(out), ldo, M, N, K, taps, act, r1, ld1, r2, ld2,
+                                      _f32(corr), rs, si, R, self._stream()), "vrd_gemm")
+
+    def layernorm(self, x, g, b, out, relu=False, lay=None, streams=1):
+        xp, ldx = _mat(x)
+        op, ldo = _mat(out)
+        rows, Cc = x.shape
+        rs, R = (lay.row_seq.data_ptr(), lay.R) if lay is not None else (None, 1)
+        self._check(self.lib.vrd_layernorm(xp, _dt(x), ldx, _f32(g), _f32(b), op, _dt(out), ldo, rows, Cc, int(relu), rs, R,
+                                           self._stream()), "vrd_layernorm")
+
+    def small_conv(self, x, cin, w, bias, ln, relu, out, lay, streams):
+        op, ldo = _mat(out)
+        assert x.shape[1] == 8 and x.is_contiguous() and x.shape[0] == streams * lay.R
+        g, b = (ln if ln is not None else (None, None))
+        self._check(self.lib.vrd_small_conv(_f32(x), cin, _f32(w), _f32(bias), _f32(g), _f32(b), int(relu), op, _dt(out), ldo,
+                                            x.shape[0], w.shape[1], lay.row_seq.data_ptr(), lay.R, self._stream()),
+                    "vrd_small_conv")
+
+    def dwconv_ln(self, x, lay_in, lay_out, stride, pre, branches, streams):
+        xp, ldx = _mat(x)
+        n = len(branches)
+        vp_arr, i32_arr, i64_arr = (C.c_void_p * n), (C.c_int32 * n), (C.c_int64 * n)
+        w = vp_arr(*[_f32(br[0]) for br in branches])
+        use_pre = i32_arr(*[int(br[1]) for br in branches])
+        g = vp_arr(*[_f32(br[2]) for br in branches])
+        b = vp_arr(*[_f32(br[3]) for br in branches])
+        outs = vp_arr(*[_mat(br[4])[0] for br in branches])
+        ldo = i64_arr(*[_mat(br[4])[1] for br in branches])
+        odt = _dt(branches[0][4])
+        assert all(_dt(br[4]) == odt for br in branches)
+        pg, pb = (pre if pre is not None else (None, None))
+        ri, sii, Ri = self._lay(lay_in)
+        ro, sio, Ro = self._lay(lay_out)
+        self._check(self.lib.vrd_dwconv_ln(xp, _dt(x), ldx, ri, sii, Ri, ro, sio, Ro, lay_in.B, stride, _f32(pg), _f32(pb), n, w,
+                                           use_pre, g, b, outs, ldo, odt, x.shape[1], streams, self._stream()), "vrd_dwconv_ln")
+
+    def window_attn(self, q, k, v, out, lay, n_head, w, streams):
+        qp, ld = _mat(q)
+        assert k.stride(0) == ld and v.stride(0) == ld and out.stride(0) == ld
+        rs, si, R = self._lay(lay)
+        self._check(self.lib.vrd_window_attn(qp, _mat(k)[0], _mat(v)[0], _mat(out)[0], _dt(q), ld, rs, si, R, lay.B, n_head,
+                                             q.shape[1], w, streams, self._stream()), "vrd_window_attn")
+
+    def full_attn(self, q, k, v, out, lay, n_head):
+        qp, ld = _mat(q)
+        assert k.stride(0) == ld and v.stride(0) == ld and out.stride(0) == ld
+        rs, si, R = self._lay(lay)
+        self._check(self.lib.vrd_full_attn(qp, _mat(k)[0], _mat(v)[0], _mat(out)[0], _dt(q), ld, rs, si, R, lay.B, n_head,
+                                           q.shape[1], lay.max_len, self._stream()), "vrd_full_attn")
+
+    def maxpool_skip(self, x, lay_in, lay_out, out):
+        xp, ldx = _mat(x)
+        op, ldo = _mat(out)
+        ri, sii, Ri = self._lay(lay_in)
+        ro, sio, Ro = self._lay(lay_out)
+        self._check(self.lib.vrd_maxpool_skip(xp, ldx, ri, sii, Ri, ro, sio, Ro, lay_in.B, op, ldo, x.shape[1], self._stream()),
+                    "vrd_maxpool_skip")
+
+    def fpn_top(self, x, lay, pre, w, ln, out):
+        xp, ldx = _mat(x)
+        op, ldo = _mat(out)
+        rs, si, R = self._lay(lay)
+        self._check(self.lib.vrd_fpn_top(xp, ldx, rs, si, R, lay.B, _f32(pre[0]), _f32(pre[1]), _f32(w), _f32(ln[0]), _f32(ln[1]),
+                                         op, ldo, self._stream()), "vrd_fpn_top")
+
+    def fpn_level(self, cur, y_up, lay, lay_up, ln_lat, beta_up, w, ln, out):
+        cp, ldc = _mat(cur)
+        up, ldu = _mat(y_up)
+        op, ldo = _mat(out)
+        rs, si, R = self._lay(lay)
+        ru, siu, Ru = self._lay(lay_up)
+        self._check(self.lib.vrd_fpn_level(cp, ldc, up, ldu, rs, si, R, ru, siu, Ru, lay.B, _f32(ln_lat[0]), _f32(ln_lat[1]),
+                                           _f32(beta_up), _f32(w), _f32(ln[0]), _f32(ln[1]), op, ldo, self._stream()),
+                    "vrd_fpn_level")
+
+    def mask_features(self, y, lay, beta, w, bias, out):
+        yp, ldy = _mat(y)
+        op, ldo = _mat(out)
+        rs, si, R = self._lay(lay)
+        self._check(self.lib.vrd_mask_features(yp, ldy, rs, si, R, lay.B, _f32(beta), _f32(w), _f32(bias), op, ldo, self._stream()),
+                    "vrd_mask_features")
+
+    def query_ln(self, x, ln, pos, Q, nrows, dw, ln2, out):
+        xp, ldx = _mat(x)
+        op, ldo = _mat(out)
+        g, b = ln if ln is not None else (None, None)
+        g2, b2 = ln2 if ln2 is not None else (None, None)
+        self._check(self.lib.vrd_query_ln(xp, ldx, _f32(g), _f32(b), _f32(pos), Q, nrows, out.shape[0], _f32(dw), _f32(g2), _f32(b2),
+                                          op, _dt(out), ldo, x.shape[1], self._stream()), "vrd_query_ln")
+
+    def query_self_attn(self, q, k, v, out, B, Q, n_head):
+        qp, ld = _mat(q)
+        assert k.stride(0) == ld and v.stride(0) == ld and out.stride(0) == ld
+        self._check(self.lib.vrd_query_self_attn(qp, _mat(k)[0], _mat(v)[0], _mat(out)[0], _dt(q), ld, B, Q, n_head, q.shape[1],
+                                                 self._stream()), "vrd_query_self_attn")
+
+    def query_cross_attn(self, q, k, v, out, lay, Q, n_head):
+        qp, ld = _mat(q)
+        assert k.stride(0) == ld and v.stride(0) == ld and out.stride(0) == ld
+        rs, si, R = self._lay(lay)
+        self._check(self.lib.vrd_query_cross_attn(qp, _mat(k)[0], _mat(v)[0], _mat(out)[0], _dt(q), ld, rs, si, R, lay.B, Q, n_head,
+                                                  q.shape[1], self._stream()), "vrd_query_cross_attn")
+
+    def mask_logits(self, me, mf, lay, Q, masks, first_last):
+        mp, ldm = _mat(me)
+        fp, ldf = _mat(mf)
+        kp, ldk = _mat(masks) if masks is not None else (None, 0)
+        rs, si, R = self._lay(lay)
+        assert first_last.dtype == torch.int32 and first_last.is_contiguous()
+        self._check(self.lib.vrd_mask_logits(mp, ldm, fp, ldf, rs, si, R, lay.B, Q, kp, ldk, first_last.data_ptr(), self._stream()),
+                    "vrd_mask_logits")
+
+    def softmax_topk(self, logits, nrows, n_cls, topk, scores, ids):
+        lp, ldl = _mat(logits)
+        assert ids.dtype == torch.int32 and scores.dtype == torch.float32 and ids.is_contiguous() and scores.is_contiguous()
+        self._check(self.lib.vrd_softmax_topk(lp, ldl, nrows, n_cls, topk, scores.data_ptr(), ids.data_ptr(), self._stream()),
+                    "vrd_softmax_topk")

@@ -53,7 +53,7 @@ class PackedWeights:
             self._pw_mlp(f"{bb}.visual_clip_fuse", 2)
         for name in ("bbox_entity_embd", "bbox_so_embd"):
             w = f32[f"{bb}.{name}.conv.weight"]
-            self._put(f"{bb}.{name}.w", w.permute(0, 2, 1).reshape(w.shape[0], -1))  # [N, 3*cin] tap-major
+            self._put(f"{bb}.{name}.w", w.permute(2, 1, 0).reshape(-1, w.shape[0]))  # [3*cin, N], rows tap-major
             self._put(f"{bb}.{name}.b", f32[f"{bb}.{name}.conv.bias"])
         self._ln(f"{bb}.bbox_entity_norm")
         for name in ("visual_bbox_fuse", "so_fuse", "so_visual_bbox_fuse"):
@@ -75,11 +75,12 @@ class PackedWeights:
             self._ln(f"neck.input_norms.{l}")
             self._ln(f"neck.fpn_norms.{l}")
             w = f32[f"neck.fpn_convs.{l}.conv.weight"]
-            self._put(f"neck.fpn_convs.{l}.w", w.reshape(w.shape[0], -1))   # [256, 3] or top: [256, 2*3]
+            # tap-major [3, channels]; the top level's grouped weight (F, 2, 3) is indexed by INPUT channel 2c+j
+            self._put(f"neck.fpn_convs.{l}.w", w.reshape(-1, 3).t())
             if l < n_lev - 1:
                 self._ln(f"neck.lateral_norms.{l}")
                 self._gemm_w(f"neck.lateral_convs.{l}", f32[f"neck.lateral_convs.{l}.conv.weight"][:, :, 0], None)
-        self._put("neck.mask_features.w", f32["neck.mask_features.conv.weight"].reshape(-1, 3))
+        self._put("neck.mask_features.w", f32["neck.mask_features.conv.weight"].reshape(-1, 3).t())
         self._put("neck.mask_features.b", f32["neck.mask_features.conv.bias"])
         pc = mc["predictor"]
         self._ln("predictor.input_norm")
@@ -135,7 +136,7 @@ class PackedWeights:
         sc = out_scale.flatten()
         for n in ("query", "key", "value"):
             w = s[f"{p}.{n}_conv.conv.weight"]
-            self._put(f"{p}.{n}_conv.w", w.reshape(w.shape[0], -1))   # [C, 3] (or [C, 1] for the predictor's query conv)
+            self._put(f"{p}.{n}_conv.w", w.reshape(w.shape[0], -1).t())   # [3, C] tap-major ([1, C] for the predictor's query conv)
             self._ln(f"{p}.{n}_norm")
             f = q_scale if n == "query" else 1.0
             self._gemm_w(f"{p}.{n}", s[f"{p}.{n}.weight"][:, :, 0] * f, s[f"{p}.{n}.bias"] * f)

@@ -52,6 +52,7 @@ class LevelLayout:
     def __init__(self, level: int, off: np.ndarray, length: np.ndarray, haspad: np.ndarray, rows: int):
         self.level = level
         self.off, self.len, self.haspad, self.R = off, length, haspad, rows
+        self.max_len = int(length.max())
         self.row_seq: torch.Tensor = None   # int32 [R]
         self.seqinfo: torch.Tensor = None   # int32 [B, 4]
 

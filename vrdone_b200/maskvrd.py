@@ -1,0 +1,237 @@
+"""Drop-in ``MaskVRD`` for the inference hot path (mirror of /root/reference/models/maskvrd.py:16-414).
+
+Same constructor (``MaskVRD(config, device)`` with ``config = yaml['model_config']`` plus the CLI-injected
+``with_clip_feature``), same parameter / buffer names and shapes (so reference checkpoints ``load_state_dict``
+unchanged), same ``_config_eval(infer_config)``, same ``forward(input_data)`` inputs and outputs.  The arithmetic
+runs in hand-written sm_100a CUDA kernels behind the C ABI of ``libvrdone_b200.so``; there is no CPU fallback.
+
+Differences that are deliberate and documented:
+  * training (``forward_training``, matching, losses) is out of scope -> ``NotImplementedError``;
+  * ``_mask_vrd`` returns ``pred_logits / pred_masks / output_mask`` (no ``aux_outputs``: training only);
+  * ties: ``torch.topk`` / ``argsort`` tie order is unspecified in the reference; here top-k ties resolve to the lower
+    class id and ranking ties to the earlier candidate.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from .engine import Engine, PackedWeights
+from .layout import PackLayout, max_div_factor, reference_padded_lengths
+from .params import Backbone, Neck, Predictor
+
+
+class MaskVRD(nn.Module):
+    def __init__(self, config: dict, device):
+        super().__init__()
+        self.config = config
+        self.visual_dim = config["visual_dim"]
+        self.clip_dim = config.get("clip_dim", None)
+        self.bbox_entity_dim = config["bbox_entity_dim"]
+        self.bbox_so_dim = config["bbox_so_dim"]
+        self.embd_dim = config["embd_dim"]
+        self.max_so_pair = config["max_so_pair"]
+        self.max_seq_len = config["max_seq_len"]
+        self.backbone_arch = tuple(config["backbone_arch"])
+        self.scale_factor = config["scale_factor"]
+        if self.scale_factor != 2 or len(self.backbone_arch) != 3:
+            raise NotImplementedError("only scale_factor == 2 and a 3-part backbone_arch are supported")
+        self.n_levels = self.backbone_arch[-1] + 1
+        self.max_div_factor = max_div_factor(config)
+        assert self.max_seq_len % self.max_div_factor == 0, "max_seq_len must be divisible by fpn stride and window size"
+        self.with_clip_feature = bool(config.get("with_clip_feature", False))
+        if self.with_clip_feature:
+            assert self.clip_dim is not None
+        empty_weight = torch.ones(config["num_classes"] + 1)
+        empty_weight[0] = config["loss_coeff_dict"]["eos_coef"]
+        self.register_buffer("empty_weight", empty_weight)
+
+        self.backbone = Backbone(config, self.with_clip_feature)
+        self.neck = Neck(config)
+        self.predictor = Predictor(config["predictor"])
+        self.deep_supervision = config["predictor"]["deep_supervision"]
+        self.device = device
+
+        # B200 execution state
+        self.precision = config.get("precision", "bf16")   # "bf16" (tcgen05 tensor cores) or "fp32" (CUDA-core fp32)
+        self.max_rows = int(config.get("max_rows", 49152))  # level-0 rows processed per engine call (bounds workspace)
+        self._engine: Optional[Engine] = None
+        self._engine_key = None
+        self._ops = None
+        self.last_stats: Dict[str, float] = {}
+
+    # ------------------------------------------------------------------------------------------------------------
+    # reference API
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _config_eval(self, infer_config):
+        assert self.training == False
+        self.topk = infer_config["topk"]
+        self.n_max_pair = infer_config["n_max_pair"]
+        self.feat_stride = infer_config["feat_stride"]
+        self.pred_min_frames = infer_config["pred_min_frames"]
+
+    def forward(self, input_data):
+        if self.training:
+            return self.forward_training(input_data)
+        return self.forward_test(input_data)
+
+    def forward_training(self, input_data):
+        raise NotImplementedError("vrdone_b200 implements the inference hot path only (training is out of scope)")
+
+    # ------------------------------------------------------------------------------------------------------------
+    # engine management: packed weights are derived state, rebuilt when parameters may have changed
+    # ------------------------------------------------------------------------------------------------------------
+    def set_precision(self, precision: str):
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        return self
+
+    def invalidate(self):
+        self._engine = None
+
+    def load_state_dict(self, *a, **k):
+        self.invalidate()
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode: bool = True):
+        self.invalidate()
+        return super().train(mode)
+
+    def _get_engine(self) -> Engine:
+        dev = self.empty_weight.device
+        key = (self.precision, str(dev))
+        if self._engine is None or self._engine_key != key:
+            if dev.type != "cuda":
+                raise RuntimeError("vrdone_b200.MaskVRD runs on a CUDA device only (call .to('cuda')); no CPU fallback")
+            if self._ops is None:
+                from .cuda_ops import CudaOps
+                self._ops = CudaOps()
+            adt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+            with torch.cuda.device(dev):
+                self._engine = Engine(PackedWeights(self.state_dict(), self.config, dev, adt), self._ops)
+            self._engine_key = key
+        return self._engine
+
+    # ------------------------------------------------------------------------------------------------------------
+    # network over a ragged list of pairs
+    # ------------------------------------------------------------------------------------------------------------
+    def _chunks(self, lens: List[int]):
+        start, rows = 0, 1
+        for i, l in enumerate(lens):
+            if i > start and rows + l + 1 > self.max_rows:
+                yield start, i
+                start, rows = i, 1
+            rows += l + 1
+        yield start, len(lens)
+
+    @torch.no_grad()
+    def run_network(self, feats: List[torch.Tensor], tpads: List[int], topk: int, want_masks: bool = False):
+        """feats: list of fp32 (C, L_i) CUDA tensors (any strides).  Returns per-pair arrays on the device:
+        logits [B,Q,K+1], topk_scores / topk_ids [B,Q,topk], first_last [B,Q,2] and (optionally) a list of (L_i, Q) masks."""
+        eng = self._get_engine()
+        dev = eng.device
+        lens = [int(f.shape[1]) for f in feats]
+        outs = {"logits": [], "topk_scores": [], "topk_ids": [], "first_last": []}
+        masks: List[torch.Tensor] = []
+        with torch.cuda.device(dev):
+            for a, b in self._chunks(lens):
+                sub = feats[a:b]
+                lay = PackLayout(lens[a:b], tpads[a:b], self.n_levels, dev)
+                meta = np.empty((b - a, 3), dtype=np.int64)
+                for i, f in enumerate(sub):
+                    assert f.is_cuda and f.dtype == torch.float32 and f.dim() == 2
+                    meta[i, 0], meta[i, 1], meta[i, 2] = f.data_ptr(), f.stride(0), f.stride(1)
+                meta_d = torch.from_numpy(meta).to(dev, non_blocking=True)
+                ptrs = meta_d[:, 0].contiguous()
+                strides = meta_d[:, 1:].contiguous()
+                r = eng.forward_packed(lay, ptrs, strides, topk, want_masks)
+                for k in outs:
+                    outs[k].append(r[k])
+                if want_masks:
+                    l0 = lay.levels[0]
+                    for i in range(b - a):
+                        masks.append(r["masks"][int(l0.off[i]): int(l0.off[i]) + int(l0.len[i])])
+        res = {k: torch.cat(v, 0) for k, v in outs.items()}
+        res["masks"] = masks if want_masks else None
+        return res
+
+    @torch.no_grad()
+    def _mask_vrd(self, batched_inputs: torch.Tensor, batched_masks: torch.Tensor):
+        """Tensor-level boundary of the reference (maskvrd.py:161-167): (B, C, T) fp32 + (B, 1, T) bool."""
+        B, _, T = batched_inputs.shape
+        lens = batched_masks[:, 0, :].sum(-1).tolist()
+        feats = [batched_inputs[i, :, : int(l)] for i, l in enumerate(lens)]
+        topk = min(getattr(self, "topk", 1), self.config["num_classes"] - 1)
+        r = self.run_network(feats, [T] * B, topk, want_masks=True)
+        Q = r["logits"].shape[1]
+        pm = torch.full((B, Q, T), -10.0, dtype=torch.float32, device=batched_inputs.device)
+        for i, m in enumerate(r["masks"]):
+            pm[i, :, : m.shape[0]] = m.t()
+        return {"pred_logits": r["logits"], "pred_masks": pm, "output_mask": batched_masks}
+
+    # ------------------------------------------------------------------------------------------------------------
+    # forward_test: network + triplet decoding (reference maskvrd.py:201-337)
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_test(self, input_data):
+        eng = self._get_engine()
+        dev = eng.device
+        feats = [f if f.is_cuda else f.to(dev, non_blocking=True) for f in input_data["so_features_list"]]
+        n_pairs = len(input_data["sids"])
+        assert len(feats) == n_pairs
+        lens = [int(f.shape[1]) for f in feats]
+        tpads = reference_padded_lengths(lens, self.config)
+        r = self.run_network(feats, tpads, self.topk)
+        # one device->host read of the compact per-(pair, query) results
+        scores = r["topk_scores"].cpu().numpy()            # [B, Q, k] fp32
+        cats = r["topk_ids"].cpu().numpy()                 # [B, Q, k] int32, 1-based predicate ids
+        fl = r["first_last"].cpu().numpy()                 # [B, Q, 2]  int32
+        return self._decode(scores, cats, fl, input_data)
+
+    def _decode(self, scores, cats, fl, input_data):
+        topk, stride = self.topk, self.feat_stride
+        to_np = lambda t: t.detach().cpu().numpy()
+        sids, oids = to_np(input_data["sids"]).astype(np.int64), to_np(input_data["oids"]).astype(np.int64)
+        durs = to_np(input_data["traj_durations"]).astype(np.int64)
+        cat_ids, cat_scores = to_np(input_data["cat_ids"]), to_np(input_data["cat_scores"]).astype(np.float32)
+        off = to_np(input_data["so_offset"]).astype(np.int64)
+        so_start = np.maximum(durs[sids, 0], durs[oids, 0])
+        so_end = np.minimum(durs[sids, 1], durs[oids, 1])
+        first, last = fl[..., 0].astype(np.int64), fl[..., 1].astype(np.int64)
+        start = first * stride + off[:, None]                      # [B, Q] relative to so_start
+        end = last * stride + off[:, None] + 1
+        keep = (last >= 0) & ((end - start) >= self.pred_min_frames)
+        assert np.all((start >= 0) | ~keep) and np.all((end <= (so_end - so_start)[:, None]) | ~keep)
+        pi, qi = np.nonzero(keep)                                  # candidates in (pair, query) order
+        if pi.size == 0:
+            return None
+        pi, qi = np.repeat(pi, topk), np.repeat(qi, topk)
+        ki = np.tile(np.arange(topk), pi.size // topk)
+        p_score = scores[pi, qi, ki].astype(np.float32)
+        trip_scores = np.stack([cat_scores[sids[pi]], p_score, cat_scores[oids[pi]]], 1).astype(np.float32)
+        avg = trip_scores.mean(-1, dtype=np.float32)
+        order = np.argsort(-avg, kind="stable")[: self.n_max_pair]
+        boxes = input_data["bboxes_list"]
+        out = {"triplets": [], "triple_scores": [], "triple_scores_avg": [], "so_trajs": [], "pred_durations": [], "so_tids": []}
+        for j in order.tolist():
+            p, q, k = int(pi[j]), int(qi[j]), int(ki[j])
+            s, o = int(sids[p]), int(oids[p])
+            a, b = int(start[p, q]), int(end[p, q])
+            s0, o0 = int(so_start[p] - durs[s, 0]), int(so_start[p] - durs[o, 0])
+            st, ot = boxes[s][s0 + a: s0 + b], boxes[o][o0 + a: o0 + b]
+            assert len(st) == len(ot)
+            out["triplets"].append([int(cat_ids[s]), int(cats[p, q, k]), int(cat_ids[o])])
+            out["triple_scores"].append([float(v) for v in trip_scores[j]])
+            out["triple_scores_avg"].append(float(avg[j]))
+            out["so_trajs"].append([st.tolist(), ot.tolist()])
+            out["pred_durations"].append([int(so_start[p]) + a, int(so_start[p]) + b])
+            out["so_tids"].append([s, o])
+        return out

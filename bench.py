@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Benchmark of the MaskVRD inference hot path: relation pairs/sec (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config vidor] [--precision bf16|fp32]
+
+A "step" is one pass of the hot path (``model(input_data)`` = network + heads epilogue + triplet decoding) over one
+synthetic VidOR-shaped video (tens of tracklets, every ordered pair with temporal overlap,
+feat_stride 4).  Prints ONE JSON line (rank 0).  For N > 1 launch with torchrun; every rank processes its own videos
+(weak scaling, no collective on the data path) and the time is the max over ranks.
+
+  value        whole-job pairs/s with the pair features already resident in HBM (CUDA events around the K steps)
+  e2e          the same through the public API with HOST (pinned) pair features: H2D copies + D2H of results inside
+  roofline     the tcgen05 GEMM kernel: algorithmic FLOPs of its launches / their CUDA-event durations vs the measured
+               bf16 peak in MEASURED_PEAKS.json (second pass over the same steps with per-launch events)
+  cpu_baseline the oracle port of the reference forward on the host cores, on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vrdone_b200 import synth, runner  # noqa: E402
+
+METRIC = "relation pairs/sec, VrdONE forward"
+UNIT = "pairs/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=6)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--config", default="vidor", choices=list(synth.CONFIG_NAMES))
+    p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    p.add_argument("--videos", type=int, default=2, help="distinct synthetic videos cycled through the steps")
+    p.add_argument("--tracklets", type=int, default=40)
+    p.add_argument("--frames", type=int, default=1200)
+    p.add_argument("--cpu-pairs", type=int, default=48, help="pairs in the bounded CPU-baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_videos(cfg, args, rank):
+    vids = []
+    for v in range(args.videos):
+        vids.append(synth.synthetic_video(cfg, 1000 * rank + v, n_tracklets=args.tracklets, n_frames=args.frames))
+    return vids
+
+
+def to_device(video, dev):
+    return {k: ([t.to(dev) for t in v] if isinstance(v, list) else (v.to(dev) if torch.is_tensor(v) else v)) for k, v in video.items()}
+
+
+def pin(video):
+    return {k: ([t.contiguous().pin_memory() if k == "so_features_list" else t for t in v] if isinstance(v, list) else v)
+            for k, v in video.items()}
+
+
+def cpu_baseline(cfg, video, n_pairs, threads):
+    """Oracle port of the reference forward on the host cores, on the first ``n_pairs`` pairs of a video."""
+    from oracle import maskvrd_oracle as O
+    from vrdone_b200 import MaskVRD
+    torch.set_num_threads(threads)
+    mc = cfg["model_config"]
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in MaskVRD(mc, "cpu").state_dict().items()}
+    n = min(n_pairs, len(video["so_features_list"]))
+    sub = dict(video)
+    sub["so_features_list"] = video["so_features_list"][:n]
+    sub["sids"], sub["oids"], sub["so_offset"] = video["sids"][:n], video["oids"][:n], video["so_offset"][:n]
+    t0 = time.perf_counter()
+    O.forward_test(sub, sd, mc, cfg["inference_config"])
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = synth.load_config(args.config)
+    threads = os.cpu_count() or 1
+    workload = (f"{args.config}.yaml forward_test, synthetic VidOR-shaped videos: {args.tracklets} tracklets x {args.frames} frames, "
+                f"feat_stride {cfg['dataset_config']['feat_stride']}, all ordered overlapping pairs")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        video = synth.synthetic_video(cfg, 0, n_tracklets=args.tracklets, n_frames=args.frames)
+        n = max(8, args.cpu_pairs // 2)
+        for _ in range(max(0, min(args.warmup, 1))):
+            cpu_baseline(cfg, video, n, threads)
+        tot_pairs = tot_t = 0.0
+        for _ in range(args.steps):
+            v, npairs, dt = cpu_baseline(cfg, video, n, threads)
+            tot_pairs += npairs
+            tot_t += dt
+        val = tot_pairs / tot_t
+        sample = f"first {n} pairs of synthetic video seed 0 per step (reference padding: short pairs to max_seq_len)"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": workload, "sample": sample},
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    from vrdone_b200 import MaskVRD
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = MaskVRD(cfg["model_config"], dev).eval().to(dev)
+    model._config_eval(cfg["inference_config"])
+    model.set_precision(args.precision)
+    host_videos = make_videos(cfg, args, rank)
+    pinned = [pin(v) for v in host_videos]
+    dev_videos = [to_device(v, dev) for v in host_videos]
+    n_pairs = [len(v["sids"]) for v in host_videos]
+    flops = [runner.video_cost(args.config, [int(f.shape[1]) for f in v["so_features_list"]]) for v in host_videos]
+    frames = [sum(int(f.shape[1]) for f in v["so_features_list"]) for v in host_videos]
+    in_bytes = [sum(f.numel() * 4 for f in v["so_features_list"]) for v in host_videos]
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(videos, steps, h2d):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pairs = 0
+        for s in range(steps):
+            v = videos[s % len(videos)]
+            if h2d:
+                v = dict(v)
+                v["so_features_list"] = [t.to(dev, non_blocking=True) for t in v["so_features_list"]]
+            model(v)
+            pairs += n_pairs[s % len(videos)]
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            p = torch.tensor([float(pairs)], device=dev)
+            dist.all_reduce(p, op=dist.ReduceOp.SUM)
+            ms, pairs = float(t), float(p)
+        return ms, pairs
+
+    for s in range(args.warmup):
+        model(dev_videos[s % len(dev_videos)])
+    ops = model._ops
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launches
+    ms, pairs = timed(dev_videos, args.steps, h2d=False)
+    launches = ops.launches - l0
+    clocks = sampler.stop()
+    ms_e2e, pairs_e2e = timed(pinned, args.steps, h2d=True)
+
+    # roofline pass: the same steps with a CUDA-event pair around every launch of the dominant (GEMM) kernel
+    ops.start_timing()
+    for s in range(args.steps):
+        model(dev_videos[s % len(dev_videos)])
+    torch.cuda.synchronize(dev)
+    prof = ops.stop_timing()
+    sustained, burst, hbm, src = peaks()
+    gemm = prof.get("vrd_gemm", {"ms": 0.0, "flops": 0.0, "n": 0})
+    total_ms = sum(p["ms"] for p in prof.values()) or 1.0
+    ach = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    peak = sustained if args.precision == "bf16" else 75.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel" if args.precision == "bf16" else "gemm_simt_kernel",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": f"{src} bf16 dense, sustained (burst {burst})" if args.precision == "bf16" else "nominal fp32 CUDA-core",
+                "launches": gemm["n"], "avg_launch_us": 1e3 * gemm["ms"] / max(1, gemm["n"]),
+                "share_of_step": gemm["ms"] / total_ms,
+                "per_kernel_ms": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "whole_path_algorithmic_tflops": sum(flops[s % len(flops)] for s in range(args.steps)) / (ms * 1e-3) / 1e12}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    out = {"metric": METRIC, "value": pairs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
+           "config": {"workload": workload, "pairs_per_step": n_pairs, "valid_frames_per_step": frames,
+                      "l2": "inputs larger than L2 (pair features of one video: %.2f GB)" % (in_bytes[0] / 1e9),
+                      "weights": "random init (torch.manual_seed(0))", "parallelism": f"dp{world} by video"},
+           "e2e": {"value": pairs_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sum(in_bytes) / len(in_bytes)),
+                   "d2h_bytes_per_step": int(sum(n * cfg["model_config"]["predictor"]["num_queries"] * (8 * cfg["inference_config"]["topk"] + 8)
+                                                 for n in n_pairs) / len(n_pairs))},
+           "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+    if not args.no_cpu_baseline:
+        v, n, dt = cpu_baseline(cfg, host_videos[0], args.cpu_pairs, threads)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"first {n} pairs of video 0 through the oracle port of forward_test ({dt:.1f} s)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""N > 1 host logic on CPU: LPT sharding + gather over a world_size-2 gloo group gives the same results as one rank."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vrdone_b200 import runner
+
+
+def _fake_forward(video):
+    # deterministic stand-in for model(video): depends only on the video's own content
+    return {"name": video["video_name"], "n": len(video["lens"]), "sum": int(sum(video["lens"]))}
+
+
+def _videos():
+    g = torch.Generator().manual_seed(0)
+    vids = []
+    for i in range(11):
+        n = int(torch.randint(1, 40, (1,), generator=g))
+        vids.append({"video_name": f"v{i}", "lens": torch.randint(2, 700, (n,), generator=g).tolist()})
+    return vids
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    vids = _videos()
+    costs = [runner.video_cost("vidor", v["lens"]) for v in vids]
+    out = runner.run_sharded(vids, costs, _fake_forward)
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lpt_partition_is_balanced_and_complete():
+    costs = [runner.video_cost("vidor", v["lens"]) for v in _videos()]
+    for world in (1, 2, 4, 8):
+        shards = runner.shard_videos(costs, world)
+        assert sorted(i for s in shards for i in s) == list(range(len(costs)))
+        loads = [sum(costs[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(costs)
+    assert abs(runner.pair_flops("vidor", 512) - 37.18e9) / 37.18e9 < 2e-3      # SURVEY.md section 8d examples
+    assert abs(runner.pair_flops("vidvrd", 96) - 6.37e9) / 6.37e9 < 2e-3
+
+
+def test_two_rank_gloo_matches_single_rank():
+    vids = _videos()
+    costs = [runner.video_cost("vidor", v["lens"]) for v in vids]
+    single = runner.run_sharded(vids, costs, _fake_forward)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert merged == single

@@ -95,6 +95,11 @@ def _f32(t: Optional[torch.Tensor]):
     return _p(t)
 
 
+_OP_NAMES = frozenset(["pack_pairs", "gemm", "layernorm", "small_conv", "dwconv_ln", "window_attn", "full_attn", "maxpool_skip",
+                       "fpn_top", "fpn_level", "mask_features", "query_ln", "query_self_attn", "query_cross_attn", "mask_logits",
+                       "softmax_topk"])
+
+
 class CudaOps:
     """Kernel provider used by ``engine.Engine``; every method enqueues one kernel on torch's current stream."""
 
@@ -106,7 +111,23 @@ class CudaOps:
         if arch < 100:
             raise RuntimeError(f"vrdone_b200 kernels are built for sm_100a only; current device is sm_{arch}")
         self.launches = 0
-        self._keep = []   # host-side argument arrays that must outlive the asynchronous launch call (ctypes temporaries)
+        self._timing = None     # list of (op name, start event, end event, algorithmic flops) while profiling
+        self._last_flops = 0.0
+
+    # -- per-launch CUDA-event timing (bench.py roofline pass) --------------------------------------------------------
+    def start_timing(self):
+        self._timing = []
+
+    def stop_timing(self):
+        torch.cuda.synchronize()
+        prof = {}
+        for name, e0, e1, fl in self._timing:
+            d = prof.setdefault(name, {"ms": 0.0, "flops": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["n"] += 1
+        self._timing = None
+        return prof
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -115,6 +136,20 @@ class CudaOps:
         self.launches += 1
         if rc != 0:
             raise RuntimeError(f"{name} failed: {self.lib.vrd_last_error().decode()}")
+
+    def __getattribute__(self, attr):
+        fn = object.__getattribute__(self, attr)
+        if attr in _OP_NAMES and object.__getattribute__(self, "_timing") is not None:
+            def timed(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self._last_flops = 0.0
+                e0.record()
+                r = fn(*a, **k)
+                e1.record()
+                self._timing.append(("vrd_" + attr, e0, e1, self._last_flops))
+                return r
+            return timed
+        return fn
 
     @staticmethod
     def _lay(lay):
@@ -139,6 +174,8 @@ class CudaOps:
             rs, si, R = self._lay(lay)
         else:
             rs, si, R = None, None, 0
+        valid_rows = streams * int(lay.len.sum()) if lay is not None else M
+        self._last_flops = 2.0 * valid_rows * N * K * taps     # algorithmic: valid rows only (no separators / tile padding)
         self._check(self.lib.vrd_gemm(ap, _dt(a), lda, _p(w), _f32(bias), op, _dt(out), ldo, M, N, K, taps, act, r1, ld1, r2, ld2,
                                       _f32(corr), rs, si, R, self._stream()), "vrd_gemm")
 

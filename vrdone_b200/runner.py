@@ -1,0 +1,62 @@
+"""Multi-GPU driver for the hot path: videos (and their pairs) are independent, so work is sharded host-side with
+no collective on the data path.  One process per GPU; results are Python objects gathered on rank 0.
+
+The reference runs inference single-process on cuda:0 (eval.py:83, 140-152); this is the 1..8 GPU version of that loop.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+# algorithmic FLOP model of one pair with valid length L: a0*L + b0*L^2 + a1*ceil(L/2) + a2*ceil(L/4) + a3*ceil(L/8) + c
+FLOP_COEFF = {
+    "vidvrd": (58.174e6, 16384.0, 6.579e6, 6.579e6, 7.678e6, 70.56e6),
+    "vidor": (58.190e6, 16384.0, 6.583e6, 6.583e6, 7.682e6, 70.18e6),
+    "vidor_local": (58.338e6, 0.0, 6.583e6, 6.583e6, 7.682e6, 70.18e6),
+    "vidor_x": (67.628e6, 16384.0, 6.583e6, 6.583e6, 7.686e6, 78.02e6),
+}
+
+
+def pair_flops(config_name: str, length: int) -> float:
+    a0, b0, a1, a2, a3, c = FLOP_COEFF[config_name]
+    L = int(length)
+    return a0 * L + b0 * L * L + a1 * ((L + 1) // 2) + a2 * ((L + 3) // 4) + a3 * ((L + 7) // 8) + c
+
+
+def video_cost(config_name: str, lengths: Sequence[int]) -> float:
+    return float(sum(pair_flops(config_name, l) for l in lengths))
+
+
+def shard_videos(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Longest-processing-time-first partition of video indices over ranks (deterministic)."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * world_size
+    shards: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda j: (loads[j], j))
+        shards[r].append(i)
+        loads[r] += costs[i]
+    return [sorted(s) for s in shards]
+
+
+def run_sharded(videos: Sequence[dict], costs: Sequence[float], fn: Callable[[dict], object]) -> Dict[int, object]:
+    """Every rank runs ``fn`` on its shard; rank 0 returns {video index: result} for all videos (other ranks: their own).
+    Works with or without an initialised process group (world size 1)."""
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(), dist.get_world_size()
+    else:
+        rank, world = 0, 1
+    mine = shard_videos(costs, world)[rank]
+    local = {i: fn(videos[i]) for i in mine}
+    if world == 1:
+        return local
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(local, gathered, dst=0)
+    if rank != 0:
+        return local
+    merged: Dict[int, object] = {}
+    for part in gathered:
+        merged.update(part)
+    return merged

@@ -254,7 +254,8 @@ def main():
            "e2e": {"value": pairs_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sum(in_bytes) / len(in_bytes)),
                    "d2h_bytes_per_step": int(sum(n * cfg["model_config"]["predictor"]["num_queries"] * (8 * cfg["inference_config"]["topk"] + 8)
                                                  for n in n_pairs) / len(n_pairs))},
-           "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+           "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+           "host_ms_last_step": {k: round(v, 2) for k, v in model.last_stats.items()}}
     if not args.no_cpu_baseline:
         v, n, dt = cpu_baseline(cfg, host_videos[0], args.cpu_pairs, threads)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -173,6 +173,149 @@ __global__ void __launch_bounds__(128) full_attn_kernel(const T* __restrict__ q,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// flash_attn_bf16: tensor-core (mma.sync m16n8k16 bf16, fp32 accumulate) flash attention for the bf16 path.
+// Block = 4 warps x 16 query rows; KV tiles of 64 keys staged in shared memory (rows padded by 16 B so that ldmatrix is
+// conflict-free); online softmax in registers with exp2.  grid = (query tiles, heads, pairs).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int HS>
+__global__ void __launch_bounds__(128) flash_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                              const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
+                                                              long long ld, Lay lay) {
+    constexpr int BM = 64, BN = 64, LDS = HS + 8, KSTEPS = HS / 16, DBLK = HS / 8, CPR = HS / 8;   // CPR: 16-byte chunks per row
+    __shared__ __align__(16) __nv_bfloat16 sK[BN * LDS];
+    __shared__ __align__(16) __nv_bfloat16 sV[BN * LDS];
+    const int seq = blockIdx.z, head = blockIdx.y;
+    const int4 si = lay.seqinfo[seq];
+    const int len = si.y;
+    const int q0 = blockIdx.x * BM;
+    if (q0 >= len) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const long long hoff = (long long)head * HS;
+    const uint32_t sK_u = (uint32_t)__cvta_generic_to_shared(sK), sV_u = (uint32_t)__cvta_generic_to_shared(sV);
+
+    // stage the Q tile through sK and pull this warp's 16 rows into A fragments
+    for (int c = tid; c < BM * CPR; c += 128) {
+        const int r = c / CPR, cc = c % CPR;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (q0 + r < len) val = *reinterpret_cast<const uint4*>(q + (long long)(si.x + q0 + r) * ld + hoff + cc * 8);
+        *reinterpret_cast<uint4*>(sK + r * LDS + cc * 8) = val;
+    }
+    __syncthreads();
+    uint32_t qf[KSTEPS][4];
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        const int row = warp * 16 + (lane & 15), col = ks * 16 + (lane >> 4) * 8;
+        ldsm_x4(sK_u + (row * LDS + col) * 2, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+    }
+    float o[DBLK][4];
+#pragma unroll
+    for (int d = 0; d < DBLK; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    for (int k0 = 0; k0 < len; k0 += BN) {
+        __syncthreads();   // previous tile (or the Q staging) fully consumed
+        for (int c = tid; c < BN * CPR; c += 128) {
+            const int r = c / CPR, cc = c % CPR;
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (k0 + r < len) {
+                const long long off = (long long)(si.x + k0 + r) * ld + hoff + cc * 8;
+                kv = *reinterpret_cast<const uint4*>(k + off);
+                vv = *reinterpret_cast<const uint4*>(v + off);
+            }
+            *reinterpret_cast<uint4*>(sK + r * LDS + cc * 8) = kv;
+            *reinterpret_cast<uint4*>(sV + r * LDS + cc * 8) = vv;
+        }
+        __syncthreads();
+        float sacc[BN / 8][4];
+#pragma unroll
+        for (int nb = 0; nb < BN / 8; ++nb) sacc[nb][0] = sacc[nb][1] = sacc[nb][2] = sacc[nb][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+            for (int nb = 0; nb < BN / 8; nb += 2) {
+                // matrices: (keys nb*8.., dims ks*16..+7), (same keys, dims +8), (keys (nb+1)*8.., dims ..+7), (.., dims +8)
+                const int row = nb * 8 + (lane & 7) + ((lane >> 4) << 3), col = ks * 16 + ((lane >> 3) & 1) * 8;
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(sK_u + (row * LDS + col) * 2, b0, b1, b2, b3);
+                mma_bf16(sacc[nb], qf[ks], b0, b1);
+                mma_bf16(sacc[nb + 1], qf[ks], b2, b3);
+            }
+        }
+        if (k0 + BN > len) {   // mask the keys past the end of the pair
+#pragma unroll
+            for (int nb = 0; nb < BN / 8; ++nb) {
+                const int c = k0 + nb * 8 + t4 * 2;
+                if (c >= len) sacc[nb][0] = sacc[nb][2] = -INFINITY;
+                if (c + 1 >= len) sacc[nb][1] = sacc[nb][3] = -INFINITY;
+            }
+        }
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int nb = 0; nb < BN / 8; ++nb) {
+            mx0 = fmaxf(mx0, fmaxf(sacc[nb][0], sacc[nb][1]));
+            mx1 = fmaxf(mx1, fmaxf(sacc[nb][2], sacc[nb][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 2));
+        const float a0 = exp2f((m0 - mx0) * LOG2E), a1 = exp2f((m1 - mx1) * LOG2E);
+        m0 = mx0; m1 = mx1;
+        const float ms0 = mx0 * LOG2E, ms1 = mx1 * LOG2E;
+        l0 *= a0; l1 *= a1;
+#pragma unroll
+        for (int d = 0; d < DBLK; ++d) { o[d][0] *= a0; o[d][1] *= a0; o[d][2] *= a1; o[d][3] *= a1; }
+        uint32_t pf[BN / 16][4];
+#pragma unroll
+        for (int nb = 0; nb < BN / 8; ++nb) {
+            const float p0 = exp2f(sacc[nb][0] * LOG2E - ms0), p1 = exp2f(sacc[nb][1] * LOG2E - ms0);
+            const float p2 = exp2f(sacc[nb][2] * LOG2E - ms1), p3 = exp2f(sacc[nb][3] * LOG2E - ms1);
+            l0 += p0 + p1; l1 += p2 + p3;
+            pf[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16(p0, p1);
+            pf[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(p2, p3);
+        }
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks) {
+#pragma unroll
+            for (int d = 0; d < DBLK; d += 2) {
+                // transposed 8x8 blocks: (keys ks*16..+7, dims d*8..), (keys +8, same dims), (keys .., dims (d+1)*8..), (keys +8, ..)
+                const int row = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = d * 8 + (lane >> 4) * 8;
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_trans(sV_u + (row * LDS + col) * 2, b0, b1, b2, b3);
+                mma_bf16(o[d], pf[ks], b0, b1);
+                mma_bf16(o[d + 1], pf[ks], b2, b3);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(FULL_MASK, l0, 1); l0 += __shfl_xor_sync(FULL_MASK, l0, 2);
+    l1 += __shfl_xor_sync(FULL_MASK, l1, 1); l1 += __shfl_xor_sync(FULL_MASK, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int d = 0; d < DBLK; ++d) {
+        const int c = d * 8 + t4 * 2;
+        if (r0 < len) *reinterpret_cast<uint32_t*>(out + (long long)(si.x + r0) * ld + hoff + c) = pack_bf16(o[d][0] * i0, o[d][1] * i0);
+        if (r1 < len) *reinterpret_cast<uint32_t*>(out + (long long)(si.x + r1) * ld + hoff + c) = pack_bf16(o[d][2] * i1, o[d][3] * i1);
+    }
+}
+
 // zero the separator rows of an attention output (full_attn only writes valid rows)
 template <typename T>
 __global__ void zero_separators_kernel(T* __restrict__ out, long long ld, int C, const int* __restrict__ row_seq, int R) {
@@ -188,11 +331,22 @@ int full_attn(const void* q, const void* k, const void* v, void* out, int dt, lo
     const int max_rows = max_len;   // longest pair of the level bounds the number of query tiles (blocks past a pair's end exit)
     if (dt == VRD_BF16) zero_separators_kernel<__nv_bfloat16><<<lay.R, 128, 0, st>>>((__nv_bfloat16*)out, ld, C, lay.row_seq, lay.R);
     else zero_separators_kernel<float><<<lay.R, 128, 0, st>>>((float*)out, ld, C, lay.row_seq, lay.R);
+    if (dt == VRD_BF16) {
+        const dim3 grid((max_rows + 63) / 64, n_head, lay.B);
+        if (hs == 64)
+            flash_attn_bf16_kernel<64><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                                                             (__nv_bfloat16*)out, ld, lay);
+        else if (hs == 128)
+            flash_attn_bf16_kernel<128><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                                                              (__nv_bfloat16*)out, ld, lay);
+        else return 1;
+        return 0;
+    }
 #define LAUNCH(T, HS) \
     full_attn_kernel<T, HS><<<dim3((max_rows + (128 / (HS / 32)) - 1) / (128 / (HS / 32)), n_head, lay.B), 128, 0, st>>>( \
         (const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay)
-    if (hs == 64) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 64); else LAUNCH(float, 64); }
-    else if (hs == 128) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 128); else LAUNCH(float, 128); }
+    if (hs == 64) LAUNCH(float, 64);
+    else if (hs == 128) LAUNCH(float, 128);
     else return 1;
 #undef LAUNCH
     return 0;

@@ -113,13 +113,31 @@ class CudaOps:
         self.launches = 0
         self._timing = None     # list of (op name, start event, end event, algorithmic flops) while profiling
         self._last_flops = 0.0
+        self._stream_handle = C.c_void_p(0)
+        self.bind_stream()
 
     # -- per-launch CUDA-event timing (bench.py roofline pass) --------------------------------------------------------
     def start_timing(self):
+        """Wrap every op of this instance with a CUDA-event pair (instance attributes shadow the class methods)."""
         self._timing = []
+        for name in _OP_NAMES:
+            fn = getattr(type(self), name).__get__(self)
+
+            def timed(*a, _fn=fn, _name=name, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self._last_flops = 0.0
+                e0.record()
+                r = _fn(*a, **k)
+                e1.record()
+                self._timing.append(("vrd_" + _name, e0, e1, self._last_flops))
+                return r
+            setattr(self, name, timed)
 
     def stop_timing(self):
         torch.cuda.synchronize()
+        for name in _OP_NAMES:
+            if name in self.__dict__:
+                delattr(self, name)
         prof = {}
         for name, e0, e1, fl in self._timing:
             d = prof.setdefault(name, {"ms": 0.0, "flops": 0.0, "n": 0})
@@ -129,27 +147,17 @@ class CudaOps:
         self._timing = None
         return prof
 
+    def bind_stream(self):
+        """Cache the handle of torch's current stream for the ops that follow (one lookup per forward, not per launch)."""
+        self._stream_handle = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return self._stream_handle
 
     def _check(self, rc, name):
         self.launches += 1
         if rc != 0:
             raise RuntimeError(f"{name} failed: {self.lib.vrd_last_error().decode()}")
-
-    def __getattribute__(self, attr):
-        fn = object.__getattribute__(self, attr)
-        if attr in _OP_NAMES and object.__getattribute__(self, "_timing") is not None:
-            def timed(*a, **k):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                self._last_flops = 0.0
-                e0.record()
-                r = fn(*a, **k)
-                e1.record()
-                self._timing.append(("vrd_" + attr, e0, e1, self._last_flops))
-                return r
-            return timed
-        return fn
 
     @staticmethod
     def _lay(lay):

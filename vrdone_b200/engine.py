@@ -23,6 +23,7 @@ import torch
 from .layout import LevelLayout, PackLayout
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+ROW_BUCKET = 8192
 
 
 class PackedWeights:
@@ -165,7 +166,10 @@ class Engine:
 
     # -- buffer helpers -------------------------------------------------------------------------
     def _buf(self, rows, cols, dtype):
-        return torch.empty(rows, cols, dtype=dtype, device=self.device)
+        # rows are rounded up to a bucket so that the caching allocator sees the same block sizes for every chunk / video
+        # (no cudaMalloc / cudaFree churn in steady state); kernels only ever touch the first ``rows`` rows.
+        bucket = (rows + ROW_BUCKET - 1) // ROW_BUCKET * ROW_BUCKET
+        return torch.empty(bucket, cols, dtype=dtype, device=self.device)[:rows]
 
     def _W(self, name):
         return self.w.t[name]
@@ -261,6 +265,8 @@ class Engine:
         (channel, time).  Returns dict(logits [B,Q,K+1] f32, topk_scores/topk_ids [B,Q,topk], first_last [B,Q,2] int32,
         masks [R0, Q] f32 or None)."""
         ops, mc, w = self.ops, self.mc, self.w
+        if hasattr(ops, "bind_stream"):
+            ops.bind_stream()
         C, adt = mc["embd_dim"], self.adt
         nv, nbe, nbs = mc["visual_dim"], mc["bbox_entity_dim"], mc["bbox_so_dim"]
         clip = bool(mc.get("with_clip_feature", False))

@@ -13,6 +13,7 @@ Differences that are deliberate and documented:
 """
 from __future__ import annotations
 
+import time
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -57,7 +58,7 @@ class MaskVRD(nn.Module):
 
         # B200 execution state
         self.precision = config.get("precision", "bf16")   # "bf16" (tcgen05 tensor cores) or "fp32" (CUDA-core fp32)
-        self.max_rows = int(config.get("max_rows", 49152))  # level-0 rows processed per engine call (bounds workspace)
+        self.max_rows = int(config.get("max_rows", 196608))  # level-0 rows processed per engine call (bounds workspace)
         self._engine: Optional[Engine] = None
         self._engine_key = None
         self._ops = None
@@ -182,6 +183,7 @@ class MaskVRD(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward_test(self, input_data):
+        t0 = time.perf_counter()
         eng = self._get_engine()
         dev = eng.device
         feats = [f if f.is_cuda else f.to(dev, non_blocking=True) for f in input_data["so_features_list"]]
@@ -190,19 +192,30 @@ class MaskVRD(nn.Module):
         lens = [int(f.shape[1]) for f in feats]
         tpads = reference_padded_lengths(lens, self.config)
         r = self.run_network(feats, tpads, self.topk)
+        t1 = time.perf_counter()
         # one device->host read of the compact per-(pair, query) results
-        scores = r["topk_scores"].cpu().numpy()            # [B, Q, k] fp32
-        cats = r["topk_ids"].cpu().numpy()                 # [B, Q, k] int32, 1-based predicate ids
-        fl = r["first_last"].cpu().numpy()                 # [B, Q, 2]  int32
-        return self._decode(scores, cats, fl, input_data)
+        packed = torch.cat([r["topk_scores"].view(torch.int32), r["topk_ids"], r["first_last"]], dim=-1).cpu().numpy()
+        t2 = time.perf_counter()
+        k = self.topk
+        scores = packed[..., :k].view(np.float32)            # [B, Q, k] fp32
+        cats = packed[..., k:2 * k]                          # [B, Q, k] int32, 1-based predicate ids
+        fl = packed[..., 2 * k:]                             # [B, Q, 2] int32 first / last active frame
+        out = self._decode(scores, cats, fl, input_data)
+        t3 = time.perf_counter()
+        self.last_stats = {"enqueue_ms": 1e3 * (t1 - t0), "gpu_wait_ms": 1e3 * (t2 - t1), "decode_ms": 1e3 * (t3 - t2)}
+        return out
 
     def _decode(self, scores, cats, fl, input_data):
+        """Candidates in (pair, query, k) order -> durations -> min-length filter -> mean score ranking -> top n_max_pair.
+        Small host-side integer work on the compact kernel outputs (the reference does this in a Python loop with one
+        device sync per candidate, maskvrd.py:262-328)."""
         topk, stride = self.topk, self.feat_stride
-        to_np = lambda t: t.detach().cpu().numpy()
-        sids, oids = to_np(input_data["sids"]).astype(np.int64), to_np(input_data["oids"]).astype(np.int64)
-        durs = to_np(input_data["traj_durations"]).astype(np.int64)
-        cat_ids, cat_scores = to_np(input_data["cat_ids"]), to_np(input_data["cat_scores"]).astype(np.float32)
-        off = to_np(input_data["so_offset"]).astype(np.int64)
+        small = [input_data[k] for k in ("sids", "oids", "traj_durations", "cat_ids", "cat_scores", "so_offset")]
+        if any(t.is_cuda for t in small):    # one sync for all the small per-video tensors
+            small = [t.cpu() for t in small]
+        sids, oids, durs, cat_ids, cat_scores, off = [t.numpy() for t in small]
+        sids, oids, durs, off = sids.astype(np.int64), oids.astype(np.int64), durs.astype(np.int64), off.astype(np.int64)
+        cat_scores = cat_scores.astype(np.float32)
         so_start = np.maximum(durs[sids, 0], durs[oids, 0])
         so_end = np.minimum(durs[sids, 1], durs[oids, 1])
         first, last = fl[..., 0].astype(np.int64), fl[..., 1].astype(np.int64)
@@ -216,20 +229,34 @@ class MaskVRD(nn.Module):
         pi, qi = np.repeat(pi, topk), np.repeat(qi, topk)
         ki = np.tile(np.arange(topk), pi.size // topk)
         p_score = scores[pi, qi, ki].astype(np.float32)
-        trip_scores = np.stack([cat_scores[sids[pi]], p_score, cat_scores[oids[pi]]], 1).astype(np.float32)
+        trip_scores = np.stack([cat_scores[sids[pi]], p_score, cat_scores[oids[pi]]], 1)
         avg = trip_scores.mean(-1, dtype=np.float32)
-        order = np.argsort(-avg, kind="stable")[: self.n_max_pair]
+        # top n_max_pair by descending mean score, ties to the earlier candidate (== stable descending argsort, truncated)
+        n = min(self.n_max_pair, avg.size)
+        if avg.size > 4 * n:
+            thr = np.partition(avg, avg.size - n)[avg.size - n]
+            cand = np.nonzero(avg >= thr)[0]
+        else:
+            cand = np.arange(avg.size)
+        order = cand[np.argsort(-avg[cand], kind="stable")][:n]
         boxes = input_data["bboxes_list"]
+        host_boxes = {}
+
+        def traj(tid, a, b):
+            if tid not in host_boxes:                               # one D2H copy per tracklet that is actually reported
+                host_boxes[tid] = boxes[tid].cpu() if boxes[tid].is_cuda else boxes[tid]
+            return host_boxes[tid][a:b]
+
         out = {"triplets": [], "triple_scores": [], "triple_scores_avg": [], "so_trajs": [], "pred_durations": [], "so_tids": []}
         for j in order.tolist():
             p, q, k = int(pi[j]), int(qi[j]), int(ki[j])
             s, o = int(sids[p]), int(oids[p])
             a, b = int(start[p, q]), int(end[p, q])
             s0, o0 = int(so_start[p] - durs[s, 0]), int(so_start[p] - durs[o, 0])
-            st, ot = boxes[s][s0 + a: s0 + b], boxes[o][o0 + a: o0 + b]
+            st, ot = traj(s, s0 + a, s0 + b), traj(o, o0 + a, o0 + b)
             assert len(st) == len(ot)
             out["triplets"].append([int(cat_ids[s]), int(cats[p, q, k]), int(cat_ids[o])])
-            out["triple_scores"].append([float(v) for v in trip_scores[j]])
+            out["triple_scores"].append(trip_scores[j].tolist())
             out["triple_scores_avg"].append(float(avg[j]))
             out["so_trajs"].append([st.tolist(), ot.tolist()])
             out["pred_durations"].append([int(so_start[p]) + a, int(so_start[p]) + b])

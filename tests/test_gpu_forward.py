@@ -126,3 +126,22 @@ def test_full_size_properties(precision):
     fl = a["first_last"].cpu()
     L = torch.tensor(lens)[:, None]
     assert bool(((fl[..., 0] <= fl[..., 1]) & (fl[..., 1] < L) & ((fl[..., 0] >= 0) | (fl[..., 1] == -1))).all())
+
+
+def test_host_resident_inputs_match_device_resident():
+    """forward(input_data) with pinned HOST pair features (read by the pack kernel over PCIe), with pageable host features
+    (copied first) and with device features must give identical results."""
+    fix = H.video_fixture("vidvrd")
+    cfg, model, sd = H.seeded_model("vidvrd", fix["wseed"], precision="bf16")
+    model.to("cuda")
+    video = synth.synthetic_video(cfg, fix["vseed"])
+    on_dev = dict(video)
+    on_dev["so_features_list"] = [t.cuda() for t in video["so_features_list"]]
+    pinned = dict(video)
+    pinned["so_features_list"] = [t.t().contiguous().pin_memory().t() for t in video["so_features_list"]]
+    dense_pinned = dict(video)
+    dense_pinned["so_features_list"] = [t.contiguous().pin_memory() for t in video["so_features_list"]]
+    a, b, c, d = model(on_dev), model(pinned), model(video), model(dense_pinned)
+    for other in (b, c, d):
+        assert other["triplets"] == a["triplets"] and other["pred_durations"] == a["pred_durations"]
+        assert other["triple_scores"] == a["triple_scores"] and other["so_trajs"] == a["so_trajs"]

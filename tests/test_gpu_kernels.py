@@ -113,8 +113,10 @@ def test_layernorm_and_small_conv(ops, lays, dt):
 
 
 @pytest.mark.parametrize("dt", ["fp32", "bf16"])
-@pytest.mark.parametrize("stride,C,streams", [(1, 512, 2), (2, 512, 1), (1, 256, 1)])
-def test_dwconv_ln(ops, lays, dt, stride, C, streams):
+@pytest.mark.parametrize("stride,C,streams,flags", [(1, 512, 2, [True, True, True]), (1, 512, 1, [True, True, False]),
+                                                    (2, 512, 1, [True, True, True]), (1, 256, 1, [False, False]),
+                                                    (1, 512, 1, [True]), (1, 512, 1, [False, False])])
+def test_dwconv_ln(ops, lays, dt, stride, C, streams, flags):
     lg, lc = lays
     odt, tol = adt_tol(dt)
     li, lo = (0, 0) if stride == 1 else (1, 2)
@@ -123,7 +125,7 @@ def test_dwconv_ln(ops, lays, dt, stride, C, streams):
     pre = (rnd((C,), 2) * 0.2 + 1, rnd((C,), 3))
     br_c, br_g = [], []
     outs_c, outs_g = [], []
-    for b, use_pre in enumerate([True, False, True]):
+    for b, use_pre in enumerate(flags):
         w, gm, be = rnd((3, C), 10 + b, 0.6), rnd((C,), 20 + b) * 0.2 + 1, rnd((C,), 30 + b)
         oc = torch.empty(streams * lc.levels[lo].R, C, dtype=odt)
         og = torch.full_like(oc, 3.0).cuda()

@@ -103,7 +103,7 @@ int vrd_dwconv_ln(const void* x, int x_dtype, int64_t ldx, const int32_t* row_se
     }
     if (vrd::dwconv_ln(x, x_dtype, ldx, make_lay(row_seq_in, seqinfo_in, R_in, B), make_lay(row_seq_out, seqinfo_out, R_out, B),
                        stride, pre_gamma, pre_beta, br, out_dtype, C, streams, (cudaStream_t)stream))
-        return fail("vrd_dwconv_ln: unsupported C / dtype combination");
+        return fail("vrd_dwconv_ln: unsupported C / dtype / branch combination (branches: qkv all pre-LN, q,k pre-LN + v raw, 2 raw, 1 pre-LN)");
     return check_launch("vrd_dwconv_ln");
 }
 

@@ -9,12 +9,14 @@
 // is three row-shifted TMA loads of the same matrix (out-of-range rows are zero-filled by TMA, sequence boundaries by
 // the zero separator rows of layout.py).
 //
-// Kernel structure (one persistent CTA per SM, 256 threads):
-//   warp 0    TMA producer          (4-stage ring of {A 128x64, W BNx64} bf16 tiles, 128B-swizzled)
-//   warp 1    tcgen05.mma issuer    (UMMA 128 x BN x 16, kind::f16, two accumulator stages of 256 TMEM columns)
-//   warp 2    TMEM allocator
-//   warps 4-7 epilogue              (tcgen05.ld 32x32b -> bias / pad correction / ReLU|GELU / residuals / separator
-//                                    zeroing -> fp32 or bf16 rows in HBM), overlapped with the next tile's MMAs
+// Kernel structure (one persistent CTA per SM, 384 threads):
+//   warp 0     TMA producer          (4-stage ring of {A 128x64, W BNx64} bf16 tiles, 128B-swizzled)
+//   warp 1     tcgen05.mma issuer    (UMMA 128 x BN x 16, kind::f16, two accumulator stages of 256 TMEM columns)
+//   warp 2     TMEM allocator
+//   warps 4-11 epilogue              (two warps per TMEM lane quarter, each owning half of the tile's columns:
+//                                     software-pipelined tcgen05.ld 32x32b.x16 -> bias / pad correction from shared
+//                                     memory / ReLU|GELU / prefetched residuals / separator zeroing -> fp32 or bf16
+//                                     rows in HBM), overlapped with the next tile's MMAs through the second TMEM stage
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>
@@ -32,8 +34,10 @@ constexpr int STAGES = 4;
 constexpr int ACC_STAGE_COLS = 256;    // TMEM columns per accumulator stage
 constexpr int TMEM_COLS = 512;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int MAX_N = 2048;             // bias / correction vectors are staged in shared memory
 constexpr unsigned SPIN_LIMIT = 1u << 24;
 
 char g_err[256] = {0};
@@ -91,7 +95,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// GELU(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 rounding of
+// this kernel's GELU outputs); ~3x cheaper than erff in an epilogue that evaluates it 32k times per tile.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float erfz = 1.0f - p * t * __expf(-z * z);           // erf(|x|/sqrt2)
+    return 0.5f * x * (1.0f + copysignf(erfz, x));
 }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart).
@@ -131,6 +152,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t* tfull = bars + 2 * STAGES;   // [2]
     uint64_t* tempty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+    float* s_bias = (float*)(bars + 2 * STAGES + 8);   // [MAX_N]
+    float* s_corr = s_bias + MAX_N;                     // [MAX_N]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_n = e.N / block_n;
@@ -138,9 +161,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int kb_per_tap = K / BLOCK_K;
     const int num_kb = taps * kb_per_tap;
 
+    for (int i = threadIdx.x; i < e.N; i += NUM_THREADS) {
+        s_bias[i] = (e.bias != nullptr) ? e.bias[i] : 0.f;
+        s_corr[i] = (e.corr != nullptr) ? e.corr[i] : 0.f;
+    }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
@@ -197,6 +224,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else if (warp >= EPI_WARP0) {
         const int wq = warp & 3;                         // TMEM lane quarter this warp may access
+        const int half = (warp - EPI_WARP0) >> 2;        // which half of the tile's 16-column chunks
+        const int n_chunks = block_n / 16;
+        const int c_begin = half == 0 ? 0 : (n_chunks + 1) / 2;
+        const int c_end = half == 0 ? (n_chunks + 1) / 2 : n_chunks;
+        const bool has_res = e.res1 != nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
@@ -213,32 +245,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     add_corr = (si.z != 0) && (rl - si.x == si.y - 1);
                 }
             }
-            mbar_wait(&tfull[as], aphase);
-            tc_fence_after();
+            const float* r1p = has_res ? e.res1 + (long long)row * e.ldr1 + n0 : nullptr;
+            const float* r2p = e.res2 != nullptr ? e.res2 + (long long)row * e.ldr2 + n0 : nullptr;
+            auto load_res = [&](int c, float4 (&dst)[4]) {
+                const float4* p = reinterpret_cast<const float4*>(r1p + c * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = p[i];
+                if (r2p != nullptr) {
+                    const float4* p2 = reinterpret_cast<const float4*>(r2p + c * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const float4 t = p2[i]; dst[i].x += t.x; dst[i].y += t.y; dst[i].z += t.z; dst[i].w += t.w; }
+                }
+            };
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * ACC_STAGE_COLS;
-            for (int c = 0; c < block_n; c += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + c, r);
+            // one pipeline step: wait for chunk c (already in flight into `cur`), launch chunk c+1 into `nxt`, finish chunk c
+            auto step = [&](int c, uint32_t (&cur)[16], float4 (&rcur)[4], uint32_t (&nxt)[16], float4 (&rnxt)[4]) {
+                tmem_ld_wait();
+                if (c + 1 < c_end) {
+                    tmem_ld16(taddr + (c + 1) * 16, nxt);
+                    if (has_res && valid) load_res(c + 1, rnxt);
+                }
+                const int n = n0 + c * 16;
                 float v[16];
-                const int n = n0 + c;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float x = __uint_as_float(r[i]);
-                    if (e.bias != nullptr) x += __ldg(e.bias + n + i);
-                    if (add_corr) x += __ldg(e.corr + n + i);
-                    if (e.act == 1) x = fmaxf(x, 0.f);
-                    else if (e.act == 2) x = gelu_erf(x);
-                    v[i] = x;
+                for (int i = 0; i < 4; ++i) {
+                    const float4 bi = *reinterpret_cast<const float4*>(s_bias + n + 4 * i);
+                    v[4 * i + 0] = __uint_as_float(cur[4 * i + 0]) + bi.x;
+                    v[4 * i + 1] = __uint_as_float(cur[4 * i + 1]) + bi.y;
+                    v[4 * i + 2] = __uint_as_float(cur[4 * i + 2]) + bi.z;
+                    v[4 * i + 3] = __uint_as_float(cur[4 * i + 3]) + bi.w;
                 }
-                if (e.res1 != nullptr) {
-                    const float4* rp = reinterpret_cast<const float4*>(e.res1 + (long long)row * e.ldr1 + n);
+                if (add_corr) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { const float4 t = rp[i]; v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
+                    for (int i = 0; i < 16; ++i) v[i] += s_corr[n + i];
                 }
-                if (e.res2 != nullptr) {
-                    const float4* rp = reinterpret_cast<const float4*>(e.res2 + (long long)row * e.ldr2 + n);
+                if (e.act == 1) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { const float4 t = rp[i]; v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                } else if (e.act == 2) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
+                }
+                if (has_res && valid) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { v[4 * i] += rcur[i].x; v[4 * i + 1] += rcur[i].y; v[4 * i + 2] += rcur[i].z; v[4 * i + 3] += rcur[i].w; }
                 }
                 if (!valid) {
 #pragma unroll
@@ -246,20 +296,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
                 if (e.out_dtype == VRD_BF16) {
                     __nv_bfloat16* op = (__nv_bfloat16*)e.out + (long long)row * e.ldo + n;
-                    uint4 pk[2];
-                    uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                        pw[i] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                    reinterpret_cast<uint4*>(op)[0] = pk[0];
-                    reinterpret_cast<uint4*>(op)[1] = pk[1];
+                    uint4 pk0, pk1;
+                    pk0.x = pack2(v[0], v[1]); pk0.y = pack2(v[2], v[3]); pk0.z = pack2(v[4], v[5]); pk0.w = pack2(v[6], v[7]);
+                    pk1.x = pack2(v[8], v[9]); pk1.y = pack2(v[10], v[11]); pk1.z = pack2(v[12], v[13]); pk1.w = pack2(v[14], v[15]);
+                    reinterpret_cast<uint4*>(op)[0] = pk0;
+                    reinterpret_cast<uint4*>(op)[1] = pk1;
                 } else {
                     float4* op = reinterpret_cast<float4*>((float*)e.out + (long long)row * e.ldo + n);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
+            };
+            uint32_t acc0[16], acc1[16];
+            float4 rs0[4], rs1[4];
+            if (has_res && valid) load_res(c_begin, rs0);         // residual rows do not depend on the accumulator
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            tmem_ld16(taddr + c_begin * 16, acc0);
+            for (int c = c_begin; c < c_end; c += 2) {
+                step(c, acc0, rs0, acc1, rs1);
+                if (c + 1 < c_end) step(c + 1, acc1, rs1, acc0, rs0);
             }
             tc_fence_before();
             __syncwarp();
@@ -321,6 +377,7 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     else if (g.N <= 256) block_n = g.N;
     else if (g.N % 128 == 0) block_n = 128;
     else { snprintf(g_err, sizeof g_err, "gemm_tcgen05: unsupported N=%d", g.N); return 1; }
+    if (g.N > MAX_N) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: N=%d exceeds %d", g.N, MAX_N); return 1; }
     if ((g.ldo % (g.out_dtype == VRD_BF16 ? 8 : 4)) != 0 || (g.res1 && g.ldr1 % 4) || (g.res2 && g.ldr2 % 4)) {
         snprintf(g_err, sizeof g_err, "gemm_tcgen05: output/residual pitch must be a multiple of 4");
         return 1;
@@ -333,7 +390,7 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     CUtensorMap map_a, map_w;
     if (!make_map(&map_a, g.A, g.M, g.K, g.lda, BLOCK_M)) return 1;
     if (!make_map(&map_w, g.W, g.N, (long long)g.taps * g.K, (long long)g.taps * g.K, block_n)) return 1;
-    const int smem = 1024 + STAGES * (A_STAGE_BYTES + block_n * BLOCK_K * 2) + 256;
+    const int smem = 1024 + STAGES * (A_STAGE_BYTES + block_n * BLOCK_K * 2) + 256 + 2 * MAX_N * 4;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(max dynamic smem) failed");

@@ -13,64 +13,84 @@ constexpr int WARPS = 8;   // warps per block for the row kernels
 // ------------------------------------------------------------------------------------------------------------
 // pack_pairs: ragged (C, L) fp32 pair tensors with arbitrary (channel, time) strides -> token-major operand rows
 // ------------------------------------------------------------------------------------------------------------
+// One block moves a 32-row x 32-channel tile through shared memory.  Rows whose pair tensor is contiguous along time
+// (dense (C, L): the data loader's transposed view after pickling / pin_memory) are read with lanes along time and
+// transposed in the tile; rows of token-major tensors (the (L, C) buffer the reference builds, vidor.py:708-711) are read
+// with lanes along channels.  Either way both the global reads and the global writes are coalesced.
 template <typename TA>
-__global__ void pack_pairs_kernel(const float* const* __restrict__ ptrs, const long long* __restrict__ strides, Lay lay,
-                                  int nv, int nc, int nbs, int nbe, TA* __restrict__ vis, TA* __restrict__ clip,
-                                  float* __restrict__ bso, float* __restrict__ bent) {
-    const int r = blockIdx.x;
-    const int seq = lay.row_seq[r];
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const float* const* __restrict__ ptrs, const long long* __restrict__ strides,
+                                                         Lay lay, int nv, int nc, int nbs, int nbe, TA* __restrict__ vis,
+                                                         TA* __restrict__ clip, float* __restrict__ bso, float* __restrict__ bent) {
+    __shared__ float tile[32][33];
+    __shared__ const float* s_src[32];     // element (t, channel 0) of the row's pair, or nullptr for separator rows
+    __shared__ long long s_sc[32];
+    __shared__ int s_tmode[32];            // 1: time-contiguous source (read lanes along time)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int r0 = blockIdx.x * 32, cb = blockIdx.y * 32;
     const long long R = lay.R;
     const int c0 = 2 * nv + 2 * nc;
     const int C = c0 + nbs + 2 * nbe;
-    if (seq < 0) {
-        for (int c = threadIdx.x; c < nv; c += blockDim.x) {
-            vis[(long long)r * nv + c] = from_f<TA>(0.f);
-            vis[(R + r) * nv + c] = from_f<TA>(0.f);
+    if (threadIdx.x < 32) {
+        const int r = r0 + threadIdx.x;
+        const int seq = (r < lay.R) ? lay.row_seq[r] : -1;
+        if (seq >= 0) {
+            const int4 si = lay.seqinfo[seq];
+            const long long sc = strides[2 * seq], st = strides[2 * seq + 1];
+            s_src[threadIdx.x] = ptrs[seq] + (long long)(r - si.x) * st;
+            s_sc[threadIdx.x] = sc;
+            s_tmode[threadIdx.x] = (st == 1 && sc != 1) ? 1 : 0;
+        } else {
+            s_src[threadIdx.x] = nullptr;
+            s_sc[threadIdx.x] = 0;
+            s_tmode[threadIdx.x] = 0;
         }
-        for (int c = threadIdx.x; c < nc; c += blockDim.x) {
-            clip[(long long)r * nc + c] = from_f<TA>(0.f);
-            clip[(R + r) * nc + c] = from_f<TA>(0.f);
-        }
-        if (threadIdx.x < 8) {
-            bso[(long long)r * 8 + threadIdx.x] = 0.f;
-            bent[(long long)r * 8 + threadIdx.x] = 0.f;
-            bent[(R + r) * 8 + threadIdx.x] = 0.f;
-        }
-        return;
     }
-    const int4 si = lay.seqinfo[seq];
-    const int t = r - si.x;
-    const float* src = ptrs[seq];
-    const long long sc = strides[2 * seq], st = strides[2 * seq + 1];
-    src += (long long)t * st;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float v = __ldg(src + (long long)c * sc);
-        if (c < nv) vis[(long long)r * nv + c] = from_f<TA>(v);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // lanes along time: row = tx, channel = ty + 8k
+        const int c = cb + ty + 8 * k;
+        if (s_tmode[tx] && c < C) tile[tx][ty + 8 * k] = __ldg(s_src[tx] + (long long)c * s_sc[tx]);
+        // lanes along channels: row = ty + 8k, channel = tx
+        const int rr = ty + 8 * k, cc = cb + tx;
+        if (!s_tmode[rr] && s_src[rr] != nullptr && cc < C) tile[rr][tx] = __ldg(s_src[rr] + (long long)cc * s_sc[rr]);
+    }
+    __syncthreads();
+    const int c = cb + tx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int rr = ty + 8 * k;
+        const long long r = r0 + rr;
+        if (r >= lay.R) continue;
+        const float v = (s_src[rr] != nullptr && c < C) ? tile[rr][tx] : 0.f;
+        if (c < nv) vis[r * nv + c] = from_f<TA>(v);
         else if (c < 2 * nv) vis[(R + r) * nv + (c - nv)] = from_f<TA>(v);
-        else if (c < 2 * nv + nc) clip[(long long)r * nc + (c - 2 * nv)] = from_f<TA>(v);
+        else if (c < 2 * nv + nc) clip[r * nc + (c - 2 * nv)] = from_f<TA>(v);
         else if (c < c0) clip[(R + r) * nc + (c - 2 * nv - nc)] = from_f<TA>(v);
-        else if (c < c0 + nbs) bso[(long long)r * 8 + (c - c0)] = v;
-        else if (c < c0 + nbs + nbe) bent[(long long)r * 8 + (c - c0 - nbs)] = v;
-        else bent[(R + r) * 8 + (c - c0 - nbs - nbe)] = v;
+        else if (c < c0 + nbs) bso[r * 8 + (c - c0)] = v;
+        else if (c < c0 + nbs + nbe) bent[r * 8 + (c - c0 - nbs)] = v;
+        else if (c < C) bent[(R + r) * 8 + (c - c0 - nbs - nbe)] = v;
     }
-    // unused tail columns of the 8-wide geometry rows
-    if (threadIdx.x < 8) {
-        if ((int)threadIdx.x >= nbs) bso[(long long)r * 8 + threadIdx.x] = 0.f;
-        if ((int)threadIdx.x >= nbe) {
-            bent[(long long)r * 8 + threadIdx.x] = 0.f;
-            bent[(R + r) * 8 + threadIdx.x] = 0.f;
+    // unused tail columns of the 8-wide geometry rows (written once, by the last channel tile)
+    if (blockIdx.y == gridDim.y - 1 && threadIdx.x < 32) {
+        const long long r = r0 + threadIdx.x;
+        if (r < lay.R) {
+            for (int j = nbs; j < 8; ++j) bso[r * 8 + j] = 0.f;
+            for (int j = nbe; j < 8; ++j) { bent[r * 8 + j] = 0.f; bent[(R + r) * 8 + j] = 0.f; }
         }
     }
 }
 
 void pack_pairs(const void* ptrs, const long long* strides, Lay lay, int nv, int nc, int nbs, int nbe, void* vis,
                 void* clip, int adt, float* bso, float* bent, cudaStream_t st) {
+    const int C = 2 * nv + 2 * nc + nbs + 2 * nbe;
+    const dim3 grid((lay.R + 31) / 32, (C + 31) / 32);
     if (adt == VRD_BF16)
-        pack_pairs_kernel<__nv_bfloat16><<<lay.R, 256, 0, st>>>((const float* const*)ptrs, strides, lay, nv, nc, nbs, nbe,
-                                                                (__nv_bfloat16*)vis, (__nv_bfloat16*)clip, bso, bent);
+        pack_pairs_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const float* const*)ptrs, strides, lay, nv, nc, nbs, nbe,
+                                                               (__nv_bfloat16*)vis, (__nv_bfloat16*)clip, bso, bent);
     else
-        pack_pairs_kernel<float><<<lay.R, 256, 0, st>>>((const float* const*)ptrs, strides, lay, nv, nc, nbs, nbe,
-                                                        (float*)vis, (float*)clip, bso, bent);
+        pack_pairs_kernel<float><<<grid, 256, 0, st>>>((const float* const*)ptrs, strides, lay, nv, nc, nbs, nbe,
+                                                       (float*)vis, (float*)clip, bso, bent);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -174,97 +194,195 @@ int small_conv(const float* x, int cin, const float* wt, const float* bias, cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// dwconv_ln: [LN_pre] -> depthwise k=3 (stride 1|2) -> LN, for up to 3 branches sharing one read of the input rows
+// dwconv_ln: [LN_pre] -> depthwise k=3 (stride 1|2) -> LN, for up to 3 branches sharing one read of the input rows.
+// A warp walks DW_RUN consecutive output rows and keeps the three input rows of the stencil in registers (raw and/or
+// pre-normalised, as the compile-time branch mask needs), so every input row is loaded and normalised once per run.
 // ------------------------------------------------------------------------------------------------------------
-template <typename TI, typename TO, int NCH>
-__global__ void dwconv_ln_kernel(const TI* __restrict__ x, long long ldx, Lay lin, Lay lout, int stride,
-                                 const float* __restrict__ pre_g, const float* __restrict__ pre_b, DwBranches br,
-                                 int streams) {
+constexpr int DW_RUN = 16;
+constexpr int DW_WARPS = 4;
+
+template <int NCH>
+__device__ __forceinline__ void row_copy(float (&d)[NCH][4], const float (&s)[NCH][4]) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[j][i] = s[j][i];
+}
+template <int NCH>
+__device__ __forceinline__ void row_zero(float (&d)[NCH][4]) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[j][i] = 0.f;
+}
+
+// PREMASK bit b: branch b convolves LN_pre(x) (else raw x)
+template <typename TI, typename TO, int NCH, int STRIDE, int NB, int PREMASK>
+__global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_kernel(const TI* __restrict__ x, long long ldx, Lay lin, Lay lout,
+                                                                 const float* __restrict__ pre_g, const float* __restrict__ pre_b,
+                                                                 DwBranches br, int streams) {
+    constexpr bool ANY_PRE = PREMASK != 0;
+    constexpr bool ANY_RAW = PREMASK != ((1 << NB) - 1);
+    constexpr int C = NCH * 128;
     const int lane = threadIdx.x & 31;
-    const int grow = blockIdx.x * WARPS + (threadIdx.x >> 5);   // row over all streams
-    if (grow >= streams * lout.R) return;
-    const int s = grow / lout.R, r = grow - s * lout.R;
-    const int seq = lout.row_seq[r];
-    if (seq < 0) {
-        for (int b = 0; b < br.n; ++b) zero_row<TO, NCH>((TO*)br.out[b] + (long long)grow * br.ldo[b], lane);
-        return;
-    }
-    const int4 so = lout.seqinfo[seq], si = lin.seqinfo[seq];
-    const int t = (r - so.x) * stride;            // centre time index at the input level
-    const int len = si.y;
-    const TI* base = x + ((long long)s * lin.R + si.x) * ldx;
-    // raw rows t-1, t, t+1 (zero when outside [0, len))
-    float raw[3][NCH][4];
-    bool inside[3];
+    const int runs_per_stream = (lout.R + DW_RUN - 1) / DW_RUN;
+    const int run = blockIdx.x * DW_WARPS + (threadIdx.x >> 5);
+    if (run >= streams * runs_per_stream) return;
+    const int s = run / runs_per_stream;
+    const int r_begin = (run - s * runs_per_stream) * DW_RUN;
+    const int r_end = min(r_begin + DW_RUN, lout.R);
+
+    // stencil window: index 0/1/2 = time t-1 / t / t+1 of the current output row
+    float raw[ANY_RAW ? 3 : 1][NCH][4];
+    float nrm[ANY_PRE ? 3 : 1][NCH][4];
+    int cur_seq = -1, cur_t = 0;
+    int4 so = make_int4(0, 0, 0, 0), si = make_int4(0, 0, 0, 0);
+    const TI* base = x;
+
+    auto fetch = [&](int slot, int tt) {    // load input time index tt of the current pair into window slot `slot`
+        const int len = si.y;
+        if (tt >= 0 && tt < len) {
+            float v[NCH][4];
+            load_row<TI, NCH>(base + (long long)tt * ldx, lane, v);
+            if constexpr (ANY_RAW) row_copy<NCH>(raw[slot], v);
+            if constexpr (ANY_PRE) { row_normalize<NCH>(v, lane, pre_g, pre_b); row_copy<NCH>(nrm[slot], v); }
+        } else {
+            if constexpr (ANY_RAW) row_zero<NCH>(raw[slot]);
+            if constexpr (ANY_PRE) {
+                // the first pad column (tt == len) carries the LN bias if it exists; stride 2 only reads it when it exists
+                if (tt == len && (si.z != 0 || STRIDE == 2)) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const int tt = t + d - 1;
-        inside[d] = (tt >= 0 && tt < len);
-        if (inside[d]) load_row<TI, NCH>(base + (long long)tt * ldx, lane, raw[d]);
-        else {
-#pragma unroll
-            for (int j = 0; j < NCH; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) raw[d][j][i] = 0.f;
-        }
-    }
-    // first pad column (time index == len) exists?  stride-2 reads it only for odd len, where it always exists.
-    const bool right_is_pad = (t + 1 == len) && (si.z != 0 || stride == 2);
-    bool any_pre = false;
-    for (int b = 0; b < br.n; ++b) any_pre |= (br.use_pre[b] != 0);
-    float nrm[3][NCH][4];
-    if (any_pre) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-#pragma unroll
-            for (int j = 0; j < NCH; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) nrm[d][j][i] = raw[d][j][i];
-            if (inside[d]) row_normalize<NCH>(nrm[d], lane, pre_g, pre_b);
-        }
-        if (right_is_pad) {
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) ld4(pre_b + (j * 32 + lane) * 4, nrm[2][j]);
-        }
-    }
-    for (int b = 0; b < br.n; ++b) {
-        const float* w = br.w[b];   // [3, C] tap-major
-        float y[NCH][4];
-        const bool pre = br.use_pre[b] != 0;
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-            float w0[4], w1[4], w2[4];
-            const int c = (j * 32 + lane) * 4;
-            ld4(w + c, w0); ld4(w + NCH * 128 + c, w1); ld4(w + 2 * NCH * 128 + c, w2);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float a0 = pre ? nrm[0][j][i] : raw[0][j][i];
-                const float a1 = pre ? nrm[1][j][i] : raw[1][j][i];
-                const float a2 = pre ? nrm[2][j][i] : raw[2][j][i];
-                y[j][i] = a0 * w0[i] + a1 * w1[i] + a2 * w2[i];
+                    for (int j = 0; j < NCH; ++j) ld4(pre_b + (j * 32 + lane) * 4, nrm[slot][j]);
+                } else {
+                    row_zero<NCH>(nrm[slot]);
+                }
             }
         }
-        row_normalize<NCH>(y, lane, br.g[b], br.b[b]);
-        store_row<TO, NCH>((TO*)br.out[b] + (long long)grow * br.ldo[b], lane, y);
+    };
+
+    for (int r = r_begin; r < r_end; ++r) {
+        const long long grow = (long long)s * lout.R + r;
+        const int seq = lout.row_seq[r];
+        if (seq < 0) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) zero_row<TO, NCH>((TO*)br.out[b] + grow * br.ldo[b], lane);
+            cur_seq = -1;
+            continue;
+        }
+        if (seq != cur_seq) {
+            so = lout.seqinfo[seq];
+            si = lin.seqinfo[seq];
+            base = x + ((long long)s * lin.R + si.x) * ldx;
+        }
+        const int t = (r - so.x) * STRIDE;
+        if (seq == cur_seq && t == cur_t + STRIDE) {          // slide the window
+            if constexpr (STRIDE == 1) {
+                if constexpr (ANY_RAW) { row_copy<NCH>(raw[0], raw[1]); row_copy<NCH>(raw[1], raw[2]); }
+                if constexpr (ANY_PRE) { row_copy<NCH>(nrm[0], nrm[1]); row_copy<NCH>(nrm[1], nrm[2]); }
+                fetch(2, t + 1);
+            } else {
+                if constexpr (ANY_RAW) row_copy<NCH>(raw[0], raw[2]);
+                if constexpr (ANY_PRE) row_copy<NCH>(nrm[0], nrm[2]);
+                fetch(1, t);
+                fetch(2, t + 1);
+            }
+        } else {
+            fetch(0, t - 1);
+            fetch(1, t);
+            fetch(2, t + 1);
+        }
+        cur_seq = seq;
+        cur_t = t;
+        float y[NB][NCH][4];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float* w = br.w[b];   // [3, C] tap-major
+            constexpr int dummy = 0; (void)dummy;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                float w0[4], w1[4], w2[4];
+                const int c = (j * 32 + lane) * 4;
+                ld4(w + c, w0); ld4(w + C + c, w1); ld4(w + 2 * C + c, w2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float a0, a1, a2;
+                    if ((PREMASK >> b) & 1) { a0 = nrm[0][j][i]; a1 = nrm[ANY_PRE ? 1 : 0][j][i]; a2 = nrm[ANY_PRE ? 2 : 0][j][i]; }
+                    else { a0 = raw[0][j][i]; a1 = raw[ANY_RAW ? 1 : 0][j][i]; a2 = raw[ANY_RAW ? 2 : 0][j][i]; }
+                    y[b][j][i] = a0 * w0[i] + a1 * w1[i] + a2 * w2[i];
+                }
+            }
+        }
+        // post-conv LayerNorm of all branches, reductions interleaved for instruction-level parallelism
+        float mean[NB], rstd[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float sm = 0.f;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) sm += (y[b][j][0] + y[b][j][1]) + (y[b][j][2] + y[b][j][3]);
+            mean[b] = sm;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) mean[b] += __shfl_xor_sync(FULL_MASK, mean[b], o);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            mean[b] *= (1.0f / C);
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float d = y[b][j][i] - mean[b]; q += d * d; }
+            rstd[b] = q;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) rstd[b] += __shfl_xor_sync(FULL_MASK, rstd[b], o);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float rs = 1.0f / sqrtf(rstd[b] * (1.0f / C) + VRD_EPS);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                float g[4], be[4];
+                ld4(br.g[b] + (j * 32 + lane) * 4, g);
+                ld4(br.b[b] + (j * 32 + lane) * 4, be);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[b][j][i] = (y[b][j][i] - mean[b]) * rs * g[i] + be[i];
+            }
+            store_row<TO, NCH>((TO*)br.out[b] + grow * br.ldo[b], lane, y[b]);
+        }
     }
+}
+
+template <typename TI, typename TO, int NCH, int STRIDE>
+static int dwconv_ln_mask(const void* x, long long ldx, Lay lin, Lay lout, const float* pre_g, const float* pre_b,
+                          const DwBranches& br, int streams, cudaStream_t st) {
+    int mask = 0;
+    for (int b = 0; b < br.n; ++b) mask |= (br.use_pre[b] ? 1 : 0) << b;
+    const int runs = streams * ((lout.R + DW_RUN - 1) / DW_RUN);
+    const int grid = (runs + DW_WARPS - 1) / DW_WARPS;
+#define LAUNCH(NB, MASK) \
+    dwconv_ln_kernel<TI, TO, NCH, STRIDE, NB, MASK><<<grid, DW_WARPS * 32, 0, st>>>((const TI*)x, ldx, lin, lout, pre_g, pre_b, br, streams)
+    if (br.n == 3 && mask == 7) LAUNCH(3, 7);
+    else if (br.n == 3 && mask == 3) LAUNCH(3, 3);
+    else if (br.n == 2 && mask == 0) LAUNCH(2, 0);
+    else if (br.n == 1 && mask == 1) LAUNCH(1, 1);
+    else return 1;
+#undef LAUNCH
+    return 0;
 }
 
 int dwconv_ln(const void* x, int xdt, long long ldx, Lay lin, Lay lout, int stride, const float* pre_g, const float* pre_b,
               const DwBranches& br, int odt, int C, int streams, cudaStream_t st) {
-    const int grid = (streams * lout.R + WARPS - 1) / WARPS;
-#define LAUNCH(TI, TO, NCH) \
-    dwconv_ln_kernel<TI, TO, NCH><<<grid, WARPS * 32, 0, st>>>((const TI*)x, ldx, lin, lout, stride, pre_g, pre_b, br, streams)
-    if (C == 512) {
-        if (xdt == VRD_F32 && odt == VRD_F32) LAUNCH(float, float, 4);
-        else if (xdt == VRD_F32 && odt == VRD_BF16) LAUNCH(float, __nv_bfloat16, 4);
-        else return 1;
-    } else if (C == 256) {
-        if (xdt == VRD_F32 && odt == VRD_F32) LAUNCH(float, float, 2);
-        else if (xdt == VRD_F32 && odt == VRD_BF16) LAUNCH(float, __nv_bfloat16, 2);
-        else return 1;
-    } else return 1;
-#undef LAUNCH
-    return 0;
+    if (xdt != VRD_F32) return 1;
+#define DISPATCH(TO, NCH) \
+    (stride == 1 ? dwconv_ln_mask<float, TO, NCH, 1>(x, ldx, lin, lout, pre_g, pre_b, br, streams, st) \
+                 : dwconv_ln_mask<float, TO, NCH, 2>(x, ldx, lin, lout, pre_g, pre_b, br, streams, st))
+    if (C == 512) return odt == VRD_BF16 ? DISPATCH(__nv_bfloat16, 4) : DISPATCH(float, 4);
+    if (C == 256) return odt == VRD_BF16 ? DISPATCH(__nv_bfloat16, 2) : DISPATCH(float, 2);
+#undef DISPATCH
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------------------

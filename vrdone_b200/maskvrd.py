@@ -13,6 +13,7 @@ Differences that are deliberate and documented:
 """
 from __future__ import annotations
 
+import gc
 import time
 from typing import Dict, List, Optional
 
@@ -63,6 +64,7 @@ class MaskVRD(nn.Module):
         self._engine_key = None
         self._ops = None
         self.last_stats: Dict[str, float] = {}
+        self._net_stats: Dict[str, float] = {}
 
     # ------------------------------------------------------------------------------------------------------------
     # reference API
@@ -142,26 +144,34 @@ class MaskVRD(nn.Module):
         lens = [int(f.shape[1]) for f in feats]
         outs = {"logits": [], "topk_scores": [], "topk_ids": [], "first_last": []}
         masks: List[torch.Tensor] = []
+        st = {"layout_ms": 0.0, "meta_ms": 0.0, "launch_ms": 0.0}
         with torch.cuda.device(dev):
             for a, b in self._chunks(lens):
+                tA = time.perf_counter()
                 sub = feats[a:b]
                 lay = PackLayout(lens[a:b], tpads[a:b], self.n_levels, dev)
-                meta = np.empty((b - a, 3), dtype=np.int64)
-                for i, f in enumerate(sub):
-                    assert f.is_cuda and f.dtype == torch.float32 and f.dim() == 2
-                    meta[i, 0], meta[i, 1], meta[i, 2] = f.data_ptr(), f.stride(0), f.stride(1)
+                tB = time.perf_counter()
+                meta = np.empty((3, b - a), dtype=np.int64)          # rows: data pointers, channel strides, time strides
+                meta[0] = [f.data_ptr() for f in sub]
+                meta[1] = [f.stride(0) for f in sub]
+                meta[2] = [f.stride(1) for f in sub]
+                assert all((f.is_cuda or f.is_pinned()) and f.dtype == torch.float32 for f in sub)
                 meta_d = torch.from_numpy(meta).to(dev, non_blocking=True)
-                ptrs = meta_d[:, 0].contiguous()
-                strides = meta_d[:, 1:].contiguous()
+                ptrs = meta_d[0]
+                strides = meta_d[1:].t().contiguous()
+                tC = time.perf_counter()
                 r = eng.forward_packed(lay, ptrs, strides, topk, want_masks)
+                tD = time.perf_counter()
+                st["layout_ms"] += 1e3 * (tB - tA); st["meta_ms"] += 1e3 * (tC - tB); st["launch_ms"] += 1e3 * (tD - tC)
                 for k in outs:
                     outs[k].append(r[k])
                 if want_masks:
                     l0 = lay.levels[0]
                     for i in range(b - a):
                         masks.append(r["masks"][int(l0.off[i]): int(l0.off[i]) + int(l0.len[i])])
-        res = {k: torch.cat(v, 0) for k, v in outs.items()}
+        res = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in outs.items()}
         res["masks"] = masks if want_masks else None
+        self._net_stats = st
         return res
 
     @torch.no_grad()
@@ -186,7 +196,9 @@ class MaskVRD(nn.Module):
         t0 = time.perf_counter()
         eng = self._get_engine()
         dev = eng.device
-        feats = [f if f.is_cuda else f.to(dev, non_blocking=True) for f in input_data["so_features_list"]]
+        # CUDA tensors are used in place; pinned host tensors are read by the pack kernel directly over PCIe (unified
+        # addressing: no staging copy, the H2D transfer IS the pack); pageable host tensors are copied first.
+        feats = [f if (f.is_cuda or f.is_pinned()) else f.to(dev, non_blocking=True) for f in input_data["so_features_list"]]
         n_pairs = len(input_data["sids"])
         assert len(feats) == n_pairs
         lens = [int(f.shape[1]) for f in feats]
@@ -194,7 +206,9 @@ class MaskVRD(nn.Module):
         r = self.run_network(feats, tpads, self.topk)
         t1 = time.perf_counter()
         # one device->host read of the compact per-(pair, query) results
-        packed = torch.cat([r["topk_scores"].view(torch.int32), r["topk_ids"], r["first_last"]], dim=-1).cpu().numpy()
+        packed = torch.cat([r["topk_scores"].view(torch.int32), r["topk_ids"], r["first_last"]], dim=-1)
+        t1b = time.perf_counter()
+        packed = packed.cpu().numpy()
         t2 = time.perf_counter()
         k = self.topk
         scores = packed[..., :k].view(np.float32)            # [B, Q, k] fp32
@@ -202,7 +216,8 @@ class MaskVRD(nn.Module):
         fl = packed[..., 2 * k:]                             # [B, Q, 2] int32 first / last active frame
         out = self._decode(scores, cats, fl, input_data)
         t3 = time.perf_counter()
-        self.last_stats = {"enqueue_ms": 1e3 * (t1 - t0), "gpu_wait_ms": 1e3 * (t2 - t1), "decode_ms": 1e3 * (t3 - t2)}
+        self.last_stats = {"enqueue_ms": 1e3 * (t1 - t0), "cat_ms": 1e3 * (t1b - t1), "gpu_wait_ms": 1e3 * (t2 - t1b),
+                           "decode_ms": 1e3 * (t3 - t2), **{k: v for k, v in self._net_stats.items()}}
         return out
 
     def _decode(self, scores, cats, fl, input_data):
@@ -244,10 +259,24 @@ class MaskVRD(nn.Module):
 
         def traj(tid, a, b):
             if tid not in host_boxes:                               # one D2H copy per tracklet that is actually reported
-                host_boxes[tid] = boxes[tid].cpu() if boxes[tid].is_cuda else boxes[tid]
+                host_boxes[tid] = boxes[tid].detach().cpu().numpy()
             return host_boxes[tid][a:b]
 
         out = {"triplets": [], "triple_scores": [], "triple_scores_avg": [], "so_trajs": [], "pred_durations": [], "so_tids": []}
+        # The result format (nested Python lists of boxes, as the reference returns) allocates ~10^5 small container objects;
+        # with the cyclic GC enabled that triggers full-heap collections costing several times the decode itself.  None of
+        # these objects can form cycles, so the collector is paused while they are built.
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            self._fill_result(out, order, pi, qi, ki, sids, oids, start, end, so_start, durs, cat_ids, cats, trip_scores, avg, traj)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+        return out
+
+    @staticmethod
+    def _fill_result(out, order, pi, qi, ki, sids, oids, start, end, so_start, durs, cat_ids, cats, trip_scores, avg, traj):
         for j in order.tolist():
             p, q, k = int(pi[j]), int(qi[j]), int(ki[j])
             s, o = int(sids[p]), int(oids[p])
@@ -261,4 +290,3 @@ class MaskVRD(nn.Module):
             out["so_trajs"].append([st.tolist(), ot.tolist()])
             out["pred_durations"].append([int(so_start[p]) + a, int(so_start[p]) + b])
             out["so_tids"].append([s, o])
-        return out

@@ -190,14 +190,30 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    gc_ms = [0.0]
+    gc_t0 = [0.0]
+
+    def gc_cb(phase, info):
+        if phase == "start":
+            gc_t0[0] = time.perf_counter()
+        else:
+            gc_ms[0] += 1e3 * (time.perf_counter() - gc_t0[0])
+    import gc
+    gc.callbacks.append(gc_cb)
+    step_wall = []
+
     def timed(videos, steps, h2d):
         sync_all()
+        gc_ms[0] = 0.0
+        step_wall.clear()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         pairs = 0
         for s in range(steps):
             v = videos[s % len(videos)]
+            tw = time.perf_counter()
             model(v)       # h2d: ``v`` holds pinned HOST pair features; the module moves them (inside the timed region)
+            step_wall.append(round(1e3 * (time.perf_counter() - tw), 1))
             pairs += n_pairs[s % len(videos)]
         e1.record()
         sync_all()
@@ -219,6 +235,8 @@ def main():
     ms, pairs = timed(dev_videos, args.steps, h2d=False)
     launches = ops.launches - l0
     host_hbm = {k: round(v, 2) for k, v in model.last_stats.items()}
+    host_hbm["python_gc_ms_per_step"] = round(gc_ms[0] / args.steps, 2)
+    host_hbm["forward_wall_ms_each_step"] = list(step_wall)
     clocks = sampler.stop()
     ms_e2e, pairs_e2e = timed(pinned, args.steps, h2d=True)
     host_e2e = {k: round(v, 2) for k, v in model.last_stats.items()}

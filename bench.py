@@ -193,11 +193,17 @@ def main():
     gc_ms = [0.0]
     gc_t0 = [0.0]
 
+    gc_gen = {}
+
     def gc_cb(phase, info):
         if phase == "start":
             gc_t0[0] = time.perf_counter()
         else:
-            gc_ms[0] += 1e3 * (time.perf_counter() - gc_t0[0])
+            d = 1e3 * (time.perf_counter() - gc_t0[0])
+            gc_ms[0] += d
+            g = gc_gen.setdefault(info["generation"], [0, 0.0])
+            g[0] += 1
+            g[1] += d
     import gc
     gc.callbacks.append(gc_cb)
     step_wall = []
@@ -205,6 +211,7 @@ def main():
     def timed(videos, steps, h2d):
         sync_all()
         gc_ms[0] = 0.0
+        gc_gen.clear()
         step_wall.clear()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -236,8 +243,11 @@ def main():
     launches = ops.launches - l0
     host_hbm = {k: round(v, 2) for k, v in model.last_stats.items()}
     host_hbm["python_gc_ms_per_step"] = round(gc_ms[0] / args.steps, 2)
+    host_hbm["python_gc_by_generation"] = {str(k): [v[0], round(v[1], 1)] for k, v in gc_gen.items()}
     host_hbm["forward_wall_ms_each_step"] = list(step_wall)
     clocks = sampler.stop()
+    for s in range(args.warmup):        # staging buffers, pinned upload blocks and the copy stream are created on first use
+        model(pinned[s % len(pinned)])
     ms_e2e, pairs_e2e = timed(pinned, args.steps, h2d=True)
     host_e2e = {k: round(v, 2) for k, v in model.last_stats.items()}
 

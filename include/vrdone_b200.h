@@ -38,6 +38,12 @@ const char* vrd_last_error(void);
 /* compute capability major*10+minor of the current device (100 on B200); <0 on error */
 int vrd_device_arch(void);
 
+/* a0 -- replaces utils.dict_to_device for the pair features (eval.py:144, utils/misc.py:98-112): n asynchronous
+ * host->device copies on `stream` (the copy engine; src[i] HOST pointers, pinned for true asynchrony) of bytes[i] bytes to
+ * dst_base + dst_offset[i].  The caller overlaps them with the kernels of the previous chunk on another stream. */
+int vrd_h2d_pairs(const void* const* src, const int64_t* bytes, void* dst_base, const int64_t* dst_offset, int n,
+                  vrd_stream_t stream);
+
 /* k9 -- replaces MaskVRD.preprocessing (maskvrd.py:363-414) + the channel split of backbones.py:161-166 / 329-341.
  * pair_ptrs[i] -> fp32 (C, L_i) tensor with element strides pair_strides[2i] (channel), pair_strides[2i+1] (time).
  * Writes vis [2R, nv], clip [2R, nc] (or NULL when nc == 0) in act_dtype, bbox_so [R, 8] and bbox_ent [2R, 8] in fp32. */

@@ -92,10 +92,194 @@ __global__ void window_attn_kernel(const T* __restrict__ q, const T* __restrict_
     store_row<T, NCH>(o, lane, acc);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// window_attn_tma: the same arithmetic, shared-memory tiled.  A CTA owns TILE consecutive rows (of the stacked streams);
+// one elected thread stages the K and V rows [r0 - 4, r0 + TILE + 4) with two TMA bulk copies (cp.async.bulk, completion
+// on an mbarrier) while the warps fetch their query rows; a warp then handles one query row at a time with every key /
+// value row read from shared memory (each is reused by up to 2w+1 queries), scores reduced with warp shuffles inside the
+// LPH lanes that share a head.  A lane owns NV 16-byte vectors: vector j = channels j*32*VEC + lane*VEC .. +VEC-1, so
+// global and shared accesses are contiguous across the warp (conflict-free LDS.128).  Requires ld == C.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) { ld4(p, v); }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { st4(p, v); }
+};
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            u[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
+    }
+};
+
+constexpr int WIN_HALO = 4;   // maximum half window
+
+template <typename T, int C, int HS, int TILE>
+__global__ void __launch_bounds__(WARPS * 32) window_attn_tma_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                                     const T* __restrict__ v, T* __restrict__ out, Lay lay, int w,
+                                                                     int total_rows) {
+    constexpr int VEC = Vec16<T>::N, NV = C / (32 * VEC), LPH = HS / VEC, MAXK = 2 * WIN_HALO + 1;
+    constexpr int ROWS = TILE + 2 * WIN_HALO;
+    extern __shared__ __align__(128) uint8_t win_smem[];
+    T* sK = reinterpret_cast<T*>(win_smem);
+    T* sV = sK + ROWS * C;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sV + ROWS * C);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * TILE;
+    const int lo = max(r0 - WIN_HALO, 0), hi = min(r0 + TILE + WIN_HALO, total_rows);
+    const uint32_t bar_u = (uint32_t)__cvta_generic_to_shared(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(hi - lo) * C * sizeof(T);
+        const long long goff = (long long)lo * C;
+        const int soff = (lo - (r0 - WIN_HALO)) * C;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_u), "r"(2 * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(sK + soff)), "l"(k + goff), "r"(bytes), "r"(bar_u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(sV + soff)), "l"(v + goff), "r"(bytes), "r"(bar_u) : "memory");
+    }
+    auto wait_tiles = [&]() {
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar_u), "r"(0u) : "memory");
+        }
+    };
+    bool waited = false;
+    for (int rr = warp; rr < TILE; rr += WARPS) {
+        const int grow = r0 + rr;
+        const int s = grow / lay.R, r = grow - s * lay.R;
+        T* o = out + (long long)grow * C;
+        const int seq = lay.row_seq[r];
+        if (seq < 0) {
+            const float z[VEC] = {};
+#pragma unroll
+            for (int j = 0; j < NV; ++j) Vec16<T>::st(o + (j * 32 + lane) * VEC, z);
+            continue;
+        }
+        const int4 si = lay.seqinfo[seq];
+        const int t = r - si.x;
+        float qv[NV][VEC];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) Vec16<T>::ld(q + (long long)grow * C + (j * 32 + lane) * VEC, qv[j]);
+        if (!waited) { wait_tiles(); waited = true; }
+        const T* kb = sK + (rr + WIN_HALO - w) * C;     // key kk of this query lives at tile row rr + HALO - w + kk
+        const T* vb = sV + (rr + WIN_HALO - w) * C;
+        float sc[MAXK][NV];
+        float mx[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) mx[j] = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < MAXK; ++kk) {
+            const int tt = t - w + kk;
+            const bool ok = (kk <= 2 * w) && tt >= 0 && tt < si.y;
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    float kv[VEC];
+                    Vec16<T>::ld(kb + kk * C + (j * 32 + lane) * VEC, kv);
+                    float d = 0.f;
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) d = fmaf(qv[j][i], kv[i], d);
+#pragma unroll
+                    for (int off = LPH / 2; off > 0; off >>= 1) d += __shfl_xor_sync(FULL_MASK, d, off);
+                    sc[kk][j] = d;
+                    mx[j] = fmaxf(mx[j], d);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) sc[kk][j] = -INFINITY;
+            }
+        }
+        float sum[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) sum[j] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < MAXK; ++kk)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const float p = (sc[kk][j] == -INFINITY) ? 0.f : expf(sc[kk][j] - mx[j]);
+                sc[kk][j] = p;
+                sum[j] += p;
+            }
+        float acc[NV][VEC];
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[j][i] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < MAXK; ++kk) {
+            const int tt = t - w + kk;
+            const bool ok = (kk <= 2 * w) && tt >= 0 && tt < si.y;
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    float vv[VEC];
+                    Vec16<T>::ld(vb + kk * C + (j * 32 + lane) * VEC, vv);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[j][i] = fmaf(sc[kk][j], vv[i], acc[j][i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float inv = 1.0f / sum[j];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[j][i] *= inv;
+            Vec16<T>::st(o + (j * 32 + lane) * VEC, acc[j]);
+        }
+    }
+    if (!waited) wait_tiles();    // never exit while the bulk copies into this CTA's shared memory are in flight
+}
+
+template <typename T, int HS, int TILE>
+static int window_attn_tma_launch(const void* q, const void* k, const void* v, void* out, Lay lay, int w, int streams,
+                                  cudaStream_t st) {
+    constexpr int C = 512;
+    constexpr int smem = 2 * (TILE + 2 * WIN_HALO) * C * (int)sizeof(T) + 16;
+    static bool attr_set = false;
+    auto kern = window_attn_tma_kernel<T, C, HS, TILE>;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+        attr_set = true;
+    }
+    const int total = streams * lay.R;    // R % 128 == 0, so TILE divides it
+    kern<<<total / TILE, WARPS * 32, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)out, lay, w, total);
+    return 0;
+}
+
 int window_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int n_head, int C, int w,
                 int streams, cudaStream_t st) {
     if (C != 512 || w > 4 || w < 1) return 1;
     const int hs = C / n_head;
+    if (ld == C && lay.R % 128 == 0 && (hs == 64 || hs == 128)) {
+        if (dt == VRD_BF16)
+            return hs == 64 ? window_attn_tma_launch<__nv_bfloat16, 64, 32>(q, k, v, out, lay, w, streams, st)
+                            : window_attn_tma_launch<__nv_bfloat16, 128, 32>(q, k, v, out, lay, w, streams, st);
+        return hs == 64 ? window_attn_tma_launch<float, 64, 16>(q, k, v, out, lay, w, streams, st)
+                        : window_attn_tma_launch<float, 128, 16>(q, k, v, out, lay, w, streams, st);
+    }
     const int grid = (streams * lay.R + WARPS - 1) / WARPS;
 #define LAUNCH(T, LPH) \
     window_attn_kernel<T, 4, LPH><<<grid, WARPS * 32, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay, w, streams)

@@ -42,6 +42,21 @@ int vrd_device_arch(void) {
     return major * 10 + minor;
 }
 
+int vrd_h2d_pairs(const void* const* src, const int64_t* bytes, void* dst_base, const int64_t* dst_offset, int n,
+                  vrd_stream_t stream) {
+    if (n < 0 || (n > 0 && (src == nullptr || bytes == nullptr || dst_base == nullptr || dst_offset == nullptr)))
+        return fail("vrd_h2d_pairs: bad arguments");
+    for (int i = 0; i < n; ++i) {
+        cudaError_t e = cudaMemcpyAsync((char*)dst_base + dst_offset[i], src[i], (size_t)bytes[i], cudaMemcpyHostToDevice,
+                                        (cudaStream_t)stream);
+        if (e != cudaSuccess) {
+            snprintf(t_err, sizeof t_err, "vrd_h2d_pairs: copy %d of %d failed: %s", i, n, cudaGetErrorString(e));
+            return 1;
+        }
+    }
+    return 0;
+}
+
 int vrd_pack_pairs(const void* pair_ptrs, const int64_t* pair_strides, const int32_t* row_seq, const int32_t* seqinfo, int R,
                    int B, int nv, int nc, int nbs, int nbe, void* vis, void* clip, int act_dtype, float* bbox_so,
                    float* bbox_ent, vrd_stream_t stream) {

@@ -22,6 +22,7 @@ _vp, _i32, _i64, _f32p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p
 _SIGNATURES = {
     "vrd_abi_version": [],
     "vrd_device_arch": [],
+    "vrd_h2d_pairs": [_vp, _vp, _vp, _vp, _i32, _vp],
     "vrd_pack_pairs": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "vrd_gemm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp,
                  _vp, _i32, _vp],
@@ -162,6 +163,15 @@ class CudaOps:
     @staticmethod
     def _lay(lay):
         return lay.row_seq.data_ptr(), lay.seqinfo.data_ptr(), lay.R
+
+    # -- host -> device staging (copy engine; not a kernel, not counted in ``launches``) --------------------------------
+    def h2d_pairs(self, src_ptrs, nbytes, dst, dst_offsets, stream):
+        """src_ptrs / nbytes / dst_offsets: contiguous int64 numpy arrays; dst: CUDA tensor; stream: torch.cuda.Stream."""
+        n = int(src_ptrs.shape[0])
+        rc = self.lib.vrd_h2d_pairs(src_ptrs.ctypes.data, nbytes.ctypes.data, dst.data_ptr(), dst_offsets.ctypes.data, n,
+                                    C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"vrd_h2d_pairs failed: {self.lib.vrd_last_error().decode()}")
 
     # -- ops ------------------------------------------------------------------------------------------------------
     def pack_pairs(self, ptrs, strides, lay, nv, nc, nbs, nbe, vis, clp, bso, bent):

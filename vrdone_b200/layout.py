@@ -87,8 +87,13 @@ class PackLayout:
             lev = LevelLayout(l, off.astype(np.int32), ll.astype(np.int32), haspad, rows)
             self.levels.append(lev)
             host += [row_seq, info.reshape(-1)]
-        flat = torch.from_numpy(np.concatenate(host))
-        dev = flat.to(device, non_blocking=True) if torch.device(device).type == "cuda" else flat
+        if torch.device(device).type == "cuda":
+            # pinned staging: a pageable source would make the copy wait for the stream's earlier work (chunk pipelining)
+            flat = torch.empty(sum(h.size for h in host), dtype=torch.int32, pin_memory=True)
+            np.concatenate(host, out=flat.numpy())
+            dev = flat.to(device, non_blocking=True)
+        else:
+            dev = torch.from_numpy(np.concatenate(host))
         pos = 0
         for lev in self.levels:
             lev.row_seq = dev[pos:pos + lev.R]

@@ -60,6 +60,11 @@ class MaskVRD(nn.Module):
         # B200 execution state
         self.precision = config.get("precision", "bf16")   # "bf16" (tcgen05 tensor cores) or "fp32" (CUDA-core fp32)
         self.max_rows = int(config.get("max_rows", 196608))  # level-0 rows processed per engine call (bounds workspace)
+        self.h2d_chunk_rows = int(config.get("h2d_chunk_rows", 36864))  # rows per chunk when pair features arrive from the host
+        self.gc_park_results = bool(config.get("gc_park_results", True))
+        self._copy_stream = None
+        self._staging = [None, None]      # double-buffered device staging of host-resident pair tensors
+        self._pack_done = [None, None]
         self._engine: Optional[Engine] = None
         self._engine_key = None
         self._ops = None
@@ -126,41 +131,94 @@ class MaskVRD(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     # network over a ragged list of pairs
     # ------------------------------------------------------------------------------------------------------------
-    def _chunks(self, lens: List[int]):
+    def _chunks(self, lens: List[int], max_rows: int):
         start, rows = 0, 1
         for i, l in enumerate(lens):
-            if i > start and rows + l + 1 > self.max_rows:
+            if i > start and rows + l + 1 > max_rows:
                 yield start, i
                 start, rows = i, 1
             rows += l + 1
         yield start, len(lens)
 
+    def _stage_chunk(self, ops, sub, slot: int, dev):
+        """Enqueue, on the copy stream, the host->device copies of the host-resident pair tensors of one chunk into staging
+        buffer ``slot`` (copy engine, overlapping the kernels of the previous chunk).  Returns (int64 [3, n] numpy table of
+        device addresses / channel strides / time strides, event to wait on before the pack kernel, or None)."""
+        n = len(sub)
+        meta = np.empty((3, n), dtype=np.int64)
+        meta[0] = [f.data_ptr() for f in sub]
+        meta[1] = [f.stride(0) for f in sub]
+        meta[2] = [f.stride(1) for f in sub]
+        on_host = np.array([not f.is_cuda for f in sub], dtype=bool)
+        if not on_host.any():
+            return meta, None
+        shape = np.array([f.shape for f in sub], dtype=np.int64)
+        # smallest address span that covers the (C, L) view: covers dense (C, L), the loader's (L, C) buffer and strided views
+        span = ((shape[:, 0] - 1) * meta[1] + (shape[:, 1] - 1) * meta[2] + 1) * 4
+        span = np.where(on_host, span, 0)
+        padded = (span + 255) // 256 * 256
+        offs = np.cumsum(padded) - padded
+        total = int(padded.sum())
+        buf = self._staging[slot]
+        if buf is None or buf.numel() < total:
+            self._staging[slot] = buf = torch.empty(max(total, 1 << 20), dtype=torch.uint8, device=dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        if self._pack_done[slot] is not None:
+            cs.wait_event(self._pack_done[slot])      # the previous user of this staging buffer has been packed
+        idx = np.nonzero(on_host)[0]
+        ops.h2d_pairs(np.ascontiguousarray(meta[0, idx]), np.ascontiguousarray(span[idx]), buf, np.ascontiguousarray(offs[idx]), cs)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        meta[0, idx] = buf.data_ptr() + offs[idx]
+        return meta, ev
+
     @torch.no_grad()
     def run_network(self, feats: List[torch.Tensor], tpads: List[int], topk: int, want_masks: bool = False):
-        """feats: list of fp32 (C, L_i) CUDA tensors (any strides).  Returns per-pair arrays on the device:
-        logits [B,Q,K+1], topk_scores / topk_ids [B,Q,topk], first_last [B,Q,2] and (optionally) a list of (L_i, Q) masks."""
+        """feats: list of fp32 (C, L_i) tensors with any strides, on the device or on the host (pinned host tensors are
+        staged by the copy engine chunk by chunk, overlapped with the previous chunk's kernels).  Returns per-pair arrays on the
+        device: logits [B,Q,K+1], topk_scores / topk_ids [B,Q,topk], first_last [B,Q,2] and (optionally) a list of (L_i, Q)
+        masks."""
         eng = self._get_engine()
         dev = eng.device
+        ops = self._ops
         lens = [int(f.shape[1]) for f in feats]
+        assert all(f.dtype == torch.float32 and f.dim() == 2 for f in feats)
+        any_host = not all(f.is_cuda for f in feats)
         outs = {"logits": [], "topk_scores": [], "topk_ids": [], "first_last": []}
         masks: List[torch.Tensor] = []
         st = {"layout_ms": 0.0, "meta_ms": 0.0, "launch_ms": 0.0}
         with torch.cuda.device(dev):
-            for a, b in self._chunks(lens):
+            cur = torch.cuda.current_stream(dev)
+            chunks = list(self._chunks(lens, min(self.max_rows, self.h2d_chunk_rows) if any_host else self.max_rows))
+            tB = time.perf_counter()
+            staged = self._stage_chunk(ops, feats[chunks[0][0]:chunks[0][1]], 0, dev)
+            st["meta_ms"] += 1e3 * (time.perf_counter() - tB)
+            for ci, (a, b) in enumerate(chunks):
                 tA = time.perf_counter()
-                sub = feats[a:b]
                 lay = PackLayout(lens[a:b], tpads[a:b], self.n_levels, dev)
                 tB = time.perf_counter()
-                meta = np.empty((3, b - a), dtype=np.int64)          # rows: data pointers, channel strides, time strides
-                meta[0] = [f.data_ptr() for f in sub]
-                meta[1] = [f.stride(0) for f in sub]
-                meta[2] = [f.stride(1) for f in sub]
-                assert all((f.is_cuda or f.is_pinned()) and f.dtype == torch.float32 for f in sub)
-                meta_d = torch.from_numpy(meta).to(dev, non_blocking=True)
+                meta, ev = staged
+                # the small uploads of THIS chunk (layout above, pointer table here) are issued before the next chunk's bulk
+                # copies: the copy engine serves host->device copies in issue order, whatever their stream
+                meta_h = torch.empty(meta.shape, dtype=torch.int64, pin_memory=True)
+                meta_h.numpy()[...] = meta
+                meta_d = meta_h.to(dev, non_blocking=True)
+                if ci + 1 < len(chunks):      # start the next chunk's copies before this chunk's kernels are enqueued
+                    staged = self._stage_chunk(ops, feats[chunks[ci + 1][0]:chunks[ci + 1][1]], (ci + 1) & 1, dev)
+                if ev is not None:
+                    cur.wait_event(ev)
                 ptrs = meta_d[0]
                 strides = meta_d[1:].t().contiguous()
                 tC = time.perf_counter()
-                r = eng.forward_packed(lay, ptrs, strides, topk, want_masks)
+
+                def packed(slot=ci & 1):
+                    if any_host:
+                        e = torch.cuda.Event()
+                        e.record(cur)
+                        self._pack_done[slot] = e
+                r = eng.forward_packed(lay, ptrs, strides, topk, want_masks, after_pack=packed)
                 tD = time.perf_counter()
                 st["layout_ms"] += 1e3 * (tB - tA); st["meta_ms"] += 1e3 * (tC - tB); st["launch_ms"] += 1e3 * (tD - tC)
                 for k in outs:
@@ -196,9 +254,9 @@ class MaskVRD(nn.Module):
         t0 = time.perf_counter()
         eng = self._get_engine()
         dev = eng.device
-        # CUDA tensors are used in place; pinned host tensors are read by the pack kernel directly over PCIe (unified
-        # addressing: no staging copy, the H2D transfer IS the pack); pageable host tensors are copied first.
-        feats = [f if (f.is_cuda or f.is_pinned()) else f.to(dev, non_blocking=True) for f in input_data["so_features_list"]]
+        # CUDA tensors are used in place; host tensors are staged chunk by chunk by the copy engine (run_network), overlapped
+        # with the kernels of the previous chunk.
+        feats = list(input_data["so_features_list"])
         n_pairs = len(input_data["sids"])
         assert len(feats) == n_pairs
         lens = [int(f.shape[1]) for f in feats]
@@ -270,6 +328,14 @@ class MaskVRD(nn.Module):
         gc.disable()
         try:
             self._fill_result(out, order, pi, qi, ki, sids, oids, start, end, so_start, durs, cat_ids, cats, trip_scores, avg, traj)
+            if gc_was_enabled and self.gc_park_results and gc.get_freeze_count() < 100000:
+                # Park the new (acyclic) result objects in the oldest generation: freeze() + unfreeze() splice every tracked
+                # object into generation 2 in O(1).  Otherwise the first young-generation collection after gc.enable() walks
+                # all ~10^5 of them (5-10 ms per video, measured) and later collections walk them again; they are freed by
+                # reference counting when the caller drops the result.  Skipped when the application keeps a large frozen
+                # set of its own (unfreeze() would hand it back to the collector).
+                gc.freeze()
+                gc.unfreeze()
         finally:
             if gc_was_enabled:
                 gc.enable()

@@ -28,7 +28,9 @@ def rnd(shape, seed, scale=1.0):
     (3, 0, 0, True, 512, 1024, torch.float32),
     (3, 0, 0, True, 512, 512, torch.float32),
     (1, 1, 1, False, 64, 256, torch.float32),
-    (1, 0, 0, False, 144, 256, torch.float32),
+    (1, 0, 0, False, 192, 256, torch.float32),
+    (1, 0, 1, False, 256, 256, torch.float32),
+    (1, 0, 1, False, 512, 512, torch.float32),
     (1, 2, 0, False, 256, 256, torch.bfloat16),
     (1, 2, 0, False, 1024, 256, torch.bfloat16),
     (1, 0, 0, False, 256, 512, torch.float32),

@@ -16,6 +16,7 @@ shapes = [  # (name, N, K, taps, res, out dtype, act)
     ("mlp0 512->2048 gelu bf16", 2048, 512, 1, 0, torch.bfloat16, 2),
     ("mlp3 2048->512 +res f32", 512, 2048, 1, 1, torch.float32, 0),
     ("lat 512->256 f32", 256, 512, 1, 0, torch.float32, 0),
+    ("fuse1 512->512 f32", 512, 512, 1, 0, torch.float32, 0),
 ]
 print(f"M = {M}")
 for name, N, K, taps, res, odt, act in shapes:

@@ -10,13 +10,17 @@
 // the zero separator rows of layout.py).
 //
 // Kernel structure (one persistent CTA per SM, 384 threads):
-//   warp 0     TMA producer          (4-stage ring of {A 128x64, W BNx64} bf16 tiles, 128B-swizzled)
+//   warp 0     TMA producer          (3-4 stage ring of {A 128x64, W BNx64} bf16 tiles, 128B-swizzled)
 //   warp 1     tcgen05.mma issuer    (UMMA 128 x BN x 16, kind::f16, two accumulator stages of 256 TMEM columns)
 //   warp 2     TMEM allocator
-//   warps 4-11 epilogue              (two warps per TMEM lane quarter, each owning half of the tile's columns:
-//                                     software-pipelined tcgen05.ld 32x32b.x16 -> bias / pad correction from shared
-//                                     memory / ReLU|GELU / prefetched residuals / separator zeroing -> fp32 or bf16
-//                                     rows in HBM), overlapped with the next tile's MMAs through the second TMEM stage
+//   warps 4-11 epilogue              (two warps per TMEM lane quarter, each owning half of the tile's columns).  Per chunk
+//                                     of 32 columns: tcgen05.ld 32x32b.x32 -> bias / pad correction / ReLU|GELU / residual /
+//                                     separator zeroing in registers (thread = row) -> swizzled shared-memory staging ->
+//                                     one TMA store of the [32 rows x 32 cols] box.  The fp32 residual tile arrives the same
+//                                     way (TMA load into the staging buffer, issued before the accumulator is waited for),
+//                                     so the epilogue warps never issue row-strided global accesses (those cost one L1
+//                                     wavefront per row and bounded the old epilogue).  Overlapped with the next tile's
+//                                     MMAs through the second TMEM stage.
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>
@@ -30,7 +34,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;            // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int ACC_STAGE_COLS = 256;    // TMEM columns per accumulator stage
 constexpr int TMEM_COLS = 512;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -38,6 +42,10 @@ constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int MAX_N = 2048;             // bias / correction vectors are staged in shared memory
+constexpr int CHUNK = 32;               // accumulator columns per epilogue step = columns of one TMA store box
+constexpr int STAGING_BYTES = 32 * CHUNK * 4;                  // one [32 rows x 32 cols] fp32 box
+constexpr int STAGING_TOTAL = EPI_WARPS * 2 * STAGING_BYTES;   // two boxes per epilogue warp
+constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr unsigned SPIN_LIMIT = 1u << 24;
 
 char g_err[256] = {0};
@@ -96,6 +104,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -103,16 +130,29 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // GELU(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 rounding of
-// this kernel's GELU outputs); ~3x cheaper than erff in an epilogue that evaluates it 32k times per tile.
+// this kernel's GELU outputs).  Phi(x) = 1 - h for x >= 0 and h for x < 0 with h = 0.5 * P(t) * exp(-x^2 / 2),
+// t = 1 / (1 + p |x| / sqrt2): two MUFU ops (rcp.approx, ex2.approx) and 13 FP32 ops per element, no slow paths.
 __device__ __forceinline__ float gelu_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float erfz = 1.0f - p * t * __expf(-z * z);           // erf(|x|/sqrt2)
-    return 0.5f * x * (1.0f + copysignf(erfz, x));
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (z * -1.4426950408889634f)));
+    const float h = p * t * e;                                   // 0.5 * erfc(|x| / sqrt2)
+    return x * (x >= 0.f ? 1.0f - h : h);
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
 }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart).
@@ -131,29 +171,32 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 }
 
 struct EpiArgs {
-    const float* bias; void* out; int out_dtype; long long ldo;
-    int M, N, act;
-    const float* res1; long long ldr1; const float* res2; long long ldr2;
+    const float* bias; int out_dtype;
+    int M, N, act, has_res;
+    const float* res2; long long ldr2;      // second residual: row-strided loads (only the SOS output projection uses it)
     const float* corr; const int* row_seq; const int4* seqinfo; int R;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, EpiArgs e, int K,
-                    int taps, int block_n) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, EpiArgs e, int K,
+                    int taps, int block_n, int stages) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: stages of A, stages of W, barriers
+    // carve: stages of A, stages of W, epilogue staging boxes, barriers, bias / correction vectors
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int w_stage_bytes = block_n * BLOCK_K * 2;
     uint8_t* smem_a = smem;
-    uint8_t* smem_w = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* bars = (uint64_t*)(smem_w + STAGES * w_stage_bytes);
-    uint64_t* full = bars;                 // [STAGES]
-    uint64_t* empty = bars + STAGES;       // [STAGES]
-    uint64_t* tfull = bars + 2 * STAGES;   // [2]
-    uint64_t* tempty = bars + 2 * STAGES + 2;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
-    float* s_bias = (float*)(bars + 2 * STAGES + 8);   // [MAX_N]
-    float* s_corr = s_bias + MAX_N;                     // [MAX_N]
+    uint8_t* smem_w = smem + stages * A_STAGE_BYTES;
+    uint8_t* staging = smem_w + stages * w_stage_bytes;          // 1024-aligned: every stage size is a multiple of 1024
+    uint64_t* bars = (uint64_t*)(staging + STAGING_TOTAL);
+    uint64_t* full = bars;                           // [MAX_STAGES]
+    uint64_t* empty = bars + MAX_STAGES;             // [MAX_STAGES]
+    uint64_t* tfull = bars + 2 * MAX_STAGES;         // [2]
+    uint64_t* tempty = bars + 2 * MAX_STAGES + 2;    // [2]
+    uint64_t* resbar = bars + 2 * MAX_STAGES + 4;    // [EPI_WARPS][2]
+    uint32_t* tmem_slot = (uint32_t*)(resbar + 2 * EPI_WARPS);
+    float* s_bias = (float*)(tmem_slot + 4);         // [MAX_N]
+    float* s_corr = s_bias + MAX_N;                  // [MAX_N]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_n = e.N / block_n;
@@ -166,8 +209,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         s_corr[i] = (e.corr != nullptr) ? e.corr[i] : 0.f;
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
+        for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&resbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
@@ -191,7 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const int row = m0 + (taps == 3 ? tap - 1 : 0);
                     tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full[stage], ka, row);
                     tma_load_2d(smem_w + stage * w_stage_bytes, &map_w, &full[stage], kb * BLOCK_K, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -217,24 +261,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);          // frees the smem stage once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[as]);                 // accumulator stage complete
             }
         }
     } else if (warp >= EPI_WARP0) {
+        const int ew = warp - EPI_WARP0;
         const int wq = warp & 3;                         // TMEM lane quarter this warp may access
-        const int half = (warp - EPI_WARP0) >> 2;        // which half of the tile's 16-column chunks
-        const int n_chunks = block_n / 16;
-        const int c_begin = half == 0 ? 0 : (n_chunks + 1) / 2;
-        const int c_end = half == 0 ? (n_chunks + 1) / 2 : n_chunks;
-        const bool has_res = e.res1 != nullptr;
+        const int half = ew >> 2;                        // which half of the tile's columns
+        const int n_ch = block_n / (2 * CHUNK);          // chunks of 32 columns per warp and tile (<= 2 when has_res)
+        const bool out_bf16 = e.out_dtype == VRD_BF16;
+        uint8_t* my_stage = staging + ew * 2 * STAGING_BYTES;
+        uint64_t* my_resbar = resbar + 2 * ew;
         int it = 0;
+        uint32_t box_cnt = 0;                            // boxes alternate across chunks AND tiles (no-residual path)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (tile / n_tiles_n) * BLOCK_M, n0 = (tile % n_tiles_n) * block_n;
-            const int row = m0 + wq * 32 + lane;
+            const int row0 = m0 + wq * 32, row = row0 + lane;
+            const int col0 = n0 + half * (block_n / 2);
             bool valid = true, add_corr = false;
             if (e.row_seq != nullptr) {
                 const int rl = row % e.R;
@@ -245,82 +292,105 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     add_corr = (si.z != 0) && (rl - si.x == si.y - 1);
                 }
             }
-            const float* r1p = has_res ? e.res1 + (long long)row * e.ldr1 + n0 : nullptr;
-            const float* r2p = e.res2 != nullptr ? e.res2 + (long long)row * e.ldr2 + n0 : nullptr;
-            auto load_res = [&](int c, float4 (&dst)[4]) {
-                const float4* p = reinterpret_cast<const float4*>(r1p + c * 16);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = p[i];
-                if (r2p != nullptr) {
-                    const float4* p2 = reinterpret_cast<const float4*>(r2p + c * 16);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { const float4 t = p2[i]; dst[i].x += t.x; dst[i].y += t.y; dst[i].z += t.z; dst[i].w += t.w; }
+            if (e.has_res) {
+                // the residual boxes do not depend on the accumulator: fetch them while the MMAs of this tile still run
+                if (lane == 0) {
+                    bulk_wait_read<0>();                 // the previous tile's stores have read both staging boxes
+                    for (int c = 0; c < min(n_ch, 2); ++c) {
+                        mbar_expect_tx(&my_resbar[c], STAGING_BYTES);
+                        tma_load_2d(my_stage + c * STAGING_BYTES, &map_res, &my_resbar[c], col0 + c * CHUNK, row0);
+                    }
                 }
-            };
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * ACC_STAGE_COLS;
-            // one pipeline step: wait for chunk c (already in flight into `cur`), launch chunk c+1 into `nxt`, finish chunk c
-            auto step = [&](int c, uint32_t (&cur)[16], float4 (&rcur)[4], uint32_t (&nxt)[16], float4 (&rnxt)[4]) {
+                __syncwarp();
+            }
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * ACC_STAGE_COLS + half * (block_n / 2);
+            for (int c = 0; c < n_ch; ++c) {
+                uint8_t* box = my_stage + (e.has_res ? (c & 1) : (int)(box_cnt++ & 1)) * STAGING_BYTES;
+                const uint32_t box_u = smem_u32(box);
+                uint32_t acc[CHUNK];
+                tmem_ld32(taddr + c * CHUNK, acc);
+                if (e.has_res) {
+                    // box c & 1 is filled once (n_ch <= 2) or twice (n_ch == 4, long-K tiles) per tile
+                    mbar_wait(&my_resbar[c & 1], n_ch <= 2 ? (it & 1) : ((c >> 1) & 1));
+                } else {
+                    if (lane == 0) bulk_wait_read<1>();  // the store issued from this box two chunks ago has read it
+                    __syncwarp();
+                }
                 tmem_ld_wait();
-                if (c + 1 < c_end) {
-                    tmem_ld16(taddr + (c + 1) * 16, nxt);
-                    if (has_res && valid) load_res(c + 1, rnxt);
+                if (c == n_ch - 1) {                     // accumulator fully read: hand the TMEM stage back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
                 }
-                const int n = n0 + c * 16;
-                float v[16];
+                const int n = col0 + c * CHUNK;
+                float v[CHUNK];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < CHUNK / 4; ++i) {
                     const float4 bi = *reinterpret_cast<const float4*>(s_bias + n + 4 * i);
-                    v[4 * i + 0] = __uint_as_float(cur[4 * i + 0]) + bi.x;
-                    v[4 * i + 1] = __uint_as_float(cur[4 * i + 1]) + bi.y;
-                    v[4 * i + 2] = __uint_as_float(cur[4 * i + 2]) + bi.z;
-                    v[4 * i + 3] = __uint_as_float(cur[4 * i + 3]) + bi.w;
+                    v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + bi.x;
+                    v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + bi.y;
+                    v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bi.z;
+                    v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + bi.w;
                 }
                 if (add_corr) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += s_corr[n + i];
+                    for (int i = 0; i < CHUNK; ++i) v[i] += s_corr[n + i];
                 }
                 if (e.act == 1) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                    for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.f);
                 } else if (e.act == 2) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
+                    for (int i = 0; i < CHUNK; ++i) v[i] = gelu_fast(v[i]);
                 }
-                if (has_res && valid) {
+                if (e.has_res) {
+                    // residual box: 128-byte rows, 16-byte chunk j of row r stored at chunk j ^ (r & 7) (TMA SWIZZLE_128B)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { v[4 * i] += rcur[i].x; v[4 * i + 1] += rcur[i].y; v[4 * i + 2] += rcur[i].z; v[4 * i + 3] += rcur[i].w; }
+                    for (int j = 0; j < CHUNK / 4; ++j) {
+                        const float4 r = lds128(box_u + lane * 128 + ((j ^ (lane & 7)) << 4));
+                        v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                    }
+                }
+                if (e.res2 != nullptr && valid) {
+                    const float4* p2 = reinterpret_cast<const float4*>(e.res2 + (long long)row * e.ldr2 + n);
+#pragma unroll
+                    for (int j = 0; j < CHUNK / 4; ++j) { const float4 t = p2[j]; v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
                 }
                 if (!valid) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                    for (int i = 0; i < CHUNK; ++i) v[i] = 0.f;
                 }
-                if (e.out_dtype == VRD_BF16) {
-                    __nv_bfloat16* op = (__nv_bfloat16*)e.out + (long long)row * e.ldo + n;
-                    uint4 pk0, pk1;
-                    pk0.x = pack2(v[0], v[1]); pk0.y = pack2(v[2], v[3]); pk0.z = pack2(v[4], v[5]); pk0.w = pack2(v[6], v[7]);
-                    pk1.x = pack2(v[8], v[9]); pk1.y = pack2(v[10], v[11]); pk1.z = pack2(v[12], v[13]); pk1.w = pack2(v[14], v[15]);
-                    reinterpret_cast<uint4*>(op)[0] = pk0;
-                    reinterpret_cast<uint4*>(op)[1] = pk1;
-                } else {
-                    float4* op = reinterpret_cast<float4*>((float*)e.out + (long long)row * e.ldo + n);
+                if (out_bf16) {
+                    // 64-byte rows, chunk j of row r stored at chunk j ^ ((r >> 1) & 3) (TMA SWIZZLE_64B)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int j = 0; j < CHUNK / 8; ++j) {
+                        uint4 pk;
+                        pk.x = pack2(v[8 * j], v[8 * j + 1]); pk.y = pack2(v[8 * j + 2], v[8 * j + 3]);
+                        pk.z = pack2(v[8 * j + 4], v[8 * j + 5]); pk.w = pack2(v[8 * j + 6], v[8 * j + 7]);
+                        sts128(box_u + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk.x, pk.y, pk.z, pk.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CHUNK / 4; ++j)
+                        sts128(box_u + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                               __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
                 }
-            };
-            uint32_t acc0[16], acc1[16];
-            float4 rs0[4], rs1[4];
-            if (has_res && valid) load_res(c_begin, rs0);         // residual rows do not depend on the accumulator
-            mbar_wait(&tfull[as], aphase);
-            tc_fence_after();
-            tmem_ld16(taddr + c_begin * 16, acc0);
-            for (int c = c_begin; c < c_end; c += 2) {
-                step(c, acc0, rs0, acc1, rs1);
-                if (c + 1 < c_end) step(c + 1, acc1, rs1, acc0, rs0);
+                fence_async_smem();                      // make the generic-proxy writes visible to the TMA engine
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&map_out, box_u, n, row0);
+                    bulk_commit();
+                    if (e.has_res && c + 2 < n_ch) {     // refill this box with the residual of chunk c + 2 (tiles with long K only:
+                        bulk_wait_read<0>();             // the MMAs of the next tile hide this latency)
+                        mbar_expect_tx(&my_resbar[c & 1], STAGING_BYTES);
+                        tma_load_2d(box, &map_res, &my_resbar[c & 1], col0 + (c + 2) * CHUNK, row0);
+                    }
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
         }
+        if (lane == 0) bulk_wait_all();                  // all output boxes written before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -346,17 +416,17 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D bf16 row-major matrix [rows, cols] with row pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle.
-bool make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+// 2-D row-major matrix [rows, cols] with row pitch ld (elements); box = [box_rows, box_cols].
+bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int esize, long long rows, long long cols, long long ld,
+              int box_rows, int box_cols, CUtensorMapSwizzle swz) {
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled entry point not found"); return false; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed: %d", (int)r); return false; }
     return true;
 }
@@ -368,40 +438,68 @@ const char* gemm_tcgen05_error() { return g_err; }
 int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     static int num_sms = 0;
     static bool attr_set = false;
-    if (g.M % BLOCK_M != 0 || g.K % BLOCK_K != 0 || g.N % 16 != 0 || g.lda % 8 != 0 || ((uintptr_t)g.A & 15) != 0) {
-        snprintf(g_err, sizeof g_err, "gemm_tcgen05: unsupported shape M=%d N=%d K=%d lda=%lld", g.M, g.N, g.K, g.lda);
+    if (g.M % BLOCK_M != 0 || g.K % BLOCK_K != 0 || g.N % 64 != 0 || g.lda % 8 != 0 || ((uintptr_t)g.A & 15) != 0) {
+        snprintf(g_err, sizeof g_err, "gemm_tcgen05: unsupported shape M=%d N=%d K=%d lda=%lld (need M%%128, K%%64, N%%64 == 0)",
+                 g.M, g.N, g.K, g.lda);
         return 1;
     }
+    const bool has_res = g.res1 != nullptr;
+    if (g.res2 != nullptr && !has_res) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: res2 without res1"); return 1; }
     int block_n;
-    if (g.N % 256 == 0) block_n = 256;
-    else if (g.N <= 256) block_n = g.N;
-    else if (g.N % 128 == 0) block_n = 128;
-    else { snprintf(g_err, sizeof g_err, "gemm_tcgen05: unsupported N=%d", g.N); return 1; }
+    if (has_res) {   // two 32-column chunks per epilogue warp (both residual boxes prefetched), four when K is long enough to hide
+        if (g.N % 256 == 0 && g.taps * g.K >= 1024) block_n = 256;
+        else if (g.N % 128 == 0) block_n = 128;
+        else if (g.N <= 128) block_n = g.N;
+        else { snprintf(g_err, sizeof g_err, "gemm_tcgen05: N=%d with a residual must be <= 128 or a multiple of 128", g.N); return 1; }
+    } else {
+        if (g.N % 256 == 0) block_n = 256;
+        else if (g.N <= 256) block_n = g.N;
+        else if (g.N % 128 == 0) block_n = 128;
+        else { snprintf(g_err, sizeof g_err, "gemm_tcgen05: unsupported N=%d", g.N); return 1; }
+    }
     if (g.N > MAX_N) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: N=%d exceeds %d", g.N, MAX_N); return 1; }
-    if ((g.ldo % (g.out_dtype == VRD_BF16 ? 8 : 4)) != 0 || (g.res1 && g.ldr1 % 4) || (g.res2 && g.ldr2 % 4)) {
-        snprintf(g_err, sizeof g_err, "gemm_tcgen05: output/residual pitch must be a multiple of 4");
+    const int osize = g.out_dtype == VRD_BF16 ? 2 : 4;
+    if ((g.ldo * osize) % 16 != 0 || ((uintptr_t)g.out & 15) != 0 || (has_res && ((g.ldr1 % 4) != 0 || ((uintptr_t)g.res1 & 15) != 0)) ||
+        (g.res2 && ((g.ldr2 % 4) != 0 || ((uintptr_t)g.res2 & 15) != 0))) {
+        snprintf(g_err, sizeof g_err, "gemm_tcgen05: output/residual base and pitch must be 16-byte aligned");
         return 1;
     }
+    if (has_res && g.out_dtype != VRD_F32) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: residual needs an fp32 output"); return 1; }
     if (num_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    CUtensorMap map_a, map_w;
-    if (!make_map(&map_a, g.A, g.M, g.K, g.lda, BLOCK_M)) return 1;
-    if (!make_map(&map_w, g.W, g.N, (long long)g.taps * g.K, (long long)g.taps * g.K, block_n)) return 1;
-    const int smem = 1024 + STAGES * (A_STAGE_BYTES + block_n * BLOCK_K * 2) + 256 + 2 * MAX_N * 4;
+    CUtensorMap map_a, map_w, map_out, map_res;
+    const long long kk = (long long)g.taps * g.K;
+    if (!make_map(&map_a, g.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (!make_map(&map_w, g.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, kk, kk, block_n, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (g.out_dtype == VRD_BF16) {
+        if (!make_map(&map_out, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    } else {
+        if (!make_map(&map_out, g.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldo, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    }
+    if (has_res) {
+        if (!make_map(&map_res, g.res1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldr1, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    } else {
+        map_res = map_out;
+    }
+    const int stage_bytes = A_STAGE_BYTES + block_n * BLOCK_K * 2;
+    const int fixed = 1024 + STAGING_TOTAL + 1024 + 2 * MAX_N * 4;   // alignment slack, staging, barriers, bias + corr
+    int stages = (SMEM_LIMIT - fixed) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    const int smem = fixed + stages * stage_bytes;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
             snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(max dynamic smem) failed");
             return 1;
         }
         attr_set = true;
     }
-    EpiArgs e{g.bias, g.out, g.out_dtype, g.ldo, g.M, g.N, g.act, g.res1, g.ldr1, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R};
+    EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R};
     const int n_tiles = (g.M / BLOCK_M) * (g.N / block_n);
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem, st>>>(map_a, map_w, e, g.K, g.taps, block_n);
+    gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem, st>>>(map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages);
     return 0;
 }
 

@@ -101,10 +101,10 @@ class PackedWeights:
             self._conv_attention(p + ".multihead_attn", pc["n_head"], f32[p + ".drop_path_attn2.scale"])
             self._mlp(p, f32[p + ".drop_path_mlp.scale"])
         self._ln("predictor.transformer.decoder.norm")
-        # class head: N (= K+1) padded up to a multiple of 16 with zero rows so it fits the GEMM N tile
+        # class head: N (= K+1) padded up to a multiple of 64 with zero rows so it fits the GEMM N tile
         wc, bc = f32["predictor.class_embed.weight"][:, :, 0], f32["predictor.class_embed.bias"]
         self.n_cls = wc.shape[0]
-        self.n_cls_pad = (self.n_cls + 15) // 16 * 16
+        self.n_cls_pad = (self.n_cls + 63) // 64 * 64
         wcp = torch.zeros(self.n_cls_pad, wc.shape[1])
         wcp[: self.n_cls] = wc
         bcp = torch.zeros(self.n_cls_pad)

@@ -62,7 +62,10 @@ class LevelLayout:
 
 
 class PackLayout:
-    def __init__(self, lengths: Sequence[int], tpads: Sequence[int], n_levels: int, device):
+    """Host-side construction of the per-level arrays; ``device`` given -> uploaded at once (one pinned staging copy);
+    ``device=None`` -> the caller uploads ``host_words()`` itself (several chunks in one copy) and calls ``bind``."""
+
+    def __init__(self, lengths: Sequence[int], tpads: Sequence[int], n_levels: int, device=None):
         lens = np.asarray(lengths, dtype=np.int64)
         tp = np.asarray(tpads, dtype=np.int64)
         assert lens.ndim == 1 and lens.shape == tp.shape and (lens >= 1).all() and (lens <= tp).all()
@@ -87,17 +90,27 @@ class PackLayout:
             lev = LevelLayout(l, off.astype(np.int32), ll.astype(np.int32), haspad, rows)
             self.levels.append(lev)
             host += [row_seq, info.reshape(-1)]
-        if torch.device(device).type == "cuda":
-            # pinned staging: a pageable source would make the copy wait for the stream's earlier work (chunk pipelining)
-            flat = torch.empty(sum(h.size for h in host), dtype=torch.int32, pin_memory=True)
-            np.concatenate(host, out=flat.numpy())
-            dev = flat.to(device, non_blocking=True)
-        else:
-            dev = torch.from_numpy(np.concatenate(host))
+        self._host = host
+        self.n_words = sum(h.size for h in host)      # int32 words; every piece is a multiple of 4 words (16 bytes)
+        self.total_frames = int(lens.sum())
+        if device is not None:
+            if torch.device(device).type == "cuda":
+                # pinned staging: a pageable source would make the copy wait for the stream's earlier work
+                flat = torch.empty(self.n_words, dtype=torch.int32, pin_memory=True)
+                self.host_words(flat.numpy())
+                self.bind(flat.to(device, non_blocking=True))
+            else:
+                self.bind(torch.from_numpy(np.concatenate(host)))
+
+    def host_words(self, out: np.ndarray) -> None:
+        """Write the int32 image of all levels into ``out`` (n_words elements)."""
+        np.concatenate(self._host, out=out)
+
+    def bind(self, dev: torch.Tensor) -> None:
+        """``dev``: int32 tensor of n_words elements (16-byte aligned) holding the image written by ``host_words``."""
         pos = 0
         for lev in self.levels:
             lev.row_seq = dev[pos:pos + lev.R]
             pos += lev.R
             lev.seqinfo = dev[pos:pos + 4 * self.B].view(self.B, 4)
             pos += 4 * self.B
-        self.total_frames = int(lens.sum())

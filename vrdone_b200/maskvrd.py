@@ -140,10 +140,10 @@ class MaskVRD(nn.Module):
             rows += l + 1
         yield start, len(lens)
 
-    def _stage_chunk(self, ops, sub, slot: int, dev):
-        """Enqueue, on the copy stream, the host->device copies of the host-resident pair tensors of one chunk into staging
-        buffer ``slot`` (copy engine, overlapping the kernels of the previous chunk).  Returns (int64 [3, n] numpy table of
-        device addresses / channel strides / time strides, event to wait on before the pack kernel, or None)."""
+    @staticmethod
+    def _pair_table(sub):
+        """int64 [3, n] table (data pointer, channel stride, time stride) of a list of (C, L) tensors, the byte span of the
+        host-resident ones (0 for device tensors) and their 256-byte aligned offsets in a staging buffer."""
         n = len(sub)
         meta = np.empty((3, n), dtype=np.int64)
         meta[0] = [f.data_ptr() for f in sub]
@@ -154,25 +154,24 @@ class MaskVRD(nn.Module):
             return meta, None
         shape = np.array([f.shape for f in sub], dtype=np.int64)
         # smallest address span that covers the (C, L) view: covers dense (C, L), the loader's (L, C) buffer and strided views
-        span = ((shape[:, 0] - 1) * meta[1] + (shape[:, 1] - 1) * meta[2] + 1) * 4
-        span = np.where(on_host, span, 0)
+        span = np.where(on_host, ((shape[:, 0] - 1) * meta[1] + (shape[:, 1] - 1) * meta[2] + 1) * 4, 0)
         padded = (span + 255) // 256 * 256
         offs = np.cumsum(padded) - padded
-        total = int(padded.sum())
-        buf = self._staging[slot]
-        if buf is None or buf.numel() < total:
-            self._staging[slot] = buf = torch.empty(max(total, 1 << 20), dtype=torch.uint8, device=dev)
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=dev)
+        idx = np.nonzero(on_host)[0]
+        plan = {"idx": idx, "src": np.ascontiguousarray(meta[0, idx]), "bytes": np.ascontiguousarray(span[idx]),
+                "offs": np.ascontiguousarray(offs[idx]), "total": int(padded.sum())}
+        return meta, plan
+
+    def _issue_copies(self, ops, plan, slot: int):
+        """Enqueue the host->device copies of one chunk on the copy stream (copy engine, overlapping the kernels of the
+        previous chunk); returns the event the pack kernel has to wait for."""
         cs = self._copy_stream
         if self._pack_done[slot] is not None:
             cs.wait_event(self._pack_done[slot])      # the previous user of this staging buffer has been packed
-        idx = np.nonzero(on_host)[0]
-        ops.h2d_pairs(np.ascontiguousarray(meta[0, idx]), np.ascontiguousarray(span[idx]), buf, np.ascontiguousarray(offs[idx]), cs)
+        ops.h2d_pairs(plan["src"], plan["bytes"], self._staging[slot], plan["offs"], cs)
         ev = torch.cuda.Event()
         ev.record(cs)
-        meta[0, idx] = buf.data_ptr() + offs[idx]
-        return meta, ev
+        return ev
 
     @torch.no_grad()
     def run_network(self, feats: List[torch.Tensor], tpads: List[int], topk: int, want_masks: bool = False):
@@ -191,40 +190,64 @@ class MaskVRD(nn.Module):
         st = {"layout_ms": 0.0, "meta_ms": 0.0, "launch_ms": 0.0}
         with torch.cuda.device(dev):
             cur = torch.cuda.current_stream(dev)
+            tA = time.perf_counter()
             chunks = list(self._chunks(lens, min(self.max_rows, self.h2d_chunk_rows) if any_host else self.max_rows))
+            lays = [PackLayout(lens[a:b], tpads[a:b], self.n_levels) for a, b in chunks]
             tB = time.perf_counter()
-            staged = self._stage_chunk(ops, feats[chunks[0][0]:chunks[0][1]], 0, dev)
-            st["meta_ms"] += 1e3 * (time.perf_counter() - tB)
+            tables = [self._pair_table(feats[a:b]) for a, b in chunks]
+            if any_host:
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+                for slot in (0, 1):
+                    need = max([p["total"] for (_, p) in tables[slot::2] if p is not None], default=0)
+                    if need and (self._staging[slot] is None or self._staging[slot].numel() < need):
+                        self._staging[slot] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+                for ci, (meta, plan) in enumerate(tables):
+                    if plan is not None:
+                        meta[0, plan["idx"]] = self._staging[ci & 1].data_ptr() + plan["offs"]
+            # ONE upload of every chunk's layout arrays and pair table, issued before any bulk copy: host->device copies of all
+            # streams share the copy engine, which drains the copy stream's queue before it looks at another stream
+            words = [(lay.n_words + 6 * lay.B + 3) // 4 * 4 for lay in lays]      # keeps every piece 16-byte aligned
+            pin = torch.empty(sum(words), dtype=torch.int32, pin_memory=True)
+            pin_np = pin.numpy()
+            pos = 0
+            for lay, (meta, _), w in zip(lays, tables, words):
+                lay.host_words(pin_np[pos:pos + lay.n_words])
+                pin_np[pos + lay.n_words: pos + lay.n_words + 6 * lay.B].view(np.int64)[:] = meta.reshape(-1)
+                pos += w
+            dev_words = pin.to(dev, non_blocking=True)
+            pos, metas_d = 0, []
+            for lay, w in zip(lays, words):
+                lay.bind(dev_words[pos:pos + lay.n_words])
+                metas_d.append(dev_words[pos + lay.n_words: pos + lay.n_words + 6 * lay.B].view(torch.int64).view(3, lay.B))
+                pos += w
+            ev = self._issue_copies(ops, tables[0][1], 0) if tables[0][1] is not None else None
+            tC = time.perf_counter()
+            st["layout_ms"] += 1e3 * (tB - tA); st["meta_ms"] += 1e3 * (tC - tB)
             for ci, (a, b) in enumerate(chunks):
-                tA = time.perf_counter()
-                lay = PackLayout(lens[a:b], tpads[a:b], self.n_levels, dev)
-                tB = time.perf_counter()
-                meta, ev = staged
-                # the small uploads of THIS chunk (layout above, pointer table here) are issued before the next chunk's bulk
-                # copies: the copy engine serves host->device copies in issue order, whatever their stream
-                meta_h = torch.empty(meta.shape, dtype=torch.int64, pin_memory=True)
-                meta_h.numpy()[...] = meta
-                meta_d = meta_h.to(dev, non_blocking=True)
-                if ci + 1 < len(chunks):      # start the next chunk's copies before this chunk's kernels are enqueued
-                    staged = self._stage_chunk(ops, feats[chunks[ci + 1][0]:chunks[ci + 1][1]], (ci + 1) & 1, dev)
+                tC = time.perf_counter()
+                ev_next = None
+                if ci + 1 < len(chunks) and tables[ci + 1][1] is not None:   # next chunk's copies go out before this chunk's kernels
+                    ev_next = self._issue_copies(ops, tables[ci + 1][1], (ci + 1) & 1)
                 if ev is not None:
                     cur.wait_event(ev)
-                ptrs = meta_d[0]
-                strides = meta_d[1:].t().contiguous()
-                tC = time.perf_counter()
+                ptrs = metas_d[ci][0]
+                strides = metas_d[ci][1:].t().contiguous()
+                tD = time.perf_counter()
 
-                def packed(slot=ci & 1):
-                    if any_host:
+                def packed(slot=ci & 1, used=tables[ci][1] is not None):
+                    if used:
                         e = torch.cuda.Event()
                         e.record(cur)
                         self._pack_done[slot] = e
-                r = eng.forward_packed(lay, ptrs, strides, topk, want_masks, after_pack=packed)
-                tD = time.perf_counter()
-                st["layout_ms"] += 1e3 * (tB - tA); st["meta_ms"] += 1e3 * (tC - tB); st["launch_ms"] += 1e3 * (tD - tC)
+                r = eng.forward_packed(lays[ci], ptrs, strides, topk, want_masks, after_pack=packed)
+                tE = time.perf_counter()
+                st["meta_ms"] += 1e3 * (tD - tC); st["launch_ms"] += 1e3 * (tE - tD)
+                ev = ev_next
                 for k in outs:
                     outs[k].append(r[k])
                 if want_masks:
-                    l0 = lay.levels[0]
+                    l0 = lays[ci].levels[0]
                     for i in range(b - a):
                         masks.append(r["masks"][int(l0.off[i]): int(l0.off[i]) + int(l0.len[i])])
         res = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in outs.items()}

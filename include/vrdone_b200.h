@@ -29,7 +29,7 @@ extern "C" {
 #define VRD_ACT_NONE 0
 #define VRD_ACT_RELU 1
 #define VRD_ACT_GELU 2
-#define VRD_ABI_VERSION 1
+#define VRD_ABI_VERSION 2
 
 typedef void* vrd_stream_t; /* cudaStream_t */
 
@@ -46,10 +46,11 @@ int vrd_h2d_pairs(const void* const* src, const int64_t* bytes, void* dst_base, 
 
 /* k9 -- replaces MaskVRD.preprocessing (maskvrd.py:363-414) + the channel split of backbones.py:161-166 / 329-341.
  * pair_ptrs[i] -> fp32 (C, L_i) tensor with element strides pair_strides[2i] (channel), pair_strides[2i+1] (time).
- * Writes vis [2R, nv], clip [2R, nc] (or NULL when nc == 0) in act_dtype, bbox_so [R, 8] and bbox_ent [2R, 8] in fp32. */
+ * Writes vis [2R, nv], clip [2R, nc] (or NULL when nc == 0) in act_dtype, bbox_so [R, 8] and bbox_ent [2R, 8] in fp32.
+ * token_major != 0 promises that every pair has channel stride 1 (the loader's (L, C) buffer): warp-per-row fast path. */
 int vrd_pack_pairs(const void* pair_ptrs, const int64_t* pair_strides, const int32_t* row_seq, const int32_t* seqinfo, int R,
                    int B, int nv, int nc, int nbs, int nbe, void* vis, void* clip, int act_dtype, float* bbox_so,
-                   float* bbox_ent, vrd_stream_t stream);
+                   float* bbox_ent, int token_major, vrd_stream_t stream);
 
 /* k1/k2 -- replaces nn.Conv1d (k=1, and dense k=3 as three row-shifted K-slabs; blocks.py:85, 46, 728-737, 1054-1060):
  * out = act(A * W^T + bias [+ corr on the last valid row of pairs with a pad column]) + res1 + res2, separator rows = 0.

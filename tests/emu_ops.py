@@ -40,7 +40,7 @@ class EmuOps:
         return v.repeat(streams)
 
     # kernels ---------------------------------------------------------------------------------
-    def pack_pairs(self, feats, strides, lay, nv, nc, nbs, nbe, vis, clp, bso, bent):
+    def pack_pairs(self, feats, strides, lay, nv, nc, nbs, nbe, vis, clp, bso, bent, token_major=False):
         """``feats``: in the emulation, the list of (C, L) tensors themselves (the CUDA op takes a pointer table)."""
         self.calls.append("pack_pairs")
         R = lay.R

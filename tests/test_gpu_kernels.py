@@ -41,13 +41,14 @@ def adt_tol(dt):
     return (torch.float32, 2e-5) if dt == "fp32" else (torch.bfloat16, 1.5e-2)
 
 
-def test_pack_pairs(ops, lays):
+@pytest.mark.parametrize("token_major", [False, True])
+def test_pack_pairs(ops, lays, token_major):
     lg, lc = lays
     nv, nc, nbs, nbe = 256, 128, 5, 8
     C = 2 * nv + 2 * nc + nbs + 2 * nbe
     feats = []
     for i, L in enumerate(LENS):
-        if i % 2 == 0:
+        if i % 2 == 0 or token_major:
             feats.append(rnd((L, C), 100 + i).permute(1, 0))          # (C, L) view of token-major memory (data loader)
         else:
             feats.append(rnd((C, L), 100 + i))                        # dense (C, L)
@@ -59,7 +60,7 @@ def test_pack_pairs(ops, lays):
         ptrs = torch.tensor([f.data_ptr() for f in dev], dtype=torch.int64).cuda()
         strides = torch.tensor([[f.stride(0), f.stride(1)] for f in dev], dtype=torch.int64).cuda()
         out = [torch.full_like(r, 7.0).cuda() for r in ref]
-        ops.pack_pairs(ptrs, strides, lg.levels[0], nv, nc, nbs, nbe, *out)
+        ops.pack_pairs(ptrs, strides, lg.levels[0], nv, nc, nbs, nbe, *out, token_major=token_major)
         torch.cuda.synchronize()
         for o, r in zip(out, ref):
             assert torch.equal(o.cpu(), r)
@@ -153,7 +154,8 @@ def test_window_and_full_attention(ops, lays, dt, n_head, w):
     EmuOps().full_attn(q[:R], k[:R], v[:R], ref[:R], lc.levels[0], n_head)
     out.fill_(5.0)
     ops.full_attn(q[:R].cuda(), k[:R].cuda(), v[:R].cuda(), out[:R], lg.levels[0], n_head)
-    close(out[:R], ref[:R], tol, "full_attn")
+    valid = lc.levels[0].row_seq >= 0     # separator rows of the full-attention output are left unwritten (don't-care for proj)
+    close(out[:R][valid], ref[:R][valid], tol, "full_attn")
 
 
 def test_maxpool_and_fpn(ops, lays):

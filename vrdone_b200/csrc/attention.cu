@@ -378,13 +378,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int HS>
-__global__ void __launch_bounds__(128) flash_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+    // 16-byte asynchronous global->shared copy; pred == false writes zeros (src-size 0), nothing is read
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// NBUF = 2: K/V tiles double-buffered with cp.async (the next tile streams in while the tensor cores work on the current
+// one; Q, K0 and V0 arrive together), NBUF = 1 for head_dim 128 (shared-memory budget).
+template <int HS, int NBUF>
+__global__ void __launch_bounds__(128, HS == 64 ? 4 : 1) flash_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                               const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
                                                               long long ld, Lay lay) {
     constexpr int BM = 64, BN = 64, LDS = HS + 8, KSTEPS = HS / 16, DBLK = HS / 8, CPR = HS / 8;   // CPR: 16-byte chunks per row
-    __shared__ __align__(16) __nv_bfloat16 sK[BN * LDS];
-    __shared__ __align__(16) __nv_bfloat16 sV[BN * LDS];
+    extern __shared__ __align__(16) uint8_t fa_smem[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);
+    __nv_bfloat16* sK = sQ + BM * LDS;                 // [NBUF][BN * LDS]
+    __nv_bfloat16* sV = sK + NBUF * BN * LDS;          // [NBUF][BN * LDS]
     const int seq = blockIdx.z, head = blockIdx.y;
     const int4 si = lay.seqinfo[seq];
     const int len = si.y;
@@ -393,42 +405,52 @@ __global__ void __launch_bounds__(128) flash_attn_bf16_kernel(const __nv_bfloat1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const long long hoff = (long long)head * HS;
+    const uint32_t sQ_u = (uint32_t)__cvta_generic_to_shared(sQ);
     const uint32_t sK_u = (uint32_t)__cvta_generic_to_shared(sK), sV_u = (uint32_t)__cvta_generic_to_shared(sV);
 
-    // stage the Q tile through sK and pull this warp's 16 rows into A fragments
+    auto load_kv = [&](int k0, int buf) {
+        for (int c = tid; c < BN * CPR; c += 128) {
+            const int r = c / CPR, cc = c % CPR;
+            const bool ok = k0 + r < len;
+            const long long off = (long long)(si.x + (ok ? k0 + r : 0)) * ld + hoff + cc * 8;
+            const uint32_t d = (uint32_t)((buf * BN * LDS + r * LDS + cc * 8) * 2);
+            cp_async16(sK_u + d, k + off, ok);
+            cp_async16(sV_u + d, v + off, ok);     // rows past the pair are zero-filled: P = 0 there, and 0 * garbage could be NaN
+        }
+    };
     for (int c = tid; c < BM * CPR; c += 128) {
         const int r = c / CPR, cc = c % CPR;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (q0 + r < len) val = *reinterpret_cast<const uint4*>(q + (long long)(si.x + q0 + r) * ld + hoff + cc * 8);
-        *reinterpret_cast<uint4*>(sK + r * LDS + cc * 8) = val;
+        const bool ok = q0 + r < len;
+        cp_async16(sQ_u + (uint32_t)((r * LDS + cc * 8) * 2), q + (long long)(si.x + (ok ? q0 + r : 0)) * ld + hoff + cc * 8, ok);
     }
-    __syncthreads();
+    load_kv(0, 0);
+    cp_async_commit();
+
     uint32_t qf[KSTEPS][4];
-#pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks) {
-        const int row = warp * 16 + (lane & 15), col = ks * 16 + (lane >> 4) * 8;
-        ldsm_x4(sK_u + (row * LDS + col) * 2, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-    }
     float o[DBLK][4];
 #pragma unroll
     for (int d = 0; d < DBLK; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     constexpr float LOG2E = 1.4426950408889634f;
 
-    for (int k0 = 0; k0 < len; k0 += BN) {
-        __syncthreads();   // previous tile (or the Q staging) fully consumed
-        for (int c = tid; c < BN * CPR; c += 128) {
-            const int r = c / CPR, cc = c % CPR;
-            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-            if (k0 + r < len) {
-                const long long off = (long long)(si.x + k0 + r) * ld + hoff + cc * 8;
-                kv = *reinterpret_cast<const uint4*>(k + off);
-                vv = *reinterpret_cast<const uint4*>(v + off);
-            }
-            *reinterpret_cast<uint4*>(sK + r * LDS + cc * 8) = kv;
-            *reinterpret_cast<uint4*>(sV + r * LDS + cc * 8) = vv;
+    for (int k0 = 0, kt = 0; k0 < len; k0 += BN, ++kt) {
+        const int buf = (NBUF == 2) ? (kt & 1) : 0;
+        if (NBUF == 2 && k0 + BN < len) {
+            load_kv(k0 + BN, buf ^ 1);             // the buffer consumed in iteration kt - 1 (all warps passed its trailing sync)
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        if (kt == 0) {
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const int row = warp * 16 + (lane & 15), col = ks * 16 + (lane >> 4) * 8;
+                ldsm_x4(sQ_u + (row * LDS + col) * 2, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+            }
+        }
+        const uint32_t bK = sK_u + buf * BN * LDS * 2, bV = sV_u + buf * BN * LDS * 2;
         float sacc[BN / 8][4];
 #pragma unroll
         for (int nb = 0; nb < BN / 8; ++nb) sacc[nb][0] = sacc[nb][1] = sacc[nb][2] = sacc[nb][3] = 0.f;
@@ -439,7 +461,7 @@ __global__ void __launch_bounds__(128) flash_attn_bf16_kernel(const __nv_bfloat1
                 // matrices: (keys nb*8.., dims ks*16..+7), (same keys, dims +8), (keys (nb+1)*8.., dims ..+7), (.., dims +8)
                 const int row = nb * 8 + (lane & 7) + ((lane >> 4) << 3), col = ks * 16 + ((lane >> 3) & 1) * 8;
                 uint32_t b0, b1, b2, b3;
-                ldsm_x4(sK_u + (row * LDS + col) * 2, b0, b1, b2, b3);
+                ldsm_x4(bK + (row * LDS + col) * 2, b0, b1, b2, b3);
                 mma_bf16(sacc[nb], qf[ks], b0, b1);
                 mma_bf16(sacc[nb + 1], qf[ks], b2, b3);
             }
@@ -482,10 +504,15 @@ __global__ void __launch_bounds__(128) flash_attn_bf16_kernel(const __nv_bfloat1
                 // transposed 8x8 blocks: (keys ks*16..+7, dims d*8..), (keys +8, same dims), (keys .., dims (d+1)*8..), (keys +8, ..)
                 const int row = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = d * 8 + (lane >> 4) * 8;
                 uint32_t b0, b1, b2, b3;
-                ldsm_x4_trans(sV_u + (row * LDS + col) * 2, b0, b1, b2, b3);
+                ldsm_x4_trans(bV + (row * LDS + col) * 2, b0, b1, b2, b3);
                 mma_bf16(o[d], pf[ks], b0, b1);
                 mma_bf16(o[d + 1], pf[ks], b2, b3);
             }
+        }
+        __syncthreads();       // every warp is done with this K/V buffer before it is refilled
+        if (NBUF == 1 && k0 + BN < len) {
+            load_kv(k0 + BN, 0);
+            cp_async_commit();
         }
     }
     l0 += __shfl_xor_sync(FULL_MASK, l0, 1); l0 += __shfl_xor_sync(FULL_MASK, l0, 2);
@@ -500,12 +527,21 @@ __global__ void __launch_bounds__(128) flash_attn_bf16_kernel(const __nv_bfloat1
     }
 }
 
-// zero the separator rows of an attention output (full_attn only writes valid rows)
-template <typename T>
-__global__ void zero_separators_kernel(T* __restrict__ out, long long ld, int C, const int* __restrict__ row_seq, int R) {
-    const int r = blockIdx.x;
-    if (row_seq[r] >= 0) return;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) out[(long long)r * ld + c] = from_f<T>(0.f);
+// Separator rows of the output are NOT written: the only consumer is the output-projection GEMM (taps == 1, with a layout),
+// whose epilogue overwrites its own separator rows with zeros whatever the operand row holds.
+template <int HS, int NBUF>
+static int flash_launch(const void* q, const void* k, const void* v, void* out, long long ld, Lay lay, int n_head, int max_rows,
+                        cudaStream_t st) {
+    constexpr int smem = (1 + 2 * NBUF) * 64 * (HS + 8) * 2;
+    static bool attr_set = false;
+    auto kern = flash_attn_bf16_kernel<HS, NBUF>;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+        attr_set = true;
+    }
+    const dim3 grid((max_rows + 63) / 64, n_head, lay.B);
+    kern<<<grid, 128, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ld, lay);
+    return 0;
 }
 
 int full_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int n_head, int C,
@@ -513,18 +549,10 @@ int full_attn(const void* q, const void* k, const void* v, void* out, int dt, lo
     const int hs = C / n_head;
     if (lay.B > 65535 || max_len < 1) return 1;
     const int max_rows = max_len;   // longest pair of the level bounds the number of query tiles (blocks past a pair's end exit)
-    if (dt == VRD_BF16) zero_separators_kernel<__nv_bfloat16><<<lay.R, 128, 0, st>>>((__nv_bfloat16*)out, ld, C, lay.row_seq, lay.R);
-    else zero_separators_kernel<float><<<lay.R, 128, 0, st>>>((float*)out, ld, C, lay.row_seq, lay.R);
     if (dt == VRD_BF16) {
-        const dim3 grid((max_rows + 63) / 64, n_head, lay.B);
-        if (hs == 64)
-            flash_attn_bf16_kernel<64><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                                                             (__nv_bfloat16*)out, ld, lay);
-        else if (hs == 128)
-            flash_attn_bf16_kernel<128><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                                                              (__nv_bfloat16*)out, ld, lay);
-        else return 1;
-        return 0;
+        if (hs == 64) return flash_launch<64, 2>(q, k, v, out, ld, lay, n_head, max_rows, st);
+        if (hs == 128) return flash_launch<128, 1>(q, k, v, out, ld, lay, n_head, max_rows, st);
+        return 1;
     }
 #define LAUNCH(T, HS) \
     full_attn_kernel<T, HS><<<dim3((max_rows + (128 / (HS / 32)) - 1) / (128 / (HS / 32)), n_head, lay.B), 128, 0, st>>>( \

@@ -59,11 +59,11 @@ int vrd_h2d_pairs(const void* const* src, const int64_t* bytes, void* dst_base, 
 
 int vrd_pack_pairs(const void* pair_ptrs, const int64_t* pair_strides, const int32_t* row_seq, const int32_t* seqinfo, int R,
                    int B, int nv, int nc, int nbs, int nbe, void* vis, void* clip, int act_dtype, float* bbox_so,
-                   float* bbox_ent, vrd_stream_t stream) {
-    if (nbs > 8 || nbe > 8 || R <= 0 || B <= 0) return fail("vrd_pack_pairs: bad sizes");
+                   float* bbox_ent, int token_major, vrd_stream_t stream) {
+    if (nbs > 8 || nbe > 8 || R <= 0 || B <= 0 || (nv & 1) || (nc & 1)) return fail("vrd_pack_pairs: bad sizes (nv, nc must be even)");
     if (nc > 0 && clip == nullptr) return fail("vrd_pack_pairs: clip output missing");
     vrd::pack_pairs(pair_ptrs, (const long long*)pair_strides, make_lay(row_seq, seqinfo, R, B), nv, nc, nbs, nbe, vis, clip,
-                    act_dtype, bbox_so, bbox_ent, (cudaStream_t)stream);
+                    act_dtype, bbox_so, bbox_ent, token_major, (cudaStream_t)stream);
     return check_launch("vrd_pack_pairs");
 }
 

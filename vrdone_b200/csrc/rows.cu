@@ -13,20 +13,28 @@ constexpr int WARPS = 8;   // warps per block for the row kernels
 // ------------------------------------------------------------------------------------------------------------
 // pack_pairs: ragged (C, L) fp32 pair tensors with arbitrary (channel, time) strides -> token-major operand rows
 // ------------------------------------------------------------------------------------------------------------
-// One block moves a 32-row x 32-channel tile through shared memory.  Rows whose pair tensor is contiguous along time
-// (dense (C, L): the data loader's transposed view after pickling / pin_memory) are read with lanes along time and
-// transposed in the tile; rows of token-major tensors (the (L, C) buffer the reference builds, vidor.py:708-711) are read
-// with lanes along channels.  Either way both the global reads and the global writes are coalesced.
+// One block owns 32 rows and walks over 64-channel tiles (blockIdx.y strides the channel tiles, so the per-row source
+// lookup is done once and a block moves ~64 KB instead of 4 KB).  Rows whose pair tensor is contiguous along time (dense
+// (C, L): the data loader's transposed view after pickling / pin_memory) are read with lanes along time and transposed in
+// the tile; rows of token-major tensors (the (L, C) buffer the reference builds, vidor.py:708-711) are read with lanes
+// along channels.  Either way the global reads are coalesced 128-byte segments and the operand rows are written as packed
+// channel pairs (bf16x2 / float2).  nv and nc must be even.
+template <typename TA> struct Pair2;
+template <> struct Pair2<float> { static __device__ __forceinline__ void st(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); } };
+template <> struct Pair2<__nv_bfloat16> {
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+};
+
 template <typename TA>
 __global__ void __launch_bounds__(256) pack_pairs_kernel(const float* const* __restrict__ ptrs, const long long* __restrict__ strides,
                                                          Lay lay, int nv, int nc, int nbs, int nbe, TA* __restrict__ vis,
                                                          TA* __restrict__ clip, float* __restrict__ bso, float* __restrict__ bent) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[32][65];
     __shared__ const float* s_src[32];     // element (t, channel 0) of the row's pair, or nullptr for separator rows
     __shared__ long long s_sc[32];
     __shared__ int s_tmode[32];            // 1: time-contiguous source (read lanes along time)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    const int r0 = blockIdx.x * 32, cb = blockIdx.y * 32;
+    const int r0 = blockIdx.x * 32;
     const long long R = lay.R;
     const int c0 = 2 * nv + 2 * nc;
     const int C = c0 + nbs + 2 * nbe;
@@ -46,33 +54,51 @@ __global__ void __launch_bounds__(256) pack_pairs_kernel(const float* const* __r
         }
     }
     __syncthreads();
+    for (int cb = blockIdx.y * 64; cb < C; cb += gridDim.y * 64) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        // lanes along time: row = tx, channel = ty + 8k
-        const int c = cb + ty + 8 * k;
-        if (s_tmode[tx] && c < C) tile[tx][ty + 8 * k] = __ldg(s_src[tx] + (long long)c * s_sc[tx]);
-        // lanes along channels: row = ty + 8k, channel = tx
-        const int rr = ty + 8 * k, cc = cb + tx;
-        if (!s_tmode[rr] && s_src[rr] != nullptr && cc < C) tile[rr][tx] = __ldg(s_src[rr] + (long long)cc * s_sc[rr]);
-    }
-    __syncthreads();
-    const int c = cb + tx;
+        for (int k = 0; k < 8; ++k) {
+            // lanes along time: row = tx, channel = ty + 8k
+            const int c = cb + ty + 8 * k;
+            if (s_tmode[tx] && c < C) tile[tx][ty + 8 * k] = __ldg(s_src[tx] + (long long)c * s_sc[tx]);
+        }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int rr = ty + 8 * k;
-        const long long r = r0 + rr;
-        if (r >= lay.R) continue;
-        const float v = (s_src[rr] != nullptr && c < C) ? tile[rr][tx] : 0.f;
-        if (c < nv) vis[r * nv + c] = from_f<TA>(v);
-        else if (c < 2 * nv) vis[(R + r) * nv + (c - nv)] = from_f<TA>(v);
-        else if (c < 2 * nv + nc) clip[r * nc + (c - 2 * nv)] = from_f<TA>(v);
-        else if (c < c0) clip[(R + r) * nc + (c - 2 * nv - nc)] = from_f<TA>(v);
-        else if (c < c0 + nbs) bso[r * 8 + (c - c0)] = v;
-        else if (c < c0 + nbs + nbe) bent[r * 8 + (c - c0 - nbs)] = v;
-        else if (c < C) bent[(R + r) * 8 + (c - c0 - nbs - nbe)] = v;
+        for (int k = 0; k < 4; ++k) {
+            // lanes along channels: row = ty + 8k, channels = tx and tx + 32
+            const int rr = ty + 8 * k;
+            if (!s_tmode[rr] && s_src[rr] != nullptr) {
+                if (cb + tx < C) tile[rr][tx] = __ldg(s_src[rr] + (long long)(cb + tx) * s_sc[rr]);
+                if (cb + 32 + tx < C) tile[rr][tx + 32] = __ldg(s_src[rr] + (long long)(cb + 32 + tx) * s_sc[rr]);
+            }
+        }
+        __syncthreads();
+        const int c = cb + 2 * tx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int rr = ty + 8 * k;
+            const long long r = r0 + rr;
+            if (r >= lay.R) continue;
+            const bool live = s_src[rr] != nullptr;
+            const float v0 = (live && c < C) ? tile[rr][2 * tx] : 0.f;
+            const float v1 = (live && c + 1 < C) ? tile[rr][2 * tx + 1] : 0.f;
+            if (c + 1 < nv) Pair2<TA>::st(vis + r * nv + c, v0, v1);
+            else if (c + 1 < 2 * nv) Pair2<TA>::st(vis + (R + r) * nv + (c - nv), v0, v1);
+            else if (c + 1 < 2 * nv + nc) Pair2<TA>::st(clip + r * nc + (c - 2 * nv), v0, v1);
+            else if (c + 1 < c0) Pair2<TA>::st(clip + (R + r) * nc + (c - 2 * nv - nc), v0, v1);
+            else {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int cc = c + u;
+                    const float v = u == 0 ? v0 : v1;
+                    if (cc < c0 + nbs) bso[r * 8 + (cc - c0)] = v;
+                    else if (cc < c0 + nbs + nbe) bent[r * 8 + (cc - c0 - nbs)] = v;
+                    else if (cc < C) bent[(R + r) * 8 + (cc - c0 - nbs - nbe)] = v;
+                }
+            }
+        }
+        __syncthreads();
     }
-    // unused tail columns of the 8-wide geometry rows (written once, by the last channel tile)
-    if (blockIdx.y == gridDim.y - 1 && threadIdx.x < 32) {
+    // unused tail columns of the 8-wide geometry rows (written once, by the blocks of the first channel slice)
+    if (blockIdx.y == 0 && threadIdx.x < 32) {
         const long long r = r0 + threadIdx.x;
         if (r < lay.R) {
             for (int j = nbs; j < 8; ++j) bso[r * 8 + j] = 0.f;
@@ -81,10 +107,76 @@ __global__ void __launch_bounds__(256) pack_pairs_kernel(const float* const* __r
     }
 }
 
+// Every source token-major (channel stride 1; the (L, C) buffer the reference's loader builds): one warp per row, lanes walk
+// the row's channel pairs, no shared memory, 8 independent loads in flight per lane.
+template <typename TA>
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* const* __restrict__ ptrs, const long long* __restrict__ strides,
+                                                        Lay lay, int nv, int nc, int nbs, int nbe, TA* __restrict__ vis,
+                                                        TA* __restrict__ clip, float* __restrict__ bso, float* __restrict__ bent) {
+    const int lane = threadIdx.x & 31;
+    const long long r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= lay.R) return;
+    const long long R = lay.R;
+    const int c0 = 2 * nv + 2 * nc;
+    const int C = c0 + nbs + 2 * nbe;
+    const int seq = lay.row_seq[r];
+    const float* src = nullptr;
+    if (seq >= 0) {
+        const int4 si = lay.seqinfo[seq];
+        src = ptrs[seq] + (long long)(r - si.x) * strides[2 * seq + 1];
+    }
+    auto put = [&](int c, float v0, float v1) {
+        if (c + 1 < nv) Pair2<TA>::st(vis + r * nv + c, v0, v1);
+        else if (c + 1 < 2 * nv) Pair2<TA>::st(vis + (R + r) * nv + (c - nv), v0, v1);
+        else if (c + 1 < 2 * nv + nc) Pair2<TA>::st(clip + r * nc + (c - 2 * nv), v0, v1);
+        else if (c + 1 < c0) Pair2<TA>::st(clip + (R + r) * nc + (c - 2 * nv - nc), v0, v1);
+        else {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int cc = c + u;
+                const float v = u == 0 ? v0 : v1;
+                if (cc < c0 + nbs) bso[r * 8 + (cc - c0)] = v;
+                else if (cc < c0 + nbs + nbe) bent[r * 8 + (cc - c0 - nbs)] = v;
+                else if (cc < C) bent[(R + r) * 8 + (cc - c0 - nbs - nbe)] = v;
+            }
+        }
+    };
+    constexpr int UNROLL = 4;
+    for (int cb = 0; cb < C; cb += 64 * UNROLL) {
+        float v0[UNROLL], v1[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int c = cb + 64 * u + 2 * lane;
+            v0[u] = (src != nullptr && c < C) ? __ldg(src + c) : 0.f;
+            v1[u] = (src != nullptr && c + 1 < C) ? __ldg(src + c + 1) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int c = cb + 64 * u + 2 * lane;
+            if (c < C) put(c, v0[u], v1[u]);
+        }
+    }
+    if (lane == 0) {
+        for (int j = nbs; j < 8; ++j) bso[r * 8 + j] = 0.f;
+        for (int j = nbe; j < 8; ++j) { bent[r * 8 + j] = 0.f; bent[(R + r) * 8 + j] = 0.f; }
+    }
+}
+
 void pack_pairs(const void* ptrs, const long long* strides, Lay lay, int nv, int nc, int nbs, int nbe, void* vis,
-                void* clip, int adt, float* bso, float* bent, cudaStream_t st) {
+                void* clip, int adt, float* bso, float* bent, int token_major, cudaStream_t st) {
+    if (token_major) {
+        const int grid = (lay.R + WARPS - 1) / WARPS;
+        if (adt == VRD_BF16)
+            pack_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const float* const*)ptrs, strides, lay, nv, nc, nbs, nbe,
+                                                                  (__nv_bfloat16*)vis, (__nv_bfloat16*)clip, bso, bent);
+        else
+            pack_rows_kernel<float><<<grid, 256, 0, st>>>((const float* const*)ptrs, strides, lay, nv, nc, nbs, nbe,
+                                                          (float*)vis, (float*)clip, bso, bent);
+        return;
+    }
     const int C = 2 * nv + 2 * nc + nbs + 2 * nbe;
-    const dim3 grid((lay.R + 31) / 32, (C + 31) / 32);
+    const int ctiles = (C + 63) / 64;
+    const dim3 grid((lay.R + 31) / 32, (ctiles + 7) / 8);      // ~8 channel tiles per block
     if (adt == VRD_BF16)
         pack_pairs_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const float* const*)ptrs, strides, lay, nv, nc, nbs, nbe,
                                                                (__nv_bfloat16*)vis, (__nv_bfloat16*)clip, bso, bent);
@@ -239,11 +331,18 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_kernel(const TI* __re
     int4 so = make_int4(0, 0, 0, 0), si = make_int4(0, 0, 0, 0);
     const TI* base = x;
 
-    auto fetch = [&](int slot, int tt) {    // load input time index tt of the current pair into window slot `slot`
+    // Software prefetch: the STRIDE input rows the NEXT output row will add to the window are requested before the arithmetic
+    // of the current row starts, so their latency hides behind ~10^3 instructions instead of stalling the first use.
+    float pre[STRIDE][NCH][4];
+    int pre_seq = -1, pre_t = 0;               // pre[i] holds input time pre_t + i of pair pre_seq (if that time is < len)
+
+    auto fetch = [&](int slot, int tt, int seq) {    // input time index tt of the current pair -> window slot `slot`
         const int len = si.y;
         if (tt >= 0 && tt < len) {
             float v[NCH][4];
-            load_row<TI, NCH>(base + (long long)tt * ldx, lane, v);
+            if (seq == pre_seq && tt == pre_t) row_copy<NCH>(v, pre[0]);
+            else if (STRIDE == 2 && seq == pre_seq && tt == pre_t + 1) row_copy<NCH>(v, pre[STRIDE - 1]);
+            else load_row<TI, NCH>(base + (long long)tt * ldx, lane, v);
             if constexpr (ANY_RAW) row_copy<NCH>(raw[slot], v);
             if constexpr (ANY_PRE) { row_normalize<NCH>(v, lane, pre_g, pre_b); row_copy<NCH>(nrm[slot], v); }
         } else {
@@ -279,20 +378,29 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_kernel(const TI* __re
             if constexpr (STRIDE == 1) {
                 if constexpr (ANY_RAW) { row_copy<NCH>(raw[0], raw[1]); row_copy<NCH>(raw[1], raw[2]); }
                 if constexpr (ANY_PRE) { row_copy<NCH>(nrm[0], nrm[1]); row_copy<NCH>(nrm[1], nrm[2]); }
-                fetch(2, t + 1);
+                fetch(2, t + 1, seq);
             } else {
                 if constexpr (ANY_RAW) row_copy<NCH>(raw[0], raw[2]);
                 if constexpr (ANY_PRE) row_copy<NCH>(nrm[0], nrm[2]);
-                fetch(1, t);
-                fetch(2, t + 1);
+                fetch(1, t, seq);
+                fetch(2, t + 1, seq);
             }
         } else {
-            fetch(0, t - 1);
-            fetch(1, t);
-            fetch(2, t + 1);
+            fetch(0, t - 1, seq);
+            fetch(1, t, seq);
+            fetch(2, t + 1, seq);
         }
         cur_seq = seq;
         cur_t = t;
+        if (r + 1 < r_end && (r + 1 - so.x) < so.y) {         // the next output row belongs to the same pair
+            pre_seq = seq;
+            pre_t = t + 2;
+#pragma unroll
+            for (int i = 0; i < STRIDE; ++i)
+                if (pre_t + i < si.y) load_row<TI, NCH>(base + (long long)(pre_t + i) * ldx, lane, pre[i]);
+        } else {
+            pre_seq = -1;
+        }
         float y[NB][NCH][4];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -355,6 +463,208 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_kernel(const TI* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// dwconv_ln_tile: the stride-1, C = 512, fp32-input case (every level-0 call: encoder q/k/v, SOS self and cross), shared-
+// memory tiled and persistent.  One CTA per SM (16 warps) walks over tiles of DWT_TILE consecutive rows of the stacked
+// streams; one thread stages the DWT_TILE + 2 input rows of the NEXT tile with a single TMA bulk copy (cp.async.bulk +
+// mbarrier, ~70 KB in flight per SM, no register staging) while all warps work on the current one.  Per tile: the warps
+// first normalise every staged row once (in place when every branch reads LN_pre(x); statistics only when a branch also
+// needs the raw row), then each warp produces output rows from the three staged neighbours, so no state is carried
+// between rows.  A staged separator row normalises to exactly beta, which is the value of the first pad column.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int DWT_TILE = 32;
+constexpr int DWT_ROWS = DWT_TILE + 2;
+constexpr int DWT_WARPS = 16;
+constexpr int DWT_SMEM = 2 * DWT_ROWS * 512 * 4 + 2 * 48 * 4 + 32;
+
+template <typename TO, int NB, int PREMASK>
+__global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const float* __restrict__ x, Lay lay,
+                                                                           const float* __restrict__ pre_g,
+                                                                           const float* __restrict__ pre_b, DwBranches br,
+                                                                           int total_rows) {
+    constexpr int NCH = 4, C = 512;
+    constexpr bool ANY_PRE = PREMASK != 0;
+    constexpr bool ALL_PRE = PREMASK == ((1 << NB) - 1);         // no branch reads the raw row: normalise in place
+    extern __shared__ __align__(128) uint8_t dwt_smem[];
+    float* sx_all = reinterpret_cast<float*>(dwt_smem);          // [2][DWT_ROWS][C]; row i <-> physical row r0 - 1 + i
+    float* s_mean = sx_all + 2 * DWT_ROWS * C;                   // [48]
+    float* s_rstd = s_mean + 48;                                 // [48]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_rstd + 48);   // [2]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_tiles = total_rows / DWT_TILE;
+    const uint32_t bar_u = (uint32_t)__cvta_generic_to_shared(bars);
+    auto issue = [&](int tile, int buf) {                         // one thread: stage the rows of `tile` into buffer `buf`
+        const int r0 = tile * DWT_TILE;
+        const int lo = max(r0 - 1, 0), hi = min(r0 + DWT_TILE + 1, total_rows);
+        const uint32_t bytes = (uint32_t)(hi - lo) * C * 4;
+        const uint32_t b = bar_u + 8 * buf;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(sx_all + buf * DWT_ROWS * C + (lo - (r0 - 1)) * C)),
+                       "l"(x + (long long)lo * C), "r"(bytes), "r"(b) : "memory");
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    }
+    __syncthreads();                                             // barriers initialised before anyone polls them
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        float* sx = sx_all + buf * DWT_ROWS * C;
+        const int r0 = tile * DWT_TILE;
+        const int lo = max(r0 - 1, 0), hi = min(r0 + DWT_TILE + 1, total_rows);
+        if (threadIdx.x == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);   // freed by the trailing sync
+        {
+            const uint32_t parity = (it >> 1) & 1;
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar_u + 8 * buf), "r"(parity) : "memory");
+            }
+        }
+        if constexpr (ANY_PRE) {
+            for (int i = warp; i < DWT_ROWS; i += DWT_WARPS) {
+                const int p = r0 - 1 + i;
+                if (p < lo || p >= hi) continue;
+                float v[NCH][4];
+                load_row<float, NCH>(sx + i * C, lane, v);
+                if constexpr (ALL_PRE) {
+                    row_normalize<NCH>(v, lane, pre_g, pre_b);
+                    store_row<float, NCH>(sx + i * C, lane, v);
+                } else {
+                    float mean, rstd;
+                    row_stats<NCH>(v, mean, rstd);
+                    if (lane == 0) { s_mean[i] = mean; s_rstd[i] = rstd; }
+                }
+            }
+            __syncthreads();
+        }
+        for (int rr = warp; rr < DWT_TILE; rr += DWT_WARPS) {
+            const int grow = r0 + rr;
+            const int s = grow / lay.R, r = grow - s * lay.R;
+            const int seq = lay.row_seq[r];
+            if (seq < 0) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) zero_row<TO, NCH>((TO*)br.out[b] + (long long)grow * br.ldo[b], lane);
+                continue;
+            }
+            const int4 si = lay.seqinfo[seq];
+            const int t = r - si.x;
+            float y[NB][NCH][4];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) row_zero<NCH>(y[b]);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int tt = t + d - 1;
+                const bool inside = tt >= 0 && tt < si.y;
+                const bool padcol = ANY_PRE && tt == si.y && si.z != 0;    // first pad column: LN of a zero column is its bias
+                if (!inside && !padcol) continue;
+                float raw[NCH][4], nrm[NCH][4];
+                if constexpr (ALL_PRE) {
+                    load_row<float, NCH>(sx + (rr + d) * C, lane, nrm);    // staged separator row == beta
+                } else {
+                    if (inside) load_row<float, NCH>(sx + (rr + d) * C, lane, raw); else row_zero<NCH>(raw);
+                    if constexpr (ANY_PRE) {
+                        const float mean = s_mean[rr + d], rstd = s_rstd[rr + d];   // separator row: mean 0 -> nrm = beta
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) {
+                            float pg[4], pb[4];                  // L1-resident; not kept in registers across rows
+                            ld4(pre_g + (j * 32 + lane) * 4, pg);
+                            ld4(pre_b + (j * 32 + lane) * 4, pb);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) nrm[j][i] = (raw[j][i] - mean) * rstd * pg[i] + pb[i];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    if (!((PREMASK >> b) & 1) && !inside) continue;       // raw branches see zeros outside the pair
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        float w[4];
+                        ld4(br.w[b] + d * C + (j * 32 + lane) * 4, w);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) y[b][j][i] = fmaf(((PREMASK >> b) & 1) ? nrm[j][i] : raw[j][i], w[i], y[b][j][i]);
+                    }
+                }
+            }
+            // post-conv LayerNorm of all branches, reductions interleaved for instruction-level parallelism
+            float mean[NB], rstd[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                float sm = 0.f;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) sm += (y[b][j][0] + y[b][j][1]) + (y[b][j][2] + y[b][j][3]);
+                mean[b] = sm;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) mean[b] += __shfl_xor_sync(FULL_MASK, mean[b], o);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                mean[b] *= (1.0f / C);
+                float q = 0.f;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const float dd = y[b][j][i] - mean[b]; q += dd * dd; }
+                rstd[b] = q;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) rstd[b] += __shfl_xor_sync(FULL_MASK, rstd[b], o);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float rs = 1.0f / sqrtf(rstd[b] * (1.0f / C) + VRD_EPS);
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    float g[4], be[4];
+                    ld4(br.g[b] + (j * 32 + lane) * 4, g);
+                    ld4(br.b[b] + (j * 32 + lane) * 4, be);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) y[b][j][i] = (y[b][j][i] - mean[b]) * rs * g[i] + be[i];
+                }
+                store_row<TO, NCH>((TO*)br.out[b] + (long long)grow * br.ldo[b], lane, y[b]);
+            }
+        }
+        if constexpr (ALL_PRE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before the next TMA fill
+        __syncthreads();                                         // this buffer may be refilled from now on
+    }
+}
+
+template <typename TO>
+static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const float* pre_b, const DwBranches& br, int streams,
+                          cudaStream_t st) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int mask = 0;
+    for (int b = 0; b < br.n; ++b) mask |= (br.use_pre[b] ? 1 : 0) << b;
+    const int total = streams * lay.R;
+    const int n_tiles = total / DWT_TILE;
+    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+#define LAUNCH(NB, MASK) do { \
+        auto kern = dwconv_ln_tile_kernel<TO, NB, MASK>; \
+        static bool attr_set = false; \
+        if (!attr_set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DWT_SMEM) != cudaSuccess) return 1; attr_set = true; } \
+        kern<<<grid, DWT_WARPS * 32, DWT_SMEM, st>>>(x, lay, pre_g, pre_b, br, total); } while (0)
+    if (br.n == 3 && mask == 7) LAUNCH(3, 7);
+    else if (br.n == 3 && mask == 3) LAUNCH(3, 3);
+    else if (br.n == 2 && mask == 0) LAUNCH(2, 0);
+    else if (br.n == 1 && mask == 1) LAUNCH(1, 1);
+    else return 1;
+#undef LAUNCH
+    return 0;
+}
+
 template <typename TI, typename TO, int NCH, int STRIDE>
 static int dwconv_ln_mask(const void* x, long long ldx, Lay lin, Lay lout, const float* pre_g, const float* pre_b,
                           const DwBranches& br, int streams, cudaStream_t st) {
@@ -376,6 +686,9 @@ static int dwconv_ln_mask(const void* x, long long ldx, Lay lin, Lay lout, const
 int dwconv_ln(const void* x, int xdt, long long ldx, Lay lin, Lay lout, int stride, const float* pre_g, const float* pre_b,
               const DwBranches& br, int odt, int C, int streams, cudaStream_t st) {
     if (xdt != VRD_F32) return 1;
+    if (stride == 1 && C == 512 && ldx == C && lin.R == lout.R && lin.R % 128 == 0)
+        return odt == VRD_BF16 ? dwconv_ln_tile<__nv_bfloat16>((const float*)x, lout, pre_g, pre_b, br, streams, st)
+                               : dwconv_ln_tile<float>((const float*)x, lout, pre_g, pre_b, br, streams, st);
 #define DISPATCH(TO, NCH) \
     (stride == 1 ? dwconv_ln_mask<float, TO, NCH, 1>(x, ldx, lin, lout, pre_g, pre_b, br, streams, st) \
                  : dwconv_ln_mask<float, TO, NCH, 2>(x, ldx, lin, lout, pre_g, pre_b, br, streams, st))

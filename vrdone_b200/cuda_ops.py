@@ -23,7 +23,7 @@ _SIGNATURES = {
     "vrd_abi_version": [],
     "vrd_device_arch": [],
     "vrd_h2d_pairs": [_vp, _vp, _vp, _vp, _i32, _vp],
-    "vrd_pack_pairs": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
+    "vrd_pack_pairs": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
     "vrd_gemm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp,
                  _vp, _i32, _vp],
     "vrd_layernorm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _vp],
@@ -63,7 +63,7 @@ def load_library() -> C.CDLL:
         fn.restype = C.c_int
     lib.vrd_last_error.argtypes = []
     lib.vrd_last_error.restype = C.c_char_p
-    if lib.vrd_abi_version() != 1:
+    if lib.vrd_abi_version() != 2:
         raise RuntimeError("libvrdone_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
@@ -174,10 +174,10 @@ class CudaOps:
             raise RuntimeError(f"vrd_h2d_pairs failed: {self.lib.vrd_last_error().decode()}")
 
     # -- ops ------------------------------------------------------------------------------------------------------
-    def pack_pairs(self, ptrs, strides, lay, nv, nc, nbs, nbe, vis, clp, bso, bent):
+    def pack_pairs(self, ptrs, strides, lay, nv, nc, nbs, nbe, vis, clp, bso, bent, token_major=False):
         rs, si, R = self._lay(lay)
         self._check(self.lib.vrd_pack_pairs(_p(ptrs), _p(strides), rs, si, R, lay.B, nv, nc, nbs, nbe, _p(vis), _p(clp),
-                                            _dt(vis), _f32(bso), _f32(bent), self._stream()), "vrd_pack_pairs")
+                                            _dt(vis), _f32(bso), _f32(bent), int(token_major), self._stream()), "vrd_pack_pairs")
 
     def gemm(self, a, w, out, bias=None, taps=1, act=0, res1=None, res2=None, corr=None, lay=None, streams=1):
         ap, lda = _mat(a)

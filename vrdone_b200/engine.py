@@ -260,7 +260,8 @@ class Engine:
         return out
 
     # -- full network ---------------------------------------------------------------------------
-    def forward_packed(self, lay: PackLayout, pair_ptrs, pair_strides, topk: int, want_masks: bool = False, after_pack=None):
+    def forward_packed(self, lay: PackLayout, pair_ptrs, pair_strides, topk: int, want_masks: bool = False, after_pack=None,
+                       token_major: bool = False):
         """pair_ptrs: int64[B] device addresses of the fp32 (C, L_i) inputs; pair_strides: int64[B, 2] element strides
         (channel, time).  Returns dict(logits [B,Q,K+1] f32, topk_scores/topk_ids [B,Q,topk], first_last [B,Q,2] int32,
         masks [R0, Q] f32 or None)."""
@@ -282,7 +283,7 @@ class Engine:
         clp = self._buf(2 * R0, nc, adt) if clip else None
         bso = self._buf(R0, 8, torch.float32)
         bent = self._buf(2 * R0, 8, torch.float32)
-        ops.pack_pairs(pair_ptrs, pair_strides, l0, nv, nc, nbs, nbe, vis, clp, bso, bent)
+        ops.pack_pairs(pair_ptrs, pair_strides, l0, nv, nc, nbs, nbe, vis, clp, bso, bent, token_major=token_major)
         if after_pack is not None:
             after_pack()     # the pair tensors (or their staging buffer) are no longer needed once this kernel has run
 

@@ -240,7 +240,8 @@ class MaskVRD(nn.Module):
                         e = torch.cuda.Event()
                         e.record(cur)
                         self._pack_done[slot] = e
-                r = eng.forward_packed(lays[ci], ptrs, strides, topk, want_masks, after_pack=packed)
+                r = eng.forward_packed(lays[ci], ptrs, strides, topk, want_masks, after_pack=packed,
+                                       token_major=bool((tables[ci][0][1] == 1).all()))
                 tE = time.perf_counter()
                 st["meta_ms"] += 1e3 * (tD - tC); st["launch_ms"] += 1e3 * (tE - tD)
                 ev = ev_next

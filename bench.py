@@ -250,6 +250,7 @@ def main():
         model(pinned[s % len(pinned)])
     ms_e2e, pairs_e2e = timed(pinned, args.steps, h2d=True)
     host_e2e = {k: round(v, 2) for k, v in model.last_stats.items()}
+    host_e2e["forward_wall_ms_each_step"] = list(step_wall)
 
     # roofline pass: the same steps with a CUDA-event pair around every launch of the dominant (GEMM) kernel
     ops.start_timing()

@@ -18,20 +18,18 @@ for _ in range(3):
 eng = model._get_engine()
 rec = []
 t0 = [0.0]
-orig_stage, orig_fwd = model._issue_copies, eng.forward_packed
+orig_prep, orig_fwd, orig_pred = model._prepare_chunk, eng.backbone, eng.predict
 
 def ev(stream):
     e = torch.cuda.Event(enable_timing=True); e.record(stream); return e
 
-def stage(ops, plan, slot):
-    cs = model._copy_stream
+def prep(ops, feats, lens, tpads, chunk, ci, dev_, cur, any_host):
+    cs = model._copy_stream if any_host else cur
     h0 = time.perf_counter()
-    if model._pack_done[slot] is not None:
-        cs.wait_event(model._pack_done[slot])
     a = ev(cs)
-    r = orig_stage(ops, plan, slot)
+    r = orig_prep(ops, feats, lens, tpads, chunk, ci, dev_, cur, any_host)
     b = ev(cs)
-    rec.append(("copy", len(plan["idx"]), a, b, 1e3 * (h0 - t0[0]), 1e3 * (time.perf_counter() - t0[0])))
+    rec.append(("copy", chunk[1] - chunk[0], a, b, 1e3 * (h0 - t0[0]), 1e3 * (time.perf_counter() - t0[0])))
     return r
 
 def fwd(lay, *a, **k):
@@ -43,8 +41,16 @@ def fwd(lay, *a, **k):
     rec.append(("compute", lay.B, s, e, 1e3 * (h0 - t0[0]), 1e3 * (time.perf_counter() - t0[0])))
     return r
 
-model._issue_copies = stage
-eng.forward_packed = fwd
+model._prepare_chunk = prep
+eng.backbone = fwd
+
+def pred(lay, *a, **k):
+    cur = torch.cuda.current_stream()
+    h0 = time.perf_counter(); s_ = ev(cur); r = orig_pred(lay, *a, **k); e_ = ev(cur)
+    rec.append(("predict", lay.B, s_, e_, 1e3 * (h0 - t0[0]), 1e3 * (time.perf_counter() - t0[0])))
+    return r
+
+eng.predict = pred
 for rep in range(2):
     rec.clear()
     torch.cuda.synchronize()

@@ -10,8 +10,7 @@ bench) echo "== bench full"; timeout 1200 python bench.py > gpurun_out/bench_ful
 launches) echo "== ncu launch list"
   $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1; echo "rc=$?"; tail -c 300 gpurun_out/ncu1.log;;
 ncu) echo "== ncu full"
-  $CMD > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"gemm_tcgen05" -s 230 -c 8 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu3.log 2>&1; echo "rc=$?"; tail -c 200 gpurun_out/ncu3.log
-  ncu --set full --clock-control none --import-source on -k regex:"dwconv_ln|flash_attn|window_attn|pack_pairs|layernorm_kernel" -s 60 -c 10 -o gpurun_out/prof_rows $CMD > gpurun_out/ncu4.log 2>&1; echo "rc=$?"; tail -c 200 gpurun_out/ncu4.log
+  $CMD > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"${NCU_K:-dwconv_ln_tile}" -s ${NCU_S:-10} -c ${NCU_C:-4} -o gpurun_out/prof_sel $CMD > gpurun_out/ncu3.log 2>&1; echo "rc=$?"; tail -c 200 gpurun_out/ncu3.log
   ls -la gpurun_out;;
 esac
 done

@@ -265,6 +265,19 @@ class Engine:
         """pair_ptrs: int64[B] device addresses of the fp32 (C, L_i) inputs; pair_strides: int64[B, 2] element strides
         (channel, time).  Returns dict(logits [B,Q,K+1] f32, topk_scores/topk_ids [B,Q,topk], first_last [B,Q,2] int32,
         masks [R0, Q] f32 or None)."""
+        e_top, mf = self.backbone(lay, pair_ptrs, pair_strides, after_pack=after_pack, token_major=token_major)
+        return self.predict(lay, e_top, mf, topk, want_masks)
+
+    def predict(self, lay, e_top, mf, topk: int, want_masks: bool = False):
+        """Query decoder + heads over the coarsest level ``e_top`` [R_top, C] and the mask features ``mf`` [R_0, F] of a batch
+        whose levels 0 and top are described by ``lay`` (a PackLayout, or a MergedLayout over several backbone chunks)."""
+        if hasattr(self.ops, "bind_stream"):
+            self.ops.bind_stream()
+        return self._predictor(e_top, mf, lay, topk, want_masks)
+
+    def backbone(self, lay: PackLayout, pair_ptrs, pair_strides, after_pack=None, token_major: bool = False):
+        """Pack + embeddings + stem / SOS + fuse + pyramid + FPN of one chunk of pairs -> (coarsest level [R_top, C] fp32, mask
+        features [R_0, fpn_dim] fp32)."""
         ops, mc, w = self.ops, self.mc, self.w
         if hasattr(ops, "bind_stream"):
             ops.bind_stream()
@@ -362,8 +375,7 @@ class Engine:
                           self._W("neck.mask_features.b"), mf)
         self._tap("mask_features", mf, l0)
 
-        # 7. query decoder over the coarsest level + heads
-        return self._predictor(e[top], mf, lay, topk, want_masks)
+        return e[top], mf
 
     def _predictor(self, e_top, mf, lay: PackLayout, topk, want_masks):
         ops, mc, adt = self.ops, self.mc, self.adt

@@ -114,3 +114,40 @@ class PackLayout:
             pos += lev.R
             lev.seqinfo = dev[pos:pos + 4 * self.B].view(self.B, 4)
             pos += 4 * self.B
+
+
+class MergedLayout:
+    """Levels 0 and top of several consecutive chunk layouts viewed as one batch (rows of chunk i follow those of chunk
+    i - 1, pair ids are renumbered): what the query decoder and the heads need when the backbone ran chunk by chunk."""
+
+    def __init__(self, lays: Sequence[PackLayout], device):
+        self.n_levels = lays[0].n_levels
+        self.B = sum(l.B for l in lays)
+        self.lengths = np.concatenate([l.lengths for l in lays])
+        self.levels: List[LevelLayout] = [None] * self.n_levels
+        host = []
+        for lv in (0, self.n_levels - 1):
+            row_base = np.cumsum([0] + [l.levels[lv].R for l in lays])
+            pair_base = np.cumsum([0] + [l.B for l in lays])
+            off = np.concatenate([l.levels[lv].off + rb for l, rb in zip(lays, row_base)]).astype(np.int32)
+            length = np.concatenate([l.levels[lv].len for l in lays]).astype(np.int32)
+            haspad = np.concatenate([l.levels[lv].haspad for l in lays]).astype(np.int32)
+            rows = int(row_base[-1])
+            row_seq = np.concatenate([np.where(l._host[2 * lv] >= 0, l._host[2 * lv] + pb, -1) for l, pb in zip(lays, pair_base)])
+            info = np.stack([off, length, haspad, np.zeros(self.B, np.int32)], 1)
+            self.levels[lv] = LevelLayout(lv, off, length, haspad, rows)
+            host += [row_seq.astype(np.int32), info.reshape(-1)]
+        n_words = sum(h.size for h in host)
+        if torch.device(device).type == "cuda":
+            flat = torch.empty(n_words, dtype=torch.int32, pin_memory=True)
+            np.concatenate(host, out=flat.numpy())
+            dev = flat.to(device, non_blocking=True)
+        else:
+            dev = torch.from_numpy(np.concatenate(host))
+        pos = 0
+        for lv in (0, self.n_levels - 1):
+            lev = self.levels[lv]
+            lev.row_seq = dev[pos:pos + lev.R]
+            pos += lev.R
+            lev.seqinfo = dev[pos:pos + 4 * self.B].view(self.B, 4)
+            pos += 4 * self.B

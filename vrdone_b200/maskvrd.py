@@ -22,7 +22,7 @@ import torch
 from torch import nn
 
 from .engine import Engine, PackedWeights
-from .layout import PackLayout, max_div_factor, reference_padded_lengths
+from .layout import MergedLayout, PackLayout, max_div_factor, reference_padded_lengths
 from .params import Backbone, Neck, Predictor
 
 
@@ -61,6 +61,9 @@ class MaskVRD(nn.Module):
         self.precision = config.get("precision", "bf16")   # "bf16" (tcgen05 tensor cores) or "fp32" (CUDA-core fp32)
         self.max_rows = int(config.get("max_rows", 196608))  # level-0 rows processed per engine call (bounds workspace)
         self.h2d_chunk_rows = int(config.get("h2d_chunk_rows", 36864))  # rows per chunk when pair features arrive from the host
+        self.h2d_edge_rows = int(config.get("h2d_edge_rows", 8192))     # ... and of the first / last chunk (not overlapped)
+        self._lay_bufs = [None] * 4       # persistent device buffers for the per-chunk layout arrays + pair tables
+        self._lay_done = [None] * 4
         self.gc_park_results = bool(config.get("gc_park_results", True))
         self._copy_stream = None
         self._staging = [None, None]      # double-buffered device staging of host-resident pair tensors
@@ -131,14 +134,32 @@ class MaskVRD(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     # network over a ragged list of pairs
     # ------------------------------------------------------------------------------------------------------------
-    def _chunks(self, lens: List[int], max_rows: int):
-        start, rows = 0, 1
-        for i, l in enumerate(lens):
-            if i > start and rows + l + 1 > max_rows:
-                yield start, i
-                start, rows = i, 1
-            rows += l + 1
-        yield start, len(lens)
+    @staticmethod
+    def _chunks(lens: List[int], max_rows: int, edge_rows: Optional[int] = None):
+        """Consecutive pair ranges of at most ~``max_rows`` level-0 rows.  With ``edge_rows`` (host-resident inputs) the first
+        and the last range are kept small: nothing overlaps the first chunk's PCIe copy or the last chunk's kernels; the rows
+        in between are split evenly."""
+        rows = np.asarray(lens, dtype=np.int64) + 1
+        total = int(rows.sum()) + 1
+        if edge_rows is None or total <= 3 * edge_rows:
+            edge_rows, n_mid = None, max(1, -(-total // max_rows))
+            cuts = [total * (i + 1) / n_mid for i in range(n_mid)]
+        else:
+            n_mid = max(1, -(-(total - 2 * edge_rows) // max_rows))
+            cuts = [edge_rows + (total - 2 * edge_rows) * i / n_mid for i in range(n_mid + 1)] + [total]
+        ends = np.searchsorted(np.cumsum(rows), cuts, side="left") + 1       # first pair index past each cut
+        out, start = [], 0
+        for e in ends.tolist():
+            e = min(max(e, start + 1), len(lens))
+            if e > start:
+                out.append((start, e))
+                start = e
+            if start >= len(lens):
+                break
+        if start < len(lens):
+            out.append((start, len(lens)))
+        # a single very long pair can exceed max_rows; that is fine (max_rows only bounds the workspace approximately)
+        return out
 
     @staticmethod
     def _pair_table(sub):
@@ -147,8 +168,8 @@ class MaskVRD(nn.Module):
         n = len(sub)
         meta = np.empty((3, n), dtype=np.int64)
         meta[0] = [f.data_ptr() for f in sub]
-        meta[1] = [f.stride(0) for f in sub]
-        meta[2] = [f.stride(1) for f in sub]
+        st = np.array([f.stride() for f in sub], dtype=np.int64)
+        meta[1], meta[2] = st[:, 0], st[:, 1]
         on_host = np.array([not f.is_cuda for f in sub], dtype=bool)
         if not on_host.any():
             return meta, None
@@ -162,16 +183,60 @@ class MaskVRD(nn.Module):
                 "offs": np.ascontiguousarray(offs[idx]), "total": int(padded.sum())}
         return meta, plan
 
-    def _issue_copies(self, ops, plan, slot: int):
-        """Enqueue the host->device copies of one chunk on the copy stream (copy engine, overlapping the kernels of the
-        previous chunk); returns the event the pack kernel has to wait for."""
-        cs = self._copy_stream
-        if self._pack_done[slot] is not None:
-            cs.wait_event(self._pack_done[slot])      # the previous user of this staging buffer has been packed
-        ops.h2d_pairs(plan["src"], plan["bytes"], self._staging[slot], plan["offs"], cs)
-        ev = torch.cuda.Event()
-        ev.record(cs)
-        return ev
+    def _fresh_block(self, cur):
+        """A block that just came from the caching allocator may still be read by kernels already enqueued on the compute
+        stream (the allocator only orders reuse within that stream): the copy stream must not write it before they finish."""
+        if self._copy_stream is not None:
+            e = torch.cuda.Event()
+            e.record(cur)
+            self._copy_stream.wait_event(e)
+
+    def _prepare_chunk(self, ops, feats, lens, tpads, chunk, ci: int, dev, cur, any_host: bool):
+        """Host-side preparation of one chunk and everything that crosses PCIe for it, enqueued in this order on ONE stream
+        (the copy stream when any pair lives on the host, else the compute stream): the chunk's layout arrays + pair table
+        (one small pinned upload), then the bulk copies of its host-resident pairs.  Host->device copies of all streams share
+        the copy engine, which serves a stream's queue until it is empty, so a small upload issued on another stream would wait
+        behind a whole chunk of bulk copies.  Returns (layout, device pair table, event to wait for or None, token_major)."""
+        a, b = chunk
+        lay = PackLayout(lens[a:b], tpads[a:b], self.n_levels)
+        meta, plan = self._pair_table(feats[a:b])
+        if plan is not None:
+            slot = ci & 1
+            buf = self._staging[slot]
+            if buf is None or buf.numel() < plan["total"]:
+                # sized for a full chunk so that steady state never reallocates (replacing a buffer whose copies are still in
+                # flight is safe: every later use of the memory is ordered behind the pack kernel that waits for them)
+                full = (self.h2d_chunk_rows + 4096) * int(feats[a].shape[0]) * 4
+                self._staging[slot] = buf = torch.empty(max(plan["total"], full), dtype=torch.uint8, device=dev)
+                self._fresh_block(cur)
+            meta[0, plan["idx"]] = buf.data_ptr() + plan["offs"]
+        words = (lay.n_words + 6 * lay.B + 3) // 4 * 4                      # keeps every piece 16-byte aligned
+        pin = torch.empty(words, dtype=torch.int32, pin_memory=True)
+        pin_np = pin.numpy()
+        lay.host_words(pin_np[:lay.n_words])
+        pin_np[lay.n_words: lay.n_words + 6 * lay.B].view(np.int64)[:] = meta.reshape(-1)
+        ls = ci % len(self._lay_bufs)           # persistent device buffers: written from the copy stream, so they must not
+        lbuf = self._lay_bufs[ls]               # come from the (compute-stream ordered) caching allocator per call
+        if lbuf is None or lbuf.numel() < words:
+            self._lay_bufs[ls] = lbuf = torch.empty(max(words, 1 << 18), dtype=torch.int32, device=dev)
+            self._lay_done[ls] = None
+            self._fresh_block(cur)
+        stream = self._copy_stream if any_host else cur
+        with torch.cuda.stream(stream):
+            if self._lay_done[ls] is not None:
+                stream.wait_event(self._lay_done[ls])      # the kernels of the chunk that used this buffer four chunks ago are done
+            lbuf[:words].copy_(pin, non_blocking=True)
+        lay.bind(lbuf[:lay.n_words])
+        meta_d = lbuf[lay.n_words: lay.n_words + 6 * lay.B].view(torch.int64).view(3, lay.B)
+        ev = None
+        if any_host:
+            if plan is not None:
+                if self._pack_done[ci & 1] is not None:
+                    stream.wait_event(self._pack_done[ci & 1])      # the previous user of this staging buffer has been packed
+                ops.h2d_pairs(plan["src"], plan["bytes"], self._staging[ci & 1], plan["offs"], stream)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return lay, meta_d, ev, bool((meta[1] == 1).all()), plan is not None
 
     @torch.no_grad()
     def run_network(self, feats: List[torch.Tensor], tpads: List[int], topk: int, want_masks: bool = False):
@@ -185,74 +250,61 @@ class MaskVRD(nn.Module):
         lens = [int(f.shape[1]) for f in feats]
         assert all(f.dtype == torch.float32 and f.dim() == 2 for f in feats)
         any_host = not all(f.is_cuda for f in feats)
-        outs = {"logits": [], "topk_scores": [], "topk_ids": [], "first_last": []}
-        masks: List[torch.Tensor] = []
-        st = {"layout_ms": 0.0, "meta_ms": 0.0, "launch_ms": 0.0}
+        st = {"prepare_ms": 0.0, "launch_ms": 0.0}
         with torch.cuda.device(dev):
             cur = torch.cuda.current_stream(dev)
-            tA = time.perf_counter()
-            chunks = list(self._chunks(lens, min(self.max_rows, self.h2d_chunk_rows) if any_host else self.max_rows))
-            lays = [PackLayout(lens[a:b], tpads[a:b], self.n_levels) for a, b in chunks]
-            tB = time.perf_counter()
-            tables = [self._pair_table(feats[a:b]) for a, b in chunks]
             if any_host:
+                chunks = self._chunks(lens, min(self.max_rows, self.h2d_chunk_rows), min(self.max_rows, self.h2d_edge_rows))
                 if self._copy_stream is None:
                     self._copy_stream = torch.cuda.Stream(device=dev)
-                for slot in (0, 1):
-                    need = max([p["total"] for (_, p) in tables[slot::2] if p is not None], default=0)
-                    if need and (self._staging[slot] is None or self._staging[slot].numel() < need):
-                        self._staging[slot] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
-                for ci, (meta, plan) in enumerate(tables):
-                    if plan is not None:
-                        meta[0, plan["idx"]] = self._staging[ci & 1].data_ptr() + plan["offs"]
-            # ONE upload of every chunk's layout arrays and pair table, issued before any bulk copy: host->device copies of all
-            # streams share the copy engine, which drains the copy stream's queue before it looks at another stream
-            words = [(lay.n_words + 6 * lay.B + 3) // 4 * 4 for lay in lays]      # keeps every piece 16-byte aligned
-            pin = torch.empty(sum(words), dtype=torch.int32, pin_memory=True)
-            pin_np = pin.numpy()
-            pos = 0
-            for lay, (meta, _), w in zip(lays, tables, words):
-                lay.host_words(pin_np[pos:pos + lay.n_words])
-                pin_np[pos + lay.n_words: pos + lay.n_words + 6 * lay.B].view(np.int64)[:] = meta.reshape(-1)
-                pos += w
-            dev_words = pin.to(dev, non_blocking=True)
-            pos, metas_d = 0, []
-            for lay, w in zip(lays, words):
-                lay.bind(dev_words[pos:pos + lay.n_words])
-                metas_d.append(dev_words[pos + lay.n_words: pos + lay.n_words + 6 * lay.B].view(torch.int64).view(3, lay.B))
-                pos += w
-            ev = self._issue_copies(ops, tables[0][1], 0) if tables[0][1] is not None else None
-            tC = time.perf_counter()
-            st["layout_ms"] += 1e3 * (tB - tA); st["meta_ms"] += 1e3 * (tC - tB)
+            else:
+                chunks = self._chunks(lens, self.max_rows)
+            tA = time.perf_counter()
+            prep = self._prepare_chunk(ops, feats, lens, tpads, chunks[0], 0, dev, cur, any_host)
+            st["prepare_ms"] += 1e3 * (time.perf_counter() - tA)
+            lays, tops, mfs = [], [], []
             for ci, (a, b) in enumerate(chunks):
                 tC = time.perf_counter()
-                ev_next = None
-                if ci + 1 < len(chunks) and tables[ci + 1][1] is not None:   # next chunk's copies go out before this chunk's kernels
-                    ev_next = self._issue_copies(ops, tables[ci + 1][1], (ci + 1) & 1)
+                nxt = None
+                if ci + 1 < len(chunks):      # the next chunk's uploads and copies go out before this chunk's kernels are enqueued
+                    nxt = self._prepare_chunk(ops, feats, lens, tpads, chunks[ci + 1], ci + 1, dev, cur, any_host)
+                lay, meta_d, ev, token_major, staged = prep
                 if ev is not None:
                     cur.wait_event(ev)
-                ptrs = metas_d[ci][0]
-                strides = metas_d[ci][1:].t().contiguous()
+                ptrs = meta_d[0]
+                strides = meta_d[1:].t().contiguous()
                 tD = time.perf_counter()
 
-                def packed(slot=ci & 1, used=tables[ci][1] is not None):
+                def packed(slot=ci & 1, used=staged):
                     if used:
                         e = torch.cuda.Event()
                         e.record(cur)
                         self._pack_done[slot] = e
-                r = eng.forward_packed(lays[ci], ptrs, strides, topk, want_masks, after_pack=packed,
-                                       token_major=bool((tables[ci][0][1] == 1).all()))
+                # backbone + FPN chunk by chunk; the query decoder and the heads (~100 small launches) run once over all chunks
+                e_top, mf = eng.backbone(lay, ptrs, strides, after_pack=packed, token_major=token_major)
+                if len(chunks) > 1:
+                    done = torch.cuda.Event()
+                    done.record(cur)
+                    self._lay_done[ci % len(self._lay_bufs)] = done
+                lays.append(lay); tops.append(e_top); mfs.append(mf)
                 tE = time.perf_counter()
-                st["meta_ms"] += 1e3 * (tD - tC); st["launch_ms"] += 1e3 * (tE - tD)
-                ev = ev_next
-                for k in outs:
-                    outs[k].append(r[k])
-                if want_masks:
-                    l0 = lays[ci].levels[0]
-                    for i in range(b - a):
-                        masks.append(r["masks"][int(l0.off[i]): int(l0.off[i]) + int(l0.len[i])])
-        res = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in outs.items()}
-        res["masks"] = masks if want_masks else None
+                st["prepare_ms"] += 1e3 * (tD - tC); st["launch_ms"] += 1e3 * (tE - tD)
+                prep = nxt
+            tC = time.perf_counter()
+            if len(chunks) == 1:
+                glay, e_top, mf = lays[0], tops[0], mfs[0]
+            else:
+                glay, e_top, mf = MergedLayout(lays, dev), torch.cat(tops, 0), torch.cat(mfs, 0)
+            tD = time.perf_counter()
+            res = eng.predict(glay, e_top, mf, topk, want_masks)
+            if len(chunks) == 1:
+                done = torch.cuda.Event()
+                done.record(cur)
+                self._lay_done[0] = done
+            st["prepare_ms"] += 1e3 * (tD - tC); st["launch_ms"] += 1e3 * (time.perf_counter() - tD)
+            if want_masks:
+                l0 = glay.levels[0]
+                res["masks"] = [res["masks"][int(l0.off[i]): int(l0.off[i]) + int(l0.len[i])] for i in range(glay.B)]
         self._net_stats = st
         return res
 

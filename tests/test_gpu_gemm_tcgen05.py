@@ -68,3 +68,40 @@ def test_gemm_bf16_large_persistent(ops):
     ref = a.float() @ w.float().t()
     torch.cuda.synchronize()
     assert float((out - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+BIG_LENS = [int(x) for x in torch.randint(40, 400, (90,), generator=torch.Generator().manual_seed(5))]
+
+
+@pytest.mark.parametrize("taps,act,res,corr,N,K,odt", [
+    (1, 0, 2, False, 512, 512, torch.float32),
+    (1, 2, 0, False, 2048, 512, torch.bfloat16),
+    (1, 0, 1, False, 512, 2048, torch.float32),
+    (3, 0, 0, True, 512, 1024, torch.float32),
+    (1, 0, 0, False, 512, 512, torch.bfloat16),
+    (1, 0, 1, False, 256, 512, torch.float32),
+])
+def test_gemm_bf16_cta_pairs(ops, taps, act, res, corr, N, K, odt):
+    """M >= 16384 rows: the cta_group::2 path (a CTA pair per 256-row tile), odd number of 128-row blocks included."""
+    tp = [512 if l > 256 else 256 for l in BIG_LENS]
+    lg, lc = PackLayout(BIG_LENS, tp, 4, "cuda"), PackLayout(BIG_LENS, tp, 4, "cpu")
+    streams = 1
+    M = streams * lc.levels[0].R
+    assert M >= 16384 and (M // 128) % 2 == 1, M
+    a = rnd((M, K), 1).to(torch.bfloat16)
+    a[(lc.levels[0].row_seq < 0).repeat(streams)] = 0
+    w = rnd((N, taps * K), 2, K ** -0.5).to(torch.bfloat16)
+    bias = rnd((N,), 3)
+    r1 = rnd((M, N), 4) if res >= 1 else None
+    r2 = rnd((M, N), 5) if res >= 2 else None
+    cv = rnd((N,), 6) if corr else None
+    ref = torch.empty(M, N)
+    EmuOps().gemm(a, w, ref, bias=bias, taps=taps, act=act, res1=r1, res2=r2, corr=cv, lay=lc.levels[0], streams=streams)
+    out = torch.full((M, N), 3.0, dtype=odt, device="cuda")
+    cu = lambda t: None if t is None else t.cuda()
+    ops.gemm(a.cuda(), w.cuda(), out, bias=bias.cuda(), taps=taps, act=act, res1=cu(r1), res2=cu(r2), corr=cu(cv), lay=lg.levels[0],
+             streams=streams)
+    torch.cuda.synchronize()
+    err = float((out.float().cpu() - ref).abs().max())
+    tol = 2e-3 if odt == torch.float32 else 2e-2
+    assert err <= tol * float(ref.abs().max()), f"max abs err {err:.3e} vs scale {float(ref.abs().max()):.3e}"

@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -81,6 +82,38 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+    // issued by both CTAs of a pair; the transaction bytes are credited to the barrier at `bar_cluster_addr` (the leader's)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -165,9 +198,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                                // SWIZZLE_128B        bits [61,64)
     return d;
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128.
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = m (128, or 256 for a CTA pair).
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct EpiArgs {
@@ -177,6 +210,11 @@ struct EpiArgs {
     const float* corr; const int* row_seq; const int4* seqinfo; int R;
 };
 
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of two SMs of one TPC) shares a 256 x BN tile through
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A but only HALF of the W tile, and keeps its 128 accumulator
+// rows in its own TMEM, so the shared-memory fill per FLOP (the L2 -> SM traffic that bounds the K = 512 GEMMs) drops by a third.
+// Only the leader CTA (rank 0) issues MMAs; its commits arrive on the barriers of both CTAs.
+template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, EpiArgs e, int K,
@@ -184,7 +222,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: stages of A, stages of W, epilogue staging boxes, barriers, bias / correction vectors
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int w_stage_bytes = block_n * BLOCK_K * 2;
+    const int w_stage_bytes = (block_n / CG) * BLOCK_K * 2;       // each CTA of a pair holds block_n / CG rows of the W tile
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+    const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;   // tiles are walked by clusters
     uint8_t* smem_a = smem;
     uint8_t* smem_w = smem + stages * A_STAGE_BYTES;
     uint8_t* staging = smem_w + stages * w_stage_bytes;          // 1024-aligned: every stage size is a multiple of 1024
@@ -200,7 +240,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_n = e.N / block_n;
-    const int n_tiles = (e.M / BLOCK_M) * n_tiles_n;
+    const int n_tiles = ((e.M + BLOCK_M * CG - 1) / (BLOCK_M * CG)) * n_tiles_n;
     const int kb_per_tap = K / BLOCK_K;
     const int num_kb = taps * kb_per_tap;
 
@@ -210,41 +250,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS * CG); }
         for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&resbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles_n) * BLOCK_M, n0 = (tile % n_tiles_n) * block_n;
+            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+                const int m0 = (tile / n_tiles_n) * (BLOCK_M * CG) + cta_rank * BLOCK_M;
+                const int n0 = (tile % n_tiles_n) * block_n + cta_rank * (block_n / CG);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], A_STAGE_BYTES + w_stage_bytes);
+                    // the leader's barrier collects the bytes of both CTAs of a pair
+                    if (cta_rank == 0) mbar_expect_tx(&full[stage], CG * (A_STAGE_BYTES + w_stage_bytes));
                     const int tap = kb / kb_per_tap;
                     const int ka = (kb - tap * kb_per_tap) * BLOCK_K;
                     const int row = m0 + (taps == 3 ? tap - 1 : 0);
-                    tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full[stage], ka, row);
-                    tma_load_2d(smem_w + stage * w_stage_bytes, &map_w, &full[stage], kb * BLOCK_K, n0);
+                    if constexpr (CG == 2) {
+                        const uint32_t bar = mapa_shared(smem_u32(&full[stage]), 0);
+                        tma_load_2d_cg2(smem_a + stage * A_STAGE_BYTES, &map_a, bar, ka, row);
+                        tma_load_2d_cg2(smem_w + stage * w_stage_bytes, &map_w, bar, kb * BLOCK_K, n0);
+                    } else {
+                        tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full[stage], ka, row);
+                        tma_load_2d(smem_w + stage * w_stage_bytes, &map_w, &full[stage], kb * BLOCK_K, n0);
+                    }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(block_n);
+        if (lane == 0 && cta_rank == 0) {
+            const uint32_t idesc = make_idesc(block_n, BLOCK_M * CG);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(&tempty[as], aphase ^ 1);
@@ -258,12 +311,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
-                        umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (CG == 2) umma_bf16_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);          // frees the smem stage once these MMAs have read it
+                    // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+                    if constexpr (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[as]);                 // accumulator stage complete
+                if constexpr (CG == 2) umma_commit_cg2(&tfull[as]); else umma_commit(&tfull[as]);   // accumulator stage complete
             }
         }
     } else if (warp >= EPI_WARP0) {
@@ -276,14 +331,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint64_t* my_resbar = resbar + 2 * ew;
         int it = 0;
         uint32_t box_cnt = 0;                            // boxes alternate across chunks AND tiles (no-residual path)
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int m0 = (tile / n_tiles_n) * BLOCK_M, n0 = (tile % n_tiles_n) * block_n;
+            const int m0 = (tile / n_tiles_n) * (BLOCK_M * CG) + cta_rank * BLOCK_M, n0 = (tile % n_tiles_n) * block_n;
             const int row0 = m0 + wq * 32, row = row0 + lane;
             const int col0 = n0 + half * (block_n / 2);
-            bool valid = true, add_corr = false;
-            if (e.row_seq != nullptr) {
+            bool valid = row < e.M, add_corr = false;     // a pair's second half can lie past M (loads zero-filled, stores clipped)
+            if (e.row_seq != nullptr && valid) {
                 const int rl = row % e.R;
                 const int seq = e.row_seq[rl];
                 valid = seq >= 0;
@@ -322,7 +377,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (c == n_ch - 1) {                     // accumulator fully read: hand the TMEM stage back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[as]);
+                    if (lane == 0) {
+                        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[as]), 0));   // the leader issues the MMAs
+                        else mbar_arrive(&tempty[as]);
+                    }
                 }
                 const int n = col0 + c * CHUNK;
                 float v[CHUNK];
@@ -393,10 +451,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) bulk_wait_all();                  // all output boxes written before the CTA retires
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // neither CTA of a pair retires while the other still uses it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+        if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
 
@@ -438,6 +497,8 @@ const char* gemm_tcgen05_error() { return g_err; }
 int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     static int num_sms = 0;
     static bool attr_set = false;
+    static int force_cg = -1;
+    if (force_cg < 0) { const char* v = getenv("VRD_GEMM_CG"); force_cg = v ? atoi(v) : 0; }
     if (g.M % BLOCK_M != 0 || g.K % BLOCK_K != 0 || g.N % 64 != 0 || g.lda % 8 != 0 || ((uintptr_t)g.A & 15) != 0) {
         snprintf(g_err, sizeof g_err, "gemm_tcgen05: unsupported shape M=%d N=%d K=%d lda=%lld (need M%%128, K%%64, N%%64 == 0)",
                  g.M, g.N, g.K, g.lda);
@@ -470,10 +531,12 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    // CTA pairs when there are enough rows to keep every pair busy (small query-decoder GEMMs keep one CTA per tile)
+    const int cg = force_cg == 1 ? 1 : ((force_cg == 2 || g.M >= 128 * 2 * 64) ? 2 : 1);
     CUtensorMap map_a, map_w, map_out, map_res;
     const long long kk = (long long)g.taps * g.K;
     if (!make_map(&map_a, g.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    if (!make_map(&map_w, g.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, kk, kk, block_n, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (!make_map(&map_w, g.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, kk, kk, block_n / cg, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (g.out_dtype == VRD_BF16) {
         if (!make_map(&map_out, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     } else {
@@ -484,22 +547,43 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     } else {
         map_res = map_out;
     }
-    const int stage_bytes = A_STAGE_BYTES + block_n * BLOCK_K * 2;
+    const int stage_bytes = A_STAGE_BYTES + (block_n / cg) * BLOCK_K * 2;
     const int fixed = 1024 + STAGING_TOTAL + 1024 + 2 * MAX_N * 4;   // alignment slack, staging, barriers, bias + corr
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     const int smem = fixed + stages * stage_bytes;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
             snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(max dynamic smem) failed");
             return 1;
         }
         attr_set = true;
     }
     EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R};
-    const int n_tiles = (g.M / BLOCK_M) * (g.N / block_n);
-    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem, st>>>(map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages);
+    const int n_tiles = ((g.M + BLOCK_M * cg - 1) / (BLOCK_M * cg)) * (g.N / block_n);
+    const int max_groups = num_sms / cg;
+    const int grid = cg * (n_tiles < max_groups ? n_tiles : max_groups);
+    if (cg == 1) {
+        gemm_tcgen05_kernel<1><<<grid, NUM_THREADS, smem, st>>>(map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages);
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages) != cudaSuccess) {
+        snprintf(g_err, sizeof g_err, "cluster launch of gemm_tcgen05_kernel<2> failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
     return 0;
 }
 

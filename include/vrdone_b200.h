@@ -119,6 +119,37 @@ int vrd_mask_logits(const float* mask_embed, int64_t ldm, const float* mask_feat
 int vrd_softmax_topk(const float* logits, int64_t ldl, int nrows, int n_cls, int topk, float* scores, int32_t* ids,
                      vrd_stream_t stream);
 
+/* ---- native backbone schedule ------------------------------------------------------------------------------------
+ * Replaces the per-operator Python schedule for MaskConvTransformerBackbone.forward + FPN1D_Fuse.forward
+ * (backbones.py:154-248 / 323-436, fpns.py:229-257) of one chunk of packed pairs: the same kernels in the same order,
+ * issued from C++ (one call instead of ~100 ctypes calls).  The query decoder and the heads stay per-operator. */
+#define VRD_MAX_LEVELS 8
+typedef struct {
+    int32_t visual_dim, clip_dim /* 0: no CLIP stream */, bbox_so_dim, bbox_entity_dim, embd_dim, n_head, fuse_head;
+    int32_t n_conv, n_stem, n_branch, win /* n_mha_win_size */, use_local, fpn_dim, act_dtype /* VRD_F32 | VRD_BF16 */;
+} vrd_model_cfg_t;
+typedef struct {
+    const int32_t* row_seq; /* device, R entries */
+    const int32_t* seqinfo; /* device, B x 4 */
+    int32_t R, B, max_len;
+} vrd_level_t;
+typedef struct vrd_engine vrd_engine_t;
+
+const char* vrd_engine_last_error(void);
+/* names[i] / ptrs[i]: kernel-layout weights of engine.PackedWeights (device pointers) with their 2-D shape rows[i] x cols[i]. */
+int vrd_engine_create(const vrd_model_cfg_t* cfg, const char* const* names, const void* const* ptrs, const int32_t* rows,
+                      const int32_t* cols, int n, vrd_engine_t** out);
+void vrd_engine_destroy(vrd_engine_t* engine);
+int64_t vrd_engine_launches(const vrd_engine_t* engine);   /* kernels launched so far through this engine */
+/* levels: n_branch + 1 entries.  Workspace need of vrd_backbone_pack + vrd_backbone_compute for this chunk (-1 on error). */
+int64_t vrd_backbone_workspace_bytes(vrd_engine_t* engine, const vrd_level_t* levels);
+/* pack kernel only (vrd_pack_pairs into the head of the workspace); the caller may recycle the pair tensors once it has run */
+int vrd_backbone_pack(vrd_engine_t* engine, const vrd_level_t* levels, const void* pair_ptrs, const int64_t* pair_strides,
+                      int token_major, void* workspace, int64_t workspace_bytes, vrd_stream_t stream);
+/* everything after the pack: e_top [R_top, embd_dim] fp32 (coarsest level), mask_feat [R_0, fpn_dim] fp32 */
+int vrd_backbone_compute(vrd_engine_t* engine, const vrd_level_t* levels, void* workspace, int64_t workspace_bytes, float* e_top,
+                         float* mask_feat, vrd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

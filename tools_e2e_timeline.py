@@ -13,6 +13,9 @@ model._config_eval(cfg["inference_config"])
 video = synth.synthetic_video(cfg, 0, n_tracklets=40, n_frames=1200)
 pinned = dict(video)
 pinned["so_features_list"] = [t.t().contiguous().pin_memory().t() for t in video["so_features_list"]]
+import os as _os
+if _os.environ.get('H2D_CHUNK'): model.h2d_chunk_rows = int(_os.environ['H2D_CHUNK'])
+if _os.environ.get('H2D_EDGE'): model.h2d_edge_rows = int(_os.environ['H2D_EDGE'])
 for _ in range(3):
     model(pinned)
 eng = model._get_engine()

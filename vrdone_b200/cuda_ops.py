@@ -44,8 +44,21 @@ _SIGNATURES = {
 }
 
 
+class ModelCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("visual_dim", "clip_dim", "bbox_so_dim", "bbox_entity_dim", "embd_dim", "n_head", "fuse_head",
+                                         "n_conv", "n_stem", "n_branch", "win", "use_local", "fpn_dim", "act_dtype")]
+
+
+class Level(C.Structure):
+    _fields_ = [("row_seq", C.c_void_p), ("seqinfo", C.c_void_p), ("R", C.c_int32), ("B", C.c_int32), ("max_len", C.c_int32)]
+
+
+_ENGINE_SYMBOLS = ["vrd_engine_last_error", "vrd_engine_create", "vrd_engine_destroy", "vrd_engine_launches",
+                   "vrd_backbone_workspace_bytes", "vrd_backbone_pack", "vrd_backbone_compute"]
+
+
 def exported_symbols():
-    return list(_SIGNATURES) + ["vrd_last_error"]
+    return list(_SIGNATURES) + ["vrd_last_error"] + _ENGINE_SYMBOLS
 
 
 def load_library() -> C.CDLL:
@@ -63,6 +76,21 @@ def load_library() -> C.CDLL:
         fn.restype = C.c_int
     lib.vrd_last_error.argtypes = []
     lib.vrd_last_error.restype = C.c_char_p
+    lib.vrd_engine_last_error.argtypes = []
+    lib.vrd_engine_last_error.restype = C.c_char_p
+    lib.vrd_engine_create.argtypes = [C.POINTER(ModelCfg), C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_void_p)]
+    lib.vrd_engine_create.restype = C.c_int
+    lib.vrd_engine_destroy.argtypes = [C.c_void_p]
+    lib.vrd_engine_destroy.restype = None
+    lib.vrd_engine_launches.argtypes = [C.c_void_p]
+    lib.vrd_engine_launches.restype = C.c_int64
+    lib.vrd_backbone_workspace_bytes.argtypes = [C.c_void_p, C.POINTER(Level)]
+    lib.vrd_backbone_workspace_bytes.restype = C.c_int64
+    lib.vrd_backbone_pack.argtypes = [C.c_void_p, C.POINTER(Level), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.vrd_backbone_pack.restype = C.c_int
+    lib.vrd_backbone_compute.argtypes = [C.c_void_p, C.POINTER(Level), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vrd_backbone_compute.restype = C.c_int
     if lib.vrd_abi_version() != 2:
         raise RuntimeError("libvrdone_b200.so ABI version mismatch; rebuild")
     _lib = lib
@@ -312,3 +340,70 @@ class CudaOps:
         assert ids.dtype == torch.int32 and scores.dtype == torch.float32 and ids.is_contiguous() and scores.is_contiguous()
         self._check(self.lib.vrd_softmax_topk(lp, ldl, nrows, n_cls, topk, scores.data_ptr(), ids.data_ptr(), self._stream()),
                     "vrd_softmax_topk")
+
+
+class NativeBackbone:
+    """The C++ schedule of backbone + FPN (csrc/engine.cu): same kernels and order as ``engine.Engine.backbone``, issued by one
+    C call per chunk.  Owns the name -> pointer table of the packed weights and a persistent activation workspace."""
+
+    def __init__(self, ops: CudaOps, weights, mc: dict):
+        self.ops, self.lib, self.weights = ops, ops.lib, weights          # ``weights`` keeps the device tensors alive
+        self.device = weights.device
+        clip = bool(mc.get("with_clip_feature", False))
+        n_conv, n_stem, n_branch = mc["backbone_arch"]
+        self.n_levels = n_branch + 1
+        self.C, self.F = mc["embd_dim"], mc["fpn_dim"]
+        cfg = ModelCfg(mc["visual_dim"], mc["clip_dim"] if clip else 0, mc["bbox_so_dim"], mc["bbox_entity_dim"], mc["embd_dim"],
+                       mc["n_head"], mc["fuse_head"], n_conv, n_stem, n_branch, mc["n_mha_win_size"], int(bool(mc["use_local"])),
+                       mc["fpn_dim"], BF16 if weights.adt == torch.bfloat16 else F32)
+        names = sorted(weights.t)
+        n = len(names)
+        c_names = (C.c_char_p * n)(*[k.encode() for k in names])
+        c_ptrs = (C.c_void_p * n)(*[weights.t[k].data_ptr() for k in names])
+        c_rows = (C.c_int32 * n)(*[weights.t[k].shape[0] for k in names])
+        c_cols = (C.c_int32 * n)(*[(weights.t[k].shape[1] if weights.t[k].dim() > 1 else 1) for k in names])
+        handle = C.c_void_p()
+        if self.lib.vrd_engine_create(C.byref(cfg), c_names, c_ptrs, c_rows, c_cols, n, C.byref(handle)) != 0:
+            raise RuntimeError(f"vrd_engine_create failed: {self.lib.vrd_engine_last_error().decode()}")
+        self.handle = handle
+        self.workspace: Optional[torch.Tensor] = None
+        self._counted = 0
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.vrd_engine_destroy(self.handle)
+            self.handle = None
+
+    def _levels(self, lay):
+        arr = (Level * self.n_levels)()
+        for i, lv in enumerate(lay.levels):
+            arr[i].row_seq, arr[i].seqinfo = lv.row_seq.data_ptr(), lv.seqinfo.data_ptr()
+            arr[i].R, arr[i].B, arr[i].max_len = lv.R, lv.B, lv.max_len
+        return arr
+
+    def _fail(self, what):
+        raise RuntimeError(f"{what} failed: {self.lib.vrd_engine_last_error().decode()}")
+
+    def backbone(self, lay, pair_ptrs, pair_strides, after_pack=None, token_major=False):
+        """-> (e_top [R_top, C] fp32, mask features [R_0, F] fp32), both fresh tensors."""
+        lv = self._levels(lay)
+        need = self.lib.vrd_backbone_workspace_bytes(self.handle, lv)
+        if need < 0:
+            self._fail("vrd_backbone_workspace_bytes")
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = None                                           # release before growing
+            self.workspace = torch.empty(int(need * 1.1) + (1 << 20), dtype=torch.uint8, device=self.device)
+        ws, nbytes = self.workspace.data_ptr(), self.workspace.numel()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.lib.vrd_backbone_pack(self.handle, lv, _p(pair_ptrs), _p(pair_strides), int(token_major), ws, nbytes, stream) != 0:
+            self._fail("vrd_backbone_pack")
+        if after_pack is not None:
+            after_pack()
+        e_top = torch.empty(lay.levels[-1].R, self.C, dtype=torch.float32, device=self.device)
+        mf = torch.empty(lay.levels[0].R, self.F, dtype=torch.float32, device=self.device)
+        if self.lib.vrd_backbone_compute(self.handle, lv, ws, nbytes, e_top.data_ptr(), mf.data_ptr(), stream) != 0:
+            self._fail("vrd_backbone_compute")
+        total = int(self.lib.vrd_engine_launches(self.handle))
+        self.ops.launches += total - self._counted
+        self._counted = total
+        return e_top, mf

@@ -60,11 +60,13 @@ class MaskVRD(nn.Module):
         # B200 execution state
         self.precision = config.get("precision", "bf16")   # "bf16" (tcgen05 tensor cores) or "fp32" (CUDA-core fp32)
         self.max_rows = int(config.get("max_rows", 196608))  # level-0 rows processed per engine call (bounds workspace)
-        self.h2d_chunk_rows = int(config.get("h2d_chunk_rows", 36864))  # rows per chunk when pair features arrive from the host
+        self.h2d_chunk_rows = int(config.get("h2d_chunk_rows", 24576))  # rows per chunk when pair features arrive from the host
         self.h2d_edge_rows = int(config.get("h2d_edge_rows", 8192))     # ... and of the first / last chunk (not overlapped)
         self._lay_bufs = [None] * 4       # persistent device buffers for the per-chunk layout arrays + pair tables
         self._lay_done = [None] * 4
         self.gc_park_results = bool(config.get("gc_park_results", True))
+        self.use_native = bool(config.get("use_native", True))            # C++ backbone schedule (csrc/engine.cu)
+        self._native = None
         self._copy_stream = None
         self._staging = [None, None]      # double-buffered device staging of host-resident pair tensors
         self._pack_done = [None, None]
@@ -103,6 +105,7 @@ class MaskVRD(nn.Module):
 
     def invalidate(self):
         self._engine = None
+        self._native = None
 
     def load_state_dict(self, *a, **k):
         self.invalidate()
@@ -128,6 +131,8 @@ class MaskVRD(nn.Module):
             adt = torch.bfloat16 if self.precision == "bf16" else torch.float32
             with torch.cuda.device(dev):
                 self._engine = Engine(PackedWeights(self.state_dict(), self.config, dev, adt), self._ops)
+                from .cuda_ops import NativeBackbone
+                self._native = NativeBackbone(self._ops, self._engine.w, self.config)
             self._engine_key = key
         return self._engine
 
@@ -281,7 +286,9 @@ class MaskVRD(nn.Module):
                         e.record(cur)
                         self._pack_done[slot] = e
                 # backbone + FPN chunk by chunk; the query decoder and the heads (~100 small launches) run once over all chunks
-                e_top, mf = eng.backbone(lay, ptrs, strides, after_pack=packed, token_major=token_major)
+                # (the C++ schedule; ``use_native = False`` runs the same kernels through the per-operator Python schedule)
+                run = self._native.backbone if (self.use_native and eng.taps is None) else eng.backbone
+                e_top, mf = run(lay, ptrs, strides, after_pack=packed, token_major=token_major)
                 if len(chunks) > 1:
                     done = torch.cuda.Event()
                     done.record(cur)

@@ -474,8 +474,11 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_kernel(const TI* __re
 // ------------------------------------------------------------------------------------------------------------
 constexpr int DWT_TILE = 32;
 constexpr int DWT_ROWS = DWT_TILE + 2;
-constexpr int DWT_WARPS = 16;
-constexpr int DWT_SMEM = 2 * DWT_ROWS * 512 * 4 + 2 * 48 * 4 + 32;
+constexpr int DWT_WARPS = 8;
+constexpr int DWT_RPW = DWT_TILE / DWT_WARPS;     // consecutive output rows per warp (4): parameter loads are shared between them
+constexpr int DWT_TILE_BYTES = DWT_ROWS * 512 * 4;
+// two TMA buffers of raw rows [+ one tile of normalised rows when a branch needs both] + a zero row + a beta row + barriers
+constexpr int dwt_smem_bytes(bool mixed) { return (mixed ? 3 : 2) * DWT_TILE_BYTES + 2 * 512 * 4 + 32; }
 
 template <typename TO, int NB, int PREMASK>
 __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const float* __restrict__ x, Lay lay,
@@ -485,11 +488,13 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
     constexpr int NCH = 4, C = 512;
     constexpr bool ANY_PRE = PREMASK != 0;
     constexpr bool ALL_PRE = PREMASK == ((1 << NB) - 1);         // no branch reads the raw row: normalise in place
+    constexpr bool MIXED = ANY_PRE && !ALL_PRE;                  // normalised rows go to their own tile
     extern __shared__ __align__(128) uint8_t dwt_smem[];
     float* sx_all = reinterpret_cast<float*>(dwt_smem);          // [2][DWT_ROWS][C]; row i <-> physical row r0 - 1 + i
-    float* s_mean = sx_all + 2 * DWT_ROWS * C;                   // [48]
-    float* s_rstd = s_mean + 48;                                 // [48]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_rstd + 48);   // [2]
+    float* s_nrm = sx_all + 2 * DWT_ROWS * C;                    // [DWT_ROWS][C] (MIXED only)
+    float* s_zero = s_nrm + (MIXED ? DWT_ROWS * C : 0);          // [C] zeros: taps outside the pair
+    float* s_beta = s_zero + C;                                  // [C] LN_pre bias: the first pad column
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + C);    // [2]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_tiles = total_rows / DWT_TILE;
     const uint32_t bar_u = (uint32_t)__cvta_generic_to_shared(bars);
@@ -509,11 +514,16 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if ((int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
     }
+    for (int i = threadIdx.x; i < C; i += DWT_WARPS * 32) {
+        s_zero[i] = 0.f;
+        s_beta[i] = ANY_PRE ? pre_b[i] : 0.f;
+    }
     __syncthreads();                                             // barriers initialised before anyone polls them
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         float* sx = sx_all + buf * DWT_ROWS * C;
+        const float* sn = MIXED ? s_nrm : sx;                    // where the normalised rows live
         const int r0 = tile * DWT_TILE;
         const int lo = max(r0 - 1, 0), hi = min(r0 + DWT_TILE + 1, total_rows);
         if (threadIdx.x == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);   // freed by the trailing sync
@@ -531,105 +541,106 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
                 if (p < lo || p >= hi) continue;
                 float v[NCH][4];
                 load_row<float, NCH>(sx + i * C, lane, v);
-                if constexpr (ALL_PRE) {
-                    row_normalize<NCH>(v, lane, pre_g, pre_b);
-                    store_row<float, NCH>(sx + i * C, lane, v);
-                } else {
-                    float mean, rstd;
-                    row_stats<NCH>(v, mean, rstd);
-                    if (lane == 0) { s_mean[i] = mean; s_rstd[i] = rstd; }
-                }
+                row_normalize<NCH>(v, lane, pre_g, pre_b);
+                store_row<float, NCH>((MIXED ? s_nrm : sx) + i * C, lane, v);
             }
             __syncthreads();
         }
-        for (int rr = warp; rr < DWT_TILE; rr += DWT_WARPS) {
-            const int grow = r0 + rr;
-            const int s = grow / lay.R, r = grow - s * lay.R;
-            const int seq = lay.row_seq[r];
-            if (seq < 0) {
+        // Each warp owns DWT_RPW consecutive output rows.  The per-channel parameters (conv taps, LayerNorm gamma / beta) are
+        // per-lane vectors that do not fit in registers for all branches, so they are re-read from L1 for every use: sharing
+        // each read between the warp's rows is what keeps the kernel off the L1 bandwidth limit (it moved ~30 KB of parameters
+        // per 5 KB of row data before).  Taps are branch-free: a tap outside the pair reads the zero row, the first pad column
+        // the beta row.
+        {
+            const int rr0 = warp * DWT_RPW;
+            // 32-bit shared-memory byte addresses of the three taps of every row, in the raw and in the normalised tile
+            uint32_t araw[DWT_RPW][3], anrm[DWT_RPW][3];
+            bool live[DWT_RPW];
+            const uint32_t sx_u = (uint32_t)__cvta_generic_to_shared(sx), sn_u = (uint32_t)__cvta_generic_to_shared(sn);
+            const uint32_t zero_u = (uint32_t)__cvta_generic_to_shared(s_zero), beta_u = (uint32_t)__cvta_generic_to_shared(s_beta);
 #pragma unroll
-                for (int b = 0; b < NB; ++b) zero_row<TO, NCH>((TO*)br.out[b] + (long long)grow * br.ldo[b], lane);
-                continue;
+            for (int u = 0; u < DWT_RPW; ++u) {
+                const int grow = r0 + rr0 + u;
+                const int s = grow / lay.R, r = grow - s * lay.R;
+                const int seq = lay.row_seq[r];
+                live[u] = seq >= 0;
+                int4 si = make_int4(0, 0, 0, 0);
+                if (live[u]) si = lay.seqinfo[seq];
+                const int t = r - si.x;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const int tt = t + d - 1;
+                    const bool inside = live[u] && tt >= 0 && tt < si.y;
+                    const uint32_t row_off = (uint32_t)(rr0 + u + d) * C * 4;
+                    araw[u][d] = (inside ? sx_u + row_off : zero_u) + lane * 16;
+                    anrm[u][d] = (inside ? sn_u + row_off : ((live[u] && tt == si.y && si.z != 0) ? beta_u : zero_u)) + lane * 16;
+                }
             }
-            const int4 si = lay.seqinfo[seq];
-            const int t = r - si.x;
-            float y[NB][NCH][4];
+#pragma unroll 1
+            for (int b = 0; b < NB; ++b) {
+                const bool pre = (PREMASK >> b) & 1;
+                const float* wb = br.w[b];
+                float y[DWT_RPW][NCH][4];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) row_zero<NCH>(y[b]);
+                for (int j = 0; j < NCH; ++j) {
+                    const int c = (j * 32 + lane) * 4;
+                    float w0[4], w1[4], w2[4];
+                    ld4(wb + c, w0); ld4(wb + C + c, w1); ld4(wb + 2 * C + c, w2);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const int tt = t + d - 1;
-                const bool inside = tt >= 0 && tt < si.y;
-                const bool padcol = ANY_PRE && tt == si.y && si.z != 0;    // first pad column: LN of a zero column is its bias
-                if (!inside && !padcol) continue;
-                float raw[NCH][4], nrm[NCH][4];
-                if constexpr (ALL_PRE) {
-                    load_row<float, NCH>(sx + (rr + d) * C, lane, nrm);    // staged separator row == beta
-                } else {
-                    if (inside) load_row<float, NCH>(sx + (rr + d) * C, lane, raw); else row_zero<NCH>(raw);
-                    if constexpr (ANY_PRE) {
-                        const float mean = s_mean[rr + d], rstd = s_rstd[rr + d];   // separator row: mean 0 -> nrm = beta
+                    for (int u = 0; u < DWT_RPW; ++u) {
+                        float a[3][4];
 #pragma unroll
-                        for (int j = 0; j < NCH; ++j) {
-                            float pg[4], pb[4];                  // L1-resident; not kept in registers across rows
-                            ld4(pre_g + (j * 32 + lane) * 4, pg);
-                            ld4(pre_b + (j * 32 + lane) * 4, pb);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) nrm[j][i] = (raw[j][i] - mean) * rstd * pg[i] + pb[i];
+                        for (int d = 0; d < 3; ++d) {
+                            const uint32_t addr = (pre ? anrm[u][d] : araw[u][d]) + j * 512;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(a[d][0]), "=f"(a[d][1]), "=f"(a[d][2]), "=f"(a[d][3]) : "r"(addr));
                         }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) y[u][j][i] = fmaf(a[2][i], w2[i], fmaf(a[1][i], w1[i], a[0][i] * w0[i]));
                     }
                 }
+                // post-conv LayerNorm of the warp's rows, reductions interleaved for instruction-level parallelism
+                float mean[DWT_RPW], rstd[DWT_RPW];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    if (!((PREMASK >> b) & 1) && !inside) continue;       // raw branches see zeros outside the pair
+                for (int u = 0; u < DWT_RPW; ++u) {
+                    float sm = 0.f;
 #pragma unroll
-                    for (int j = 0; j < NCH; ++j) {
-                        float w[4];
-                        ld4(br.w[b] + d * C + (j * 32 + lane) * 4, w);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) y[b][j][i] = fmaf(((PREMASK >> b) & 1) ? nrm[j][i] : raw[j][i], w[i], y[b][j][i]);
-                    }
+                    for (int j = 0; j < NCH; ++j) sm += (y[u][j][0] + y[u][j][1]) + (y[u][j][2] + y[u][j][3]);
+                    mean[u] = sm;
                 }
-            }
-            // post-conv LayerNorm of all branches, reductions interleaved for instruction-level parallelism
-            float mean[NB], rstd[NB];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                float sm = 0.f;
+                for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int j = 0; j < NCH; ++j) sm += (y[b][j][0] + y[b][j][1]) + (y[b][j][2] + y[b][j][3]);
-                mean[b] = sm;
-            }
+                    for (int u = 0; u < DWT_RPW; ++u) mean[u] += __shfl_xor_sync(FULL_MASK, mean[u], o);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
+                for (int u = 0; u < DWT_RPW; ++u) {
+                    mean[u] *= (1.0f / C);
+                    float q = 0.f;
 #pragma unroll
-                for (int b = 0; b < NB; ++b) mean[b] += __shfl_xor_sync(FULL_MASK, mean[b], o);
+                    for (int j = 0; j < NCH; ++j)
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                mean[b] *= (1.0f / C);
-                float q = 0.f;
+                        for (int i = 0; i < 4; ++i) { y[u][j][i] -= mean[u]; q = fmaf(y[u][j][i], y[u][j][i], q); }
+                    rstd[u] = q;
+                }
 #pragma unroll
-                for (int j = 0; j < NCH; ++j)
+                for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { const float dd = y[b][j][i] - mean[b]; q += dd * dd; }
-                rstd[b] = q;
-            }
+                    for (int u = 0; u < DWT_RPW; ++u) rstd[u] += __shfl_xor_sync(FULL_MASK, rstd[u], o);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int b = 0; b < NB; ++b) rstd[b] += __shfl_xor_sync(FULL_MASK, rstd[b], o);
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float rs = 1.0f / sqrtf(rstd[b] * (1.0f / C) + VRD_EPS);
+                for (int u = 0; u < DWT_RPW; ++u) rstd[u] = 1.0f / sqrtf(rstd[u] * (1.0f / C) + VRD_EPS);
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     float g[4], be[4];
                     ld4(br.g[b] + (j * 32 + lane) * 4, g);
                     ld4(br.b[b] + (j * 32 + lane) * 4, be);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) y[b][j][i] = (y[b][j][i] - mean[b]) * rs * g[i] + be[i];
+                    for (int u = 0; u < DWT_RPW; ++u)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) y[u][j][i] = live[u] ? y[u][j][i] * rstd[u] * g[i] + be[i] : 0.f;   // separator rows -> 0
                 }
-                store_row<TO, NCH>((TO*)br.out[b] + (long long)grow * br.ldo[b], lane, y[b]);
+#pragma unroll
+                for (int u = 0; u < DWT_RPW; ++u)
+                    store_row<TO, NCH>((TO*)br.out[b] + (long long)(r0 + rr0 + u) * br.ldo[b], lane, y[u]);
             }
         }
         if constexpr (ALL_PRE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before the next TMA fill
@@ -653,9 +664,10 @@ static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const flo
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
 #define LAUNCH(NB, MASK) do { \
         auto kern = dwconv_ln_tile_kernel<TO, NB, MASK>; \
+        constexpr int smem = dwt_smem_bytes(MASK != 0 && MASK != ((1 << NB) - 1)); \
         static bool attr_set = false; \
-        if (!attr_set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DWT_SMEM) != cudaSuccess) return 1; attr_set = true; } \
-        kern<<<grid, DWT_WARPS * 32, DWT_SMEM, st>>>(x, lay, pre_g, pre_b, br, total); } while (0)
+        if (!attr_set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1; attr_set = true; } \
+        kern<<<grid, DWT_WARPS * 32, smem, st>>>(x, lay, pre_g, pre_b, br, total); } while (0)
     if (br.n == 3 && mask == 7) LAUNCH(3, 7);
     else if (br.n == 3 && mask == 3) LAUNCH(3, 3);
     else if (br.n == 2 && mask == 0) LAUNCH(2, 0);

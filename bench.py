@@ -59,6 +59,17 @@ def peaks():
     return 1400.0, 1590.0, 6650.0, "fallback"
 
 
+def gemm_traffic(args):
+    """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the 118 launches of one forward)
+    from the committed ncu capture of the DEFAULT workload; None for any other workload or precision."""
+    path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    default = args.config == "vidor" and args.precision == "bf16" and args.tracklets == 40 and args.frames == 1200
+    if not (default and os.path.exists(path)):
+        return None
+    with open(path) as f:
+        return json.load(f)["traffic_bytes_per_launch"]
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -266,7 +277,7 @@ def main():
     ach = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     peak = sustained if args.precision == "bf16" else 75.0
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel" if args.precision == "bf16" else "gemm_simt_kernel",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": gemm_traffic(args),
                 "peak_source": f"{src} bf16 dense, sustained (burst {burst})" if args.precision == "bf16" else "nominal fp32 CUDA-core",
                 "launches": gemm["n"], "avg_launch_us": 1e3 * gemm["ms"] / max(1, gemm["n"]),
                 "share_of_step": gemm["ms"] / total_ms,

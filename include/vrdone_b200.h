@@ -146,6 +146,13 @@ int64_t vrd_backbone_workspace_bytes(vrd_engine_t* engine, const vrd_level_t* le
 /* pack kernel only (vrd_pack_pairs into the head of the workspace); the caller may recycle the pair tensors once it has run */
 int vrd_backbone_pack(vrd_engine_t* engine, const vrd_level_t* levels, const void* pair_ptrs, const int64_t* pair_strides,
                       int token_major, void* workspace, int64_t workspace_bytes, vrd_stream_t stream);
+/* SURVEY 8f row 1 -- the data loader's pair construction on the device (dataloaders/vidor.py:659-711, utils/misc.py:158-217)
+ * instead of vrd_backbone_pack: vis_all [T, visual_dim] / clip_all [T, clip_dim] / boxes_all [T, 4] fp32 hold every tracklet's
+ * frames back to back; pair_tab[i] = (row of the subject's first sub-sampled frame, same for the object, feat_stride, 0).
+ * Copies the two feature rows of every packed row and computes the 5-d relative and 8-d entity box features. */
+int vrd_backbone_pack_tracklets(vrd_engine_t* engine, const vrd_level_t* levels, const float* vis_all, const float* clip_all,
+                                const float* boxes_all, const int32_t* pair_tab, float video_w, float video_h, void* workspace,
+                                int64_t workspace_bytes, vrd_stream_t stream);
 /* everything after the pack: e_top [R_top, embd_dim] fp32 (coarsest level), mask_feat [R_0, fpn_dim] fp32 */
 int vrd_backbone_compute(vrd_engine_t* engine, const vrd_level_t* levels, void* workspace, int64_t workspace_bytes, float* e_top,
                          float* mask_feat, vrd_stream_t stream);

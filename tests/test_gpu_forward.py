@@ -167,3 +167,79 @@ def test_native_schedule_equals_python_schedule(name, precision):
         assert torch.equal(a[key], b[key]), key
     for ma, mb in zip(a["masks"], b["masks"]):
         assert torch.equal(ma, mb)
+
+
+@pytest.mark.parametrize("name,kw", [("vidvrd", {}), ("vidor", dict(n_tracklets=10, n_frames=600)), ("vidor_x", dict(n_tracklets=6, n_frames=400))])
+def test_tracklet_pack_matches_loader_built_pairs(name, kw):
+    """the pack stage fed from per-tracklet arrays must produce the operand rows the pair lists produce
+    (feature rows bit-exact; box-geometry channels to float rounding: logf / division order on the device vs the CPU)."""
+    from vrdone_b200.layout import PackLayout
+    cfg, model, sd = H.seeded_model(name, 7, precision="fp32")
+    model.to("cuda")
+    mc = cfg["model_config"]
+    trk = synth.synthetic_tracklet_video(cfg, 4, **kw)
+    vid = synth.synthetic_video(cfg, 4, **kw)
+    st = cfg["dataset_config"]["feat_stride"]
+    eng = model._get_engine()
+    nat = model._native
+    keep, L, s_off, o_off = model.pair_table(trk["traj_durations"].numpy(), trk["sids"].numpy(), trk["oids"].numpy(), st, 0, 0)
+    lens = L.tolist()
+    tpads = reference_padded_lengths(lens, mc)
+    lay = PackLayout(lens, tpads, model.n_levels, "cuda")
+    import numpy as np
+    n_frames = np.array([v.shape[0] for v in trk["visual_features_list"]])
+    base = np.cumsum(n_frames) - n_frames
+    tab = np.zeros((len(lens), 4), dtype=np.int32)
+    tab[:, 0] = base[trk["sids"].numpy()] + s_off
+    tab[:, 1] = base[trk["oids"].numpy()] + o_off
+    tab[:, 2] = st
+    vis_all = torch.cat(trk["visual_features_list"]).cuda()
+    clip_all = torch.cat(trk["clip_features_list"]).cuda() if "clip_features_list" in trk else None
+    boxes_all = torch.cat(trk["bboxes_list"]).cuda()
+    a_top, a_mf = nat.backbone_tracklets(lay, vis_all, clip_all, boxes_all, torch.from_numpy(tab).cuda(), trk["video_wh"])
+    feats = [f.cuda() for f in vid["so_features_list"]]
+    ptrs = torch.tensor([f.data_ptr() for f in feats], dtype=torch.int64).cuda()
+    strides = torch.tensor([[f.stride(0), f.stride(1)] for f in feats], dtype=torch.int64).cuda()
+    b_top, b_mf = nat.backbone(lay, ptrs, strides, token_major=True)
+    torch.cuda.synchronize()
+    assert H.rel_err(a_top, b_top) < 2e-5 and H.rel_err(a_mf, b_mf) < 2e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_tracklets_matches_forward_on_pair_lists(precision):
+    cfg, model, sd = H.seeded_model("vidor", 21, precision=precision)
+    model.to("cuda")
+    kw = dict(n_tracklets=8, n_frames=700)
+    trk = synth.synthetic_tracklet_video(cfg, 3, **kw)
+    vid = synth.synthetic_video(cfg, 3, **kw)
+    dev_vid = {k: ([t.cuda() for t in v] if isinstance(v, list) else (v.cuda() if torch.is_tensor(v) else v)) for k, v in vid.items()}
+    a = model(dev_vid)
+    b = model.forward_tracklets(trk, cfg["dataset_config"])
+    assert len(a["triplets"]) == len(b["triplets"])
+    same = [x == y and u == v and p == q for x, y, u, v, p, q in
+            zip(a["triplets"], b["triplets"], a["pred_durations"], b["pred_durations"], a["so_tids"], b["so_tids"])]
+    # the box-geometry channels differ in the last bit (logf / division on the device vs the CPU); on the bf16 path that can
+    # flip the rounding of an embedding and with it the order of near-tied candidates
+    assert np.mean(same) > (0.98 if precision == "fp32" else 0.9)
+    assert np.allclose(np.array(a["triple_scores_avg"]), np.array(b["triple_scores_avg"]), atol=1e-3 if precision == "fp32" else 1e-2)
+    for ta, tb, ok in zip(a["so_trajs"], b["so_trajs"], same):
+        if ok:
+            assert ta == tb
+
+
+def test_forward_returns_none_without_candidates_and_handles_many_slices():
+    """More pairs than max_so_pair (several 200-pair slices with their own long-pair padding) against the oracle, and the
+    ``None`` result when no candidate passes ``pred_min_frames`` (reference maskvrd.py:311-312)."""
+    cfg, model, sd = H.seeded_model("vidvrd", 11, precision="fp32")
+    model.to("cuda")
+    video = synth.synthetic_video(cfg, 5, n_tracklets=17, n_frames=150)
+    assert len(video["sids"]) > 200 and max(int(f.shape[1]) for f in video["so_features_list"]) > cfg["model_config"]["max_seq_len"]
+    dev_video = {k: ([t.cuda() for t in v] if isinstance(v, list) else (v.cuda() if torch.is_tensor(v) else v)) for k, v in video.items()}
+    out = model(dev_video)
+    ref = O.forward_test(video, sd, cfg["model_config"], cfg["inference_config"])
+    assert len(out["triplets"]) == len(ref["triplets"])
+    same = [x == y and u == v and p == q for x, y, u, v, p, q in
+            zip(out["triplets"], ref["triplets"], out["pred_durations"], ref["pred_durations"], out["so_tids"], ref["so_tids"])]
+    assert np.mean(same) > 0.98
+    model.pred_min_frames = 10 ** 6
+    assert model(dev_video) is None

@@ -390,6 +390,30 @@ int vrd_backbone_pack(vrd_engine_t* e, const vrd_level_t* levels, const void* pa
     return 0;
 }
 
+int vrd_backbone_pack_tracklets(vrd_engine_t* e, const vrd_level_t* levels, const float* vis_all, const float* clip_all,
+                                const float* boxes_all, const int32_t* pair_tab, float video_w, float video_h, void* workspace,
+                                int64_t workspace_bytes, vrd_stream_t stream) {
+    Arena a{(char*)workspace, (size_t)workspace_bytes, 0, 0, false};
+    Run r{e, levels, (cudaStream_t)stream, &a, e->cfg.act_dtype, false};
+    Mat vis, clp, bso, bent;
+    r.pack_buffers(vis, clp, bso, bent);
+    if (a.peak > a.cap) { snprintf(t_eng_err, sizeof t_eng_err, "vrd_backbone_pack_tracklets: workspace too small"); return 1; }
+    const vrd_model_cfg_t& c = e->cfg;
+    if (c.bbox_so_dim != 5 || c.bbox_entity_dim != 8) {
+        snprintf(t_eng_err, sizeof t_eng_err, "vrd_backbone_pack_tracklets: geometry features are 5 + 8 + 8 channels");
+        return 1;
+    }
+    if (c.clip_dim > 0 && clip_all == nullptr) { snprintf(t_eng_err, sizeof t_eng_err, "vrd_backbone_pack_tracklets: CLIP features missing"); return 1; }
+    if (vrd::pack_tracklets(vis_all, clip_all, boxes_all, pair_tab, r.lay(0), c.visual_dim, c.clip_dim, video_w, video_h, vis.p, clp.p,
+                            e->cfg.act_dtype, (float*)bso.p, (float*)bent.p, (cudaStream_t)stream)) {
+        snprintf(t_eng_err, sizeof t_eng_err, "vrd_backbone_pack_tracklets: feature dims must be multiples of 4");
+        return 1;
+    }
+    r.check("pack_tracklets");
+    if (r.fail) { snprintf(t_eng_err, sizeof t_eng_err, "%s", e->err); return 1; }
+    return 0;
+}
+
 int vrd_backbone_compute(vrd_engine_t* e, const vrd_level_t* levels, void* workspace, int64_t workspace_bytes, float* e_top,
                          float* mask_feat, vrd_stream_t stream) {
     {   // size check with the same schedule

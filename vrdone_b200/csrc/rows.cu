@@ -186,6 +186,115 @@ void pack_pairs(const void* ptrs, const long long* strides, Lay lay, int nv, int
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// pack_tracklets: the pair enumeration + feature gather of the reference DATA LOADER on the device (SURVEY 8f row 1;
+// dataloaders/vidor.py:659-711, utils/misc.py:158-217).  Per-tracklet features are uploaded once; a pair (s, o) is
+// described by the rows of its first sub-sampled frame in the concatenated tracklet arrays and the sub-sampling stride.
+// One warp per packed row: the lanes copy the two visual (and CLIP) rows, lanes 0..2 compute the 5-d relative and the two
+// 8-d entity box features with the reference's formulas and operation order (true divisions, logf).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void box_cwh(const float4 b, float& cx, float& cy, float& w, float& h) {
+    cx = (b.z + b.x) / 2; cy = (b.w + b.y) / 2; w = b.z - b.x; h = b.w - b.y;
+}
+// 8-d entity feature of frame t (sub-sampled sequence of length L): [cx, dcx, cy, dcy, w, dw, h, dh] of the box normalised by
+// the video size; d[t] = v[t] - v[t-1], d[0] extrapolated as d[1] - (d[2] - d[1]) (or d[1] when L == 2).
+__device__ __forceinline__ void entity_feature(const float4* __restrict__ boxes, long long row0, int stride, int t, int L, float vw,
+                                               float vh, float* out) {
+    auto norm = [&](int tt, float (&v)[4]) {
+        float4 b = boxes[row0 + (long long)tt * stride];
+        b.x = b.x / vw; b.z = b.z / vw; b.y = b.y / vh; b.w = b.w / vh;
+        box_cwh(b, v[0], v[1], v[2], v[3]);
+    };
+    float cur[4];
+    norm(t, cur);
+    float d[4];
+    if (t >= 1) {
+        float prev[4];
+        norm(t - 1, prev);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = cur[i] - prev[i];
+    } else {
+        float v1[4];
+        norm(1, v1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = v1[i] - cur[i];
+        if (L > 2) {
+            float v2[4];
+            norm(2, v2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float d2 = v2[i] - v1[i]; d[i] = d[i] - (d2 - d[i]); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { out[2 * i] = cur[i]; out[2 * i + 1] = d[i]; }
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(256) pack_tracklets_kernel(const float* __restrict__ vis_all, const float* __restrict__ clip_all,
+                                                             const float4* __restrict__ boxes_all, const int4* __restrict__ pair_tab,
+                                                             Lay lay, int nv, int nc, float vw, float vh, TA* __restrict__ vis,
+                                                             TA* __restrict__ clip, float* __restrict__ bso, float* __restrict__ bent) {
+    const int lane = threadIdx.x & 31;
+    const long long r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= lay.R) return;
+    const long long R = lay.R;
+    const int seq = lay.row_seq[r];
+    if (seq < 0) {
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = lane * 4; c < nv; c += 128) { st4(vis + r * nv + c, z); st4(vis + (R + r) * nv + c, z); }
+        for (int c = lane * 4; c < nc; c += 128) { st4(clip + r * nc + c, z); st4(clip + (R + r) * nc + c, z); }
+        if (lane < 8) { bso[r * 8 + lane] = 0.f; bent[r * 8 + lane] = 0.f; bent[(R + r) * 8 + lane] = 0.f; }
+        return;
+    }
+    const int4 si = lay.seqinfo[seq];
+    const int4 pt = pair_tab[seq];                   // (subject row of frame 0, object row of frame 0, stride, -)
+    const int t = (int)r - si.x, L = si.y, stride = pt.z;
+    const long long fs = (long long)pt.x + (long long)t * stride, fo = (long long)pt.y + (long long)t * stride;
+    for (int c = lane * 4; c < nv; c += 128) {
+        float a[4], b[4];
+        ld4(vis_all + fs * nv + c, a);
+        ld4(vis_all + fo * nv + c, b);
+        st4(vis + r * nv + c, a);
+        st4(vis + (R + r) * nv + c, b);
+    }
+    for (int c = lane * 4; c < nc; c += 128) {
+        float a[4], b[4];
+        ld4(clip_all + fs * nc + c, a);
+        ld4(clip_all + fo * nc + c, b);
+        st4(clip + r * nc + c, a);
+        st4(clip + (R + r) * nc + c, b);
+    }
+    if (lane == 0) {
+        float scx, scy, sw, sh, ocx, ocy, ow, oh;
+        box_cwh(boxes_all[fs], scx, scy, sw, sh);
+        box_cwh(boxes_all[fo], ocx, ocy, ow, oh);
+        float* o = bso + r * 8;
+        o[0] = (scx - ocx) / ocx;
+        o[1] = (scy - ocy) / ocy;
+        o[2] = logf(sw / ow);
+        o[3] = logf(sh / oh);
+        o[4] = logf((sw * sh) / (ow * oh));
+        o[5] = o[6] = o[7] = 0.f;
+    } else if (lane == 1) {
+        entity_feature(boxes_all, pt.x, stride, t, L, vw, vh, bent + r * 8);
+    } else if (lane == 2) {
+        entity_feature(boxes_all, pt.y, stride, t, L, vw, vh, bent + (R + r) * 8);
+    }
+}
+
+int pack_tracklets(const float* vis_all, const float* clip_all, const float* boxes_all, const int* pair_tab, Lay lay, int nv, int nc,
+                   float vw, float vh, void* vis, void* clip, int adt, float* bso, float* bent, cudaStream_t st) {
+    if ((nv & 3) || (nc & 3)) return 1;
+    const int grid = (lay.R + WARPS - 1) / WARPS;
+    if (adt == VRD_BF16)
+        pack_tracklets_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(vis_all, clip_all, (const float4*)boxes_all, (const int4*)pair_tab, lay, nv,
+                                                                   nc, vw, vh, (__nv_bfloat16*)vis, (__nv_bfloat16*)clip, bso, bent);
+    else
+        pack_tracklets_kernel<float><<<grid, 256, 0, st>>>(vis_all, clip_all, (const float4*)boxes_all, (const int4*)pair_tab, lay, nv, nc,
+                                                           vw, vh, (float*)vis, (float*)clip, bso, bent);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // layernorm (+ReLU): out = [relu](LN(x)), separator rows -> 0
 // ------------------------------------------------------------------------------------------------------------
 template <typename TI, typename TO, int NCH>

@@ -54,7 +54,7 @@ class Level(C.Structure):
 
 
 _ENGINE_SYMBOLS = ["vrd_engine_last_error", "vrd_engine_create", "vrd_engine_destroy", "vrd_engine_launches",
-                   "vrd_backbone_workspace_bytes", "vrd_backbone_pack", "vrd_backbone_compute"]
+                   "vrd_backbone_workspace_bytes", "vrd_backbone_pack", "vrd_backbone_pack_tracklets", "vrd_backbone_compute"]
 
 
 def exported_symbols():
@@ -89,6 +89,9 @@ def load_library() -> C.CDLL:
     lib.vrd_backbone_workspace_bytes.restype = C.c_int64
     lib.vrd_backbone_pack.argtypes = [C.c_void_p, C.POINTER(Level), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.vrd_backbone_pack.restype = C.c_int
+    lib.vrd_backbone_pack_tracklets.argtypes = [C.c_void_p, C.POINTER(Level), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                                C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.vrd_backbone_pack_tracklets.restype = C.c_int
     lib.vrd_backbone_compute.argtypes = [C.c_void_p, C.POINTER(Level), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vrd_backbone_compute.restype = C.c_int
     if lib.vrd_abi_version() != 2:
@@ -386,6 +389,24 @@ class NativeBackbone:
 
     def backbone(self, lay, pair_ptrs, pair_strides, after_pack=None, token_major=False):
         """-> (e_top [R_top, C] fp32, mask features [R_0, F] fp32), both fresh tensors."""
+        def pack(lv, ws, nbytes, stream):
+            if self.lib.vrd_backbone_pack(self.handle, lv, _p(pair_ptrs), _p(pair_strides), int(token_major), ws, nbytes, stream) != 0:
+                self._fail("vrd_backbone_pack")
+        return self._run(lay, pack, after_pack)
+
+    def backbone_tracklets(self, lay, vis_all, clip_all, boxes_all, pair_tab, video_wh):
+        """Same, with the pack stage gathering from per-tracklet arrays: vis_all [T, nv] / clip_all [T, nc] or
+        None / boxes_all [T, 4] fp32 and pair_tab [B, 4] int32 on the device."""
+        assert vis_all.dtype == torch.float32 and boxes_all.dtype == torch.float32 and pair_tab.dtype == torch.int32
+        assert boxes_all.shape[1] == 4 and pair_tab.shape == (lay.B, 4)
+
+        def pack(lv, ws, nbytes, stream):
+            if self.lib.vrd_backbone_pack_tracklets(self.handle, lv, _p(vis_all), _p(clip_all), _p(boxes_all), _p(pair_tab),
+                                                    float(video_wh[0]), float(video_wh[1]), ws, nbytes, stream) != 0:
+                self._fail("vrd_backbone_pack_tracklets")
+        return self._run(lay, pack, None)
+
+    def _run(self, lay, pack, after_pack):
         lv = self._levels(lay)
         need = self.lib.vrd_backbone_workspace_bytes(self.handle, lv)
         if need < 0:
@@ -395,8 +416,7 @@ class NativeBackbone:
             self.workspace = torch.empty(int(need * 1.1) + (1 << 20), dtype=torch.uint8, device=self.device)
         ws, nbytes = self.workspace.data_ptr(), self.workspace.numel()
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        if self.lib.vrd_backbone_pack(self.handle, lv, _p(pair_ptrs), _p(pair_strides), int(token_major), ws, nbytes, stream) != 0:
-            self._fail("vrd_backbone_pack")
+        pack(lv, ws, nbytes, stream)
         if after_pack is not None:
             after_pack()
         e_top = torch.empty(lay.levels[-1].R, self.C, dtype=torch.float32, device=self.device)

@@ -361,6 +361,97 @@ class MaskVRD(nn.Module):
                            "decode_ms": 1e3 * (t3 - t2), **{k: v for k, v in self._net_stats.items()}}
         return out
 
+    # ------------------------------------------------------------------------------------------------------------
+    # tracklet-level input -- the data loader's pair construction on the device
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def pair_table(traj_durations, sids, oids, feat_stride: int, stride_offset: int = 0, proposal_min_frames: int = 0):
+        """Host-side half of the reference's ``_val_getitem`` pair loop (dataloaders/vidor.py:659-711): which (s, o) pairs
+        survive, their sub-sampled length and where their first sub-sampled frame sits inside each tracklet.
+        Returns (keep mask over the input pairs, lengths L, subject frame offset, object frame offset) as numpy arrays."""
+        durs = np.asarray(traj_durations, dtype=np.int64)
+        sids, oids = np.asarray(sids, dtype=np.int64), np.asarray(oids, dtype=np.int64)
+        so_start = np.maximum(durs[sids, 0], durs[oids, 0])
+        so_end = np.minimum(durs[sids, 1], durs[oids, 1])
+        raw = so_end - so_start                                           # overlapping frames (s_feat.shape[0] before sub-sampling)
+        L = np.maximum(0, (raw - stride_offset + feat_stride - 1) // feat_stride)     # len(range(offset, raw, stride))
+        keep = (raw >= proposal_min_frames) & (L >= 2) & (raw > 0)
+        s_off = so_start - durs[sids, 0] + stride_offset
+        o_off = so_start - durs[oids, 0] + stride_offset
+        return keep, L, s_off, o_off
+
+    @torch.no_grad()
+    def forward_tracklets(self, data: dict, dataset_config: dict):
+        """Additional entry point (the drop-in ``forward(input_data)`` stays): takes the input of the reference's
+        ``_val_getitem`` -- per-tracklet ``visual_features_list`` [(T_i, visual_dim)], optional ``clip_features_list``,
+        ``bboxes_list`` [(T_i, 4)], ``traj_durations``, candidate ``sids`` / ``oids``, ``cat_ids``, ``cat_scores``, ``video_wh``
+        (tensors on the host or on the device) -- and returns what ``forward`` returns for the pair lists the data loader would
+        have built from it (dataloaders/vidor.py:659-734).  Tracklet features cross PCIe once (the pair lists repeat every
+        tracklet ~N times); the gather and the box-geometry features (utils/misc.py:158-217) run in the pack kernel.
+        ``dataset_config``: ``feat_stride`` and optionally ``stride_offset`` (0) / ``proposal_min_frames`` (0).  Boxes are
+        clamped to the frame as the loader does; its duplicate-tracklet vIoU filter is expected to have been applied to
+        ``sids`` / ``oids`` already."""
+        t0 = time.perf_counter()
+        eng = self._get_engine()
+        dev = eng.device
+        stride = int(dataset_config.get("feat_stride", 1))
+        offset = int(dataset_config.get("stride_offset", 0))
+        min_frames = int(dataset_config.get("proposal_min_frames", 0))
+        vw, vh = (float(x) for x in data["video_wh"])
+        vis_list, box_list = data["visual_features_list"], data["bboxes_list"]
+        clip_list = data.get("clip_features_list") if self.with_clip_feature else None
+        n_frames = np.array([int(v.shape[0]) for v in vis_list], dtype=np.int64)
+        base = np.cumsum(n_frames) - n_frames                             # first row of every tracklet in the concatenated arrays
+        keep, L, s_off, o_off = self.pair_table(data["traj_durations"].cpu().numpy(), data["sids"].cpu().numpy(),
+                                                data["oids"].cpu().numpy(), stride, offset, min_frames)
+        if not keep.any():
+            return None
+        sids = data["sids"].cpu().numpy().astype(np.int64)[keep]
+        oids = data["oids"].cpu().numpy().astype(np.int64)[keep]
+        lens = L[keep].tolist()
+        tab = np.zeros((len(lens), 4), dtype=np.int32)
+        tab[:, 0] = base[sids] + s_off[keep]
+        tab[:, 1] = base[oids] + o_off[keep]
+        tab[:, 2] = stride
+        with torch.cuda.device(dev):
+            def gather(lst, width):
+                # one device array for all tracklets; host tensors cross PCIe once (non_blocking from pinned memory)
+                out = torch.empty(int(n_frames.sum()), width, dtype=torch.float32, device=dev)
+                for b, n, t in zip(base.tolist(), n_frames.tolist(), lst):
+                    out[b:b + n].copy_(t, non_blocking=True)
+                return out
+            vis_all = gather(vis_list, self.visual_dim)
+            clip_all = gather(clip_list, self.clip_dim) if clip_list is not None else None
+            boxes_all = gather(box_list, 4)
+            boxes_all[:, 0].clamp_(min=0); boxes_all[:, 1].clamp_(min=0)          # _val_getitem, vidor.py:572-577
+            boxes_all[:, 2].clamp_(max=vw - 1); boxes_all[:, 3].clamp_(max=vh - 1)
+            tpads = reference_padded_lengths(lens, self.config)
+            chunks = self._chunks(lens, self.max_rows)
+            lays, tops, mfs = [], [], []
+            for a, b in chunks:
+                lay = PackLayout(lens[a:b], tpads[a:b], self.n_levels, dev)
+                tab_h = torch.from_numpy(tab[a:b]).pin_memory()
+                e_top, mf = self._native.backbone_tracklets(lay, vis_all, clip_all, boxes_all, tab_h.to(dev, non_blocking=True), (vw, vh))
+                lays.append(lay); tops.append(e_top); mfs.append(mf)
+            if len(chunks) == 1:
+                glay, e_top, mf = lays[0], tops[0], mfs[0]
+            else:
+                glay, e_top, mf = MergedLayout(lays, dev), torch.cat(tops, 0), torch.cat(mfs, 0)
+            r = eng.predict(glay, e_top, mf, self.topk, False)
+            t1 = time.perf_counter()
+            packed = torch.cat([r["topk_scores"].view(torch.int32), r["topk_ids"], r["first_last"]], dim=-1).cpu().numpy()
+        t2 = time.perf_counter()
+        k = self.topk
+        pairs = {"sids": torch.from_numpy(sids), "oids": torch.from_numpy(oids), "traj_durations": data["traj_durations"],
+                 "cat_ids": data["cat_ids"], "cat_scores": data["cat_scores"],
+                 "so_offset": torch.full((len(lens),), offset, dtype=torch.int64),
+                 "bboxes_list": [b.clone() for b in box_list]}
+        for b in pairs["bboxes_list"]:                                    # the loader clamps the boxes it hands on
+            b[:, 0].clamp_(min=0); b[:, 1].clamp_(min=0); b[:, 2].clamp_(max=vw - 1); b[:, 3].clamp_(max=vh - 1)
+        out = self._decode(packed[..., :k].view(np.float32), packed[..., k:2 * k], packed[..., 2 * k:], pairs)
+        self.last_stats = {"enqueue_ms": 1e3 * (t1 - t0), "gpu_wait_ms": 1e3 * (t2 - t1), "decode_ms": 1e3 * (time.perf_counter() - t2)}
+        return out
+
     def _decode(self, scores, cats, fl, input_data):
         """Candidates in (pair, query, k) order -> durations -> min-length filter -> mean score ranking -> top n_max_pair.
         Small host-side integer work on the compact kernel outputs (the reference does this in a Python loop with one

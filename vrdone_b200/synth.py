@@ -90,10 +90,10 @@ def _geometry(sb, ob, w, h):
     return rel, ent(sb), ent(ob)
 
 
-def synthetic_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None, name: str = None) -> dict:
-    """A synthetic ``input_data`` dict with the reference data loader's contract (SURVEY.md section 8a row a0): every
-    ordered pair of tracklets with enough temporal overlap, features sub-sampled with ``feat_stride``."""
-    mc, dc, ic = cfg["model_config"], cfg["dataset_config"], cfg["inference_config"]
+def _tracklets(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None):
+    """Seeded per-tracklet data (durations, boxes, visual / CLIP features); the RNG is returned so that callers draw the
+    remaining per-video quantities in the historical order (the golden fixtures depend on it)."""
+    mc, dc = cfg["model_config"], cfg["dataset_config"]
     g = torch.Generator().manual_seed(seed)
     stride = dc.get("feat_stride", 1)
     clip = mc.get("with_clip_feature", False)
@@ -109,7 +109,6 @@ def synthetic_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int
             n_frames = [900, 1200, 1800, 3600][int(torch.multinomial(torch.tensor([.3, .4, .2, .1]), 1, generator=g))]
     if n_tracklets is None:
         n_tracklets = 6 if stride == 1 else randint(20, 61)
-    n_cat = 35 if mc["num_classes"] > 100 else 80
     durs, boxes, vis, clips = [], [], [], []
     for _ in range(n_tracklets):
         if stride == 1:
@@ -125,29 +124,71 @@ def synthetic_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int
         vis.append(torch.randn(length, mc["visual_dim"], generator=g))
         if clip:
             clips.append(torch.randn(length, mc["clip_dim"], generator=g))
+    return g, n_tracklets, durs, boxes, vis, clips, (vid_w, vid_h)
+
+
+def _overlapping_pairs(durs, stride):
+    """Ordered (subject, object) tracklet pairs the synthetic loader keeps: temporal overlap of at least ``min_frames`` frames
+    and at least two sub-sampled frames."""
     min_frames = 5 if stride > 1 else 2
-    sids, oids, feats, offs = [], [], [], []
-    for s in range(n_tracklets):
-        for o in range(n_tracklets):
+    out = []
+    for s in range(len(durs)):
+        for o in range(len(durs)):
             if s == o:
                 continue
             a, b = max(durs[s][0], durs[o][0]), min(durs[s][1], durs[o][1])
-            if b - a < min_frames:
+            if b - a < min_frames or len(range(0, b - a, stride)) < 2:
                 continue
-            ss, os_ = a - durs[s][0], a - durs[o][0]
-            sl_s = slice(ss, ss + b - a, stride)
-            sl_o = slice(os_, os_ + b - a, stride)
-            if vis[s][sl_s].shape[0] < 2:
-                continue
-            rel, es, eo = _geometry(boxes[s][sl_s], boxes[o][sl_o], vid_w, vid_h)
-            parts = [vis[s][sl_s], vis[o][sl_o]]
-            if clip:
-                parts += [clips[s][sl_s], clips[o][sl_o]]
-            parts += [rel, es, eo]
-            feats.append(torch.cat(parts, -1).permute(1, 0))
-            sids.append(s)
-            oids.append(o)
-            offs.append(0)
+            out.append((s, o))
+    return out
+
+
+def synthetic_tracklet_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None, name: str = None) -> dict:
+    """The same synthetic video as ``synthetic_video`` BEFORE the data loader's pair construction: the contract of the input of
+    the reference's ``_val_getitem`` (dataloaders/vidor.py:556-571) with ``sids`` / ``oids`` already enumerated."""
+    mc, dc = cfg["model_config"], cfg["dataset_config"]
+    g, n_tracklets, durs, boxes, vis, clips, wh = _tracklets(cfg, seed, n_tracklets, n_frames)
+    pairs = _overlapping_pairs(durs, dc.get("feat_stride", 1))
+    n_cat = 35 if mc["num_classes"] > 100 else 80
+    out = {
+        "video_name": name or f"synthetic_{seed}",
+        "video_wh": wh,
+        "sids": torch.tensor([p[0] for p in pairs], dtype=torch.int64),
+        "oids": torch.tensor([p[1] for p in pairs], dtype=torch.int64),
+        "cat_ids": torch.randint(1, n_cat + 1, (n_tracklets,), generator=g),
+        "cat_scores": 0.4 + 0.6 * torch.rand(n_tracklets, generator=g),
+        "traj_durations": torch.tensor(durs, dtype=torch.int64),
+        "bboxes_list": boxes,
+        "visual_features_list": vis,
+    }
+    if mc.get("with_clip_feature", False):
+        out["clip_features_list"] = clips
+    return out
+
+
+def synthetic_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None, name: str = None) -> dict:
+    """A synthetic ``input_data`` dict with the reference data loader's contract (SURVEY.md section 8a row a0): every
+    ordered pair of tracklets with enough temporal overlap, features sub-sampled with ``feat_stride``."""
+    mc, dc, ic = cfg["model_config"], cfg["dataset_config"], cfg["inference_config"]
+    stride = dc.get("feat_stride", 1)
+    clip = mc.get("with_clip_feature", False)
+    g, n_tracklets, durs, boxes, vis, clips, (vid_w, vid_h) = _tracklets(cfg, seed, n_tracklets, n_frames)
+    n_cat = 35 if mc["num_classes"] > 100 else 80
+    sids, oids, feats, offs = [], [], [], []
+    for s, o in _overlapping_pairs(durs, stride):
+        a, b = max(durs[s][0], durs[o][0]), min(durs[s][1], durs[o][1])
+        ss, os_ = a - durs[s][0], a - durs[o][0]
+        sl_s = slice(ss, ss + b - a, stride)
+        sl_o = slice(os_, os_ + b - a, stride)
+        rel, es, eo = _geometry(boxes[s][sl_s], boxes[o][sl_o], vid_w, vid_h)
+        parts = [vis[s][sl_s], vis[o][sl_o]]
+        if clip:
+            parts += [clips[s][sl_s], clips[o][sl_o]]
+        parts += [rel, es, eo]
+        feats.append(torch.cat(parts, -1).permute(1, 0))
+        sids.append(s)
+        oids.append(o)
+        offs.append(0)
     return {
         "video_name": name or f"synthetic_{seed}",
         "sids": torch.tensor(sids, dtype=torch.int64),

@@ -559,9 +559,9 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    // CTA pairs for the long-K GEMMs (embedding convs, K = 1024 / 2048 MLPs) with enough rows to keep every pair busy: measured
-    // +6..10 % there; the K = 512 projections are bound by HBM / epilogue traffic and are no faster in pairs
-    const int cg = force_cg == 1 ? 1 : ((force_cg == 2 || (g.M >= 128 * 2 * 64 && (long long)g.taps * g.K >= 1024)) ? 2 : 1);
+    // CTA pairs whenever there are enough rows to keep every pair busy (the small query-decoder GEMMs keep one CTA per tile):
+    // measured +6..10 % on the long-K GEMMs, +4..9 % on the K = 512 ones, neutral on the HBM-bound residual projections
+    const int cg = force_cg == 1 ? 1 : ((force_cg == 2 || g.M >= 128 * 2 * 64) ? 2 : 1);
     CUtensorMap map_a, map_w, map_out, map_res;
     const long long kk = (long long)g.taps * g.K;
     if (!make_map(&map_a, g.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;

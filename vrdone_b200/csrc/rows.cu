@@ -3,6 +3,7 @@
 // Reference semantics (file:line under /root/reference/models/): channel LayerNorm blocks.py:143-158,
 // masked depthwise conv blocks.py:91-113 + 706-724, max-pool skip blocks.py:1040-1046 + 1074,
 // FPN fpns.py:229-257, input contract maskvrd.py:363-414 (padding, re-derived analytically per SURVEY appendix B).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -593,7 +594,7 @@ template <typename TO, int NB, int PREMASK>
 __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const float* __restrict__ x, Lay lay,
                                                                            const float* __restrict__ pre_g,
                                                                            const float* __restrict__ pre_b, DwBranches br,
-                                                                           int total_rows) {
+                                                                           int total_rows, int dbg) {
     constexpr int NCH = 4, C = 512;
     constexpr bool ANY_PRE = PREMASK != 0;
     constexpr bool ALL_PRE = PREMASK == ((1 << NB) - 1);         // no branch reads the raw row: normalise in place
@@ -644,14 +645,63 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
                              : "=r"(ok) : "r"(bar_u + 8 * buf), "r"(parity) : "memory");
             }
         }
-        if constexpr (ANY_PRE) {
-            for (int i = warp; i < DWT_ROWS; i += DWT_WARPS) {
+        if (ANY_PRE && !(dbg & 4)) {
+            // normalise every staged row once.  Each warp takes up to NPW rows and works on them together (loads, the two
+            // shuffle reductions and the parameter reads of all its rows are interleaved), not one after the other: the serial
+            // version spent 22-40 % of the kernel here on exposed latency.
+            constexpr int NPW = (DWT_ROWS + DWT_WARPS - 1) / DWT_WARPS;
+            float v[NPW][NCH][4];
+            bool on[NPW];
+#pragma unroll
+            for (int u = 0; u < NPW; ++u) {
+                const int i = warp + u * DWT_WARPS;
                 const int p = r0 - 1 + i;
-                if (p < lo || p >= hi) continue;
-                float v[NCH][4];
-                load_row<float, NCH>(sx + i * C, lane, v);
-                row_normalize<NCH>(v, lane, pre_g, pre_b);
-                store_row<float, NCH>((MIXED ? s_nrm : sx) + i * C, lane, v);
+                on[u] = i < DWT_ROWS && p >= lo && p < hi;
+                if (on[u]) load_row<float, NCH>(sx + i * C, lane, v[u]);
+                else row_zero<NCH>(v[u]);
+            }
+            float mean[NPW], rstd[NPW];
+#pragma unroll
+            for (int u = 0; u < NPW; ++u) {
+                float sm = 0.f;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) sm += (v[u][j][0] + v[u][j][1]) + (v[u][j][2] + v[u][j][3]);
+                mean[u] = sm;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < NPW; ++u) mean[u] += __shfl_xor_sync(FULL_MASK, mean[u], o);
+#pragma unroll
+            for (int u = 0; u < NPW; ++u) {
+                mean[u] *= (1.0f / C);
+                float q = 0.f;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { v[u][j][i] -= mean[u]; q = fmaf(v[u][j][i], v[u][j][i], q); }
+                rstd[u] = q;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < NPW; ++u) rstd[u] += __shfl_xor_sync(FULL_MASK, rstd[u], o);
+#pragma unroll
+            for (int u = 0; u < NPW; ++u) rstd[u] = 1.0f / sqrtf(rstd[u] * (1.0f / C) + VRD_EPS);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                float g[4], be[4];
+                ld4(pre_g + (j * 32 + lane) * 4, g);
+                ld4(pre_b + (j * 32 + lane) * 4, be);
+#pragma unroll
+                for (int u = 0; u < NPW; ++u)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[u][j][i] = v[u][j][i] * rstd[u] * g[i] + be[i];
+            }
+#pragma unroll
+            for (int u = 0; u < NPW; ++u) {
+                const int i = warp + u * DWT_WARPS;
+                if (on[u]) store_row<float, NCH>((MIXED ? s_nrm : sx) + i * C, lane, v[u]);
             }
             __syncthreads();
         }
@@ -693,8 +743,8 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     const int c = (j * 32 + lane) * 4;
-                    float w0[4], w1[4], w2[4];
-                    ld4(wb + c, w0); ld4(wb + C + c, w1); ld4(wb + 2 * C + c, w2);
+                    float w0[4] = {1.f, 1.f, 1.f, 1.f}, w1[4] = {1.f, 1.f, 1.f, 1.f}, w2[4] = {1.f, 1.f, 1.f, 1.f};
+                    if (!(dbg & 2)) { ld4(wb + c, w0); ld4(wb + C + c, w1); ld4(wb + 2 * C + c, w2); }
 #pragma unroll
                     for (int u = 0; u < DWT_RPW; ++u) {
                         float a[3][4];
@@ -717,6 +767,7 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
                     for (int j = 0; j < NCH; ++j) sm += (y[u][j][0] + y[u][j][1]) + (y[u][j][2] + y[u][j][3]);
                     mean[u] = sm;
                 }
+                if (!(dbg & 8))
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -731,6 +782,7 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
                         for (int i = 0; i < 4; ++i) { y[u][j][i] -= mean[u]; q = fmaf(y[u][j][i], y[u][j][i], q); }
                     rstd[u] = q;
                 }
+                if (!(dbg & 8))
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -739,9 +791,8 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
                 for (int u = 0; u < DWT_RPW; ++u) rstd[u] = 1.0f / sqrtf(rstd[u] * (1.0f / C) + VRD_EPS);
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
-                    float g[4], be[4];
-                    ld4(br.g[b] + (j * 32 + lane) * 4, g);
-                    ld4(br.b[b] + (j * 32 + lane) * 4, be);
+                    float g[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (!(dbg & 2)) { ld4(br.g[b] + (j * 32 + lane) * 4, g); ld4(br.b[b] + (j * 32 + lane) * 4, be); }
 #pragma unroll
                     for (int u = 0; u < DWT_RPW; ++u)
 #pragma unroll
@@ -749,7 +800,8 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
                 }
 #pragma unroll
                 for (int u = 0; u < DWT_RPW; ++u)
-                    store_row<TO, NCH>((TO*)br.out[b] + (long long)(r0 + rr0 + u) * br.ldo[b], lane, y[u]);
+                    if (!(dbg & 1) || y[u][0][0] == 1234.567f)
+                        store_row<TO, NCH>((TO*)br.out[b] + (long long)(r0 + rr0 + u) * br.ldo[b], lane, y[u]);
             }
         }
         if constexpr (ALL_PRE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before the next TMA fill
@@ -768,6 +820,8 @@ static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const flo
     }
     int mask = 0;
     for (int b = 0; b < br.n; ++b) mask |= (br.use_pre[b] ? 1 : 0) << b;
+    const char* dv = getenv("VRD_DW_DEBUG");          // timing experiments only (skips parts of the kernel: wrong results)
+    const int dbg = dv ? atoi(dv) : 0;
     const int total = streams * lay.R;
     const int n_tiles = total / DWT_TILE;
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
@@ -776,7 +830,7 @@ static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const flo
         constexpr int smem = dwt_smem_bytes(MASK != 0 && MASK != ((1 << NB) - 1)); \
         static bool attr_set = false; \
         if (!attr_set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1; attr_set = true; } \
-        kern<<<grid, DWT_WARPS * 32, smem, st>>>(x, lay, pre_g, pre_b, br, total); } while (0)
+        kern<<<grid, DWT_WARPS * 32, smem, st>>>(x, lay, pre_g, pre_b, br, total, dbg); } while (0)
     if (br.n == 3 && mask == 7) LAUNCH(3, 7);
     else if (br.n == 3 && mask == 3) LAUNCH(3, 3);
     else if (br.n == 2 && mask == 0) LAUNCH(2, 0);

@@ -344,6 +344,8 @@ int layernorm(const void* x, int xdt, long long ldx, const float* g, const float
 // small_conv: k=3 conv with cin <= 8 input channels on 8-wide fp32 rows (+bias [+LN] [+ReLU]); N = 512 outputs
 // wt is [3*cin, N] (tap-major rows) so that lanes read contiguous output channels.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int SC_RPW = 4;   // consecutive rows per warp: every weight vector read from L1 serves four rows
+
 template <typename TO, int NCH>
 __global__ void small_conv_kernel(const float* __restrict__ x, int cin, const float* __restrict__ wt,
                                   const float* __restrict__ bias, const float* __restrict__ gamma,
@@ -351,43 +353,59 @@ __global__ void small_conv_kernel(const float* __restrict__ x, int cin, const fl
                                   const int* __restrict__ row_seq, int R) {
     constexpr int N = NCH * 128;
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    TO* o = out + (long long)row * ldo;
-    if (row_seq[row % R] < 0) { zero_row<TO, NCH>(o, lane); return; }
-    float v[NCH][4];
+    const int row0 = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * SC_RPW;
+    if (row0 >= rows) return;
+    float v[SC_RPW][NCH][4];
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) ld4(bias + (j * 32 + lane) * 4, v[j]);
+    for (int j = 0; j < NCH; ++j) {
+        float bj[4];
+        ld4(bias + (j * 32 + lane) * 4, bj);
+#pragma unroll
+        for (int u = 0; u < SC_RPW; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[u][j][i] = bj[i];
+    }
     for (int tap = 0; tap < 3; ++tap) {
-        const int rr = row + tap - 1;
-        if (rr < 0 || rr >= rows) continue;
-        const float* xr = x + (long long)rr * 8;
         for (int c = 0; c < cin; ++c) {
-            const float xv = __ldg(xr + c);
+            float xv[SC_RPW];
+#pragma unroll
+            for (int u = 0; u < SC_RPW; ++u) {
+                const int rr = row0 + u + tap - 1;
+                xv[u] = (rr >= 0 && rr < rows) ? __ldg(x + (long long)rr * 8 + c) : 0.f;
+            }
             const float* w = wt + (long long)(tap * cin + c) * N;
 #pragma unroll
             for (int j = 0; j < NCH; ++j) {
                 float wv[4];
                 ld4(w + (j * 32 + lane) * 4, wv);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[j][i] = fmaf(xv, wv[i], v[j][i]);
+                for (int u = 0; u < SC_RPW; ++u)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[u][j][i] = fmaf(xv[u], wv[i], v[u][j][i]);
             }
         }
     }
-    if (gamma != nullptr) row_normalize<NCH>(v, lane, gamma, beta);
-    if (relu) {
 #pragma unroll
-        for (int j = 0; j < NCH; ++j)
+    for (int u = 0; u < SC_RPW; ++u) {
+        const int row = row0 + u;
+        if (row >= rows) break;
+        TO* o = out + (long long)row * ldo;
+        if (row_seq[row % R] < 0) { zero_row<TO, NCH>(o, lane); continue; }
+        if (gamma != nullptr) row_normalize<NCH>(v[u], lane, gamma, beta);
+        if (relu) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[j][i] = fmaxf(v[j][i], 0.f);
+            for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[u][j][i] = fmaxf(v[u][j][i], 0.f);
+        }
+        store_row<TO, NCH>(o, lane, v[u]);
     }
-    store_row<TO, NCH>(o, lane, v);
 }
 
 int small_conv(const float* x, int cin, const float* wt, const float* bias, const float* g, const float* b, int relu,
                void* out, int odt, long long ldo, int rows, int N, const int* row_seq, int R, cudaStream_t st) {
     if (N != 512 || cin > 8) return 1;
-    const int grid = (rows + WARPS - 1) / WARPS;
+    const int grid = (rows + WARPS * SC_RPW - 1) / (WARPS * SC_RPW);
     if (odt == VRD_BF16)
         small_conv_kernel<__nv_bfloat16, 4><<<grid, WARPS * 32, 0, st>>>(x, cin, wt, bias, g, b, relu, (__nv_bfloat16*)out, ldo, rows, row_seq, R);
     else

@@ -221,7 +221,10 @@ def main():
     step_wall = []
     free_ms = []
 
-    def timed(videos, steps, h2d):
+    def timed(videos, steps, h2d, pipelined=True, dataset_config=None):
+        """K steps between two CUDA events.  ``pipelined``: through ``runner.run_videos`` (two videos in flight: the decode of
+        one overlaps the kernels of the next; every result is produced and dropped inside the timed region); otherwise one
+        synchronous ``model(v)`` call after the other, as the reference's eval loop does."""
         sync_all()
         gc_ms[0] = 0.0
         gc_gen.clear()
@@ -230,15 +233,24 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         pairs = 0
-        for s in range(steps):
-            v = videos[s % len(videos)]
+        if pipelined:
             tw = time.perf_counter()
-            out = model(v)  # h2d: ``v`` holds pinned HOST pair features; the module moves them (inside the timed region)
-            tm = time.perf_counter()
-            del out         # dropping the ~2*10^5 Python objects of the result is part of the step
-            step_wall.append(round(1e3 * (time.perf_counter() - tw), 1))
-            free_ms.append(round(1e3 * (time.perf_counter() - tm), 1))
-            pairs += n_pairs[s % len(videos)]
+            for out in runner.run_videos(model, (videos[s % len(videos)] for s in range(steps)), dataset_config=dataset_config):
+                del out     # dropping the ~2*10^5 Python objects of the result is part of the step
+                step_wall.append(round(1e3 * (time.perf_counter() - tw), 1))
+                tw = time.perf_counter()
+            pairs = sum(n_pairs[s % len(videos)] for s in range(steps))
+        else:
+            for s in range(steps):
+                v = videos[s % len(videos)]
+                tw = time.perf_counter()
+                # h2d: ``v`` holds pinned HOST pair features; the module moves them (inside the timed region)
+                out = model(v) if dataset_config is None else model.forward_tracklets(v, dataset_config)
+                tm = time.perf_counter()
+                del out
+                step_wall.append(round(1e3 * (time.perf_counter() - tw), 1))
+                free_ms.append(round(1e3 * (time.perf_counter() - tm), 1))
+                pairs += n_pairs[s % len(videos)]
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
@@ -258,6 +270,8 @@ def main():
     l0 = ops.launches
     ms, pairs = timed(dev_videos, args.steps, h2d=False)
     launches = ops.launches - l0
+    wall_pipe = list(step_wall)
+    ms_sync, pairs_sync = timed(dev_videos, args.steps, h2d=False, pipelined=False)
     host_hbm = {k: round(v, 2) for k, v in model.last_stats.items()}
     host_hbm["python_gc_ms_per_step"] = round(gc_ms[0] / args.steps, 2)
     host_hbm["python_gc_by_generation"] = {str(k): [v[0], round(v[1], 1)] for k, v in gc_gen.items()}
@@ -267,6 +281,8 @@ def main():
     for s in range(args.warmup):        # staging buffers, pinned upload blocks and the copy stream are created on first use
         model(pinned[s % len(pinned)])
     ms_e2e, pairs_e2e = timed(pinned, args.steps, h2d=True)
+    wall_pipe_e2e = list(step_wall)
+    ms_e2e_sync, pairs_e2e_sync = timed(pinned, args.steps, h2d=True, pipelined=False)
     host_e2e = {k: round(v, 2) for k, v in model.last_stats.items()}
     host_e2e["forward_wall_ms_each_step"] = list(step_wall)
 
@@ -283,19 +299,8 @@ def main():
                  for t in trk_videos]
     for s in range(args.warmup):
         model.forward_tracklets(trk_videos[s % len(trk_videos)], cfg["dataset_config"])
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(args.steps):
-        model.forward_tracklets(trk_videos[s % len(trk_videos)], cfg["dataset_config"])
-    e1.record()
-    sync_all()
-    ms_trk = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_trk], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_trk = float(t)
-    pairs_trk = world * sum(n_pairs[s % len(n_pairs)] for s in range(args.steps))
+    ms_trk, pairs_trk = timed(trk_videos, args.steps, h2d=True, dataset_config=cfg["dataset_config"])
+    ms_trk_sync, _ = timed(trk_videos, args.steps, h2d=True, pipelined=False, dataset_config=cfg["dataset_config"])
 
     # roofline pass: the same steps with a CUDA-event pair around every launch of the dominant (GEMM) kernel
     model.use_native = False        # same kernels, same order, issued one by one from Python so that each launch can be timed
@@ -334,6 +339,12 @@ def main():
            "e2e_tracklet_api": {"value": pairs_trk / (ms_trk * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sum(trk_bytes) / len(trk_bytes)),
                                 "note": "MaskVRD.forward_tracklets: host tracklet features in, triplets out (SURVEY 8f row 1)"},
            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+           "api": "runner.run_videos(model, videos): submit video i+1, then wait for + decode video i (two videos in flight)",
+           "sync_call": {"note": "one blocking model(input_data) call after the other (the reference's eval loop), no overlap of "
+                                 "host decode and device work",
+                         "value": pairs_sync / (ms_sync * 1e-3), "e2e": pairs_e2e_sync / (ms_e2e_sync * 1e-3),
+                         "e2e_tracklet_api": pairs_trk / (ms_trk_sync * 1e-3), "unit": UNIT},
+           "step_wall_ms_pipelined": {"hbm_resident": wall_pipe, "e2e": wall_pipe_e2e},
            "host_ms_last_step": host_hbm, "host_ms_last_step_e2e": host_e2e}
     if not args.no_cpu_baseline:
         v, n, dt = cpu_baseline(cfg, host_videos[0], args.cpu_pairs, threads)

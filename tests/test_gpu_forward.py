@@ -243,3 +243,36 @@ def test_forward_returns_none_without_candidates_and_handles_many_slices():
     assert np.mean(same) > 0.98
     model.pred_min_frames = 10 ** 6
     assert model(dev_video) is None
+
+
+def test_pipelined_run_videos_equals_blocking_calls():
+    """runner.run_videos keeps two videos in flight (device-resident, pinned-host and tracklet-level inputs mixed sizes): every
+    result must equal the blocking ``model(video)`` call's, in input order, including ``None`` results."""
+    from vrdone_b200 import runner
+    cfg, model, sd = H.seeded_model("vidor", 21, precision="bf16")
+    model.to("cuda")
+    model.h2d_chunk_rows, model.h2d_edge_rows = 4096, 1024          # several chunks per video: staging buffers are reused across videos
+    vids = [synth.synthetic_video(cfg, s, n_tracklets=n, n_frames=f) for s, n, f in ((1, 8, 700), (2, 5, 300), (3, 9, 900), (4, 6, 500))]
+
+    def dev(v):
+        return {k: ([t.cuda() for t in x] if isinstance(x, list) else (x.cuda() if torch.is_tensor(x) else x)) for k, x in v.items()}
+
+    def pinned(v):
+        return {k: ([t.t().contiguous().pin_memory().t() for t in x] if k == "so_features_list" else x) for k, x in v.items()}
+
+    keys = ("triplets", "triple_scores", "triple_scores_avg", "so_trajs", "pred_durations", "so_tids")
+    for make in (dev, pinned):
+        inputs = [make(v) for v in vids] * 2
+        blocking = [model(v) for v in inputs]
+        for depth in (1, 2, 3):
+            piped = list(runner.run_videos(model, iter(inputs), depth=depth))
+            assert len(piped) == len(blocking)
+            for a, b in zip(blocking, piped):
+                assert all(a[k] == b[k] for k in keys)
+    trk = [synth.synthetic_tracklet_video(cfg, s, n_tracklets=n, n_frames=f) for s, n, f in ((1, 8, 700), (2, 5, 300), (3, 9, 900))]
+    blocking = [model.forward_tracklets(t, cfg["dataset_config"]) for t in trk]
+    piped = list(runner.run_videos(model, trk, dataset_config=cfg["dataset_config"]))
+    for a, b in zip(blocking, piped):
+        assert all(a[k] == b[k] for k in keys)
+    model.pred_min_frames = 10 ** 6
+    assert list(runner.run_videos(model, [dev(v) for v in vids[:3]])) == [None, None, None]

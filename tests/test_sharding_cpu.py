@@ -63,3 +63,40 @@ def test_two_rank_gloo_matches_single_rank():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert merged == single
+
+
+def test_run_videos_keeps_order_and_depth():
+    """Host logic of the pipelined eval loop: results come back in input order, at most ``depth`` videos are in flight, and a
+    video is waited for only after the next one has been submitted."""
+    from vrdone_b200 import runner
+    log = []
+
+    class Pending:
+        def __init__(self, v):
+            self.v = v
+
+        def result(self):
+            log.append(("result", self.v))
+            return self.v * 10
+
+    class Model:
+        def submit(self, v):
+            log.append(("submit", v))
+            return Pending(v)
+
+        def submit_tracklets(self, v, dc):
+            log.append(("submit_trk", v))
+            return Pending(v)
+
+    assert list(runner.run_videos(Model(), range(4), depth=2)) == [0, 10, 20, 30]
+    assert log[:4] == [("submit", 0), ("submit", 1), ("result", 0), ("submit", 2)]
+    in_flight = peak = 0
+    for what, _ in log:
+        in_flight += 1 if what == "submit" else -1
+        peak = max(peak, in_flight)
+    assert peak == 2
+    log.clear()
+    assert list(runner.run_videos(Model(), range(3), depth=1)) == [0, 10, 20]
+    assert [w for w, _ in log] == ["submit", "result"] * 3
+    assert list(runner.run_videos(Model(), [5], depth=2, dataset_config={})) == [50]
+    assert list(runner.run_videos(Model(), [], depth=2)) == []

@@ -26,6 +26,40 @@ from .layout import MergedLayout, PackLayout, max_div_factor, reference_padded_l
 from .params import Backbone, Neck, Predictor
 
 
+class PendingVideo:
+    """A video whose copies and kernels are enqueued (``MaskVRD.submit``); ``result()`` waits for the read-back of the compact
+    per-(pair, query) records and decodes them into the reference's output dict (or ``None``)."""
+
+    __slots__ = ("_model", "_host", "_event", "_input", "stats", "_done", "_out")
+
+    def __init__(self, model, host, event, input_data, stats):
+        self._model, self._host, self._event, self._input, self.stats = model, host, event, input_data, stats
+        self._done, self._out = False, None
+
+    def result(self):
+        if self._done:
+            return self._out
+        m = self._model
+        t0 = time.perf_counter()
+        if self._event is not None:
+            self._event.synchronize()
+            t1 = time.perf_counter()
+            packed = self._host.numpy()
+            k = m.topk
+            self._out = m._decode(packed[..., :k].view(np.float32),   # [B, Q, k] fp32 scores
+                                  packed[..., k:2 * k],               # [B, Q, k] int32, 1-based predicate ids
+                                  packed[..., 2 * k:],                # [B, Q, 2] int32 first / last active frame
+                                  self._input)
+            self.stats.update(gpu_wait_ms=1e3 * (t1 - t0), decode_ms=1e3 * (time.perf_counter() - t1))
+        self._done, self._host, self._event, self._input = True, None, None, None
+        m.last_stats = self.stats
+        return self._out
+
+
+_NO_PAIRS = PendingVideo(None, None, None, None, {})
+_NO_PAIRS._done = True
+
+
 class MaskVRD(nn.Module):
     def __init__(self, config: dict, device):
         super().__init__()
@@ -334,6 +368,25 @@ class MaskVRD(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward_test(self, input_data):
+        return self.submit(input_data).result()
+
+    def _read_back(self, r, dev):
+        """Asynchronous device->host read of the compact per-(pair, query) results into pinned memory: one [B, Q, 2*topk + 2]
+        int32 record array (top-k scores as raw bits, 1-based predicate ids, first / last active frame) and the event that
+        marks its arrival."""
+        packed = torch.cat([r["topk_scores"].view(torch.int32), r["topk_ids"], r["first_last"]], dim=-1)
+        host = torch.empty(packed.shape, dtype=torch.int32, pin_memory=True)
+        host.copy_(packed, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        return host, ev
+
+    @torch.no_grad()
+    def submit(self, input_data) -> "PendingVideo":
+        """First half of ``forward_test``: enqueue every copy and kernel of one video and the asynchronous read-back of its
+        results, without waiting for the device.  ``PendingVideo.result()`` waits and decodes.  ``forward(input_data)`` is
+        ``submit(input_data).result()``; ``runner.run_videos`` keeps two videos in flight so that the host-side decode of
+        one video overlaps the kernels of the next."""
         t0 = time.perf_counter()
         eng = self._get_engine()
         dev = eng.device
@@ -345,20 +398,27 @@ class MaskVRD(nn.Module):
         lens = [int(f.shape[1]) for f in feats]
         tpads = reference_padded_lengths(lens, self.config)
         r = self.run_network(feats, tpads, self.topk)
-        t1 = time.perf_counter()
-        # one device->host read of the compact per-(pair, query) results
-        packed = torch.cat([r["topk_scores"].view(torch.int32), r["topk_ids"], r["first_last"]], dim=-1)
-        t1b = time.perf_counter()
-        packed = packed.cpu().numpy()
-        t2 = time.perf_counter()
-        k = self.topk
-        scores = packed[..., :k].view(np.float32)            # [B, Q, k] fp32
-        cats = packed[..., k:2 * k]                          # [B, Q, k] int32, 1-based predicate ids
-        fl = packed[..., 2 * k:]                             # [B, Q, 2] int32 first / last active frame
-        out = self._decode(scores, cats, fl, input_data)
-        t3 = time.perf_counter()
-        self.last_stats = {"enqueue_ms": 1e3 * (t1 - t0), "cat_ms": 1e3 * (t1b - t1), "gpu_wait_ms": 1e3 * (t2 - t1b),
-                           "decode_ms": 1e3 * (t3 - t2), **{k: v for k, v in self._net_stats.items()}}
+        with torch.cuda.device(dev):
+            small = self._stage_decode_inputs(input_data)
+            host, ev = self._read_back(r, dev)
+        stats = {"enqueue_ms": 1e3 * (time.perf_counter() - t0), **self._net_stats}
+        return PendingVideo(self, host, ev, small, stats)
+
+    _DECODE_KEYS = ("sids", "oids", "traj_durations", "cat_ids", "cat_scores", "so_offset")
+
+    @classmethod
+    def _stage_decode_inputs(cls, input_data):
+        """The small per-video tensors the decode reads (ids, durations, detection scores, boxes).  Device-resident ones are
+        read back asynchronously into pinned memory here, ahead of the result event: a blocking ``.cpu()`` inside the decode
+        would wait behind the kernels of the NEXT video when two videos are in flight."""
+        def host(t):
+            if not t.is_cuda:
+                return t
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t.detach(), non_blocking=True)
+            return h
+        out = {k: host(input_data[k]) for k in cls._DECODE_KEYS}
+        out["bboxes_list"] = [host(b) for b in input_data["bboxes_list"]]
         return out
 
     # ------------------------------------------------------------------------------------------------------------
@@ -380,8 +440,11 @@ class MaskVRD(nn.Module):
         o_off = so_start - durs[oids, 0] + stride_offset
         return keep, L, s_off, o_off
 
-    @torch.no_grad()
     def forward_tracklets(self, data: dict, dataset_config: dict):
+        return self.submit_tracklets(data, dataset_config).result()
+
+    @torch.no_grad()
+    def submit_tracklets(self, data: dict, dataset_config: dict) -> Optional["PendingVideo"]:
         """Additional entry point (the drop-in ``forward(input_data)`` stays): takes the input of the reference's
         ``_val_getitem`` -- per-tracklet ``visual_features_list`` [(T_i, visual_dim)], optional ``clip_features_list``,
         ``bboxes_list`` [(T_i, 4)], ``traj_durations``, candidate ``sids`` / ``oids``, ``cat_ids``, ``cat_scores``, ``video_wh``
@@ -405,7 +468,7 @@ class MaskVRD(nn.Module):
         keep, L, s_off, o_off = self.pair_table(data["traj_durations"].cpu().numpy(), data["sids"].cpu().numpy(),
                                                 data["oids"].cpu().numpy(), stride, offset, min_frames)
         if not keep.any():
-            return None
+            return _NO_PAIRS
         sids = data["sids"].cpu().numpy().astype(np.int64)[keep]
         oids = data["oids"].cpu().numpy().astype(np.int64)[keep]
         lens = L[keep].tolist()
@@ -438,28 +501,21 @@ class MaskVRD(nn.Module):
             else:
                 glay, e_top, mf = MergedLayout(lays, dev), torch.cat(tops, 0), torch.cat(mfs, 0)
             r = eng.predict(glay, e_top, mf, self.topk, False)
-            t1 = time.perf_counter()
-            packed = torch.cat([r["topk_scores"].view(torch.int32), r["topk_ids"], r["first_last"]], dim=-1).cpu().numpy()
-        t2 = time.perf_counter()
-        k = self.topk
+            host, ev = self._read_back(r, dev)
         pairs = {"sids": torch.from_numpy(sids), "oids": torch.from_numpy(oids), "traj_durations": data["traj_durations"],
                  "cat_ids": data["cat_ids"], "cat_scores": data["cat_scores"],
                  "so_offset": torch.full((len(lens),), offset, dtype=torch.int64),
                  "bboxes_list": [b.clone() for b in box_list]}
         for b in pairs["bboxes_list"]:                                    # the loader clamps the boxes it hands on
             b[:, 0].clamp_(min=0); b[:, 1].clamp_(min=0); b[:, 2].clamp_(max=vw - 1); b[:, 3].clamp_(max=vh - 1)
-        out = self._decode(packed[..., :k].view(np.float32), packed[..., k:2 * k], packed[..., 2 * k:], pairs)
-        self.last_stats = {"enqueue_ms": 1e3 * (t1 - t0), "gpu_wait_ms": 1e3 * (t2 - t1), "decode_ms": 1e3 * (time.perf_counter() - t2)}
-        return out
+        return PendingVideo(self, host, ev, pairs, {"enqueue_ms": 1e3 * (time.perf_counter() - t0)})
 
     def _decode(self, scores, cats, fl, input_data):
         """Candidates in (pair, query, k) order -> durations -> min-length filter -> mean score ranking -> top n_max_pair.
         Small host-side integer work on the compact kernel outputs (the reference does this in a Python loop with one
         device sync per candidate, maskvrd.py:262-328)."""
         topk, stride = self.topk, self.feat_stride
-        small = [input_data[k] for k in ("sids", "oids", "traj_durations", "cat_ids", "cat_scores", "so_offset")]
-        if any(t.is_cuda for t in small):    # one sync for all the small per-video tensors
-            small = [t.cpu() for t in small]
+        small = [input_data[k] for k in self._DECODE_KEYS]     # host tensors (``_stage_decode_inputs``)
         sids, oids, durs, cat_ids, cat_scores, off = [t.numpy() for t in small]
         sids, oids, durs, off = sids.astype(np.int64), oids.astype(np.int64), durs.astype(np.int64), off.astype(np.int64)
         cat_scores = cat_scores.astype(np.float32)
@@ -490,8 +546,8 @@ class MaskVRD(nn.Module):
         host_boxes = {}
 
         def traj(tid, a, b):
-            if tid not in host_boxes:                               # one D2H copy per tracklet that is actually reported
-                host_boxes[tid] = boxes[tid].detach().cpu().numpy()
+            if tid not in host_boxes:
+                host_boxes[tid] = boxes[tid].detach().numpy()
             return host_boxes[tid][a:b]
 
         out = {"triplets": [], "triple_scores": [], "triple_scores_avg": [], "so_trajs": [], "pred_durations": [], "so_tids": []}

@@ -5,7 +5,8 @@ The reference runs inference single-process on cuda:0 (eval.py:83, 140-152); thi
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Sequence
+from collections import deque
+from typing import Callable, Dict, Iterable, Iterator, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -39,6 +40,20 @@ def shard_videos(costs: Sequence[float], world_size: int) -> List[List[int]]:
         shards[r].append(i)
         loads[r] += costs[i]
     return [sorted(s) for s in shards]
+
+
+def run_videos(model, videos: Iterable[dict], depth: int = 2, dataset_config: Optional[dict] = None) -> Iterator[object]:
+    """The reference's eval loop ``for proposal in loader: out = model(proposal)`` (eval.py:140-152) with ``depth`` videos in
+    flight: video i + 1 is enqueued (copies, kernels, asynchronous read-back) before video i is waited for and decoded, so the
+    host-side decode of one video overlaps the device work of the next.  Yields exactly what ``model(video)`` returns, in
+    input order.  With ``dataset_config`` the videos are tracklet-level inputs (``MaskVRD.submit_tracklets``)."""
+    pending = deque()
+    for v in videos:
+        pending.append(model.submit(v) if dataset_config is None else model.submit_tracklets(v, dataset_config))
+        if len(pending) >= depth:
+            yield pending.popleft().result()
+    while pending:
+        yield pending.popleft().result()
 
 
 def run_sharded(videos: Sequence[dict], costs: Sequence[float], fn: Callable[[dict], object]) -> Dict[int, object]:

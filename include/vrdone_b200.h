@@ -44,6 +44,16 @@ int vrd_device_arch(void);
 int vrd_h2d_pairs(const void* const* src, const int64_t* bytes, void* dst_base, const int64_t* dst_offset, int n,
                   vrd_stream_t stream);
 
+/* SURVEY 8f row 2 -- replaces the duplicate-tracklet filter of the data loader (dataloaders/vidor.py:583-641, vidvrd.py same
+ * code): boxes [T, 4] fp32 hold every tracklet's (already clamped) boxes back to back, trk_base[i] the first row of tracklet
+ * i, durations [N, 2] int32 (start, end frame), cat_ids [N] int32.  For base < ref of one category with overlapping durations
+ * the intersection / base / ref box volumes over the common frames (fp64 sums of the reference's fp32 per-frame terms) decide
+ * rule 1 (ref dropped: inter / vol_ref > thr and base covers ref in time) or rule 2 (base dropped); flags [N, N] uint8 receives
+ * the decision (0 / 1 / 2), sums [N, N, 3] fp64 (optional, may be NULL) the three volumes, valid [N] int32 the result of the
+ * reference's greedy scan in tracklet order.  N <= 1024. */
+int vrd_viou_filter(const float* boxes, const int32_t* trk_base, const int32_t* durations, const int32_t* cat_ids, int n_tracklets,
+                    float viou_threshold, double* sums, uint8_t* flags, int32_t* valid, vrd_stream_t stream);
+
 /* k9 -- replaces MaskVRD.preprocessing (maskvrd.py:363-414) + the channel split of backbones.py:161-166 / 329-341.
  * pair_ptrs[i] -> fp32 (C, L_i) tensor with element strides pair_strides[2i] (channel), pair_strides[2i+1] (time).
  * Writes vis [2R, nv], clip [2R, nc] (or NULL when nc == 0) in act_dtype, bbox_so [R, 8] and bbox_ent [2R, 8] in fp32.

@@ -50,7 +50,52 @@ def build_ref(Ref, name, wseed):
     return cfg, ref, sd
 
 
+LOADER_CASES = {
+    "vidor": [dict(seed=0, n_tracklets=10, n_frames=600, n_dup=8), dict(seed=1, n_tracklets=14, n_frames=900, n_dup=10),
+              dict(seed=2, n_tracklets=7, n_frames=400, n_dup=0)],
+    "vidor_x": [dict(seed=3, n_tracklets=8, n_frames=500, n_dup=6)],
+    "vidvrd": [dict(seed=4, n_tracklets=8, n_frames=150, n_dup=6)],
+}
+
+
+def loader_fixtures():
+    """the unmodified ``VidOR._val_getitem`` (dataloaders/vidor.py:556-734; vidvrd.py:552-716 is the same
+    code) on seeded synthetic tracklet videos with injected near-duplicates.  The method only reads four attributes of its
+    dataset object, so it is called on a stand-in that carries them (constructing the dataset needs the annotation files)."""
+    import types
+    sys.path.insert(0, "/root/reference")
+    for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k.startswith("dataloaders")]:
+        del sys.modules[m]
+    import dataloaders.vidor as V
+    sys.path.pop(0)
+    for name, cases in LOADER_CASES.items():
+        cfg = synth.load_config(name)
+        dc = cfg["dataset_config"]
+        fixes = []
+        for case in cases:
+            trk = synth.synthetic_tracklet_video(cfg, case["seed"], n_tracklets=case["n_tracklets"], n_frames=case["n_frames"])
+            if case["n_dup"]:
+                trk = synth.with_duplicates(trk, cfg, case["seed"], case["n_dup"])
+            stand_in = types.SimpleNamespace(with_clip_feature="clip_features_list" in trk, feat_stride=dc.get("feat_stride", 1),
+                                             random_stride=False, stride_offset=0,
+                                             proposal_min_frames=dc.get("proposal_min_frames", 0))
+            out = V.VidOR._val_getitem(stand_in, trk, viou_threshold=0.9)
+            fixes.append({**case, "n_candidate_pairs": len(trk["sids"]), "n_tracklets_total": len(trk["bboxes_list"]),
+                          "inputs_checksum": checksum(trk["visual_features_list"] + trk["bboxes_list"]),
+                          "proposal_min_frames": stand_in.proposal_min_frames, "feat_stride": stand_in.feat_stride,
+                          "sids": out["sids"].tolist(), "oids": out["oids"].tolist(), "so_offset": out["so_offset"].tolist(),
+                          "lens": [int(f.shape[1]) for f in out["so_features_list"]],
+                          "pair_checksums": [float(f.double().abs().sum()) for f in out["so_features_list"]],
+                          "boxes_checksum": checksum(out["bboxes_list"])})
+            print(name, case, "loader fixture:", len(trk["sids"]), "candidate pairs ->", len(out["sids"]), "kept")
+        with open(os.path.join(HERE, f"loader_{name}.json"), "w") as f:
+            json.dump({"config": name, "viou_threshold": 0.9, "cases": fixes}, f)
+
+
 def main():
+    if "--loader-only" in sys.argv:
+        return loader_fixtures()
+    loader_fixtures()
     Ref = load_reference()
     torch.manual_seed(0)
     for name, case in CASES.items():

@@ -56,3 +56,16 @@ def seeded_model(name, wseed, device="cpu", precision="fp32"):
 
 def rel_err(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12))
+
+
+def loader_fixture(name):
+    with open(os.path.join(GOLDEN, f"loader_{name}.json")) as f:
+        return json.load(f)
+
+
+def loader_case_video(cfg, case):
+    """The seeded tracklet-level video of a loader fixture case."""
+    trk = synth.synthetic_tracklet_video(cfg, case["seed"], n_tracklets=case["n_tracklets"], n_frames=case["n_frames"])
+    if case["n_dup"]:
+        trk = synth.with_duplicates(trk, cfg, case["seed"], case["n_dup"])
+    return trk

@@ -276,3 +276,90 @@ def test_pipelined_run_videos_equals_blocking_calls():
         assert all(a[k] == b[k] for k in keys)
     model.pred_min_frames = 10 ** 6
     assert list(runner.run_videos(model, [dev(v) for v in vids[:3]])) == [None, None, None]
+
+
+def _viou_inputs(trk):
+    import numpy as np
+    from oracle import loader_oracle as LO
+    boxes = LO.clamp_boxes(trk["bboxes_list"], trk["video_wh"])
+    n_frames = np.array([b.shape[0] for b in boxes])
+    base = torch.from_numpy(np.cumsum(n_frames) - n_frames).to(torch.int32).cuda()
+    return boxes, torch.cat(boxes).cuda(), base, trk["traj_durations"].to(torch.int32).cuda(), trk["cat_ids"].to(torch.int32).cuda()
+
+
+@pytest.mark.parametrize("name", ["vidor", "vidor_x", "vidvrd"])
+def test_viou_filter_kernel_matches_loader_oracle(name):
+    """volumes, rule decisions and the greedy scan of the device filter against the loader oracle (which is
+    pinned to the reference's ``_val_getitem``), on the fixture videos with injected near-duplicates."""
+    from oracle import loader_oracle as LO
+    from vrdone_b200.cuda_ops import CudaOps
+    ops = CudaOps()
+    cfg = synth.load_config(name)
+    for case in H.loader_fixture(name)["cases"]:
+        trk = H.loader_case_video(cfg, case)
+        boxes, boxes_d, base, durs, cats = _viou_inputs(trk)
+        valid, flags, sums = ops.viou_filter(boxes_d, base, durs, cats, 0.9, torch.cuda.current_stream(), want_sums=True)
+        torch.cuda.synchronize()
+        assert valid.bool().tolist() == LO.duplicate_filter(boxes, trk["traj_durations"], trk["cat_ids"], 0.9)
+        n, d, n_checked = len(boxes), trk["traj_durations"].tolist(), 0
+        for b in range(n):
+            for r in range(b + 1, n):
+                if int(trk["cat_ids"][b]) != int(trk["cat_ids"][r]) or d[r][0] >= d[b][1] or d[r][1] <= d[b][0]:
+                    assert int(flags[b, r]) == 0
+                    continue
+                s, e = max(d[b][0], d[r][0]), min(d[b][1], d[r][1])
+                ref = LO.viou_sums(boxes[b][s - d[b][0]: e - d[b][0]].double(), boxes[r][s - d[r][0]: e - d[r][0]].double())
+                got = sums[b, r].cpu()
+                assert torch.allclose(got, torch.stack(ref), rtol=1e-6), (b, r)      # fp32 per-frame terms, fp64 sums
+                n_checked += 1
+        assert n_checked > 0 or case["n_dup"] == 0
+
+
+def test_viou_filter_rules_on_device():
+    from oracle import loader_oracle as LO
+    from vrdone_b200.cuda_ops import CudaOps
+    ops = CudaOps()
+    box = torch.tensor([[100.0, 100.0, 200.0, 220.0]])
+    for lens, shifts, durs, cats in (
+            ([100, 40, 40, 40, 50, 50, 30, 60], [0, 0, 0, 500.0, 1.0, 1.0, 2.0, 2.0],
+             [[0, 100], [10, 50], [10, 50], [10, 50], [200, 250], [200, 250], [310, 340], [300, 360]], [1, 1, 2, 1, 3, 3, 4, 4]),
+            ([30, 60, 30], [0, 0, 0], [[10, 40], [0, 60], [10, 40]], [1, 1, 1]),
+            ([5], [0], [[0, 5]], [7])):
+        trk = {"bboxes_list": [box.repeat(n, 1) + s for n, s in zip(lens, shifts)], "video_wh": (1280.0, 720.0),
+               "traj_durations": torch.tensor(durs), "cat_ids": torch.tensor(cats)}
+        boxes, boxes_d, base, d, c = _viou_inputs(trk)
+        valid, _, _ = ops.viou_filter(boxes_d, base, d, c, 0.9, torch.cuda.current_stream())
+        assert valid.bool().tolist() == LO.duplicate_filter(boxes, trk["traj_durations"], trk["cat_ids"], 0.9)
+
+
+@pytest.mark.parametrize("name", ["vidor", "vidor_x"])
+def test_forward_tracklets_with_duplicate_filter_matches_loader_then_forward(name):
+    """The whole 8f rows 1-2 path: forward_tracklets(viou_threshold=0.9) on raw tracklets == forward on the item the loader
+    oracle builds (duplicate filter + pair construction on the CPU), host- and device-resident tracklet inputs."""
+    from oracle import loader_oracle as LO
+    fix = H.loader_fixture(name)
+    cfg, model, sd = H.seeded_model(name, 21, precision="fp32")
+    model.to("cuda")
+    case = fix["cases"][0]
+    trk = H.loader_case_video(cfg, case)
+    item = LO.val_getitem(trk, case["feat_stride"], 0, case["proposal_min_frames"], 0.9, with_clip="clip_features_list" in trk)
+    assert item["sids"].tolist() == case["sids"]
+    dev_item = {k: ([t.cuda() for t in v] if isinstance(v, list) and torch.is_tensor(v[0]) else (v.cuda() if torch.is_tensor(v) else v))
+                for k, v in item.items() if k != "valid_tracklets"}
+    a = model(dev_item)
+    dc = dict(cfg["dataset_config"], viou_threshold=0.9, proposal_min_frames=case["proposal_min_frames"])
+    dev_trk = {k: ([t.cuda() for t in v] if isinstance(v, list) else (v.cuda() if torch.is_tensor(v) else v)) for k, v in trk.items()}
+    for inp in (trk, dev_trk):
+        b = model.forward_tracklets(inp, dc)
+        assert len(a["triplets"]) == len(b["triplets"])
+        same = [x == y and u == v and p == q for x, y, u, v, p, q in
+                zip(a["triplets"], b["triplets"], a["pred_durations"], b["pred_durations"], a["so_tids"], b["so_tids"])]
+        assert np.mean(same) > 0.98            # box-geometry channels differ in the last bit (device logf / division)
+        assert np.allclose(np.array(a["triple_scores_avg"]), np.array(b["triple_scores_avg"]), atol=1e-3)
+        for ta, tb, ok in zip(a["so_trajs"], b["so_trajs"], same):
+            if ok:
+                assert ta == tb
+    unfiltered = model.forward_tracklets(trk, cfg["dataset_config"])
+    removed = {i for i, v in enumerate(item["valid_tracklets"]) if not v}
+    assert removed and not any(s in removed or o in removed for s, o in b["so_tids"])
+    assert unfiltered is not None

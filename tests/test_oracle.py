@@ -60,3 +60,49 @@ def test_oracle_matches_live_reference(name):
         r, o = ref._mask_vrd(x, m), O.mask_vrd(x, m, sd, mc)
     assert H.rel_err(o["pred_logits"], r["pred_logits"]) < 2e-5
     assert H.rel_err(o["pred_masks"], r["pred_masks"]) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["vidor", "vidor_x", "vidvrd"])
+def test_loader_oracle_matches_golden_loader_output(name):
+    """the loader oracle (clamp, duplicate-tracklet vIoU filter, pair loop, feature gather, box geometry)
+    against outputs of the unmodified reference ``_val_getitem`` on videos with injected near-duplicate tracklets."""
+    from oracle import loader_oracle as LO
+    fix = H.loader_fixture(name)
+    cfg = synth.load_config(name)
+    removed = 0
+    for case in fix["cases"]:
+        trk = H.loader_case_video(cfg, case)
+        assert H.checksum(trk["visual_features_list"] + trk["bboxes_list"]) == pytest.approx(case["inputs_checksum"], rel=1e-12)
+        out = LO.val_getitem(trk, case["feat_stride"], 0, case["proposal_min_frames"], fix["viou_threshold"],
+                             with_clip="clip_features_list" in trk)
+        assert out["sids"].tolist() == case["sids"] and out["oids"].tolist() == case["oids"]
+        assert out["so_offset"].tolist() == case["so_offset"]
+        assert [int(f.shape[1]) for f in out["so_features_list"]] == case["lens"]
+        got = torch.tensor([float(f.double().abs().sum()) for f in out["so_features_list"]], dtype=torch.float64)
+        assert torch.allclose(got, torch.tensor(case["pair_checksums"], dtype=torch.float64), rtol=1e-9)
+        assert H.checksum(out["bboxes_list"]) == pytest.approx(case["boxes_checksum"], rel=1e-12)
+        removed += out["valid_tracklets"].count(False)
+        assert (out["valid_tracklets"].count(False) > 0) == (case["n_dup"] > 0)
+    assert removed > 0
+
+
+def test_duplicate_filter_rules():
+    """Both removal rules and the scan order of the greedy filter (dataloaders/vidor.py:583-641) on hand-made tracklets."""
+    from oracle import loader_oracle as LO
+    box = torch.tensor([[100.0, 100.0, 200.0, 220.0]])
+
+    def trk(n, shift=0.0):
+        return box.repeat(n, 1) + shift
+
+    # 0: long; 1: same boxes over a sub-interval (rule 1 drops 1); 2: other category; 3: far away; 4: covers 5 (listed after it
+    # as ref) -> rule 2 drops the base 5?  no: base < ref, so 4 is base of 5: rule 1 drops 5.  6 is covered by the later 7: rule 2.
+    boxes = [trk(100), trk(40), trk(40), trk(40, 500.0), trk(50, 1.0), trk(50, 1.0), trk(30, 2.0), trk(60, 2.0)]
+    durs = torch.tensor([[0, 100], [10, 50], [10, 50], [10, 50], [200, 250], [200, 250], [310, 340], [300, 360]])
+    cats = torch.tensor([1, 1, 2, 1, 3, 3, 4, 4])
+    assert LO.duplicate_filter(boxes, durs, cats, 0.9) == [True, False, True, True, True, False, False, True]
+    # a dropped ref is skipped by later bases; a dropped base ends its own scan
+    boxes = [trk(30), trk(60), trk(30)]
+    durs = torch.tensor([[10, 40], [0, 60], [10, 40]])
+    cats = torch.tensor([1, 1, 1])
+    # base 0 vs ref 1: rule 2 drops base 0 and breaks (ref 2 is not examined by base 0); base 1 vs ref 2: rule 1 drops 2
+    assert LO.duplicate_filter(boxes, durs, cats, 0.9) == [False, True, False]

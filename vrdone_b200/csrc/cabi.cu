@@ -57,6 +57,16 @@ int vrd_h2d_pairs(const void* const* src, const int64_t* bytes, void* dst_base, 
     return 0;
 }
 
+int vrd_viou_filter(const float* boxes, const int32_t* trk_base, const int32_t* durations, const int32_t* cat_ids, int n_tracklets,
+                    float viou_threshold, double* sums, uint8_t* flags, int32_t* valid, vrd_stream_t stream) {
+    if (boxes == nullptr || trk_base == nullptr || durations == nullptr || cat_ids == nullptr || flags == nullptr || valid == nullptr)
+        return fail("vrd_viou_filter: null argument");
+    if (n_tracklets < 1 || n_tracklets > 1024) return fail("vrd_viou_filter: n_tracklets must be in [1, 1024]");
+    if (vrd::viou_filter(boxes, trk_base, durations, cat_ids, n_tracklets, viou_threshold, sums, flags, valid, (cudaStream_t)stream) != 0)
+        return fail("vrd_viou_filter: bad arguments");
+    return check_launch("vrd_viou_filter");
+}
+
 int vrd_pack_pairs(const void* pair_ptrs, const int64_t* pair_strides, const int32_t* row_seq, const int32_t* seqinfo, int R,
                    int B, int nv, int nc, int nbs, int nbe, void* vis, void* clip, int act_dtype, float* bbox_so,
                    float* bbox_ent, int token_major, vrd_stream_t stream) {

@@ -31,6 +31,8 @@ void pack_pairs(const void* ptrs, const long long* strides, Lay lay, int nv, int
                 int adt, float* bso, float* bent, int token_major, cudaStream_t st);
 int pack_tracklets(const float* vis_all, const float* clip_all, const float* boxes_all, const int* pair_tab, Lay lay, int nv, int nc,
                    float vw, float vh, void* vis, void* clip, int adt, float* bso, float* bent, cudaStream_t st);
+int viou_filter(const float* boxes, const int* trk_base, const int* durs, const int* cat_ids, int N, float thr, double* sums,
+                unsigned char* flags, int* valid, cudaStream_t st);
 int layernorm(const void* x, int xdt, long long ldx, const float* g, const float* b, void* out, int odt, long long ldo, int rows,
               int C, int relu, const int* row_seq, int R, cudaStream_t st);
 int small_conv(const float* x, int cin, const float* wt, const float* bias, const float* g, const float* b, int relu, void* out,

@@ -3,6 +3,7 @@
 // Reference semantics (file:line under /root/reference/models/): channel LayerNorm blocks.py:143-158,
 // masked depthwise conv blocks.py:91-113 + 706-724, max-pool skip blocks.py:1040-1046 + 1074,
 // FPN fpns.py:229-257, input contract maskvrd.py:363-414 (padding, re-derived analytically per SURVEY appendix B).
+#include <type_traits>
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
@@ -600,20 +601,23 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_kernel(const TI* __re
 // needs the raw row), then each warp produces output rows from the three staged neighbours, so no state is carried
 // between rows.  A staged separator row normalises to exactly beta, which is the value of the first pad column.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int DWT_TILE = 32;
-constexpr int DWT_ROWS = DWT_TILE + 2;
-constexpr int DWT_WARPS = 8;
-constexpr int DWT_RPW = DWT_TILE / DWT_WARPS;     // consecutive output rows per warp (4): parameter loads are shared between them
-constexpr int DWT_TILE_BYTES = DWT_ROWS * 512 * 4;
+// TILE output rows per CTA iteration (TILE + 2 staged rows).  Each tile is a chain of dependent phases (TMA wait, normalise,
+// barrier, per-branch conv + two shuffle reductions): with ONE tile in flight per SM the chain's latency is exposed whatever the
+// number of warps working on it.  TILE = 16 halves the shared memory so that two independent CTAs share an SM and their phases
+// interleave.
+// NW warps per CTA, DWT_TILE / NW consecutive output rows per warp (parameter loads are shared between a warp's rows).  8 warps x 4
+// rows left the SM with two warps per scheduler (issue active 31 %: every shuffle / shared-memory latency exposed); 16 warps x 2
+// rows doubles the warps that can cover for each other at the price of ~30 % more L1 parameter traffic.
 // two TMA buffers of raw rows [+ one tile of normalised rows when a branch needs both] + a zero row + a beta row + barriers
-constexpr int dwt_smem_bytes(bool mixed) { return (mixed ? 3 : 2) * DWT_TILE_BYTES + 2 * 512 * 4 + 32; }
+constexpr int dwt_smem_bytes(bool mixed, int tile) { return (mixed ? 3 : 2) * (tile + 2) * 512 * 4 + 2 * 512 * 4 + 32; }
 
-template <typename TO, int NB, int PREMASK>
-__global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const float* __restrict__ x, Lay lay,
+template <typename TO, int NB, int PREMASK, int NW, int TILE>
+__global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(const float* __restrict__ x, Lay lay,
                                                                            const float* __restrict__ pre_g,
                                                                            const float* __restrict__ pre_b, DwBranches br,
-                                                                           int total_rows, int dbg) {
+                                                                           int total_rows) {
     constexpr int NCH = 4, C = 512;
+    constexpr int DWT_TILE = TILE, DWT_ROWS = TILE + 2, DWT_WARPS = NW, DWT_RPW = TILE / NW;
     constexpr bool ANY_PRE = PREMASK != 0;
     constexpr bool ALL_PRE = PREMASK == ((1 << NB) - 1);         // no branch reads the raw row: normalise in place
     constexpr bool MIXED = ANY_PRE && !ALL_PRE;                  // normalised rows go to their own tile
@@ -663,95 +667,101 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
                              : "=r"(ok) : "r"(bar_u + 8 * buf), "r"(parity) : "memory");
             }
         }
-        if (ANY_PRE && !(dbg & 4)) {
-            // normalise every staged row once.  Each warp takes up to NPW rows and works on them together (loads, the two
-            // shuffle reductions and the parameter reads of all its rows are interleaved), not one after the other: the serial
-            // version spent 22-40 % of the kernel here on exposed latency.
-            constexpr int NPW = (DWT_ROWS + DWT_WARPS - 1) / DWT_WARPS;
-            float v[NPW][NCH][4];
-            bool on[NPW];
+        if (ANY_PRE) {
+            // normalise every staged row once.  A warp works on its rows of a round together (loads, the two shuffle reductions
+            // and the parameter reads are interleaved, not one row after the other: the serial version spent 22-40 % of the
+            // kernel here on exposed latency).  DWT_ROWS is not a multiple of the warp count: the full rounds run on every warp,
+            // the remainder only on the warps that have a row in it (a warp-uniform branch, not predicated-off work).
+            constexpr int NFULL = DWT_ROWS / DWT_WARPS, NREM = DWT_ROWS % DWT_WARPS;
+            auto normalise = [&](auto nr_tag, int first) {
+                constexpr int NR = decltype(nr_tag)::value;
+                float v[NR][NCH][4];
+                bool on[NR];
 #pragma unroll
-            for (int u = 0; u < NPW; ++u) {
-                const int i = warp + u * DWT_WARPS;
-                const int p = r0 - 1 + i;
-                on[u] = i < DWT_ROWS && p >= lo && p < hi;
-                if (on[u]) load_row<float, NCH>(sx + i * C, lane, v[u]);
-                else row_zero<NCH>(v[u]);
-            }
-            float mean[NPW], rstd[NPW];
+                for (int u = 0; u < NR; ++u) {
+                    const int i = first + warp + u * DWT_WARPS;
+                    const int p = r0 - 1 + i;
+                    on[u] = p >= lo && p < hi;
+                    if (on[u]) load_row<float, NCH>(sx + i * C, lane, v[u]);
+                    else row_zero<NCH>(v[u]);
+                }
+                float mean[NR], rstd[NR];
 #pragma unroll
-            for (int u = 0; u < NPW; ++u) {
-                float sm = 0.f;
+                for (int u = 0; u < NR; ++u) {
+                    float sm = 0.f;
 #pragma unroll
-                for (int j = 0; j < NCH; ++j) sm += (v[u][j][0] + v[u][j][1]) + (v[u][j][2] + v[u][j][3]);
-                mean[u] = sm;
-            }
+                    for (int j = 0; j < NCH; ++j) sm += (v[u][j][0] + v[u][j][1]) + (v[u][j][2] + v[u][j][3]);
+                    mean[u] = sm;
+                }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
+                for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int u = 0; u < NPW; ++u) mean[u] += __shfl_xor_sync(FULL_MASK, mean[u], o);
+                    for (int u = 0; u < NR; ++u) mean[u] += __shfl_xor_sync(FULL_MASK, mean[u], o);
 #pragma unroll
-            for (int u = 0; u < NPW; ++u) {
-                mean[u] *= (1.0f / C);
-                float q = 0.f;
+                for (int u = 0; u < NR; ++u) {
+                    mean[u] *= (1.0f / C);
+                    float q = 0.f;
 #pragma unroll
-                for (int j = 0; j < NCH; ++j)
+                    for (int j = 0; j < NCH; ++j)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { v[u][j][i] -= mean[u]; q = fmaf(v[u][j][i], v[u][j][i], q); }
-                rstd[u] = q;
-            }
+                        for (int i = 0; i < 4; ++i) { v[u][j][i] -= mean[u]; q = fmaf(v[u][j][i], v[u][j][i], q); }
+                    rstd[u] = q;
+                }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
+                for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int u = 0; u < NPW; ++u) rstd[u] += __shfl_xor_sync(FULL_MASK, rstd[u], o);
+                    for (int u = 0; u < NR; ++u) rstd[u] += __shfl_xor_sync(FULL_MASK, rstd[u], o);
 #pragma unroll
-            for (int u = 0; u < NPW; ++u) rstd[u] = 1.0f / sqrtf(rstd[u] * (1.0f / C) + VRD_EPS);
+                for (int u = 0; u < NR; ++u) rstd[u] = rsqrtf(rstd[u] * (1.0f / C) + VRD_EPS);
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                float g[4], be[4];
-                ld4(pre_g + (j * 32 + lane) * 4, g);
-                ld4(pre_b + (j * 32 + lane) * 4, be);
+                for (int j = 0; j < NCH; ++j) {
+                    float g[4], be[4];
+                    ld4(pre_g + (j * 32 + lane) * 4, g);
+                    ld4(pre_b + (j * 32 + lane) * 4, be);
 #pragma unroll
-                for (int u = 0; u < NPW; ++u)
+                    for (int u = 0; u < NR; ++u)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[u][j][i] = v[u][j][i] * rstd[u] * g[i] + be[i];
-            }
+                        for (int i = 0; i < 4; ++i) v[u][j][i] = v[u][j][i] * rstd[u] * g[i] + be[i];
+                }
 #pragma unroll
-            for (int u = 0; u < NPW; ++u) {
-                const int i = warp + u * DWT_WARPS;
-                if (on[u]) store_row<float, NCH>((MIXED ? s_nrm : sx) + i * C, lane, v[u]);
-            }
+                for (int u = 0; u < NR; ++u) {
+                    const int i = first + warp + u * DWT_WARPS;
+                    if (on[u]) store_row<float, NCH>((MIXED ? s_nrm : sx) + i * C, lane, v[u]);
+                }
+            };
+            normalise(std::integral_constant<int, NFULL>{}, 0);
+            if (NREM > 0 && warp < NREM) normalise(std::integral_constant<int, 1>{}, NFULL * DWT_WARPS);
             __syncthreads();
         }
-        // Each warp owns DWT_RPW consecutive output rows.  The per-channel parameters (conv taps, LayerNorm gamma / beta) are
-        // per-lane vectors that do not fit in registers for all branches, so they are re-read from L1 for every use: sharing
-        // each read between the warp's rows is what keeps the kernel off the L1 bandwidth limit (it moved ~30 KB of parameters
-        // per 5 KB of row data before).  Taps are branch-free: a tap outside the pair reads the zero row, the first pad column
-        // the beta row.
+        // Each warp owns DWT_RPW consecutive output rows and reads the DWT_RPW + 2 staged rows around them ONCE per branch and
+        // channel chunk (a register window shared by the rows' taps): the shared-memory pipe, not the FMA pipe, bounds this
+        // kernel (per tile ~4600 of its ~6900 LSU cycles were the 3 x DWT_RPW tap reads per branch).  The per-channel parameters
+        // (conv taps, LayerNorm gamma / beta) are re-read from L1 per use and shared between the warp's rows.  A window row
+        // that is a separator reads the zero row; the one case where a separator carries a value -- the first pad column of a
+        // pair (LN_pre bias) seen by the tap +1 of the pair's last row -- is added afterwards under a warp-uniform branch.
         {
+            constexpr int NWIN = DWT_RPW + 2;
             const int rr0 = warp * DWT_RPW;
-            // 32-bit shared-memory byte addresses of the three taps of every row, in the raw and in the normalised tile
-            uint32_t araw[DWT_RPW][3], anrm[DWT_RPW][3];
+            uint32_t araw[NWIN], anrm[NWIN];
             bool live[DWT_RPW];
+            uint32_t hib = 0;                                    // bit u: tap +1 of output row u is a first pad column
             const uint32_t sx_u = (uint32_t)__cvta_generic_to_shared(sx), sn_u = (uint32_t)__cvta_generic_to_shared(sn);
             const uint32_t zero_u = (uint32_t)__cvta_generic_to_shared(s_zero), beta_u = (uint32_t)__cvta_generic_to_shared(s_beta);
+            int wseq[NWIN];
+#pragma unroll
+            for (int w = 0; w < NWIN; ++w) {
+                const int grow = r0 + rr0 - 1 + w;
+                int seq = -1;
+                if (grow >= 0 && grow < total_rows) seq = lay.row_seq[grow % lay.R];
+                wseq[w] = seq;
+                const uint32_t row_off = (uint32_t)(rr0 + w) * C * 4;
+                araw[w] = (seq >= 0 ? sx_u + row_off : zero_u) + lane * 16;
+                anrm[w] = (seq >= 0 ? sn_u + row_off : zero_u) + lane * 16;
+            }
 #pragma unroll
             for (int u = 0; u < DWT_RPW; ++u) {
-                const int grow = r0 + rr0 + u;
-                const int s = grow / lay.R, r = grow - s * lay.R;
-                const int seq = lay.row_seq[r];
-                live[u] = seq >= 0;
-                int4 si = make_int4(0, 0, 0, 0);
-                if (live[u]) si = lay.seqinfo[seq];
-                const int t = r - si.x;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const int tt = t + d - 1;
-                    const bool inside = live[u] && tt >= 0 && tt < si.y;
-                    const uint32_t row_off = (uint32_t)(rr0 + u + d) * C * 4;
-                    araw[u][d] = (inside ? sx_u + row_off : zero_u) + lane * 16;
-                    anrm[u][d] = (inside ? sn_u + row_off : ((live[u] && tt == si.y && si.z != 0) ? beta_u : zero_u)) + lane * 16;
-                }
+                live[u] = wseq[u + 1] >= 0;
+                if (ANY_PRE && live[u] && wseq[u + 2] < 0 && lay.seqinfo[wseq[u + 1]].z != 0) hib |= 1u << u;
             }
 #pragma unroll 1
             for (int b = 0; b < NB; ++b) {
@@ -761,19 +771,29 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     const int c = (j * 32 + lane) * 4;
-                    float w0[4] = {1.f, 1.f, 1.f, 1.f}, w1[4] = {1.f, 1.f, 1.f, 1.f}, w2[4] = {1.f, 1.f, 1.f, 1.f};
-                    if (!(dbg & 2)) { ld4(wb + c, w0); ld4(wb + C + c, w1); ld4(wb + 2 * C + c, w2); }
+                    float w0[4], w1[4], w2[4];
+                    ld4(wb + c, w0); ld4(wb + C + c, w1); ld4(wb + 2 * C + c, w2);
+                    float a[NWIN][4];
 #pragma unroll
-                    for (int u = 0; u < DWT_RPW; ++u) {
-                        float a[3][4];
+                    for (int w = 0; w < NWIN; ++w) {
+                        const uint32_t addr = (pre ? anrm[w] : araw[w]) + j * 512;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(a[w][0]), "=f"(a[w][1]), "=f"(a[w][2]), "=f"(a[w][3]) : "r"(addr));
+                    }
 #pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            const uint32_t addr = (pre ? anrm[u][d] : araw[u][d]) + j * 512;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(a[d][0]), "=f"(a[d][1]), "=f"(a[d][2]), "=f"(a[d][3]) : "r"(addr));
-                        }
+                    for (int u = 0; u < DWT_RPW; ++u)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) y[u][j][i] = fmaf(a[2][i], w2[i], fmaf(a[1][i], w1[i], a[0][i] * w0[i]));
+                        for (int i = 0; i < 4; ++i) y[u][j][i] = fmaf(a[u + 2][i], w2[i], fmaf(a[u + 1][i], w1[i], a[u][i] * w0[i]));
+                    if (pre && hib != 0) {                       // warp-uniform and rare (one row per padded pair)
+                        float bt[4];
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(bt[0]), "=f"(bt[1]), "=f"(bt[2]), "=f"(bt[3]) : "r"(beta_u + lane * 16 + j * 512));
+#pragma unroll
+                        for (int u = 0; u < DWT_RPW; ++u)
+                            if ((hib >> u) & 1) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) y[u][j][i] = fmaf(bt[i], w2[i], y[u][j][i]);   // the tap read 0 above
+                            }
                     }
                 }
                 // post-conv LayerNorm of the warp's rows, reductions interleaved for instruction-level parallelism
@@ -785,7 +805,6 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
                     for (int j = 0; j < NCH; ++j) sm += (y[u][j][0] + y[u][j][1]) + (y[u][j][2] + y[u][j][3]);
                     mean[u] = sm;
                 }
-                if (!(dbg & 8))
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -800,26 +819,28 @@ __global__ void __launch_bounds__(DWT_WARPS * 32, 1) dwconv_ln_tile_kernel(const
                         for (int i = 0; i < 4; ++i) { y[u][j][i] -= mean[u]; q = fmaf(y[u][j][i], y[u][j][i], q); }
                     rstd[u] = q;
                 }
-                if (!(dbg & 8))
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
                     for (int u = 0; u < DWT_RPW; ++u) rstd[u] += __shfl_xor_sync(FULL_MASK, rstd[u], o);
 #pragma unroll
-                for (int u = 0; u < DWT_RPW; ++u) rstd[u] = 1.0f / sqrtf(rstd[u] * (1.0f / C) + VRD_EPS);
+                for (int u = 0; u < DWT_RPW; ++u) rstd[u] = rsqrtf(rstd[u] * (1.0f / C) + VRD_EPS);
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
-                    float g[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (!(dbg & 2)) { ld4(br.g[b] + (j * 32 + lane) * 4, g); ld4(br.b[b] + (j * 32 + lane) * 4, be); }
+                    float g[4], be[4];
+                    ld4(br.g[b] + (j * 32 + lane) * 4, g);
+                    ld4(br.b[b] + (j * 32 + lane) * 4, be);
 #pragma unroll
                     for (int u = 0; u < DWT_RPW; ++u)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) y[u][j][i] = live[u] ? y[u][j][i] * rstd[u] * g[i] + be[i] : 0.f;   // separator rows -> 0
+                        for (int i = 0; i < 4; ++i) y[u][j][i] = y[u][j][i] * rstd[u] * g[i] + be[i];
                 }
 #pragma unroll
-                for (int u = 0; u < DWT_RPW; ++u)
-                    if (!(dbg & 1) || y[u][0][0] == 1234.567f)
-                        store_row<TO, NCH>((TO*)br.out[b] + (long long)(r0 + rr0 + u) * br.ldo[b], lane, y[u]);
+                for (int u = 0; u < DWT_RPW; ++u) {
+                    TO* o = (TO*)br.out[b] + (long long)(r0 + rr0 + u) * br.ldo[b];
+                    if (live[u]) store_row<TO, NCH>(o, lane, y[u]);        // warp-uniform
+                    else zero_row<TO, NCH>(o, lane);                        // separator rows -> 0
+                }
             }
         }
         if constexpr (ALL_PRE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before the next TMA fill
@@ -838,23 +859,27 @@ static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const flo
     }
     int mask = 0;
     for (int b = 0; b < br.n; ++b) mask |= (br.use_pre[b] ? 1 : 0) << b;
-    const char* dv = getenv("VRD_DW_DEBUG");          // timing experiments only (skips parts of the kernel: wrong results)
-    const int dbg = dv ? atoi(dv) : 0;
+    static const int cfg = getenv("VRD_DW_CFG") ? atoi(getenv("VRD_DW_CFG")) : 2;   // 0: 8 warps x 32 rows, 1: 16 x 32, 2: 2 CTAs/SM of 8 x 16
+    const int tile_rows = cfg == 2 ? 16 : 32;
     const int total = streams * lay.R;
-    const int n_tiles = total / DWT_TILE;
-    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-#define LAUNCH(NB, MASK) do { \
-        auto kern = dwconv_ln_tile_kernel<TO, NB, MASK>; \
-        constexpr int smem = dwt_smem_bytes(MASK != 0 && MASK != ((1 << NB) - 1)); \
+    const int n_tiles = total / tile_rows;
+    const int max_ctas = num_sms * (32 / tile_rows);
+    const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+#define LAUNCH_NW(NB, MASK, NW, TILE) do { \
+        auto kern = dwconv_ln_tile_kernel<TO, NB, MASK, NW, TILE>; \
+        constexpr int smem = dwt_smem_bytes(MASK != 0 && MASK != ((1 << NB) - 1), TILE); \
         static bool attr_set = false; \
         if (!attr_set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1; attr_set = true; } \
-        kern<<<grid, DWT_WARPS * 32, smem, st>>>(x, lay, pre_g, pre_b, br, total, dbg); } while (0)
+        kern<<<grid, NW * 32, smem, st>>>(x, lay, pre_g, pre_b, br, total); } while (0)
+#define LAUNCH(NB, MASK) do { if (cfg == 0) LAUNCH_NW(NB, MASK, 8, 32); else if (cfg == 1) LAUNCH_NW(NB, MASK, 16, 32); \
+                               else LAUNCH_NW(NB, MASK, 8, 16); } while (0)
     if (br.n == 3 && mask == 7) LAUNCH(3, 7);
     else if (br.n == 3 && mask == 3) LAUNCH(3, 3);
     else if (br.n == 2 && mask == 0) LAUNCH(2, 0);
     else if (br.n == 1 && mask == 1) LAUNCH(1, 1);
     else return 1;
 #undef LAUNCH
+#undef LAUNCH_NW
     return 0;
 }
 

@@ -23,6 +23,7 @@ _SIGNATURES = {
     "vrd_abi_version": [],
     "vrd_device_arch": [],
     "vrd_h2d_pairs": [_vp, _vp, _vp, _vp, _i32, _vp],
+    "vrd_viou_filter": [_vp, _vp, _vp, _vp, _i32, C.c_float, _vp, _vp, _vp, _vp],
     "vrd_pack_pairs": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
     "vrd_gemm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp,
                  _vp, _i32, _vp],
@@ -203,6 +204,21 @@ class CudaOps:
                                     C.c_void_p(stream.cuda_stream))
         if rc != 0:
             raise RuntimeError(f"vrd_h2d_pairs failed: {self.lib.vrd_last_error().decode()}")
+
+    def viou_filter(self, boxes, trk_base, durations, cat_ids, threshold, stream, want_sums=False):
+        """SURVEY 8f row 2.  boxes [T, 4] fp32, trk_base / cat_ids [N] int32, durations [N, 2] int32 (CUDA tensors); enqueued on
+        ``stream``.  Returns (valid [N] int32, flags [N, N] uint8, sums [N, N, 3] fp64 or None) on the device."""
+        n = int(trk_base.shape[0])
+        assert boxes.dtype == torch.float32 and boxes.is_contiguous() and boxes.shape[1] == 4
+        assert all(t.dtype == torch.int32 and t.is_contiguous() for t in (trk_base, durations, cat_ids))
+        with torch.cuda.stream(stream):
+            valid = torch.empty(n, dtype=torch.int32, device=boxes.device)
+            flags = torch.empty(n, n, dtype=torch.uint8, device=boxes.device)
+            sums = torch.empty(n, n, 3, dtype=torch.float64, device=boxes.device) if want_sums else None
+        rc = self.lib.vrd_viou_filter(_p(boxes), _p(trk_base), _p(durations), _p(cat_ids), n, float(threshold), _p(sums), _p(flags),
+                                      _p(valid), C.c_void_p(stream.cuda_stream))
+        self._check(rc, "vrd_viou_filter")
+        return valid, flags, sums
 
     # -- ops ------------------------------------------------------------------------------------------------------
     def pack_pairs(self, ptrs, strides, lay, nv, nc, nbs, nbe, vis, clp, bso, bent, token_major=False):

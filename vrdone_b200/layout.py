@@ -74,6 +74,7 @@ class PackLayout:
         self.B = len(lens)
         self.levels: List[LevelLayout] = []
         host = []
+        ids = np.arange(self.B, dtype=np.int32)
         for l in range(n_levels):
             ll = (lens + (1 << l) - 1) >> l
             off = np.empty(self.B, dtype=np.int64)
@@ -83,10 +84,13 @@ class PackLayout:
             used = int(off[-1] + ll[-1] + 1)
             rows = (used + ROW_TILE - 1) // ROW_TILE * ROW_TILE
             haspad = (ll < (tp >> l)).astype(np.int32)
+            # rows: separator, then per pair its ll rows and one separator; the tail up to ``rows`` are separators too
             row_seq = np.full(rows, -1, dtype=np.int32)
-            row_seq[np.repeat(off, ll) + (np.arange(int(ll.sum())) - np.repeat(np.cumsum(ll) - ll, ll))] = \
-                np.repeat(np.arange(self.B, dtype=np.int32), ll)
-            info = np.stack([off.astype(np.int32), ll.astype(np.int32), haspad, np.zeros(self.B, np.int32)], 1)
+            body = row_seq[1:used]
+            body[:] = np.repeat(ids, ll + 1)
+            body[off + ll - 1] = -1
+            info = np.zeros((self.B, 4), dtype=np.int32)
+            info[:, 0], info[:, 1], info[:, 2] = off, ll, haspad
             lev = LevelLayout(l, off.astype(np.int32), ll.astype(np.int32), haspad, rows)
             self.levels.append(lev)
             host += [row_seq, info.reshape(-1)]

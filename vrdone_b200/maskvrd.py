@@ -14,6 +14,7 @@ Differences that are deliberate and documented:
 from __future__ import annotations
 
 import gc
+import itertools
 import time
 from typing import Dict, List, Optional
 
@@ -102,6 +103,7 @@ class MaskVRD(nn.Module):
         self.use_native = bool(config.get("use_native", True))            # C++ backbone schedule (csrc/engine.cu)
         self._native = None
         self._copy_stream = None
+        self._aux_stream = None
         self._staging = [None, None]      # double-buffered device staging of host-resident pair tensors
         self._pack_done = [None, None]
         self._engine: Optional[Engine] = None
@@ -201,18 +203,30 @@ class MaskVRD(nn.Module):
         return out
 
     @staticmethod
-    def _pair_table(sub):
-        """int64 [3, n] table (data pointer, channel stride, time stride) of a list of (C, L) tensors, the byte span of the
-        host-resident ones (0 for device tensors) and their 256-byte aligned offsets in a staging buffer."""
-        n = len(sub)
-        meta = np.empty((3, n), dtype=np.int64)
-        meta[0] = [f.data_ptr() for f in sub]
-        st = np.array([f.stride() for f in sub], dtype=np.int64)
-        meta[1], meta[2] = st[:, 0], st[:, 1]
-        on_host = np.array([not f.is_cuda for f in sub], dtype=bool)
+    def _describe(feats):
+        """One pass over a list of fp32 (C, L) tensors: data pointers, element strides, shapes and residency as numpy arrays
+        (per-tensor Python calls are the bulk of the host-side preparation at ~10^3 pairs per video)."""
+        n = len(feats)
+        try:
+            stride = np.fromiter(itertools.chain.from_iterable([f.stride() for f in feats]), dtype=np.int64, count=2 * n).reshape(n, 2)
+            shape = np.fromiter(itertools.chain.from_iterable([f.shape for f in feats]), dtype=np.int64, count=2 * n).reshape(n, 2)
+        except ValueError:
+            raise AssertionError("so_features_list must hold 2-D (C, L) tensors") from None
+        assert all([f.dtype is torch.float32 for f in feats]), "so_features_list must hold float32 tensors"
+        return {"ptr": np.array([f.data_ptr() for f in feats], dtype=np.int64), "stride": stride, "shape": shape,
+                "on_host": np.array([not f.is_cuda for f in feats], dtype=bool)}
+
+    @staticmethod
+    def _pair_table(desc, a: int, b: int):
+        """int64 [3, n] table (data pointer, channel stride, time stride) of pairs [a, b) of a described list, the byte span
+        of the host-resident ones (0 for device tensors) and their 256-byte aligned offsets in a staging buffer."""
+        meta = np.empty((3, b - a), dtype=np.int64)
+        meta[0] = desc["ptr"][a:b]
+        meta[1:] = desc["stride"][a:b].T
+        on_host = desc["on_host"][a:b]
         if not on_host.any():
             return meta, None
-        shape = np.array([f.shape for f in sub], dtype=np.int64)
+        shape = desc["shape"][a:b]
         # smallest address span that covers the (C, L) view: covers dense (C, L), the loader's (L, C) buffer and strided views
         span = np.where(on_host, ((shape[:, 0] - 1) * meta[1] + (shape[:, 1] - 1) * meta[2] + 1) * 4, 0)
         padded = (span + 255) // 256 * 256
@@ -230,7 +244,7 @@ class MaskVRD(nn.Module):
             e.record(cur)
             self._copy_stream.wait_event(e)
 
-    def _prepare_chunk(self, ops, feats, lens, tpads, chunk, ci: int, dev, cur, any_host: bool):
+    def _prepare_chunk(self, ops, desc, lens, tpads, chunk, ci: int, dev, cur, any_host: bool):
         """Host-side preparation of one chunk and everything that crosses PCIe for it, enqueued in this order on ONE stream
         (the copy stream when any pair lives on the host, else the compute stream): the chunk's layout arrays + pair table
         (one small pinned upload), then the bulk copies of its host-resident pairs.  Host->device copies of all streams share
@@ -238,14 +252,14 @@ class MaskVRD(nn.Module):
         behind a whole chunk of bulk copies.  Returns (layout, device pair table, event to wait for or None, token_major)."""
         a, b = chunk
         lay = PackLayout(lens[a:b], tpads[a:b], self.n_levels)
-        meta, plan = self._pair_table(feats[a:b])
+        meta, plan = self._pair_table(desc, a, b)
         if plan is not None:
             slot = ci & 1
             buf = self._staging[slot]
             if buf is None or buf.numel() < plan["total"]:
                 # sized for a full chunk so that steady state never reallocates (replacing a buffer whose copies are still in
                 # flight is safe: every later use of the memory is ordered behind the pack kernel that waits for them)
-                full = (self.h2d_chunk_rows + 4096) * int(feats[a].shape[0]) * 4
+                full = (self.h2d_chunk_rows + 4096) * int(desc["shape"][a, 0]) * 4
                 self._staging[slot] = buf = torch.empty(max(plan["total"], full), dtype=torch.uint8, device=dev)
                 self._fresh_block(cur)
             meta[0, plan["idx"]] = buf.data_ptr() + plan["offs"]
@@ -261,24 +275,30 @@ class MaskVRD(nn.Module):
             self._lay_done[ls] = None
             self._fresh_block(cur)
         stream = self._copy_stream if any_host else cur
-        with torch.cuda.stream(stream):
-            if self._lay_done[ls] is not None:
-                stream.wait_event(self._lay_done[ls])      # the kernels of the chunk that used this buffer four chunks ago are done
-            lbuf[:words].copy_(pin, non_blocking=True)
         lay.bind(lbuf[:lay.n_words])
         meta_d = lbuf[lay.n_words: lay.n_words + 6 * lay.B].view(torch.int64).view(3, lay.B)
-        ev = None
-        if any_host:
-            if plan is not None:
-                if self._pack_done[ci & 1] is not None:
-                    stream.wait_event(self._pack_done[ci & 1])      # the previous user of this staging buffer has been packed
-                ops.h2d_pairs(plan["src"], plan["bytes"], self._staging[ci & 1], plan["offs"], stream)
-            ev = torch.cuda.Event()
-            ev.record(stream)
+        ev = torch.cuda.Event() if any_host else None
+        lay_done, pack_done, staging = self._lay_done[ls], self._pack_done[ci & 1], self._staging[ci & 1]
+
+        def issue():
+            with torch.cuda.device(dev), torch.cuda.stream(stream):
+                if lay_done is not None:
+                    stream.wait_event(lay_done)      # the kernels of the chunk that used this buffer four chunks ago are done
+                lbuf[:words].copy_(pin, non_blocking=True)
+                if any_host:
+                    if plan is not None:
+                        if pack_done is not None:
+                            stream.wait_event(pack_done)      # the previous user of this staging buffer has been packed
+                        ops.h2d_pairs(plan["src"], plan["bytes"], staging, plan["offs"], stream)
+                    ev.record(stream)
+
+        # (Issuing the ~10^3 cudaMemcpyAsync calls of a video from a helper thread was measured and is slower: 33.7k vs 38.4k
+        # pairs/s end to end -- the two threads contend for the driver's locks and the GIL.)
+        issue()
         return lay, meta_d, ev, bool((meta[1] == 1).all()), plan is not None
 
     @torch.no_grad()
-    def run_network(self, feats: List[torch.Tensor], tpads: List[int], topk: int, want_masks: bool = False):
+    def run_network(self, feats: List[torch.Tensor], tpads: List[int], topk: int, want_masks: bool = False, desc=None):
         """feats: list of fp32 (C, L_i) tensors with any strides, on the device or on the host (pinned host tensors are
         staged by the copy engine chunk by chunk, overlapped with the previous chunk's kernels).  Returns per-pair arrays on the
         device: logits [B,Q,K+1], topk_scores / topk_ids [B,Q,topk], first_last [B,Q,2] and (optionally) a list of (L_i, Q)
@@ -286,9 +306,10 @@ class MaskVRD(nn.Module):
         eng = self._get_engine()
         dev = eng.device
         ops = self._ops
-        lens = [int(f.shape[1]) for f in feats]
-        assert all(f.dtype == torch.float32 and f.dim() == 2 for f in feats)
-        any_host = not all(f.is_cuda for f in feats)
+        if desc is None:
+            desc = self._describe(feats)
+        lens = desc["shape"][:, 1].tolist()
+        any_host = bool(desc["on_host"].any())
         st = {"prepare_ms": 0.0, "launch_ms": 0.0}
         with torch.cuda.device(dev):
             cur = torch.cuda.current_stream(dev)
@@ -299,14 +320,14 @@ class MaskVRD(nn.Module):
             else:
                 chunks = self._chunks(lens, self.max_rows)
             tA = time.perf_counter()
-            prep = self._prepare_chunk(ops, feats, lens, tpads, chunks[0], 0, dev, cur, any_host)
+            prep = self._prepare_chunk(ops, desc, lens, tpads, chunks[0], 0, dev, cur, any_host)
             st["prepare_ms"] += 1e3 * (time.perf_counter() - tA)
             lays, tops, mfs = [], [], []
             for ci, (a, b) in enumerate(chunks):
                 tC = time.perf_counter()
                 nxt = None
                 if ci + 1 < len(chunks):      # the next chunk's uploads and copies go out before this chunk's kernels are enqueued
-                    nxt = self._prepare_chunk(ops, feats, lens, tpads, chunks[ci + 1], ci + 1, dev, cur, any_host)
+                    nxt = self._prepare_chunk(ops, desc, lens, tpads, chunks[ci + 1], ci + 1, dev, cur, any_host)
                 lay, meta_d, ev, token_major, staged = prep
                 if ev is not None:
                     cur.wait_event(ev)
@@ -395,9 +416,9 @@ class MaskVRD(nn.Module):
         feats = list(input_data["so_features_list"])
         n_pairs = len(input_data["sids"])
         assert len(feats) == n_pairs
-        lens = [int(f.shape[1]) for f in feats]
-        tpads = reference_padded_lengths(lens, self.config)
-        r = self.run_network(feats, tpads, self.topk)
+        desc = self._describe(feats)
+        tpads = reference_padded_lengths(desc["shape"][:, 1].tolist(), self.config)
+        r = self.run_network(feats, tpads, self.topk, desc=desc)
         with torch.cuda.device(dev):
             small = self._stage_decode_inputs(input_data)
             host, ev = self._read_back(r, dev)
@@ -444,33 +465,59 @@ class MaskVRD(nn.Module):
         return self.submit_tracklets(data, dataset_config).result()
 
     @torch.no_grad()
-    def submit_tracklets(self, data: dict, dataset_config: dict) -> Optional["PendingVideo"]:
+    def submit_tracklets(self, data: dict, dataset_config: dict) -> "PendingVideo":
         """Additional entry point (the drop-in ``forward(input_data)`` stays): takes the input of the reference's
         ``_val_getitem`` -- per-tracklet ``visual_features_list`` [(T_i, visual_dim)], optional ``clip_features_list``,
         ``bboxes_list`` [(T_i, 4)], ``traj_durations``, candidate ``sids`` / ``oids``, ``cat_ids``, ``cat_scores``, ``video_wh``
         (tensors on the host or on the device) -- and returns what ``forward`` returns for the pair lists the data loader would
-        have built from it (dataloaders/vidor.py:659-734).  Tracklet features cross PCIe once (the pair lists repeat every
+        have built from it (dataloaders/vidor.py:556-734).  Tracklet features cross PCIe once (the pair lists repeat every
         tracklet ~N times); the gather and the box-geometry features (utils/misc.py:158-217) run in the pack kernel.
-        ``dataset_config``: ``feat_stride`` and optionally ``stride_offset`` (0) / ``proposal_min_frames`` (0).  Boxes are
-        clamped to the frame as the loader does; its duplicate-tracklet vIoU filter is expected to have been applied to
-        ``sids`` / ``oids`` already."""
+        ``dataset_config``: ``feat_stride`` and optionally ``stride_offset`` (0), ``proposal_min_frames`` (0) and
+        ``viou_threshold`` (None).  Boxes are clamped to the frame as the loader does.  With ``viou_threshold`` (the loader's
+        default is 0.9) its duplicate-tracklet filter (vidor.py:583-650) runs on the device first; without,
+        ``sids`` / ``oids`` are expected to be filtered already."""
         t0 = time.perf_counter()
         eng = self._get_engine()
         dev = eng.device
         stride = int(dataset_config.get("feat_stride", 1))
         offset = int(dataset_config.get("stride_offset", 0))
         min_frames = int(dataset_config.get("proposal_min_frames", 0))
+        viou_threshold = dataset_config.get("viou_threshold")
         vw, vh = (float(x) for x in data["video_wh"])
         vis_list, box_list = data["visual_features_list"], data["bboxes_list"]
         clip_list = data.get("clip_features_list") if self.with_clip_feature else None
         n_frames = np.array([int(v.shape[0]) for v in vis_list], dtype=np.int64)
         base = np.cumsum(n_frames) - n_frames                             # first row of every tracklet in the concatenated arrays
-        keep, L, s_off, o_off = self.pair_table(data["traj_durations"].cpu().numpy(), data["sids"].cpu().numpy(),
-                                                data["oids"].cpu().numpy(), stride, offset, min_frames)
+        durs_np = data["traj_durations"].cpu().numpy().astype(np.int64)
+        sids_np = data["sids"].cpu().numpy().astype(np.int64)
+        oids_np = data["oids"].cpu().numpy().astype(np.int64)
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            # boxes: one [T, 4] array, clamped to the frame (_val_getitem, vidor.py:572-577); the decode reads the same clamped
+            # boxes on the host (views of one pinned array when the boxes arrive on the host)
+            if box_list[0].is_cuda:
+                boxes_all = torch.cat([b.float() for b in box_list])
+                boxes_all[:, 0].clamp_(min=0); boxes_all[:, 1].clamp_(min=0)
+                boxes_all[:, 2].clamp_(max=vw - 1); boxes_all[:, 3].clamp_(max=vh - 1)
+                boxes_host = None
+            else:
+                boxes_pin = torch.empty(int(n_frames.sum()), 4, dtype=torch.float32, pin_memory=True)
+                torch.cat([b.float() for b in box_list], out=boxes_pin)
+                boxes_pin[:, 0].clamp_(min=0); boxes_pin[:, 1].clamp_(min=0)
+                boxes_pin[:, 2].clamp_(max=vw - 1); boxes_pin[:, 3].clamp_(max=vh - 1)
+                boxes_all = None
+                boxes_host = list(boxes_pin.split(n_frames.tolist()))
+            if viou_threshold is not None:
+                valid, boxes_all = self._filter_duplicates(boxes_all, None if boxes_all is not None else boxes_pin, base, durs_np,
+                                                           data["cat_ids"], float(viou_threshold), dev, cur)
+                ok = valid[sids_np] & valid[oids_np]
+                sids_np, oids_np = sids_np[ok], oids_np[ok]
+            elif boxes_all is None:
+                boxes_all = boxes_pin.to(dev, non_blocking=True)
+        keep, L, s_off, o_off = self.pair_table(durs_np, sids_np, oids_np, stride, offset, min_frames)
         if not keep.any():
             return _NO_PAIRS
-        sids = data["sids"].cpu().numpy().astype(np.int64)[keep]
-        oids = data["oids"].cpu().numpy().astype(np.int64)[keep]
+        sids, oids = sids_np[keep], oids_np[keep]
         lens = L[keep].tolist()
         tab = np.zeros((len(lens), 4), dtype=np.int32)
         tab[:, 0] = base[sids] + s_off[keep]
@@ -485,9 +532,6 @@ class MaskVRD(nn.Module):
                 return out
             vis_all = gather(vis_list, self.visual_dim)
             clip_all = gather(clip_list, self.clip_dim) if clip_list is not None else None
-            boxes_all = gather(box_list, 4)
-            boxes_all[:, 0].clamp_(min=0); boxes_all[:, 1].clamp_(min=0)          # _val_getitem, vidor.py:572-577
-            boxes_all[:, 2].clamp_(max=vw - 1); boxes_all[:, 3].clamp_(max=vh - 1)
             tpads = reference_padded_lengths(lens, self.config)
             chunks = self._chunks(lens, self.max_rows)
             lays, tops, mfs = [], [], []
@@ -501,14 +545,49 @@ class MaskVRD(nn.Module):
             else:
                 glay, e_top, mf = MergedLayout(lays, dev), torch.cat(tops, 0), torch.cat(mfs, 0)
             r = eng.predict(glay, e_top, mf, self.topk, False)
+            if boxes_host is None:                                        # device-resident boxes: read the clamped copy back
+                boxes_pin = torch.empty(boxes_all.shape, dtype=torch.float32, pin_memory=True)
+                boxes_pin.copy_(boxes_all, non_blocking=True)
+                boxes_host = list(boxes_pin.split(n_frames.tolist()))
+            pairs = self._stage_decode_inputs({
+                "sids": torch.from_numpy(sids), "oids": torch.from_numpy(oids), "traj_durations": data["traj_durations"],
+                "cat_ids": data["cat_ids"], "cat_scores": data["cat_scores"],
+                "so_offset": torch.full((len(lens),), offset, dtype=torch.int64), "bboxes_list": boxes_host})
             host, ev = self._read_back(r, dev)
-        pairs = {"sids": torch.from_numpy(sids), "oids": torch.from_numpy(oids), "traj_durations": data["traj_durations"],
-                 "cat_ids": data["cat_ids"], "cat_scores": data["cat_scores"],
-                 "so_offset": torch.full((len(lens),), offset, dtype=torch.int64),
-                 "bboxes_list": [b.clone() for b in box_list]}
-        for b in pairs["bboxes_list"]:                                    # the loader clamps the boxes it hands on
-            b[:, 0].clamp_(min=0); b[:, 1].clamp_(min=0); b[:, 2].clamp_(max=vw - 1); b[:, 3].clamp_(max=vh - 1)
         return PendingVideo(self, host, ev, pairs, {"enqueue_ms": 1e3 * (time.perf_counter() - t0)})
+
+    def _filter_duplicates(self, boxes_dev, boxes_pin, base, durs_np, cat_ids, threshold: float, dev, cur):
+        """the loader's duplicate-tracklet vIoU filter (dataloaders/vidor.py:583-641) on the device.  Runs on a
+        high-priority side stream and waits for that stream only, so that with several videos in flight the host does not
+        wait for the kernels of the previous video (host-resident boxes; device-resident boxes are ordered behind the work
+        already enqueued on the current stream, which may have produced them).  Returns (valid [N] numpy bool, device boxes)."""
+        if self._aux_stream is None:
+            self._aux_stream = torch.cuda.Stream(device=dev, priority=-1)
+        aux = self._aux_stream
+        n = len(base)
+        meta = torch.empty(4 * n, dtype=torch.int32, pin_memory=True)       # trk_base | durations (start, end) | cat_ids
+        m = meta.numpy()
+        m[:n] = base
+        m[n:3 * n] = durs_np.reshape(-1)
+        m[3 * n:] = cat_ids.cpu().numpy()
+        if boxes_dev is not None:
+            e = torch.cuda.Event()
+            e.record(cur)
+            aux.wait_event(e)
+        with torch.cuda.stream(aux):
+            if boxes_dev is None:
+                boxes_dev = boxes_pin.to(dev, non_blocking=True)
+            meta_d = meta.to(dev, non_blocking=True)
+            valid_d, flags, _ = self._ops.viou_filter(boxes_dev, meta_d[:n], meta_d[n:3 * n].view(n, 2), meta_d[3 * n:], threshold, aux)
+            valid_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
+            valid_h.copy_(valid_d, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(aux)
+        for t in (boxes_dev, meta_d, valid_d, flags):
+            t.record_stream(cur)
+        cur.wait_event(done)                                                # the pack kernel reads boxes_dev on the current stream
+        done.synchronize()
+        return valid_h.numpy().astype(bool), boxes_dev
 
     def _decode(self, scores, cats, fl, input_data):
         """Candidates in (pair, query, k) order -> durations -> min-length filter -> mean score ranking -> top n_max_pair.

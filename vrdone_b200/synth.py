@@ -200,3 +200,48 @@ def synthetic_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int
         "so_features_list": feats,
         "so_offset": torch.tensor(offs, dtype=torch.int64),
     }
+
+
+def with_duplicates(trk: dict, cfg: dict, seed: int, n_dup: int = 6) -> dict:
+    """A tracklet-level video with ``n_dup`` near-duplicate tracklets inserted at random positions, so that the data loader's
+    duplicate-tracklet vIoU filter (dataloaders/vidor.py:583-641) has work to do: copies of existing tracklets over a
+    sub-interval (dropped by the filter when listed after their source: rule 1; their source is dropped when the longer
+    copy comes later: rule 2), with box jitter small (vIoU ~0.97) or large (~0.8, survives), some with another category.
+    ``sids`` / ``oids`` are re-enumerated over the new tracklet list."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    mc, dc = cfg["model_config"], cfg["dataset_config"]
+    clip = "clip_features_list" in trk
+    durs = [list(map(int, d)) for d in trk["traj_durations"].tolist()]
+    items = [dict(dur=durs[i], box=trk["bboxes_list"][i], vis=trk["visual_features_list"][i],
+                  clip=trk["clip_features_list"][i] if clip else None, cat=int(trk["cat_ids"][i]), score=float(trk["cat_scores"][i]))
+             for i in range(len(durs))]
+    n0 = len(items)
+    for d in range(n_dup):
+        src = items[int(torch.randint(0, n0, (1,), generator=g))]
+        a, b = src["dur"]
+        length = b - a
+        lo = int(torch.randint(0, max(1, length // 3), (1,), generator=g))
+        hi = length - int(torch.randint(0, max(1, length // 3), (1,), generator=g))
+        if d % 3 == 0:
+            lo, hi = 0, length                                     # same duration: either rule may fire, depending on the order
+        jitter = 1.5 if d % 4 != 3 else 14.0                        # pixels; the large one keeps vIoU below 0.9
+        box = src["box"][lo:hi] + jitter * (torch.rand(hi - lo, 4, generator=g) - 0.5)
+        item = dict(dur=[a + lo, a + hi], box=box, vis=torch.randn(hi - lo, mc["visual_dim"], generator=g),
+                    clip=torch.randn(hi - lo, mc["clip_dim"], generator=g) if clip else None,
+                    cat=src["cat"] if d % 5 != 4 else src["cat"] % 30 + 1, score=float(0.4 + 0.6 * torch.rand(1, generator=g)))
+        items.insert(int(torch.randint(0, len(items) + 1, (1,), generator=g)), item)
+    durs = [it["dur"] for it in items]
+    pairs = _overlapping_pairs(durs, dc.get("feat_stride", 1))
+    out = dict(trk)
+    out.update({
+        "sids": torch.tensor([p[0] for p in pairs], dtype=torch.int64),
+        "oids": torch.tensor([p[1] for p in pairs], dtype=torch.int64),
+        "cat_ids": torch.tensor([it["cat"] for it in items], dtype=torch.int64),
+        "cat_scores": torch.tensor([it["score"] for it in items], dtype=torch.float32),
+        "traj_durations": torch.tensor(durs, dtype=torch.int64),
+        "bboxes_list": [it["box"] for it in items],
+        "visual_features_list": [it["vis"] for it in items],
+    })
+    if clip:
+        out["clip_features_list"] = [it["clip"] for it in items]
+    return out

@@ -37,7 +37,7 @@ UNIT = "pairs/s"
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=6)
+    p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--config", default="vidor", choices=list(synth.CONFIG_NAMES))
@@ -301,6 +301,11 @@ def main():
         model.forward_tracklets(trk_videos[s % len(trk_videos)], cfg["dataset_config"])
     ms_trk, pairs_trk = timed(trk_videos, args.steps, h2d=True, dataset_config=cfg["dataset_config"])
     ms_trk_sync, _ = timed(trk_videos, args.steps, h2d=True, pipelined=False, dataset_config=cfg["dataset_config"])
+    # the same loops with so_trajs returned as a lazy sequence (no eager per-frame box lists)
+    model.lazy_trajs = True
+    ms_lazy, pairs_lazy = timed(dev_videos, args.steps, h2d=False)
+    ms_lazy_e2e, _ = timed(pinned, args.steps, h2d=True)
+    model.lazy_trajs = False
 
     # roofline pass: the same steps with a CUDA-event pair around every launch of the dominant (GEMM) kernel
     model.use_native = False        # same kernels, same order, issued one by one from Python so that each launch can be timed
@@ -344,6 +349,8 @@ def main():
                                  "host decode and device work",
                          "value": pairs_sync / (ms_sync * 1e-3), "e2e": pairs_e2e_sync / (ms_e2e_sync * 1e-3),
                          "e2e_tracklet_api": pairs_trk / (ms_trk_sync * 1e-3), "unit": UNIT},
+           "lazy_trajs": {"note": "model.lazy_trajs = True: so_trajs is a LazyTrajs sequence (SURVEY 8f row 3); same pipelined loops",
+                          "value": pairs_lazy / (ms_lazy * 1e-3), "e2e": pairs_lazy / (ms_lazy_e2e * 1e-3), "unit": UNIT},
            "step_wall_ms_pipelined": {"hbm_resident": wall_pipe, "e2e": wall_pipe_e2e},
            "host_ms_last_step": host_hbm, "host_ms_last_step_e2e": host_e2e}
     if not args.no_cpu_baseline:

@@ -16,6 +16,7 @@ from __future__ import annotations
 import gc
 import itertools
 import time
+from collections.abc import Sequence
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -25,6 +26,46 @@ from torch import nn
 from .engine import Engine, PackedWeights
 from .layout import MergedLayout, PackLayout, max_div_factor, reference_padded_lengths
 from .params import Backbone, Neck, Predictor
+
+
+class LazyTrajs(Sequence):
+    """``so_trajs`` of a result without the eager ``ndarray.tolist()`` (building the nested lists of per-frame
+    boxes for <= 200 triplets is most of the host-side decode, and freeing them costs as much again).  Behaves like the list of
+    ``[subject_boxes, object_boxes]`` the reference returns (maskvrd.py:300-309): ``len``, indexing, slicing, iteration and
+    ``==`` against a list materialise entries on demand (and cache them); ``arrays(i)`` returns the two (n, 4) float32 numpy
+    views without any conversion.  Enabled with ``model.lazy_trajs = True`` (config key ``lazy_trajs``); off by default so that
+    ``forward`` returns plain lists exactly as the reference does."""
+
+    __slots__ = ("_views", "_cache")
+
+    def __init__(self, views):
+        self._views = views                  # [(subject (n, 4) float32 array, object (n, 4) float32 array)]
+        self._cache = {}
+
+    def __len__(self):
+        return len(self._views)
+
+    def arrays(self, i):
+        return self._views[i]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self._views)))]
+        if i < 0:
+            i += len(self._views)
+        item = self._cache.get(i)
+        if item is None:
+            st, ot = self._views[i]
+            item = self._cache[i] = [st.tolist(), ot.tolist()]
+        return item
+
+    def __eq__(self, other):
+        if isinstance(other, (list, tuple, LazyTrajs)):
+            return len(other) == len(self) and all(a == b for a, b in zip(self, other))
+        return NotImplemented
+
+    def __repr__(self):
+        return f"LazyTrajs({len(self)} triplets)"
 
 
 class PendingVideo:
@@ -100,6 +141,7 @@ class MaskVRD(nn.Module):
         self._lay_bufs = [None] * 4       # persistent device buffers for the per-chunk layout arrays + pair tables
         self._lay_done = [None] * 4
         self.gc_park_results = bool(config.get("gc_park_results", True))
+        self.lazy_trajs = bool(config.get("lazy_trajs", False))           # so_trajs as a LazyTrajs sequence
         self.use_native = bool(config.get("use_native", True))            # C++ backbone schedule (csrc/engine.cu)
         self._native = None
         self._copy_stream = None
@@ -650,8 +692,9 @@ class MaskVRD(nn.Module):
                 gc.enable()
         return out
 
-    @staticmethod
-    def _fill_result(out, order, pi, qi, ki, sids, oids, start, end, so_start, durs, cat_ids, cats, trip_scores, avg, traj):
+    def _fill_result(self, out, order, pi, qi, ki, sids, oids, start, end, so_start, durs, cat_ids, cats, trip_scores, avg, traj):
+        lazy = self.lazy_trajs
+        views = []
         for j in order.tolist():
             p, q, k = int(pi[j]), int(qi[j]), int(ki[j])
             s, o = int(sids[p]), int(oids[p])
@@ -662,6 +705,11 @@ class MaskVRD(nn.Module):
             out["triplets"].append([int(cat_ids[s]), int(cats[p, q, k]), int(cat_ids[o])])
             out["triple_scores"].append(trip_scores[j].tolist())
             out["triple_scores_avg"].append(float(avg[j]))
-            out["so_trajs"].append([st.tolist(), ot.tolist()])
+            if lazy:
+                views.append((st, ot))
+            else:
+                out["so_trajs"].append([st.tolist(), ot.tolist()])
             out["pred_durations"].append([int(so_start[p]) + a, int(so_start[p]) + b])
             out["so_tids"].append([s, o])
+        if lazy:
+            out["so_trajs"] = LazyTrajs(views)

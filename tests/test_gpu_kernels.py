@@ -150,7 +150,8 @@ def test_window_and_full_attention(ops, lays, dt, n_head, w):
     out = torch.full((2 * R, 512), 5.0, dtype=adt, device="cuda")
     EmuOps().window_attn(q, k, v, ref, lc.levels[0], n_head, w, 2)
     ops.window_attn(q.cuda(), k.cuda(), v.cuda(), out, lg.levels[0], n_head, w, 2)
-    close(out, ref, tol, "window_attn")
+    valid2 = (lc.levels[0].row_seq >= 0).repeat(2)    # separator rows are don't-care for the only consumer (the projection GEMM)
+    close(out[valid2], ref[valid2], tol, "window_attn")
     EmuOps().full_attn(q[:R], k[:R], v[:R], ref[:R], lc.levels[0], n_head)
     out.fill_(5.0)
     ops.full_attn(q[:R].cuda(), k[:R].cuda(), v[:R].cuda(), out[:R], lg.levels[0], n_head)

@@ -4,6 +4,8 @@
 // padded batch reduces to "valid keys only" in the varlen layout); full attention local_transformer.py:144-187;
 // query self/cross attention of the predictor local_transformer.py:33-67, 144-187.
 // The 1/sqrt(head_dim) scale is folded into the query projection weights by the host.
+#include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -269,9 +271,8 @@ static int window_attn_tma_launch(const void* q, const void* k, const void* v, v
     return 0;
 }
 
-int window_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int n_head, int C, int w,
-                int streams, cudaStream_t st) {
-    if (C != 512 || w > 4 || w < 1) return 1;
+static int window_attn_simt(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int n_head, int C,
+                            int w, int streams, cudaStream_t st) {
     const int hs = C / n_head;
     if (ld == C && lay.R % 128 == 0 && (hs == 64 || hs == 128)) {
         if (dt == VRD_BF16)
@@ -562,6 +563,206 @@ int full_attn(const void* q, const void* k, const void* v, void* out, int dt, lo
     else return 1;
 #undef LAUNCH
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// window_attn_mma: the sliding-window attention (reference blocks.py:746-989, local_transformer.py:553-623) on tensor cores
+// for the bf16 path, head_dim 64.  The unit of work is 16 consecutive query rows of ONE pair, aligned to the pair's first row
+// (so a pair's result does not depend on where its rows sit in the layout), handled by one warp with no CTA-level barrier:
+// per head the warp stages its 16 query rows and the 32 key / value rows [u0 - 8, u0 + 24) with cp.async (two stages: the next
+// head streams in while this one is computed), multiplies Q K^T (mma.sync m16n8k16, 16 MMAs), masks everything outside the band
+// |i - j| <= w and outside the pair, takes ONE softmax (no online rescaling: the band fits the key block) and multiplies with
+// V (16 MMAs): ~25 instructions per row and head instead of the ~100 of the CUDA-core kernel (9 keys x (16-byte load, 8 FMAs,
+// 3 shuffles) per 8 channels).  Warp b owns the units that START in rows [16 b, 16 b + 16) of the stacked layout: one for the
+// inside of a long pair, one more for every pair that begins there.  The output tile goes through the warp's query rows in
+// shared memory so that global stores are 16-byte vectors.  Separator rows are not written (as in flash_attn_bf16: the only
+// consumer is the projection GEMM, whose epilogue zeroes its own separator rows whatever the operand holds).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int WM_HALO = 8, WM_WARPS = 4;
+
+template <int NH>
+__global__ void __launch_bounds__(WM_WARPS * 32, 2) window_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                                           const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
+                                                                           Lay lay, int w, int total_rows) {
+    constexpr int HS = 64, BM = 16, KR = BM + 2 * WM_HALO, LDS = HS + 8, CPR = HS / 8, C = NH * HS;
+    constexpr int STAGE = (BM + 2 * KR) * LDS;          // elements per pipeline stage: Q, K, V
+    extern __shared__ __align__(16) uint8_t wm_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    __nv_bfloat16* smem_p = reinterpret_cast<__nv_bfloat16*>(wm_smem) + warp * 2 * STAGE;
+    const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(smem_p);
+    const int b0 = (blockIdx.x * WM_WARPS + warp) * BM;      // first row of this warp's block of the stacked layout
+    if (b0 >= total_rows) return;
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    // units that start in this block: row r of pair p with (r - first row of p) % 16 == 0
+    int my_first = 0, my_last = -1;
+    {
+        const int i = b0 + (lane & 15);
+        const int s = i / lay.R, r = i - s * lay.R;
+        const int seq = lay.row_seq[r];
+        if (seq >= 0) {
+            const int4 si = lay.seqinfo[seq];
+            my_first = s * lay.R + si.x;
+            my_last = my_first + si.y - 1;
+        }
+        const bool starts = lane < 16 && my_last >= 0 && ((i - my_first) & 15) == 0;
+        uint32_t units = __ballot_sync(FULL_MASK, starts);
+        while (units != 0) {                              // warp-uniform
+            const int ul = __ffs(units) - 1;
+            units &= units - 1;
+            const int u0 = b0 + ul;
+            const int first = __shfl_sync(FULL_MASK, my_first, ul), last = __shfl_sync(FULL_MASK, my_last, ul);
+            // band limits of this thread's two query rows (rows past the pair's end: a finite dummy softmax, never written)
+            int lo[2], hi[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int qi = u0 + g + 8 * h;
+                lo[h] = hi[h] = qi;
+                if (qi <= last) { lo[h] = max(qi - w, first); hi[h] = min(qi + w, last); }
+            }
+            const int kb = u0 - WM_HALO;                  // row of the first staged key
+            auto load = [&](int head, int stage) {
+                const uint32_t sQ = smem_u + (uint32_t)(stage * STAGE) * 2, sK = sQ + BM * LDS * 2, sV = sK + KR * LDS * 2;
+                const long long hoff = (long long)head * HS;
+#pragma unroll
+                for (int c = lane; c < BM * CPR; c += 32) {
+                    const int r = c / CPR, cc = c % CPR;
+                    const bool ok = u0 + r < total_rows;
+                    cp_async16(sQ + (uint32_t)((r * LDS + cc * 8) * 2), q + (long long)(ok ? u0 + r : 0) * C + hoff + cc * 8, ok);
+                }
+#pragma unroll
+                for (int c = lane; c < KR * CPR; c += 32) {
+                    const int r = c / CPR, cc = c % CPR;
+                    const int pr = kb + r;
+                    const bool ok = pr >= 0 && pr < total_rows;
+                    const long long off = (long long)(ok ? pr : 0) * C + hoff + cc * 8;
+                    const uint32_t d = (uint32_t)((r * LDS + cc * 8) * 2);
+                    cp_async16(sK + d, k + off, ok);
+                    cp_async16(sV + d, v + off, ok);
+                }
+            };
+            load(0, 0);
+            cp_async_commit();
+            for (int head = 0; head < NH; ++head) {
+                const int stage = head & 1;
+                if (head + 1 < NH) {
+                    load(head + 1, stage ^ 1);            // its last readers finished before the previous iteration's __syncwarp
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncwarp();
+                const uint32_t sQ = smem_u + (uint32_t)(stage * STAGE) * 2, sK = sQ + BM * LDS * 2, sV = sK + KR * LDS * 2;
+                uint32_t qf[HS / 16][4];
+#pragma unroll
+                for (int ks = 0; ks < HS / 16; ++ks) {
+                    const int row = lane & 15, col = ks * 16 + (lane >> 4) * 8;
+                    ldsm_x4(sQ + (row * LDS + col) * 2, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+                }
+                float sacc[4][4];
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) sacc[nb][0] = sacc[nb][1] = sacc[nb][2] = sacc[nb][3] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < HS / 16; ++ks) {
+#pragma unroll
+                    for (int nb = 0; nb < 4; nb += 2) {
+                        const int row = nb * 8 + (lane & 7) + ((lane >> 4) << 3), col = ks * 16 + ((lane >> 3) & 1) * 8;
+                        uint32_t x0, x1, x2, x3;
+                        ldsm_x4(sK + (row * LDS + col) * 2, x0, x1, x2, x3);
+                        mma_bf16(sacc[nb], qf[ks], x0, x1);
+                        mma_bf16(sacc[nb + 1], qf[ks], x2, x3);
+                    }
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const int c = kb + nb * 8 + t4 * 2;
+                    if (c < lo[0] || c > hi[0]) sacc[nb][0] = -INFINITY;
+                    if (c + 1 < lo[0] || c + 1 > hi[0]) sacc[nb][1] = -INFINITY;
+                    if (c < lo[1] || c > hi[1]) sacc[nb][2] = -INFINITY;
+                    if (c + 1 < lo[1] || c + 1 > hi[1]) sacc[nb][3] = -INFINITY;
+                    mx0 = fmaxf(mx0, fmaxf(sacc[nb][0], sacc[nb][1]));
+                    mx1 = fmaxf(mx1, fmaxf(sacc[nb][2], sacc[nb][3]));
+                }
+                mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 2));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 2));
+                const float ms0 = mx0 * LOG2E, ms1 = mx1 * LOG2E;   // finite: the diagonal key is always inside the band
+                float l0 = 0.f, l1 = 0.f;
+                uint32_t pf[2][4];
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const float p0 = exp2f(sacc[nb][0] * LOG2E - ms0), p1 = exp2f(sacc[nb][1] * LOG2E - ms0);
+                    const float p2 = exp2f(sacc[nb][2] * LOG2E - ms1), p3 = exp2f(sacc[nb][3] * LOG2E - ms1);
+                    l0 += p0 + p1; l1 += p2 + p3;
+                    pf[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16(p0, p1);
+                    pf[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(p2, p3);
+                }
+                float o[HS / 8][4];
+#pragma unroll
+                for (int d = 0; d < HS / 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                    for (int d = 0; d < HS / 8; d += 2) {
+                        const int row = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = d * 8 + (lane >> 4) * 8;
+                        uint32_t x0, x1, x2, x3;
+                        ldsm_x4_trans(sV + (row * LDS + col) * 2, x0, x1, x2, x3);
+                        mma_bf16(o[d], pf[ks], x0, x1);
+                        mma_bf16(o[d + 1], pf[ks], x2, x3);
+                    }
+                }
+                l0 += __shfl_xor_sync(FULL_MASK, l0, 1); l0 += __shfl_xor_sync(FULL_MASK, l0, 2);
+                l1 += __shfl_xor_sync(FULL_MASK, l1, 1); l1 += __shfl_xor_sync(FULL_MASK, l1, 2);
+                const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+                // the query rows (their fragments are in registers) stage the output tile
+                __nv_bfloat16* sO = smem_p + stage * STAGE;
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < HS / 8; ++d) {
+                    const int c = d * 8 + t4 * 2;
+                    *reinterpret_cast<uint32_t*>(sO + g * LDS + c) = pack_bf16(o[d][0] * i0, o[d][1] * i0);
+                    *reinterpret_cast<uint32_t*>(sO + (g + 8) * LDS + c) = pack_bf16(o[d][2] * i1, o[d][3] * i1);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int c = lane; c < BM * CPR; c += 32) {
+                    const int r = c / CPR, cc = c % CPR;
+                    if (u0 + r <= last) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(sO + r * LDS + cc * 8);
+                        *reinterpret_cast<uint4*>(out + (long long)(u0 + r) * C + head * HS + cc * 8) = val;
+                    }
+                }
+                __syncwarp();      // this stage may be refilled by the next iteration's prefetch
+            }
+        }
+    }
+}
+
+static int window_attn_mma_launch(const void* q, const void* k, const void* v, void* out, Lay lay, int w, int streams,
+                                  cudaStream_t st) {
+    constexpr int smem = WM_WARPS * 2 * (16 + 2 * (16 + 2 * WM_HALO)) * (64 + 8) * 2;
+    static bool attr_set = false;
+    auto kern = window_attn_mma_kernel<8>;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+        attr_set = true;
+    }
+    const int total = streams * lay.R;    // R % 128 == 0
+    kern<<<total / (16 * WM_WARPS), WM_WARPS * 32, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                                                             (__nv_bfloat16*)out, lay, w, total);
+    return 0;
+}
+
+int window_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int n_head, int C, int w,
+                int streams, cudaStream_t st) {
+    if (C != 512 || w > 4 || w < 1) return 1;
+    const int hs = C / n_head;
+    static const bool use_mma = !(getenv("VRD_WINATTN") != nullptr && strcmp(getenv("VRD_WINATTN"), "simt") == 0);
+    if (use_mma && dt == VRD_BF16 && hs == 64 && n_head == 8 && ld == C && lay.R % 128 == 0)
+        return window_attn_mma_launch(q, k, v, out, lay, w, streams, st);
+    return window_attn_simt(q, k, v, out, dt, ld, lay, n_head, C, w, streams, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -323,6 +323,10 @@ def main():
     model.use_native = True
     sustained, burst, hbm, src = peaks()
     gemm = prof.get("vrd_gemm", {"ms": 0.0, "flops": 0.0, "n": 0})
+    by_shape = {k.split(": ", 1)[1]: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["n"] / args.steps,
+                                       "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)}
+                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if ": " in k}
+    prof = {k: v for k, v in prof.items() if ": " not in k}
     total_ms = sum(p["ms"] for p in prof.values()) or 1.0
     ach = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     peak = sustained if args.precision == "bf16" else 75.0
@@ -332,6 +336,7 @@ def main():
                 "launches": gemm["n"], "avg_launch_us": 1e3 * gemm["ms"] / max(1, gemm["n"]),
                 "share_of_step": gemm["ms"] / total_ms,
                 "per_kernel_ms": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "gemm_by_shape": by_shape,
                 "whole_path_algorithmic_tflops": sum(flops[s % len(flops)] for s in range(args.steps)) / (ms * 1e-3) / 1e12}
 
     if rank != 0:

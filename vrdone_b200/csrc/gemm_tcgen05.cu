@@ -231,6 +231,7 @@ struct EpiArgs {
     int M, N, act, has_res;
     const float* res2; long long ldr2;      // second residual: row-strided loads (only the SOS output projection uses it)
     const float* corr; const int* row_seq; const int4* seqinfo; int R;
+    int wide;                               // bf16 output without residual: [32 x 64] store boxes (map in the map_res slot)
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of two SMs of one TPC) shares a 256 x BN tile through
@@ -350,6 +351,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int half = ew >> 2;                        // which half of the tile's columns
         const int n_ch = block_n / (2 * CHUNK);          // chunks of 32 columns per warp and tile (<= 2 when has_res)
         const bool out_bf16 = e.out_dtype == VRD_BF16;
+        // bf16 outputs without a residual: two 32-column chunks share one [32 x 64] box (128-byte rows, same 4 KB as an fp32
+        // [32 x 32] box) and ONE TMA store -- the TMA unit handles requests at a fixed rate, and with 32 small store boxes
+        // per 128 x 256 tile on top of the 16 operand loads it, not the tensor pipe, set the pace of the K = 512 GEMMs
+        const bool wide = e.wide != 0;
         uint8_t* my_stage = staging + ew * 2 * STAGING_BYTES;
         uint64_t* my_resbar = resbar + 2 * ew;
         int it = 0;
@@ -385,15 +390,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * ACC_STAGE_COLS + half * (block_n / 2);
             for (int c = 0; c < n_ch; ++c) {
-                uint8_t* box = my_stage + (e.has_res ? (c & 1) : (int)(box_cnt++ & 1)) * STAGING_BYTES;
+                const int box_i = e.has_res ? (c & 1) : (wide ? (int)((box_cnt >> 1) & 1) : (int)(box_cnt & 1));
+                const bool box_first = !wide || (c & 1) == 0, box_last = !wide || (c & 1) == 1;
+                ++box_cnt;
+                uint8_t* box = my_stage + box_i * STAGING_BYTES;
                 const uint32_t box_u = smem_u32(box);
                 uint32_t acc[CHUNK];
                 tmem_ld32(taddr + c * CHUNK, acc);
                 if (e.has_res) {
                     // box c & 1 is filled once (n_ch <= 2) or twice (n_ch == 4, long-K tiles) per tile
                     mbar_wait(&my_resbar[c & 1], n_ch <= 2 ? (it & 1) : ((c >> 1) & 1));
-                } else {
-                    if (lane == 0) bulk_wait_read<1>();  // the store issued from this box two chunks ago has read it
+                } else if (box_first) {
+                    if (lane == 0) bulk_wait_read<1>();  // the store issued from this box two boxes ago has read it
                     __syncwarp();
                 }
                 tmem_ld_wait();
@@ -455,7 +463,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             pk.x = pack2(v[8 * j], v[8 * j + 1]); pk.y = pack2(v[8 * j + 2], v[8 * j + 3]);
                             pk.z = pack2(v[8 * j + 4], v[8 * j + 5]); pk.w = pack2(v[8 * j + 6], v[8 * j + 7]);
                         }
-                        sts128(box_u + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk.x, pk.y, pk.z, pk.w);
+                        if (wide)   // 128-byte rows: chunk jj of row r stored at chunk jj ^ (r & 7) (TMA SWIZZLE_128B)
+                            sts128(box_u + lane * 128 + (((j + 4 * (c & 1)) ^ (lane & 7)) << 4), pk.x, pk.y, pk.z, pk.w);
+                        else
+                            sts128(box_u + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk.x, pk.y, pk.z, pk.w);
                     }
                 } else {
 #pragma unroll
@@ -463,10 +474,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         sts128(box_u + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
                 }
+                if (!box_last) continue;                 // the second chunk of a wide box completes it
                 fence_async_smem();                      // make the generic-proxy writes visible to the TMA engine
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(&map_out, box_u, n, row0);
+                    if (wide) tma_store_2d(&map_res, box_u, n - CHUNK, row0);   // map_res carries the [32 x 64] bf16 box map
+                    else tma_store_2d(&map_out, box_u, n, row0);
                     bulk_commit();
                     if (e.has_res && c + 2 < n_ch) {     // refill this box with the residual of chunk c + 2 (tiles with long K only:
                         bulk_wait_read<0>();             // the MMAs of the next tile hide this latency)
@@ -525,6 +538,7 @@ const char* gemm_tcgen05_error() { return g_err; }
 int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     static int num_sms = 0;
     static bool attr_set = false;
+    static const bool wide_ok = !(getenv("VRD_GEMM_WIDE") != nullptr && atoi(getenv("VRD_GEMM_WIDE")) == 0);   // A/B switch
     static int force_cg = -1;
     if (force_cg < 0) { const char* v = getenv("VRD_GEMM_CG"); force_cg = v ? atoi(v) : 0; }
     if (g.M % BLOCK_M != 0 || g.K % BLOCK_K != 0 || g.N % 64 != 0 || g.lda % 8 != 0 || ((uintptr_t)g.A & 15) != 0) {
@@ -573,6 +587,9 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     }
     if (has_res) {
         if (!make_map(&map_res, g.res1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldr1, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    } else if (wide_ok && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) {
+        // no residual: the slot carries the [32 rows x 64 cols] box map of the wide bf16 epilogue
+        if (!make_map(&map_res, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, 2 * CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     } else {
         map_res = map_out;
     }
@@ -589,7 +606,8 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
         }
         attr_set = true;
     }
-    EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R};
+    const int wide = (!has_res && wide_ok && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) ? 1 : 0;
+    EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R, wide};
     const int n_tiles = ((g.M + BLOCK_M * cg - 1) / (BLOCK_M * cg)) * (g.N / block_n);
     const int max_groups = num_sms / cg;
     const int grid = cg * (n_tiles < max_groups ? n_tiles : max_groups);

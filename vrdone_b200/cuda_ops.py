@@ -146,6 +146,7 @@ class CudaOps:
         self.launches = 0
         self._timing = None     # list of (op name, start event, end event, algorithmic flops) while profiling
         self._last_flops = 0.0
+        self._last_tag = None
         self._stream_handle = C.c_void_p(0)
         self.bind_stream()
 
@@ -159,10 +160,11 @@ class CudaOps:
             def timed(*a, _fn=fn, _name=name, **k):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 self._last_flops = 0.0
+                self._last_tag = None
                 e0.record()
                 r = _fn(*a, **k)
                 e1.record()
-                self._timing.append(("vrd_" + _name, e0, e1, self._last_flops))
+                self._timing.append(("vrd_" + _name, e0, e1, self._last_flops, self._last_tag))
                 return r
             setattr(self, name, timed)
 
@@ -172,11 +174,13 @@ class CudaOps:
             if name in self.__dict__:
                 delattr(self, name)
         prof = {}
-        for name, e0, e1, fl in self._timing:
-            d = prof.setdefault(name, {"ms": 0.0, "flops": 0.0, "n": 0})
-            d["ms"] += e0.elapsed_time(e1)
-            d["flops"] += fl
-            d["n"] += 1
+        for name, e0, e1, fl, tag in self._timing:
+            ms = e0.elapsed_time(e1)
+            for key in ((name,) if tag is None else (name, name + ": " + tag)):
+                d = prof.setdefault(key, {"ms": 0.0, "flops": 0.0, "n": 0})
+                d["ms"] += ms
+                d["flops"] += fl
+                d["n"] += 1
         self._timing = None
         return prof
 
@@ -241,6 +245,8 @@ class CudaOps:
             rs, si, R = None, None, 0
         valid_rows = streams * int(lay.len.sum()) if lay is not None else M
         self._last_flops = 2.0 * valid_rows * N * K * taps     # algorithmic: valid rows only (no separators / tile padding)
+        self._last_tag = (f"{'big' if M >= 16384 else 'small'} M, {taps}x{K}->{N} {'bf16' if out.dtype == torch.bfloat16 else 'f32'}"
+                          f"{' gelu' if act == 2 else ''}{' +res' if res1 is not None else ''}")
         self._check(self.lib.vrd_gemm(ap, _dt(a), lda, _p(w), _f32(bias), op, _dt(out), ldo, M, N, K, taps, act, r1, ld1, r2, ld2,
                                       _f32(corr), rs, si, R, self._stream()), "vrd_gemm")
 

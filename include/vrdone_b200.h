@@ -167,6 +167,20 @@ int vrd_backbone_pack_tracklets(vrd_engine_t* engine, const vrd_level_t* levels,
 int vrd_backbone_compute(vrd_engine_t* engine, const vrd_level_t* levels, void* workspace, int64_t workspace_bytes, float* e_top,
                          float* mask_feat, vrd_stream_t stream);
 
+/* a15-a16 -- the query decoder and the heads (predictor.py:85-115, local_transformer.py:773-835, 875-976) as ONE native
+ * schedule over a batch described by its level 0 (mask features, R_0 rows) and its coarsest level (e_top, R_top rows): the
+ * ~80 launches of MaskedTransformerPredictor.forward + the top-k / mask epilogue of maskvrd.py:242-299.  Outputs: logits
+ * [ceil128(B*Q), n_cls_pad] fp32, topk_scores / topk_ids [B*Q, topk], first_last [B, Q, 2] int32 (first / last frame with
+ * sigmoid(mask) > 0.5, -1 if none), masks [R_0, Q] fp32 mask logits or NULL. */
+typedef struct {
+    int32_t n_embd, num_queries, n_head, num_layers, n_hidden, n_cls /* K + 1 */, n_cls_pad /* rows of the padded class head */;
+} vrd_predictor_cfg_t;
+int64_t vrd_predict_workspace_bytes(vrd_engine_t* engine, const vrd_predictor_cfg_t* cfg, const vrd_level_t* level0,
+                                    const vrd_level_t* level_top);
+int vrd_predict(vrd_engine_t* engine, const vrd_predictor_cfg_t* cfg, const vrd_level_t* level0, const vrd_level_t* level_top,
+                const float* e_top, const float* mask_feat, int topk, void* workspace, int64_t workspace_bytes, float* logits,
+                float* topk_scores, int32_t* topk_ids, int32_t* first_last, float* masks, vrd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

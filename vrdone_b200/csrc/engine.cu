@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 #include "../../include/vrdone_b200.h"
 #include "kernels.h"
@@ -335,6 +336,89 @@ struct Run {
             if (!fail && !dry()) { vrd::mask_features((const float*)y.p, y.ld, lay(0), beta, w, b, mf_out, Fd, st); check("mask_features"); }
         }
     }
+
+    // Query decoder + heads (predictor.py:85-115, local_transformer.py:773-835 / 875-976): L[0] = level 0 (mask features),
+    // L[1] = the coarsest level.  Same kernels and order as engine.Engine._predictor.
+    void query_ln(const Mat& x, const char* ln, const float* pos, int Q, int nrows, const float* dw, const char* ln2, const Mat& out,
+                  const std::string& p) {
+        const float* g = ln ? F(p + ln + ".g") : nullptr; const float* b = ln ? F(p + ln + ".be") : nullptr;
+        const float* g2 = ln2 ? F(p + ln2 + ".g") : nullptr; const float* b2 = ln2 ? F(p + ln2 + ".be") : nullptr;
+        if (fail || dry()) return;
+        if (vrd::query_ln((const float*)x.p, x.ld, g, b, pos, Q, nrows, out.rows, dw, g2, b2, out.p, out.dt, out.ld, x.cols, st))
+            error("query_ln: unsupported shape", p);
+        check("query_ln");
+    }
+
+    void predict(const vrd_predictor_cfg_t& pc, const float* e_top, int e_top_cols, const float* mf, int mf_cols, int topk, float* logits,
+                 float* scores, int* ids, int* first_last, float* masks) {
+        const int D = pc.n_embd, Q = pc.num_queries, nh = pc.n_head;
+        const int B = L[0].B;
+        const long long Rt = L[1].R, R0 = L[0].R;
+        const long long MQ = ((long long)B * Q + 127) / 128 * 128;
+        const Mat top{(char*)e_top, e_top_cols, (int)Rt, e_top_cols, VRD_F32};
+        Mat n = A->alloc(Rt, e_top_cols, adt);
+        layernorm(top, "predictor.input_norm", n, false, 1);
+        Mat src = A->alloc(Rt, D, VRD_F32);
+        gemm(n, "predictor.input_proj", src, 1);
+        Mat tgt = A->alloc(MQ, D, VRD_F32), tgt_next = A->alloc(MQ, D, VRD_F32);
+        if (!fail && !dry()) cudaMemsetAsync(tgt.p, 0, (size_t)MQ * D * 4, st);
+        const float* pos = F("predictor.query_pos");
+        for (int j = 0; j < pc.num_layers; ++j) {
+            const size_t mark = A->top;
+            const std::string p = "predictor.transformer.decoder.layers." + std::to_string(j);
+            const std::string sa = p + ".self_attn", ca = p + ".multihead_attn";
+            // self-attention among the Q queries of each pair: q = k = LN1(tgt) + pos, v = tgt
+            Mat qk = A->alloc(MQ, D, adt), tv = A->alloc(MQ, D, adt);
+            query_ln(tgt, ".ln1", pos, Q, B * Q, nullptr, nullptr, qk, p);
+            query_ln(tgt, nullptr, nullptr, Q, B * Q, nullptr, nullptr, tv, p);
+            Mat q = A->alloc(MQ, D, adt), k = A->alloc(MQ, D, adt), v = A->alloc(MQ, D, adt), a = A->alloc(MQ, D, adt);
+            gemm(qk, sa + ".query", q, -1);
+            gemm(qk, sa + ".key", k, -1);
+            gemm(tv, sa + ".value", v, -1);
+            if (!fail && !dry()) {
+                if (vrd::query_self_attn(q.p, k.p, v.p, a.p, adt, a.ld, B, Q, nh, D, st)) error("query_self_attn: unsupported", p);
+                check("query_self_attn");
+            }
+            Mat tgt1 = A->alloc(MQ, D, VRD_F32);
+            gemm(a, sa + ".proj", tgt1, -1, 1, 0, &tgt);
+            // cross-attention to the coarsest pyramid level
+            const Branch bkv[2] = {{"key", false}, {"value", false}};
+            Mat kv[2];
+            attention_qkv(ca, src, nullptr, bkv, 2, 1, 1, 1, 1, kv);
+            Mat h = A->alloc(MQ, D, adt);
+            query_ln(tgt1, ".ln2", pos, Q, B * Q, F(ca + ".query_conv.w"), ".multihead_attn.query_norm", h, p);
+            Mat q2 = A->alloc(MQ, D, adt), a2 = A->alloc(MQ, D, adt);
+            gemm(h, ca + ".query", q2, -1);
+            if (!fail && !dry()) {
+                if (vrd::query_cross_attn(q2.p, kv[0].p, kv[1].p, a2.p, adt, a2.ld, lay(1), Q, nh, D, st)) error("query_cross_attn: unsupported", p);
+                check("query_cross_attn");
+            }
+            Mat tgt2 = A->alloc(MQ, D, VRD_F32);
+            gemm(a2, ca + ".proj", tgt2, -1, 1, 0, &tgt1);
+            // FFN
+            Mat h3 = A->alloc(MQ, D, adt), h4 = A->alloc(MQ, pc.n_hidden, adt);
+            query_ln(tgt2, ".ln3", nullptr, Q, B * Q, nullptr, nullptr, h3, p);
+            gemm(h3, p + ".mlp.0", h4, -1, 1, VRD_ACT_GELU);
+            gemm(h4, p + ".mlp.3", tgt_next, -1, 1, 0, &tgt2);
+            std::swap(tgt, tgt_next);
+            A->top = mark;
+        }
+        Mat hs = A->alloc(MQ, D, adt);
+        query_ln(tgt, ".norm", nullptr, Q, B * Q, nullptr, nullptr, hs, "predictor.transformer.decoder");
+        const Mat lg{(char*)logits, pc.n_cls_pad, (int)MQ, pc.n_cls_pad, VRD_F32};
+        gemm(hs, "predictor.class_embed", lg, -1);
+        Mat m0 = A->alloc(MQ, D, adt), m1 = A->alloc(MQ, D, adt), me = A->alloc(MQ, D, VRD_F32);
+        gemm(hs, "predictor.mask_embed.0", m0, -1, 1, VRD_ACT_GELU);
+        gemm(m0, "predictor.mask_embed.1", m1, -1, 1, VRD_ACT_GELU);
+        gemm(m1, "predictor.mask_embed.2", me, -1);
+        if (!fail && !dry()) {
+            if (vrd::mask_logits((const float*)me.p, me.ld, mf, mf_cols, lay(0), Q, masks, Q, first_last, st)) error("mask_logits: unsupported", "");
+            check("mask_logits");
+            if (vrd::softmax_topk(logits, pc.n_cls_pad, B * Q, pc.n_cls, topk, scores, ids, st)) error("softmax_topk: unsupported", "");
+            check("softmax_topk");
+        }
+        (void)R0;
+    }
 };
 
 thread_local char t_eng_err[512] = {0};
@@ -430,6 +514,38 @@ int vrd_backbone_compute(vrd_engine_t* e, const vrd_level_t* levels, void* works
     Arena a{(char*)workspace, (size_t)workspace_bytes, 0, 0, false};
     Run r{e, levels, (cudaStream_t)stream, &a, e->cfg.act_dtype, false};
     r.compute(e_top, mask_feat);
+    if (r.fail) { snprintf(t_eng_err, sizeof t_eng_err, "%s", e->err); return 1; }
+    return 0;
+}
+
+int64_t vrd_predict_workspace_bytes(vrd_engine_t* e, const vrd_predictor_cfg_t* pc, const vrd_level_t* level0, const vrd_level_t* level_top) {
+    const vrd_level_t lv[2] = {*level0, *level_top};
+    Arena a{nullptr, 0, 0, 0, true};
+    Run r{e, lv, nullptr, &a, e->cfg.act_dtype, false};
+    r.predict(*pc, nullptr, e->cfg.embd_dim, nullptr, e->cfg.fpn_dim, 1, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (r.fail) { snprintf(t_eng_err, sizeof t_eng_err, "%s", e->err); return -1; }
+    return (int64_t)a.peak;
+}
+
+int vrd_predict(vrd_engine_t* e, const vrd_predictor_cfg_t* pc, const vrd_level_t* level0, const vrd_level_t* level_top, const float* e_top,
+                const float* mask_feat, int topk, void* workspace, int64_t workspace_bytes, float* logits, float* topk_scores,
+                int32_t* topk_ids, int32_t* first_last, float* masks, vrd_stream_t stream) {
+    if (pc == nullptr || level0 == nullptr || level_top == nullptr || e_top == nullptr || mask_feat == nullptr || logits == nullptr ||
+        topk_scores == nullptr || topk_ids == nullptr || first_last == nullptr) {
+        snprintf(t_eng_err, sizeof t_eng_err, "vrd_predict: null argument");
+        return 1;
+    }
+    if (pc->n_embd != e->cfg.fpn_dim) { snprintf(t_eng_err, sizeof t_eng_err, "vrd_predict: predictor width must equal fpn_dim"); return 1; }
+    const int64_t need = vrd_predict_workspace_bytes(e, pc, level0, level_top);
+    if (need < 0) return 1;
+    if (need > workspace_bytes) {
+        snprintf(t_eng_err, sizeof t_eng_err, "vrd_predict: workspace of %lld bytes needed, %lld given", (long long)need, (long long)workspace_bytes);
+        return 1;
+    }
+    const vrd_level_t lv[2] = {*level0, *level_top};
+    Arena a{(char*)workspace, (size_t)workspace_bytes, 0, 0, false};
+    Run r{e, lv, (cudaStream_t)stream, &a, e->cfg.act_dtype, false};
+    r.predict(*pc, e_top, e->cfg.embd_dim, mask_feat, e->cfg.fpn_dim, topk, logits, topk_scores, topk_ids, first_last, masks);
     if (r.fail) { snprintf(t_eng_err, sizeof t_eng_err, "%s", e->err); return 1; }
     return 0;
 }

@@ -55,7 +55,12 @@ class Level(C.Structure):
 
 
 _ENGINE_SYMBOLS = ["vrd_engine_last_error", "vrd_engine_create", "vrd_engine_destroy", "vrd_engine_launches",
-                   "vrd_backbone_workspace_bytes", "vrd_backbone_pack", "vrd_backbone_pack_tracklets", "vrd_backbone_compute"]
+                   "vrd_backbone_workspace_bytes", "vrd_backbone_pack", "vrd_backbone_pack_tracklets", "vrd_backbone_compute",
+                   "vrd_predict_workspace_bytes", "vrd_predict"]
+
+
+class PredictorCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_embd", "num_queries", "n_head", "num_layers", "n_hidden", "n_cls", "n_cls_pad")]
 
 
 def exported_symbols():
@@ -95,6 +100,11 @@ def load_library() -> C.CDLL:
     lib.vrd_backbone_pack_tracklets.restype = C.c_int
     lib.vrd_backbone_compute.argtypes = [C.c_void_p, C.POINTER(Level), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vrd_backbone_compute.restype = C.c_int
+    lib.vrd_predict_workspace_bytes.argtypes = [C.c_void_p, C.POINTER(PredictorCfg), C.POINTER(Level), C.POINTER(Level)]
+    lib.vrd_predict_workspace_bytes.restype = C.c_int64
+    lib.vrd_predict.argtypes = [C.c_void_p, C.POINTER(PredictorCfg), C.POINTER(Level), C.POINTER(Level), C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vrd_predict.restype = C.c_int
     if lib.vrd_abi_version() != 2:
         raise RuntimeError("libvrdone_b200.so ABI version mismatch; rebuild")
     _lib = lib
@@ -393,6 +403,11 @@ class NativeBackbone:
         self.handle = handle
         self.workspace: Optional[torch.Tensor] = None
         self._counted = 0
+        pc = mc["predictor"]
+        self.Q = pc["num_queries"]
+        self.pcfg = PredictorCfg(pc["n_embd"], pc["num_queries"], pc["n_head"], pc["num_layers"], pc["n_hidden"], weights.n_cls,
+                                 weights.n_cls_pad)
+        self.pred_workspace: Optional[torch.Tensor] = None
 
     def __del__(self):
         if getattr(self, "handle", None):
@@ -445,7 +460,42 @@ class NativeBackbone:
         mf = torch.empty(lay.levels[0].R, self.F, dtype=torch.float32, device=self.device)
         if self.lib.vrd_backbone_compute(self.handle, lv, ws, nbytes, e_top.data_ptr(), mf.data_ptr(), stream) != 0:
             self._fail("vrd_backbone_compute")
+        self._count()
+        return e_top, mf
+
+    def _count(self):
         total = int(self.lib.vrd_engine_launches(self.handle))
         self.ops.launches += total - self._counted
         self._counted = total
-        return e_top, mf
+
+    def predict(self, lay, e_top, mf, topk: int, want_masks: bool = False):
+        """The C++ schedule of the query decoder + heads (same kernels and order as ``engine.Engine._predictor``) over a batch
+        whose levels 0 and top are described by ``lay`` (a PackLayout, or a MergedLayout over several backbone chunks)."""
+        def level(lv):
+            x = Level()
+            x.row_seq, x.seqinfo, x.R, x.B, x.max_len = lv.row_seq.data_ptr(), lv.seqinfo.data_ptr(), lv.R, lv.B, lv.max_len
+            return x
+        l0, lt = level(lay.levels[0]), level(lay.levels[-1])
+        B, Q, pc = lay.B, self.Q, self.pcfg
+        need = self.lib.vrd_predict_workspace_bytes(self.handle, C.byref(pc), C.byref(l0), C.byref(lt))
+        if need < 0:
+            self._fail("vrd_predict_workspace_bytes")
+        if self.pred_workspace is None or self.pred_workspace.numel() < need:
+            self.pred_workspace = None
+            self.pred_workspace = torch.empty(int(need * 1.1) + (1 << 20), dtype=torch.uint8, device=self.device)
+        MQ = (B * Q + 127) // 128 * 128
+        dev = self.device
+        logits = torch.empty(MQ, pc.n_cls_pad, dtype=torch.float32, device=dev)
+        scores = torch.empty(B * Q, topk, dtype=torch.float32, device=dev)
+        ids = torch.empty(B * Q, topk, dtype=torch.int32, device=dev)
+        first_last = torch.empty(B, Q, 2, dtype=torch.int32, device=dev)
+        masks = torch.empty(lay.levels[0].R, Q, dtype=torch.float32, device=dev) if want_masks else None
+        assert e_top.is_contiguous() and mf.is_contiguous() and e_top.dtype == torch.float32 and mf.dtype == torch.float32
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.lib.vrd_predict(self.handle, C.byref(pc), C.byref(l0), C.byref(lt), e_top.data_ptr(), mf.data_ptr(), int(topk),
+                                self.pred_workspace.data_ptr(), self.pred_workspace.numel(), logits.data_ptr(), scores.data_ptr(),
+                                ids.data_ptr(), first_last.data_ptr(), _p(masks), stream) != 0:
+            self._fail("vrd_predict")
+        self._count()
+        return {"logits": logits[: B * Q, : pc.n_cls].view(B, Q, -1), "topk_scores": scores.view(B, Q, topk),
+                "topk_ids": ids.view(B, Q, topk), "first_last": first_last, "masks": masks}

@@ -400,7 +400,8 @@ class MaskVRD(nn.Module):
             else:
                 glay, e_top, mf = MergedLayout(lays, dev), torch.cat(tops, 0), torch.cat(mfs, 0)
             tD = time.perf_counter()
-            res = eng.predict(glay, e_top, mf, topk, want_masks)
+            predict = self._native.predict if (self.use_native and eng.taps is None) else eng.predict
+            res = predict(glay, e_top, mf, topk, want_masks)
             if len(chunks) == 1:
                 done = torch.cuda.Event()
                 done.record(cur)
@@ -586,7 +587,7 @@ class MaskVRD(nn.Module):
                 glay, e_top, mf = lays[0], tops[0], mfs[0]
             else:
                 glay, e_top, mf = MergedLayout(lays, dev), torch.cat(tops, 0), torch.cat(mfs, 0)
-            r = eng.predict(glay, e_top, mf, self.topk, False)
+            r = (self._native.predict if self.use_native else eng.predict)(glay, e_top, mf, self.topk, False)
             if boxes_host is None:                                        # device-resident boxes: read the clamped copy back
                 boxes_pin = torch.empty(boxes_all.shape, dtype=torch.float32, pin_memory=True)
                 boxes_pin.copy_(boxes_all, non_blocking=True)

@@ -93,3 +93,14 @@ def test_lazy_trajs_behave_like_the_eager_lists():
     # the consumer of the reference (utils/evaluate.py:62-66) only indexes and takes len()
     d = eager["pred_durations"][3]
     assert len(lazy["so_trajs"][3][0]) == len(lazy["so_trajs"][3][1]) == d[1] - d[0]
+
+
+def test_forward_without_pairs_returns_none_before_touching_the_device():
+    """A video without candidate pairs has no triplets: ``None`` (maskvrd.py:311-312), decided on the host."""
+    cfg = synth.load_config("vidvrd")
+    model = MaskVRD(cfg["model_config"], "cpu").eval()
+    model._config_eval(cfg["inference_config"])
+    import types
+    model._get_engine = lambda: types.SimpleNamespace(device="cpu")      # no CUDA engine exists on this box
+    empty = {"so_features_list": [], "sids": torch.zeros(0, dtype=torch.int64), "oids": torch.zeros(0, dtype=torch.int64)}
+    assert model(empty) is None

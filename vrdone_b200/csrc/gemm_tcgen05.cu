@@ -232,6 +232,7 @@ struct EpiArgs {
     const float* res2; long long ldr2;      // second residual: row-strided loads (only the SOS output projection uses it)
     const float* corr; const int* row_seq; const int4* seqinfo; int R;
     int wide;                               // bf16 output without residual: [32 x 64] store boxes (map in the map_res slot)
+    int dbg;                                // timing experiments only (wrong results): 1 = no TMA stores, 2 = nothing after the TMEM load
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of two SMs of one TPC) shares a 256 x BN tile through
@@ -413,6 +414,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         else mbar_arrive(&tempty[as]);
                     }
                 }
+                if (e.dbg & 2) continue;
                 const int n = col0 + c * CHUNK;
                 float v[CHUNK];
 #pragma unroll
@@ -478,8 +480,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 fence_async_smem();                      // make the generic-proxy writes visible to the TMA engine
                 __syncwarp();
                 if (lane == 0) {
-                    if (wide) tma_store_2d(&map_res, box_u, n - CHUNK, row0);   // map_res carries the [32 x 64] bf16 box map
-                    else tma_store_2d(&map_out, box_u, n, row0);
+                    if (!(e.dbg & 1)) {
+                        if (wide) tma_store_2d(&map_res, box_u, n - CHUNK, row0);   // map_res carries the [32 x 64] bf16 box map
+                        else tma_store_2d(&map_out, box_u, n, row0);
+                    }
                     bulk_commit();
                     if (e.has_res && c + 2 < n_ch) {     // refill this box with the residual of chunk c + 2 (tiles with long K only:
                         bulk_wait_read<0>();             // the MMAs of the next tile hide this latency)
@@ -539,6 +543,7 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     static int num_sms = 0;
     static bool attr_set = false;
     static const bool wide_ok = !(getenv("VRD_GEMM_WIDE") != nullptr && atoi(getenv("VRD_GEMM_WIDE")) == 0);   // A/B switch
+    static const int dbg = getenv("VRD_GEMM_DBG") ? atoi(getenv("VRD_GEMM_DBG")) : 0;
     static int force_cg = -1;
     if (force_cg < 0) { const char* v = getenv("VRD_GEMM_CG"); force_cg = v ? atoi(v) : 0; }
     if (g.M % BLOCK_M != 0 || g.K % BLOCK_K != 0 || g.N % 64 != 0 || g.lda % 8 != 0 || ((uintptr_t)g.A & 15) != 0) {
@@ -607,7 +612,7 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
         attr_set = true;
     }
     const int wide = (!has_res && wide_ok && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) ? 1 : 0;
-    EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R, wide};
+    EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R, wide, dbg};
     const int n_tiles = ((g.M + BLOCK_M * cg - 1) / (BLOCK_M * cg)) * (g.N / block_n);
     const int max_groups = num_sms / cg;
     const int grid = cg * (n_tiles < max_groups ? n_tiles : max_groups);

@@ -459,6 +459,8 @@ class MaskVRD(nn.Module):
         feats = list(input_data["so_features_list"])
         n_pairs = len(input_data["sids"])
         assert len(feats) == n_pairs
+        if n_pairs == 0:                     # the loader hands on {} for such videos (vidor.py:652-653); nothing to rank
+            return _NO_PAIRS
         desc = self._describe(feats)
         tpads = reference_padded_lengths(desc["shape"][:, 1].tolist(), self.config)
         r = self.run_network(feats, tpads, self.topk, desc=desc)

@@ -185,12 +185,12 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // x * 0.5 * (1 + tanh(x * (c0 + c1 x^2))) with (c0, c1) fitted to the exact erf form (max |deviation| 2.7e-4), evaluated in
 // f16x2 (cvt / 4 HFMA2-class ops / one MUFU.TANH per PAIR).  Its error (mean 2.8e-4 absolute on N(0, 1.5) inputs) is a third of
 // the rounding error of the bf16 result it feeds (mean 8.4e-4), and it is 3x cheaper than the fp32 erf form, which made the
-// 512 -> 2048 MLP GEMM epilogue-bound (0.80 PFLOP/s).  Inputs are clamped to [-10, 60000] so that no inf - inf can form.
+// 512 -> 2048 MLP GEMM epilogue-bound (0.80 PFLOP/s).
 __device__ __forceinline__ uint32_t gelu_pair_bf16(float a, float b) {
     uint32_t xh, x2, p, u, t, hx, r;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(b), "f"(a));           // upper half = b, lower half = a
-    asm("max.f16x2 %0, %1, %2;" : "=r"(xh) : "r"(xh), "r"(0xc900c900u));       // -10
-    asm("min.f16x2 %0, %1, %2;" : "=r"(xh) : "r"(xh), "r"(0x7b537b53u));       // 60000
+    // upper half = b, lower half = a; saturating: |x| > 65504 becomes +-65504, not inf, so the last step never sees inf - inf
+    // (x^2 may still overflow to inf: then tanh(+-inf) = +-1 and the result is x or 0, as it should be)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(b), "f"(a));
     asm("mul.f16x2 %0, %1, %1;" : "=r"(x2) : "r"(xh));
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(x2), "r"(0x28712871u), "r"(0x3a673a67u));   // c1 = 0.034701, c0 = 0.800157
     asm("mul.f16x2 %0, %1, %2;" : "=r"(u) : "r"(xh), "r"(p));
@@ -204,6 +204,12 @@ __device__ __forceinline__ uint32_t gelu_pair_bf16(float a, float b) {
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// read-only shared data (bias vector, written once before the kernel's first barrier): schedulable, no memory clobber
+__device__ __forceinline__ float4 lds128_ro(uint32_t addr) {
+    float4 r;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 r;
@@ -352,6 +358,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int half = ew >> 2;                        // which half of the tile's columns
         const int n_ch = block_n / (2 * CHUNK);          // chunks of 32 columns per warp and tile (<= 2 when has_res)
         const bool out_bf16 = e.out_dtype == VRD_BF16;
+        const uint32_t s_bias_u = smem_u32(s_bias);
         // bf16 outputs without a residual: two 32-column chunks share one [32 x 64] box (128-byte rows, same 4 KB as an fp32
         // [32 x 32] box) and ONE TMA store -- the TMA unit handles requests at a fixed rate, and with 32 small store boxes
         // per 128 x 256 tile on top of the 16 operand loads it, not the tensor pipe, set the pace of the K = 512 GEMMs
@@ -419,7 +426,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 float v[CHUNK];
 #pragma unroll
                 for (int i = 0; i < CHUNK / 4; ++i) {
-                    const float4 bi = *reinterpret_cast<const float4*>(s_bias + n + 4 * i);
+                    const float4 bi = lds128_ro(s_bias_u + (uint32_t)(n + 4 * i) * 4);
                     v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + bi.x;
                     v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + bi.y;
                     v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bi.z;

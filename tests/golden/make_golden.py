@@ -67,6 +67,7 @@ def loader_fixtures():
     for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k.startswith("dataloaders")]:
         del sys.modules[m]
     import dataloaders.vidor as V
+    import dataloaders.vidvrd as VV
     sys.path.pop(0)
     for name, cases in LOADER_CASES.items():
         cfg = synth.load_config(name)
@@ -79,7 +80,10 @@ def loader_fixtures():
             stand_in = types.SimpleNamespace(with_clip_feature="clip_features_list" in trk, feat_stride=dc.get("feat_stride", 1),
                                              random_stride=False, stride_offset=0,
                                              proposal_min_frames=dc.get("proposal_min_frames", 0))
-            out = V.VidOR._val_getitem(stand_in, trk, viou_threshold=0.9)
+            if name == "vidvrd":      # the ImageNet-VidVRD loader's own copy of the method (dataloaders/vidvrd.py:552-716)
+                out = VV.VidVRD._test_getitem(stand_in, trk, viou_threshold=0.9)
+            else:
+                out = V.VidOR._val_getitem(stand_in, trk, viou_threshold=0.9)
             fixes.append({**case, "n_candidate_pairs": len(trk["sids"]), "n_tracklets_total": len(trk["bboxes_list"]),
                           "inputs_checksum": checksum(trk["visual_features_list"] + trk["bboxes_list"]),
                           "proposal_min_frames": stand_in.proposal_min_frames, "feat_stride": stand_in.feat_stride,

@@ -404,16 +404,33 @@ __global__ void __launch_bounds__(128, HS == 64 ? 4 : 1) flash_attn_bf16_kernel(
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);
     __nv_bfloat16* sK = sQ + BM * LDS;                 // [NBUF][BN * LDS]
     __nv_bfloat16* sV = sK + NBUF * BN * LDS;          // [NBUF][BN * LDS]
-    const int seq = blockIdx.z, head = blockIdx.y;
-    const int4 si = lay.seqinfo[seq];
-    const int len = si.y;
-    const int q0 = blockIdx.x * BM;
-    if (q0 >= len) return;
+    const int head = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const long long hoff = (long long)head * HS;
     const uint32_t sQ_u = (uint32_t)__cvta_generic_to_shared(sQ);
     const uint32_t sK_u = (uint32_t)__cvta_generic_to_shared(sK), sV_u = (uint32_t)__cvta_generic_to_shared(sV);
+    // The CTA owns the query tiles (64 rows of one pair, aligned to the pair's first row) that START in rows
+    // [64 b, 64 b + 64) of the layout: one for the inside of a long pair, one more for every pair that begins there.  (A grid
+    // of (longest pair / 64, heads, pairs) launched 52 k CTAs per call of which two thirds exited at once.)
+    __shared__ int s_starts[BM];
+    __shared__ int s_nstart;
+    if (tid == 0) s_nstart = 0;
+    __syncthreads();
+    if (tid < BM) {
+        const int r = blockIdx.x * BM + tid;
+        const int sq = r < lay.R ? lay.row_seq[r] : -1;
+        if (sq >= 0 && ((r - lay.seqinfo[sq].x) & (BM - 1)) == 0) s_starts[atomicAdd(&s_nstart, 1)] = r;
+    }
+    __syncthreads();
+    const int n_start = s_nstart;
+  for (int ui = 0; ui < n_start; ++ui) {
+    // order of the list does not matter: tiles are independent and each writes its own rows
+    const int u_row = s_starts[ui];
+    const int seq = lay.row_seq[u_row];
+    const int4 si = lay.seqinfo[seq];
+    const int len = si.y;
+    const int q0 = u_row - si.x;
 
     // every thread copies the same 16-byte column chunk of rows lr, lr + RPP, ...: one pointer per operand, advanced by a
     // constant stride (the generic c / CPR, c % CPR form spent ~15 % of the kernel's instructions on 64-bit address math)
@@ -541,6 +558,8 @@ __global__ void __launch_bounds__(128, HS == 64 ? 4 : 1) flash_attn_bf16_kernel(
         if (r0 < len) *reinterpret_cast<uint32_t*>(out + (long long)(si.x + r0) * ld + hoff + c) = pack_bf16(o[d][0] * i0, o[d][1] * i0);
         if (r1 < len) *reinterpret_cast<uint32_t*>(out + (long long)(si.x + r1) * ld + hoff + c) = pack_bf16(o[d][2] * i1, o[d][3] * i1);
     }
+    __syncthreads();           // the next tile of this CTA refills sQ / sK / sV
+  }
 }
 
 // Separator rows of the output are NOT written: the only consumer is the output-projection GEMM (taps == 1, with a layout),
@@ -555,7 +574,8 @@ static int flash_launch(const void* q, const void* k, const void* v, void* out, 
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
         attr_set = true;
     }
-    const dim3 grid((max_rows + 63) / 64, n_head, lay.B);
+    (void)max_rows;
+    const dim3 grid((lay.R + 63) / 64, n_head);
     kern<<<grid, 128, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ld, lay);
     return 0;
 }

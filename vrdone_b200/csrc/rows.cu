@@ -299,31 +299,44 @@ int pack_tracklets(const float* vis_all, const float* clip_all, const float* box
 // ------------------------------------------------------------------------------------------------------------
 // layernorm (+ReLU): out = [relu](LN(x)), separator rows -> 0
 // ------------------------------------------------------------------------------------------------------------
+constexpr int LN_RPW = 2;   // rows per warp: both rows' loads are in flight before the first reduction starts (HBM-bound kernel)
+
 template <typename TI, typename TO, int NCH>
 __global__ void layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, TO* __restrict__ out, long long ldo, int rows, int relu,
                                  const int* __restrict__ row_seq, int R) {
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    TO* o = out + (long long)row * ldo;
-    if (row_seq != nullptr && row_seq[row % R] < 0) { zero_row<TO, NCH>(o, lane); return; }
-    float v[NCH][4];
-    load_row<TI, NCH>(x + (long long)row * ldx, lane, v);
-    row_normalize<NCH>(v, lane, gamma, beta);
-    if (relu) {
+    const int row0 = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * LN_RPW;
+    if (row0 >= rows) return;
+    float v[LN_RPW][NCH][4];
+    bool live[LN_RPW];
 #pragma unroll
-        for (int j = 0; j < NCH; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[j][i] = fmaxf(v[j][i], 0.f);
+    for (int u = 0; u < LN_RPW; ++u) {
+        const int row = row0 + u;
+        live[u] = row < rows && !(row_seq != nullptr && row_seq[row % R] < 0);
+        if (live[u]) load_row<TI, NCH>(x + (long long)row * ldx, lane, v[u]);
     }
-    store_row<TO, NCH>(o, lane, v);
+#pragma unroll
+    for (int u = 0; u < LN_RPW; ++u) {
+        const int row = row0 + u;
+        if (row >= rows) break;
+        TO* o = out + (long long)row * ldo;
+        if (!live[u]) { zero_row<TO, NCH>(o, lane); continue; }      // warp-uniform
+        row_normalize<NCH>(v[u], lane, gamma, beta);
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[u][j][i] = fmaxf(v[u][j][i], 0.f);
+        }
+        store_row<TO, NCH>(o, lane, v[u]);
+    }
 }
 
 template <typename TI, typename TO>
 static int layernorm_t(const void* x, long long ldx, const float* g, const float* b, void* out, long long ldo, int rows,
                        int C, int relu, const int* row_seq, int R, cudaStream_t st) {
-    const int grid = (rows + WARPS - 1) / WARPS;
+    const int grid = (rows + WARPS * LN_RPW - 1) / (WARPS * LN_RPW);
     if (C == 512)
         layernorm_kernel<TI, TO, 4><<<grid, WARPS * 32, 0, st>>>((const TI*)x, ldx, g, b, (TO*)out, ldo, rows, relu, row_seq, R);
     else if (C == 256)

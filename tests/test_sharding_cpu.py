@@ -23,14 +23,29 @@ def _videos():
     return vids
 
 
+class _FakeModel:
+    """Stand-in with the submit / result protocol of MaskVRD (the pipelined per-rank loop)."""
+
+    class _Pending:
+        def __init__(self, video):
+            self.video = video
+
+        def result(self):
+            return _fake_forward(self.video)
+
+    def submit(self, video):
+        return self._Pending(video)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     vids = _videos()
     costs = [runner.video_cost("vidor", v["lens"]) for v in vids]
     out = runner.run_sharded(vids, costs, _fake_forward)
+    piped = runner.run_sharded(vids, costs, model=_FakeModel())
     if rank == 0:
-        q.put(out)
+        q.put((out, piped))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,11 +73,12 @@ def test_two_rank_gloo_matches_single_rank():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    merged = q.get(timeout=120)
+    merged, piped = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert merged == single
+    assert merged == single and piped == single
+    assert runner.run_sharded(vids, costs, model=_FakeModel()) == single
 
 
 def test_run_videos_keeps_order_and_depth():

@@ -56,15 +56,21 @@ def run_videos(model, videos: Iterable[dict], depth: int = 2, dataset_config: Op
         yield pending.popleft().result()
 
 
-def run_sharded(videos: Sequence[dict], costs: Sequence[float], fn: Callable[[dict], object]) -> Dict[int, object]:
-    """Every rank runs ``fn`` on its shard; rank 0 returns {video index: result} for all videos (other ranks: their own).
-    Works with or without an initialised process group (world size 1)."""
+def run_sharded(videos: Sequence[dict], costs: Sequence[float], fn: Optional[Callable[[dict], object]] = None, model=None,
+                dataset_config: Optional[dict] = None) -> Dict[int, object]:
+    """Every rank processes its shard -- with ``fn(video)`` one video after the other, or with ``model`` through the pipelined
+    ``run_videos`` loop (two videos in flight per GPU); rank 0 returns {video index: result} for all videos (other ranks:
+    their own).  Works with or without an initialised process group (world size 1)."""
+    assert (fn is None) != (model is None), "give either fn or model"
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(), dist.get_world_size()
     else:
         rank, world = 0, 1
     mine = shard_videos(costs, world)[rank]
-    local = {i: fn(videos[i]) for i in mine}
+    if model is not None:
+        local = dict(zip(mine, run_videos(model, (videos[i] for i in mine), dataset_config=dataset_config)))
+    else:
+        local = {i: fn(videos[i]) for i in mine}
     if world == 1:
         return local
     gathered = [None] * world if rank == 0 else None

@@ -542,6 +542,9 @@ class MaskVRD(nn.Module):
         n_frames = np.array([int(v.shape[0]) for v in vis_list], dtype=np.int64)
         base = np.cumsum(n_frames) - n_frames                             # first row of every tracklet in the concatenated arrays
         durs_np = data["traj_durations"].cpu().numpy().astype(np.int64)
+        # the kernels index tracklet frames through the durations: they must describe the arrays (vidor.py:531-538 asserts the same)
+        assert np.array_equal(durs_np[:, 1] - durs_np[:, 0], n_frames), "traj_durations do not match the tracklet lengths"
+        assert all(int(b.shape[0]) == int(n) for b, n in zip(box_list, n_frames)), "bboxes_list does not match the tracklet lengths"
         sids_np = data["sids"].cpu().numpy().astype(np.int64)
         oids_np = data["oids"].cpu().numpy().astype(np.int64)
         with torch.cuda.device(dev):

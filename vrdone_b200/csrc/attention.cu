@@ -808,7 +808,9 @@ __global__ void __launch_bounds__(256) query_self_attn_kernel(const T* __restric
                                                               const T* __restrict__ v, T* __restrict__ out, long long ld,
                                                               int Q, int n_head) {
     constexpr int D = 256, MAXQ = 12, MAXH = 8;
-    __shared__ float sq[MAXQ][D], sk[MAXQ][D], sv[MAXQ][D];
+    // sk rows are padded by four words: in the score phase consecutive threads read the SAME column of consecutive key rows
+    // (a 1 KB row pitch would put all of them on one bank)
+    __shared__ float sq[MAXQ][D], sk[MAXQ][D + 4], sv[MAXQ][D];
     __shared__ float sp[MAXH][MAXQ][MAXQ];
     const int pair = blockIdx.x;
     const int hs = D / n_head;
@@ -857,60 +859,84 @@ int query_self_attn(const void* q, const void* k, const void* v, void* out, int 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// query_cross_attn: Q queries of a pair attend to the pair's rows of the coarsest level.  One block per pair; a warp
-// handles one (query, head) at a time: lanes = keys for the scores, lanes = head dims for P.V.
+// query_cross_attn: Q queries of a pair attend to the pair's rows of the coarsest level.  One block per pair; a warp owns
+// one HEAD and works on all Q queries of the pair at once: lanes = keys for the scores (a key's row is loaded once and used by
+// every query: Q-way instruction-level parallelism instead of Q dependent passes over the same rows), lanes = head dims for
+// P.V (a value row is loaded once per key, the Q probabilities arrive by shuffle).  Online softmax over tiles of 32 keys.
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int HS>
 __global__ void __launch_bounds__(256) query_cross_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                                const T* __restrict__ v, T* __restrict__ out, long long ld,
                                                                Lay lay, int Q, int n_head) {
     constexpr int D = 256, MAXQ = 12, DPL = HS / 32;
-    __shared__ float sq[MAXQ][D];
+    __shared__ __align__(16) float sq[MAXQ][D];
     const int pair = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int4 si = lay.seqinfo[pair];
     const long long r0 = (long long)pair * Q;
-    for (int i = threadIdx.x; i < Q * D; i += 256) sq[i / D][i % D] = to_f(q[(r0 + i / D) * ld + (i % D)]);
+    for (int i = threadIdx.x; i < MAXQ * D; i += 256) sq[i / D][i % D] = (i / D < Q) ? to_f(q[(r0 + i / D) * ld + (i % D)]) : 0.f;
     __syncthreads();
-    for (int combo = warp; combo < Q * n_head; combo += 8) {
-        const int qi = combo / n_head, h = combo % n_head;
-        const float* qh = &sq[qi][h * HS];
-        float m = -INFINITY, l = 0.f;
-        float acc[DPL];
+    for (int h = warp; h < n_head; h += 8) {
+        float m[MAXQ], l[MAXQ], acc[MAXQ][DPL];
 #pragma unroll
-        for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+        for (int qi = 0; qi < MAXQ; ++qi) {
+            m[qi] = -INFINITY; l[qi] = 0.f;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) acc[qi][i] = 0.f;
+        }
         for (int k0 = 0; k0 < si.y; k0 += 32) {
             const int kj = k0 + lane;
-            float s = -INFINITY;
-            if (kj < si.y) {
+            const bool ok = kj < si.y;
+            float s[MAXQ];
+#pragma unroll
+            for (int qi = 0; qi < MAXQ; ++qi) s[qi] = 0.f;
+            if (ok) {
                 const T* kr = k + (long long)(si.x + kj) * ld + h * HS;
-                float d = 0.f;
 #pragma unroll
                 for (int c = 0; c < HS; c += 4) {
                     float kv[4];
                     ld4(kr + c, kv);
-                    d += qh[c] * kv[0] + qh[c + 1] * kv[1] + qh[c + 2] * kv[2] + qh[c + 3] * kv[3];
-                }
-                s = d;
-            }
-            const float mn = fmaxf(m, warp_max(s));
-            const float corr = expf(m - mn);
-            const float p = (kj < si.y) ? expf(s - mn) : 0.f;
-            l = l * corr + warp_sum(p);
 #pragma unroll
-            for (int i = 0; i < DPL; ++i) acc[i] *= corr;
+                    for (int qi = 0; qi < MAXQ; ++qi) {
+                        const float4 qv = *reinterpret_cast<const float4*>(&sq[qi][h * HS + c]);   // same address for all lanes
+                        s[qi] = fmaf(qv.x, kv[0], fmaf(qv.y, kv[1], fmaf(qv.z, kv[2], fmaf(qv.w, kv[3], s[qi]))));
+                    }
+                }
+            }
+            float p[MAXQ];
+#pragma unroll
+            for (int qi = 0; qi < MAXQ; ++qi) {
+                const float sv = ok ? s[qi] : -INFINITY;
+                const float mn = fmaxf(m[qi], warp_max(sv));
+                const float corr = expf(m[qi] - mn);       // exp(-inf) = 0 on the first tile
+                p[qi] = ok ? expf(sv - mn) : 0.f;
+                l[qi] = l[qi] * corr + warp_sum(p[qi]);
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) acc[qi][i] *= corr;
+                m[qi] = mn;
+            }
             const int nk = min(32, si.y - k0);
             for (int jj = 0; jj < nk; ++jj) {
-                const float pj = __shfl_sync(FULL_MASK, p, jj);
                 const T* vr = v + (long long)(si.x + k0 + jj) * ld + h * HS;
+                float vv[DPL];
 #pragma unroll
-                for (int i = 0; i < DPL; ++i) acc[i] = fmaf(pj, to_f(vr[lane + 32 * i]), acc[i]);
+                for (int i = 0; i < DPL; ++i) vv[i] = to_f(vr[lane + 32 * i]);
+#pragma unroll
+                for (int qi = 0; qi < MAXQ; ++qi) {
+                    const float pj = __shfl_sync(FULL_MASK, p[qi], jj);
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) acc[qi][i] = fmaf(pj, vv[i], acc[qi][i]);
+                }
             }
-            m = mn;
         }
-        const float inv = 1.0f / l;
 #pragma unroll
-        for (int i = 0; i < DPL; ++i) out[(r0 + qi) * ld + h * HS + lane + 32 * i] = from_f<T>(acc[i] * inv);
+        for (int qi = 0; qi < MAXQ; ++qi) {
+            if (qi < Q) {
+                const float inv = 1.0f / l[qi];
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) out[(r0 + qi) * ld + h * HS + lane + 32 * i] = from_f<T>(acc[qi][i] * inv);
+            }
+        }
     }
 }
 

@@ -4,6 +4,9 @@
 // padded batch reduces to "valid keys only" in the varlen layout); full attention local_transformer.py:144-187;
 // query self/cross attention of the predictor local_transformer.py:33-67, 144-187.
 // The 1/sqrt(head_dim) scale is folded into the query projection weights by the host.
+// Kernels: window_attn_mma (bf16, head_dim 64: mma.sync, pair-aligned 16-row warp units) with window_attn_tma / window_attn as
+// the fp32 and head_dim 128 paths; flash_attn_bf16 (mma.sync flash attention inside each pair) with full_attn as the fp32 path;
+// query_self_attn / query_cross_attn for the Q queries of each pair.
 #include <cstring>
 #include <cstdlib>
 #include "common.cuh"

@@ -16,7 +16,8 @@
 //   warps 4-11 epilogue              (two warps per TMEM lane quarter, each owning half of the tile's columns).  Per chunk
 //                                     of 32 columns: tcgen05.ld 32x32b.x32 -> bias / pad correction / ReLU|GELU / residual /
 //                                     separator zeroing in registers (thread = row) -> swizzled shared-memory staging ->
-//                                     one TMA store of the [32 rows x 32 cols] box.  The fp32 residual tile arrives the same
+//                                     one TMA store of the [32 rows x 32 cols] box ([32 x 64] for bf16 outputs without a
+//                                     residual: two chunks per store).  The fp32 residual tile arrives the same
 //                                     way (TMA load into the staging buffer, issued before the accumulator is waited for),
 //                                     so the epilogue warps never issue row-strided global accesses (those cost one L1
 //                                     wavefront per row and bounded the old epilogue).  Overlapped with the next tile's

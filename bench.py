@@ -279,6 +279,7 @@ def main():
     ms, pairs = timed(dev_videos, args.steps, h2d=False)
     launches = ops.launches - l0
     wall_pipe = list(step_wall)
+    host_pipe = {k: round(v, 2) for k, v in model.last_stats.items()}
     ms_sync, pairs_sync = timed(dev_videos, args.steps, h2d=False, pipelined=False)
     host_hbm = {k: round(v, 2) for k, v in model.last_stats.items()}
     host_hbm["python_gc_ms_per_step"] = round(gc_ms[0] / args.steps, 2)
@@ -289,6 +290,7 @@ def main():
     warm(pinned)                        # staging buffers, pinned upload blocks and the copy stream are created on first use
     ms_e2e, pairs_e2e = timed(pinned, args.steps, h2d=True)
     wall_pipe_e2e = list(step_wall)
+    host_pipe_e2e = {k: round(v, 2) for k, v in model.last_stats.items()}
     ms_e2e_sync, pairs_e2e_sync = timed(pinned, args.steps, h2d=True, pipelined=False)
     host_e2e = {k: round(v, 2) for k, v in model.last_stats.items()}
     host_e2e["forward_wall_ms_each_step"] = list(step_wall)
@@ -394,6 +396,7 @@ def main():
                             "ms_per_step": ms_net / args.steps, "clocks": net_clocks},
            "valid_frames_per_s": world * sum(frames[s % len(frames)] for s in range(args.steps)) / (ms * 1e-3),
            "step_wall_ms_pipelined": {"hbm_resident": wall_pipe, "e2e": wall_pipe_e2e},
+           "host_ms_last_step_pipelined": {"hbm_resident": host_pipe, "e2e": host_pipe_e2e},
            "host_ms_last_step": host_hbm, "host_ms_last_step_e2e": host_e2e}
     if not args.no_cpu_baseline:
         v, n, dt = cpu_baseline(cfg, host_videos[0], args.cpu_pairs, threads)

@@ -661,14 +661,15 @@ class MaskVRD(nn.Module):
         end = last * stride + off[:, None] + 1
         keep = (last >= 0) & ((end - start) >= self.pred_min_frames)
         assert np.all((start >= 0) | ~keep) and np.all((end <= (so_end - so_start)[:, None]) | ~keep)
-        pi, qi = np.nonzero(keep)                                  # candidates in (pair, query) order
-        if pi.size == 0:
+        if not keep.any():
             return None
-        pi, qi = np.repeat(pi, topk), np.repeat(qi, topk)
-        ki = np.tile(np.arange(topk), pi.size // topk)
-        p_score = scores[pi, qi, ki].astype(np.float32)
-        trip_scores = np.stack([cat_scores[sids[pi]], p_score, cat_scores[oids[pi]]], 1)
-        avg = trip_scores.mean(-1, dtype=np.float32)
+        # mean of (subject score, predicate score, object score) for every (pair, query, k), in the order and precision of the
+        # reference's ``torch.tensor([s, p, o]).mean()``: ((s + p) + o) / 3 in fp32.  Computed on the dense [B, Q, k] grid (a
+        # gather of the ~7 * 10^4 surviving candidates into [n, 3] rows and a mean along the short axis cost 3 ms per video)
+        cs_s, cs_o = cat_scores[sids], cat_scores[oids]
+        avg_all = ((cs_s[:, None, None] + scores) + cs_o[:, None, None]) / np.float32(3)
+        cand_all = np.flatnonzero(np.broadcast_to(keep[:, :, None], avg_all.shape))      # candidates in (pair, query, k) order
+        avg = avg_all.reshape(-1)[cand_all]
         # top n_max_pair by descending mean score, ties to the earlier candidate (== stable descending argsort, truncated)
         n = min(self.n_max_pair, avg.size)
         if avg.size > 4 * n:
@@ -676,7 +677,13 @@ class MaskVRD(nn.Module):
             cand = np.nonzero(avg >= thr)[0]
         else:
             cand = np.arange(avg.size)
-        order = cand[np.argsort(-avg[cand], kind="stable")][:n]
+        sel = cand[np.argsort(-avg[cand], kind="stable")][:n]                             # positions in the candidate list
+        flat = cand_all[sel]
+        Qn = scores.shape[1]
+        pi, qi, ki = flat // (Qn * topk), (flat // topk) % Qn, flat % topk                # the reported candidates only
+        trip_scores = np.stack([cs_s[pi], scores[pi, qi, ki].astype(np.float32), cs_o[pi]], 1)
+        avg = avg[sel]
+        order = np.arange(sel.size)
         boxes = input_data["bboxes_list"]
         host_boxes = {}
 

@@ -44,6 +44,18 @@ int vrd_device_arch(void);
 int vrd_h2d_pairs(const void* const* src, const int64_t* bytes, void* dst_base, const int64_t* dst_offset, int n,
                   vrd_stream_t stream);
 
+/* a1 -- one pyramid level of n_chunks (<= 16) consecutive chunk layouts merged into the layout of ONE batch on the device (rows
+ * of chunk c follow those of chunk c - 1, pair ids renumbered, row offsets shifted): the slices of MaskVRD.forward_test
+ * (maskvrd.py:201-240) seen as one batch by the query decoder and the heads.  row_seq / seqinfo / R / B are HOST arrays holding
+ * the device pointers and the row / pair counts of the chunk layouts; the outputs have sum(R) and 4 * sum(B) int32 entries. */
+int vrd_merge_layout(int n_chunks, const int32_t* const* row_seq, const int32_t* const* seqinfo, const int32_t* R, const int32_t* B,
+                     int32_t* row_seq_out, int32_t* seqinfo_out, vrd_stream_t stream);
+
+/* a0 -- small host->device upload done by a kernel (host_src: PINNED host memory, read by the SMs through UVA) instead of the
+ * copy engine, for per-video bookkeeping arrays on a stream whose kernels must not wait behind bulk copies of other streams
+ * (replaces the .to(device) of small index tensors, utils/misc.py:98-112).  bytes % 4 == 0, both pointers 16-byte aligned. */
+int vrd_upload(const void* host_src, void* dev_dst, int64_t bytes, vrd_stream_t stream);
+
 /* SURVEY 8f row 2 -- replaces the duplicate-tracklet filter of the data loader (dataloaders/vidor.py:583-641, vidvrd.py same
  * code): boxes [T, 4] fp32 hold every tracklet's (already clamped) boxes back to back, trk_base[i] the first row of tracklet
  * i, durations [N, 2] int32 (start, end frame), cat_ids [N] int32.  For base < ref of one category with overlapping durations

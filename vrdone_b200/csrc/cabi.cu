@@ -57,6 +57,22 @@ int vrd_h2d_pairs(const void* const* src, const int64_t* bytes, void* dst_base, 
     return 0;
 }
 
+int vrd_merge_layout(int n_chunks, const int32_t* const* row_seq, const int32_t* const* seqinfo, const int32_t* R, const int32_t* B,
+                     int32_t* row_seq_out, int32_t* seqinfo_out, vrd_stream_t stream) {
+    if (row_seq == nullptr || seqinfo == nullptr || R == nullptr || B == nullptr || row_seq_out == nullptr || seqinfo_out == nullptr)
+        return fail("vrd_merge_layout: null argument");
+    if (vrd::merge_layout(n_chunks, row_seq, seqinfo, R, B, row_seq_out, seqinfo_out, (cudaStream_t)stream) != 0)
+        return fail("vrd_merge_layout: 1..16 chunks per call");
+    return check_launch("vrd_merge_layout");
+}
+
+int vrd_upload(const void* host_src, void* dev_dst, int64_t bytes, vrd_stream_t stream) {
+    if (host_src == nullptr || dev_dst == nullptr) return fail("vrd_upload: null argument");
+    if (vrd::upload(host_src, dev_dst, bytes, (cudaStream_t)stream) != 0)
+        return fail("vrd_upload: bytes must be a positive multiple of 4, both pointers 16-byte aligned");
+    return check_launch("vrd_upload");
+}
+
 int vrd_viou_filter(const float* boxes, const int32_t* trk_base, const int32_t* durations, const int32_t* cat_ids, int n_tracklets,
                     float viou_threshold, double* sums, uint8_t* flags, int32_t* valid, vrd_stream_t stream) {
     if (boxes == nullptr || trk_base == nullptr || durations == nullptr || cat_ids == nullptr || flags == nullptr || valid == nullptr)

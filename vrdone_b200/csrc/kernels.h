@@ -33,6 +33,9 @@ int pack_tracklets(const float* vis_all, const float* clip_all, const float* box
                    float vw, float vh, void* vis, void* clip, int adt, float* bso, float* bent, cudaStream_t st);
 int viou_filter(const float* boxes, const int* trk_base, const int* durs, const int* cat_ids, int N, float thr, double* sums,
                 unsigned char* flags, int* valid, cudaStream_t st);
+int merge_layout(int n, const int* const* rs, const int* const* si, const int* R, const int* B, int* rs_out, int* si_out,
+                 cudaStream_t st);
+int upload(const void* host_src, void* dev_dst, long long bytes, cudaStream_t st);
 int layernorm(const void* x, int xdt, long long ldx, const float* g, const float* b, void* out, int odt, long long ldo, int rows,
               int C, int relu, const int* row_seq, int R, cudaStream_t st);
 int small_conv(const float* x, int cin, const float* wt, const float* bias, const float* g, const float* b, int relu, void* out,

@@ -355,6 +355,78 @@ int layernorm(const void* x, int xdt, long long ldx, const float* g, const float
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// upload: device copy of a small pinned host array made by a KERNEL (the SMs read the host memory through UVA), not by the copy
+// engine.  Used for per-video layout arrays on the compute stream: a cudaMemcpyAsync there queues behind whatever bulk
+// host->device copies other streams have in flight (measured: the network of a resident video slowed from 18.5 to 32.7 ms while a
+// side stream copied 1.1 GB, although neither GEMMs, LayerNorms nor empty launches are slowed by such copies).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void upload_kernel(const int4* __restrict__ src, int4* __restrict__ dst, long long n16, const int* __restrict__ src4,
+                              int* __restrict__ dst4, int tail4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail4) dst4[threadIdx.x] = src4[threadIdx.x];
+}
+
+int upload(const void* host_src, void* dev_dst, long long bytes, cudaStream_t st) {
+    if (bytes <= 0 || (bytes & 3) != 0 || ((uintptr_t)host_src & 15) != 0 || ((uintptr_t)dev_dst & 15) != 0) return 1;
+    const long long n16 = bytes / 16;
+    const int tail4 = (int)((bytes - n16 * 16) / 4);
+    const int grid = (int)((n16 + 255) / 256 < 64 ? ((n16 + 255) / 256 > 0 ? (n16 + 255) / 256 : 1) : 64);
+    upload_kernel<<<grid, 256, 0, st>>>((const int4*)host_src, (int4*)dev_dst, n16, (const int*)host_src + n16 * 4, (int*)dev_dst + n16 * 4, tail4);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// merge_layout: one level of several consecutive chunk layouts viewed as ONE batch (rows of chunk c follow those of chunk c - 1,
+// pair ids are renumbered), built on the device from the chunk layouts that are already there.  The query decoder and the
+// heads run once per video over this merged layout; building it on the host meant one more small host->device copy per video
+// on the compute stream, which queues behind the bulk pair copies of the next video.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MERGE_MAX = 16;
+struct MergeArgs {
+    const int* rs[MERGE_MAX];
+    const int4* si[MERGE_MAX];
+    int row_base[MERGE_MAX + 1], pair_base[MERGE_MAX + 1];
+    int n;
+};
+
+__global__ void merge_layout_kernel(MergeArgs a, int* __restrict__ rs_out, int4* __restrict__ si_out) {
+    const int total_rows = a.row_base[a.n], total_pairs = a.pair_base[a.n];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_rows; i += gridDim.x * blockDim.x) {
+        int c = 0;
+        while (c + 1 < a.n && i >= a.row_base[c + 1]) ++c;
+        const int v = a.rs[c][i - a.row_base[c]];
+        rs_out[i] = v >= 0 ? v + a.pair_base[c] : -1;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_pairs; i += gridDim.x * blockDim.x) {
+        int c = 0;
+        while (c + 1 < a.n && i >= a.pair_base[c + 1]) ++c;
+        int4 s = a.si[c][i - a.pair_base[c]];
+        s.x += a.row_base[c];
+        si_out[i] = s;
+    }
+}
+
+// rs / si / R / B: HOST arrays (device pointers of the chunk layouts, their row and pair counts); n <= MERGE_MAX
+int merge_layout(int n, const int* const* rs, const int* const* si, const int* R, const int* B, int* rs_out, int* si_out,
+                 cudaStream_t st) {
+    if (n < 1 || n > MERGE_MAX) return 1;
+    MergeArgs a;
+    a.n = n;
+    a.row_base[0] = a.pair_base[0] = 0;
+    for (int c = 0; c < n; ++c) {
+        a.rs[c] = rs[c];
+        a.si[c] = reinterpret_cast<const int4*>(si[c]);
+        a.row_base[c + 1] = a.row_base[c] + R[c];
+        a.pair_base[c + 1] = a.pair_base[c] + B[c];
+    }
+    const int work = a.row_base[n] > a.pair_base[n] ? a.row_base[n] : a.pair_base[n];
+    int grid = (work + 255) / 256;
+    grid = grid < 1 ? 1 : (grid > 296 ? 296 : grid);
+    merge_layout_kernel<<<grid, 256, 0, st>>>(a, rs_out, reinterpret_cast<int4*>(si_out));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // small_conv: k=3 conv with cin <= 8 input channels on 8-wide fp32 rows (+bias [+LN] [+ReLU]); N = 512 outputs
 // wt is [3*cin, N] (tap-major rows) so that lanes read contiguous output channels.
 // ------------------------------------------------------------------------------------------------------------

@@ -23,6 +23,8 @@ _SIGNATURES = {
     "vrd_abi_version": [],
     "vrd_device_arch": [],
     "vrd_h2d_pairs": [_vp, _vp, _vp, _vp, _i32, _vp],
+    "vrd_merge_layout": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "vrd_upload": [_vp, _vp, _i64, _vp],
     "vrd_viou_filter": [_vp, _vp, _vp, _vp, _i32, C.c_float, _vp, _vp, _vp, _vp],
     "vrd_pack_pairs": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
     "vrd_gemm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp,
@@ -218,6 +220,26 @@ class CudaOps:
                                     C.c_void_p(stream.cuda_stream))
         if rc != 0:
             raise RuntimeError(f"vrd_h2d_pairs failed: {self.lib.vrd_last_error().decode()}")
+
+    def merge_layout(self, levels, row_seq_out, seqinfo_out):
+        """levels: the LevelLayouts (one pyramid level) of <= 16 consecutive chunks, arrays on the device -> merged row_seq [sum R]
+        and seqinfo [sum B, 4] written by one kernel on torch's current stream."""
+        n = len(levels)
+        rs = (C.c_void_p * n)(*[lv.row_seq.data_ptr() for lv in levels])
+        si = (C.c_void_p * n)(*[lv.seqinfo.data_ptr() for lv in levels])
+        R = (C.c_int32 * n)(*[lv.R for lv in levels])
+        B = (C.c_int32 * n)(*[lv.B for lv in levels])
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._check(self.lib.vrd_merge_layout(n, rs, si, R, B, row_seq_out.data_ptr(), seqinfo_out.data_ptr(), st), "vrd_merge_layout")
+
+    def upload(self, host_pinned: torch.Tensor, dev: torch.Tensor, stream=None):
+        """Kernel-made copy of a small PINNED host tensor into ``dev`` on ``stream`` (default: torch's current stream).  The
+        caller keeps ``host_pinned`` alive until the kernel has run."""
+        assert host_pinned.is_pinned() and host_pinned.is_contiguous() and dev.is_cuda and dev.is_contiguous()
+        nbytes = host_pinned.numel() * host_pinned.element_size()
+        assert nbytes == dev.numel() * dev.element_size()
+        st = C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+        self._check(self.lib.vrd_upload(host_pinned.data_ptr(), dev.data_ptr(), nbytes, st), "vrd_upload")
 
     def viou_filter(self, boxes, trk_base, durations, cat_ids, threshold, stream, want_sums=False):
         """SURVEY 8f row 2.  boxes [T, 4] fp32, trk_base / cat_ids [N] int32, durations [N, 2] int32 (CUDA tensors); enqueued on

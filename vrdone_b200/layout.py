@@ -122,25 +122,36 @@ class PackLayout:
 
 class MergedLayout:
     """Levels 0 and top of several consecutive chunk layouts viewed as one batch (rows of chunk i follow those of chunk
-    i - 1, pair ids are renumbered): what the query decoder and the heads need when the backbone ran chunk by chunk."""
+    i - 1, pair ids are renumbered): what the query decoder and the heads need when the backbone ran chunk by chunk.
+    ``device_merge(levels, row_seq_out, seqinfo_out)`` (``CudaOps.merge_layout``) builds the device arrays from the chunk layouts
+    already on the device; without it they are built on the host and uploaded (CPU tests, more than 16 chunks)."""
 
-    def __init__(self, lays: Sequence[PackLayout], device):
+    def __init__(self, lays: Sequence[PackLayout], device, device_merge=None):
         self.n_levels = lays[0].n_levels
         self.B = sum(l.B for l in lays)
         self.lengths = np.concatenate([l.lengths for l in lays])
         self.levels: List[LevelLayout] = [None] * self.n_levels
+        on_device = device_merge is not None and len(lays) <= 16 and torch.device(device).type == "cuda"
         host = []
         for lv in (0, self.n_levels - 1):
             row_base = np.cumsum([0] + [l.levels[lv].R for l in lays])
-            pair_base = np.cumsum([0] + [l.B for l in lays])
             off = np.concatenate([l.levels[lv].off + rb for l, rb in zip(lays, row_base)]).astype(np.int32)
             length = np.concatenate([l.levels[lv].len for l in lays]).astype(np.int32)
             haspad = np.concatenate([l.levels[lv].haspad for l in lays]).astype(np.int32)
             rows = int(row_base[-1])
+            self.levels[lv] = LevelLayout(lv, off, length, haspad, rows)
+            if on_device:
+                lev = self.levels[lv]
+                lev.row_seq = torch.empty(rows, dtype=torch.int32, device=device)
+                lev.seqinfo = torch.empty(self.B, 4, dtype=torch.int32, device=device)
+                device_merge([l.levels[lv] for l in lays], lev.row_seq, lev.seqinfo)
+                continue
+            pair_base = np.cumsum([0] + [l.B for l in lays])
             row_seq = np.concatenate([np.where(l._host[2 * lv] >= 0, l._host[2 * lv] + pb, -1) for l, pb in zip(lays, pair_base)])
             info = np.stack([off, length, haspad, np.zeros(self.B, np.int32)], 1)
-            self.levels[lv] = LevelLayout(lv, off, length, haspad, rows)
             host += [row_seq.astype(np.int32), info.reshape(-1)]
+        if on_device:
+            return
         n_words = sum(h.size for h in host)
         if torch.device(device).type == "cuda":
             flat = torch.empty(n_words, dtype=torch.int32, pin_memory=True)

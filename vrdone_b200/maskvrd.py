@@ -137,15 +137,25 @@ class MaskVRD(nn.Module):
         # B200 execution state
         self.precision = config.get("precision", "bf16")   # "bf16" (tcgen05 tensor cores) or "fp32" (CUDA-core fp32)
         self.max_rows = int(config.get("max_rows", 196608))  # level-0 rows processed per engine call (bounds workspace)
-        self.h2d_chunk_rows = int(config.get("h2d_chunk_rows", 24576))  # rows per chunk when pair features arrive from the host
-        self.h2d_edge_rows = int(config.get("h2d_edge_rows", 8192))     # ... and of the first / last chunk (not overlapped)
-        self._lay_bufs = [None] * 4       # persistent device buffers for the per-chunk layout arrays + pair tables
-        self._lay_done = [None] * 4
+        self.h2d_chunk_rows = int(config.get("h2d_chunk_rows", os.environ.get("VRD_H2D_CHUNK", 49152)))  # rows per chunk when pair features arrive from the host
+        self.h2d_edge_rows = int(config.get("h2d_edge_rows", os.environ.get("VRD_H2D_EDGE", 16384)))    # ... and of the first / last chunk (not overlapped)
+        # persistent device buffers for the per-chunk layout arrays + pair tables, used round-robin across chunks AND videos: a
+        # ring of 4 indexed per video made the upload of the next video's third chunk wait for the LAST chunk of the previous
+        # video to be computed (the copy engine idled ~4 ms at every video boundary)
+        self._lay_bufs = [None] * 16
+        self._lay_done = [None] * 16
+        self._lay_seq = 0
         self.gc_park_results = bool(config.get("gc_park_results", True))
         self.lazy_trajs = bool(config.get("lazy_trajs", False))           # so_trajs as a LazyTrajs sequence
         self.use_native = bool(config.get("use_native", True))            # C++ backbone schedule (csrc/engine.cu)
         self._native = None
-        self._copy_stream = None
+        # Copy streams used round-robin by chunk, chained by events so that chunks still cross PCIe in order.  One stream's queue
+        # holds ~10^3 pending operations: with two videos (2 x ~1300 per-pair copies) in flight cudaMemcpyAsync blocked the host
+        # for ~10 ms per video until the copy engine had drained enough of it (measured: issue time 2.5 -> 12.4 ms).
+        self._copy_streams = None
+        self._copy_seq = 0
+        self._copy_tail = None
+        self.n_copy_streams = int(config.get("h2d_copy_streams", os.environ.get("VRD_H2D_STREAMS", 4)))
         self._aux_stream = None
         # ring of device staging buffers for host-resident pair tensors, used round-robin across chunks and videos.  Two slots
         # measured best end to end (41.0 k pairs/s; three: 37.3 k, four: 33.8 k -- letting the copy engine run further ahead of
@@ -154,6 +164,7 @@ class MaskVRD(nn.Module):
         self._staging = [None] * n_slots
         self._pack_done = [None] * n_slots
         self._stage_base = 0
+        self._dbg = {}
         self._engine: Optional[Engine] = None
         self._engine_key = None
         self._ops = None
@@ -287,10 +298,11 @@ class MaskVRD(nn.Module):
     def _fresh_block(self, cur):
         """A block that just came from the caching allocator may still be read by kernels already enqueued on the compute
         stream (the allocator only orders reuse within that stream): the copy stream must not write it before they finish."""
-        if self._copy_stream is not None:
+        if self._copy_streams is not None:
             e = torch.cuda.Event()
             e.record(cur)
-            self._copy_stream.wait_event(e)
+            for cs in self._copy_streams:
+                cs.wait_event(e)
 
     def _prepare_chunk(self, ops, desc, lens, tpads, chunk, ci: int, dev, cur, any_host: bool):
         """Host-side preparation of one chunk and everything that crosses PCIe for it, enqueued in this order on ONE stream
@@ -312,17 +324,25 @@ class MaskVRD(nn.Module):
                 self._fresh_block(cur)
             meta[0, plan["idx"]] = buf.data_ptr() + plan["offs"]
         words = (lay.n_words + 6 * lay.B + 3) // 4 * 4                      # keeps every piece 16-byte aligned
+        _t = time.perf_counter()
         pin = torch.empty(words, dtype=torch.int32, pin_memory=True)
+        self._dbg["pin_ms"] = self._dbg.get("pin_ms", 0.0) + 1e3 * (time.perf_counter() - _t)
         pin_np = pin.numpy()
         lay.host_words(pin_np[:lay.n_words])
         pin_np[lay.n_words: lay.n_words + 6 * lay.B].view(np.int64)[:] = meta.reshape(-1)
-        ls = ci % len(self._lay_bufs)           # persistent device buffers: written from the copy stream, so they must not
+        ls = self._lay_seq % len(self._lay_bufs)    # persistent device buffers: written from the copy stream, so they must not
+        self._lay_seq += 1
         lbuf = self._lay_bufs[ls]               # come from the (compute-stream ordered) caching allocator per call
         if lbuf is None or lbuf.numel() < words:
             self._lay_bufs[ls] = lbuf = torch.empty(max(words, 1 << 18), dtype=torch.int32, device=dev)
             self._lay_done[ls] = None
             self._fresh_block(cur)
-        stream = self._copy_stream if any_host else cur
+        if any_host:
+            stream = self._copy_streams[self._copy_seq % len(self._copy_streams)]
+            self._copy_seq += 1
+        else:
+            stream = cur
+        prev_tail = self._copy_tail if any_host else None
         lay.bind(lbuf[:lay.n_words])
         meta_d = lbuf[lay.n_words: lay.n_words + 6 * lay.B].view(torch.int64).view(3, lay.B)
         ev = torch.cuda.Event() if any_host else None
@@ -330,6 +350,8 @@ class MaskVRD(nn.Module):
 
         def issue():
             with torch.cuda.device(dev), torch.cuda.stream(stream):
+                if prev_tail is not None:
+                    stream.wait_event(prev_tail)     # chunks cross PCIe in order although their streams differ
                 if lay_done is not None:
                     stream.wait_event(lay_done)      # the kernels of the chunk that used this buffer four chunks ago are done
                 lbuf[:words].copy_(pin, non_blocking=True)
@@ -339,11 +361,14 @@ class MaskVRD(nn.Module):
                             stream.wait_event(pack_done)      # the previous user of this staging buffer has been packed
                         ops.h2d_pairs(plan["src"], plan["bytes"], staging, plan["offs"], stream)
                     ev.record(stream)
+                    self._copy_tail = ev
 
         # (Issuing the ~10^3 cudaMemcpyAsync calls of a video from a helper thread was measured and is slower: 33.7k vs 38.4k
         # pairs/s end to end -- the two threads contend for the driver's locks and the GIL.)
+        _t = time.perf_counter()
         issue()
-        return lay, meta_d, ev, bool((meta[1] == 1).all()), plan is not None
+        self._dbg["issue_ms"] = self._dbg.get("issue_ms", 0.0) + 1e3 * (time.perf_counter() - _t)
+        return lay, meta_d, ev, bool((meta[1] == 1).all()), plan is not None, ls
 
     @torch.no_grad()
     def run_network(self, feats: List[torch.Tensor], tpads: List[int], topk: int, want_masks: bool = False, desc=None):
@@ -359,24 +384,25 @@ class MaskVRD(nn.Module):
         lens = desc["shape"][:, 1].tolist()
         any_host = bool(desc["on_host"].any())
         st = {"prepare_ms": 0.0, "launch_ms": 0.0}
+        self._dbg = {}
         with torch.cuda.device(dev):
             cur = torch.cuda.current_stream(dev)
             if any_host:
                 chunks = self._chunks(lens, min(self.max_rows, self.h2d_chunk_rows), min(self.max_rows, self.h2d_edge_rows))
-                if self._copy_stream is None:
-                    self._copy_stream = torch.cuda.Stream(device=dev)
+                if self._copy_streams is None:
+                    self._copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, self.n_copy_streams))]
             else:
                 chunks = self._chunks(lens, self.max_rows)
             tA = time.perf_counter()
             prep = self._prepare_chunk(ops, desc, lens, tpads, chunks[0], 0, dev, cur, any_host)
             st["prepare_ms"] += 1e3 * (time.perf_counter() - tA)
-            lays, tops, mfs = [], [], []
+            lays, tops, mfs, used_ls = [], [], [], []
             for ci, (a, b) in enumerate(chunks):
                 tC = time.perf_counter()
                 nxt = None
                 if ci + 1 < len(chunks):      # the next chunk's uploads and copies go out before this chunk's kernels are enqueued
                     nxt = self._prepare_chunk(ops, desc, lens, tpads, chunks[ci + 1], ci + 1, dev, cur, any_host)
-                lay, meta_d, ev, token_major, staged = prep
+                lay, meta_d, ev, token_major, staged, ls = prep
                 if ev is not None:
                     cur.wait_event(ev)
                 ptrs = meta_d[0]
@@ -392,10 +418,7 @@ class MaskVRD(nn.Module):
                 # (the C++ schedule; ``use_native = False`` runs the same kernels through the per-operator Python schedule)
                 run = self._native.backbone if (self.use_native and eng.taps is None) else eng.backbone
                 e_top, mf = run(lay, ptrs, strides, after_pack=packed, token_major=token_major)
-                if len(chunks) > 1:
-                    done = torch.cuda.Event()
-                    done.record(cur)
-                    self._lay_done[ci % len(self._lay_bufs)] = done
+                used_ls.append(ls)
                 lays.append(lay); tops.append(e_top); mfs.append(mf)
                 tE = time.perf_counter()
                 st["prepare_ms"] += 1e3 * (tD - tC); st["launch_ms"] += 1e3 * (tE - tD)
@@ -404,20 +427,23 @@ class MaskVRD(nn.Module):
             if len(chunks) == 1:
                 glay, e_top, mf = lays[0], tops[0], mfs[0]
             else:
-                glay, e_top, mf = MergedLayout(lays, dev), torch.cat(tops, 0), torch.cat(mfs, 0)
+                glay, e_top, mf = MergedLayout(lays, dev, self._ops.merge_layout), torch.cat(tops, 0), torch.cat(mfs, 0)
             tD = time.perf_counter()
+            self._dbg["merge_ms"] = 1e3 * (tD - tC)
             predict = self._native.predict if (self.use_native and eng.taps is None) else eng.predict
             res = predict(glay, e_top, mf, topk, want_masks)
-            if len(chunks) == 1:
-                done = torch.cuda.Event()
-                done.record(cur)
-                self._lay_done[0] = done
+            # the chunk layouts are read until the merged layout has been built from them and the heads have run
+            done = torch.cuda.Event()
+            done.record(cur)
+            for ls in used_ls:
+                self._lay_done[ls] = done
             st["prepare_ms"] += 1e3 * (tD - tC); st["launch_ms"] += 1e3 * (time.perf_counter() - tD)
             if want_masks:
                 l0 = glay.levels[0]
                 res["masks"] = [res["masks"][int(l0.off[i]): int(l0.off[i]) + int(l0.len[i])] for i in range(glay.B)]
         if any_host:
             self._stage_base = (self._stage_base + len(chunks)) % len(self._staging)
+        st.update({k: round(v, 2) for k, v in self._dbg.items()})
         self._net_stats = st
         return res
 
@@ -599,7 +625,7 @@ class MaskVRD(nn.Module):
             if len(chunks) == 1:
                 glay, e_top, mf = lays[0], tops[0], mfs[0]
             else:
-                glay, e_top, mf = MergedLayout(lays, dev), torch.cat(tops, 0), torch.cat(mfs, 0)
+                glay, e_top, mf = MergedLayout(lays, dev, self._ops.merge_layout), torch.cat(tops, 0), torch.cat(mfs, 0)
             r = (self._native.predict if self.use_native else eng.predict)(glay, e_top, mf, self.topk, False)
             if boxes_host is None:                                        # device-resident boxes: read the clamped copy back
                 boxes_pin = torch.empty(boxes_all.shape, dtype=torch.float32, pin_memory=True)

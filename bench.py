@@ -91,6 +91,8 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        # NVML queries contend with the CUDA driver for a few ms each: a handful of samples per timed region, not a busy poll
+        self._stop_evt.wait(0.02)
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -100,11 +102,16 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.1)
+            self._stop_evt.wait(0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
+        if not self.samples and self.nv is not None:      # a region shorter than the first sampling delay: sample at its end
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            except Exception:
+                pass
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 

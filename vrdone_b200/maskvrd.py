@@ -157,6 +157,7 @@ class MaskVRD(nn.Module):
         self._copy_tail = None
         self.n_copy_streams = int(config.get("h2d_copy_streams", os.environ.get("VRD_H2D_STREAMS", 4)))
         self._aux_stream = None
+        self._trk_stream = None
         # ring of device staging buffers for host-resident pair tensors, used round-robin across chunks and videos.  Two slots
         # measured best end to end (41.0 k pairs/s; three: 37.3 k, four: 33.8 k -- letting the copy engine run further ahead of
         # the kernels slows the whole pipeline down, so the depth stays at "one chunk being copied, one being computed")
@@ -594,8 +595,6 @@ class MaskVRD(nn.Module):
                                                            data["cat_ids"], float(viou_threshold), dev, cur)
                 ok = valid[sids_np] & valid[oids_np]
                 sids_np, oids_np = sids_np[ok], oids_np[ok]
-            elif boxes_all is None:
-                boxes_all = boxes_pin.to(dev, non_blocking=True)
         keep, L, s_off, o_off = self.pair_table(durs_np, sids_np, oids_np, stride, offset, min_frames)
         if not keep.any():
             return _NO_PAIRS
@@ -606,22 +605,41 @@ class MaskVRD(nn.Module):
         tab[:, 1] = base[oids] + o_off[keep]
         tab[:, 2] = stride
         with torch.cuda.device(dev):
-            def gather(lst, width):
-                # one device array for all tracklets; host tensors cross PCIe once (non_blocking from pinned memory)
-                out = torch.empty(int(n_frames.sum()), width, dtype=torch.float32, device=dev)
-                for b, n, t in zip(base.tolist(), n_frames.tolist(), lst):
-                    out[b:b + n].copy_(t, non_blocking=True)
-                return out
-            vis_all = gather(vis_list, self.visual_dim)
-            clip_all = gather(clip_list, self.clip_dim) if clip_list is not None else None
+            # Everything that crosses PCIe for this video goes on ONE copy stream, small arrays first: the kernels of the
+            # previous video keep running while the tracklet features arrive, and no small upload sits on the compute stream
+            # behind another video's bulk copies.  Device-resident inputs are used in place on the compute stream.
+            host_in = not all(t.is_cuda for t in vis_list) or (clip_list is not None and not all(t.is_cuda for t in clip_list))
+            if host_in and self._trk_stream is None:
+                self._trk_stream = torch.cuda.Stream(device=dev)
+            up = self._trk_stream if host_in else cur
             tpads = reference_padded_lengths(lens, self.config)
             chunks = self._chunks(lens, self.max_rows)
-            lays, tops, mfs = [], [], []
-            for a, b in chunks:
-                lay = PackLayout(lens[a:b], tpads[a:b], self.n_levels, dev)
-                tab_h = torch.from_numpy(tab[a:b]).pin_memory()
-                e_top, mf = self._native.backbone_tracklets(lay, vis_all, clip_all, boxes_all, tab_h.to(dev, non_blocking=True), (vw, vh))
-                lays.append(lay); tops.append(e_top); mfs.append(mf)
+            with torch.cuda.stream(up):
+                if boxes_all is None:
+                    boxes_all = boxes_pin.to(dev, non_blocking=True)
+                lays = [PackLayout(lens[a:b], tpads[a:b], self.n_levels, dev) for a, b in chunks]
+                tabs = [torch.from_numpy(tab[a:b]).pin_memory().to(dev, non_blocking=True) for a, b in chunks]
+
+                def gather(lst, width):
+                    # one device array for all tracklets; host tensors cross PCIe once (non_blocking from pinned memory)
+                    out = torch.empty(int(n_frames.sum()), width, dtype=torch.float32, device=dev)
+                    for b, n, t in zip(base.tolist(), n_frames.tolist(), lst):
+                        out[b:b + n].copy_(t, non_blocking=True)
+                    return out
+                vis_all = gather(vis_list, self.visual_dim)
+                clip_all = gather(clip_list, self.clip_dim) if clip_list is not None else None
+                if host_in:
+                    arrived = torch.cuda.Event()
+                    arrived.record(up)
+            if host_in:
+                cur.wait_event(arrived)
+                for t in [vis_all, clip_all, boxes_all] + tabs + [lv.row_seq for lay in lays for lv in lay.levels]:
+                    if t is not None:
+                        t.record_stream(cur)            # allocated on the copy stream, consumed by kernels of the compute stream
+            tops, mfs = [], []
+            for lay, tab_d in zip(lays, tabs):
+                e_top, mf = self._native.backbone_tracklets(lay, vis_all, clip_all, boxes_all, tab_d, (vw, vh))
+                tops.append(e_top); mfs.append(mf)
             if len(chunks) == 1:
                 glay, e_top, mf = lays[0], tops[0], mfs[0]
             else:

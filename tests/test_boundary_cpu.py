@@ -104,3 +104,32 @@ def test_forward_without_pairs_returns_none_before_touching_the_device():
     model._get_engine = lambda: types.SimpleNamespace(device="cpu")      # no CUDA engine exists on this box
     empty = {"so_features_list": [], "sids": torch.zeros(0, dtype=torch.int64), "oids": torch.zeros(0, dtype=torch.int64)}
     assert model(empty) is None
+
+
+def test_pair_table_merges_back_to_back_host_pairs_into_one_copy():
+    """Host pairs laid out back to back in one buffer (a loader that pins a video in one arena) are staged with ONE copy per run;
+    separately allocated pairs keep one copy each; every pair's staged address stays consistent with its run."""
+    import numpy as np
+    C, lens = 37, [5, 9, 2, 14]
+    arena = torch.randn(sum(lens) * C)
+    views, pos = [], 0
+    for L in lens:
+        views.append(arena[pos:pos + L * C].view(L, C).t())          # (C, L) view of token-major memory, pairs back to back
+        pos += L * C
+    loose = [torch.randn(L, C).t() for L in lens]
+    for feats, n_copies in ((views, 1), (loose, 4), (views[:2] + loose[2:3] + views[3:], 3)):
+        desc = MaskVRD._describe(feats)
+        meta, plan = MaskVRD._pair_table(desc, 0, len(feats))
+        assert len(plan["src"]) == n_copies and int(plan["bytes"].sum()) == sum(L * C * 4 for L in lens)
+        assert (plan["offs"] % 256 == 0).all() and plan["total"] >= int(plan["bytes"].sum())
+        # replay the copies into a staging buffer and read every pair back through its staged offset
+        stage = np.zeros(plan["total"], dtype=np.uint8)
+        for src, nb, off in zip(plan["src"].tolist(), plan["bytes"].tolist(), plan["offs"].tolist()):
+            owner = next(f for f in feats if f.data_ptr() <= src < f.data_ptr() + f.numel() * 4 or f.data_ptr() == src)
+            base = owner.untyped_storage()
+            start = src - base.data_ptr()
+            stage[off:off + nb] = np.frombuffer(bytes(base)[start:start + nb], dtype=np.uint8)
+        for f, off in zip(feats, plan["offs_pair"].tolist()):
+            L = f.shape[1]
+            got = torch.from_numpy(stage[off:off + L * C * 4].view(np.float32).copy()).view(L, C).t()
+            assert torch.equal(got, f)

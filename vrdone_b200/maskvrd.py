@@ -289,11 +289,24 @@ class MaskVRD(nn.Module):
         shape = desc["shape"][a:b]
         # smallest address span that covers the (C, L) view: covers dense (C, L), the loader's (L, C) buffer and strided views
         span = np.where(on_host, ((shape[:, 0] - 1) * meta[1] + (shape[:, 1] - 1) * meta[2] + 1) * 4, 0)
-        padded = (span + 255) // 256 * 256
-        offs = np.cumsum(padded) - padded
+        # Host pairs that sit back to back in memory (a loader that pins a video's pairs in ONE arena) travel as one copy: per-pair
+        # copies cost ~3.5 us of driver time each and reach 43 GB/s where one large copy gets 55 GB/s.  A run starts at every
+        # pair that does not begin exactly where the previous host pair ended; runs are placed 256-byte aligned.
+        n = b - a
+        starts = np.ones(n, dtype=bool)
+        starts[1:] = ~(on_host[1:] & on_host[:-1] & (meta[0, 1:] == meta[0, :-1] + span[:-1]))
+        run_id = np.cumsum(starts) - 1
+        before = np.cumsum(span) - span                              # bytes of the chunk's host pairs before each pair
+        run_first = np.flatnonzero(starts)
+        run_bytes = np.add.reduceat(span, run_first)
+        run_padded = (run_bytes + 255) // 256 * 256
+        run_off = np.cumsum(run_padded) - run_padded
+        offs = run_off[run_id] + (before - before[run_first][run_id])
         idx = np.nonzero(on_host)[0]
-        plan = {"idx": idx, "src": np.ascontiguousarray(meta[0, idx]), "bytes": np.ascontiguousarray(span[idx]),
-                "offs": np.ascontiguousarray(offs[idx]), "total": int(padded.sum())}
+        live = run_bytes > 0
+        plan = {"idx": idx, "offs_pair": np.ascontiguousarray(offs[idx]),
+                "src": np.ascontiguousarray(meta[0, run_first[live]]), "bytes": np.ascontiguousarray(run_bytes[live]),
+                "offs": np.ascontiguousarray(run_off[live]), "total": int(run_padded.sum())}
         return meta, plan
 
     def _fresh_block(self, cur):
@@ -323,7 +336,7 @@ class MaskVRD(nn.Module):
                 full = (self.h2d_chunk_rows + 4096) * int(desc["shape"][a, 0]) * 4
                 self._staging[slot] = buf = torch.empty(max(plan["total"], full), dtype=torch.uint8, device=dev)
                 self._fresh_block(cur)
-            meta[0, plan["idx"]] = buf.data_ptr() + plan["offs"]
+            meta[0, plan["idx"]] = buf.data_ptr() + plan["offs_pair"]
         words = (lay.n_words + 6 * lay.B + 3) // 4 * 4                      # keeps every piece 16-byte aligned
         _t = time.perf_counter()
         pin = torch.empty(words, dtype=torch.int32, pin_memory=True)

@@ -22,7 +22,14 @@ CASES = {
     "vidor_local": dict(lens=[512, 509, 33, 200, 576], wseed=31, xseed=32),
     "vidor_x": dict(lens=[512, 510, 17, 3, 130], wseed=41, xseed=42),
 }
-VIDEO_CASES = {"vidvrd": dict(wseed=11, vseed=0), "vidor": dict(wseed=21, vseed=3, n_tracklets=5, n_frames=700)}
+VIDEO_CASES = {"vidvrd": dict(wseed=11, vseed=0), "vidor": dict(wseed=21, vseed=3, n_tracklets=5, n_frames=700),
+               # round 2: the SOS-windowed and CLIP configs, and a VidOR video with more than max_so_pair pairs whose 200-pair
+               # slices each hold long pairs (L > max_seq_len: the reference's long-batch padding, maskvrd.py:364-379)
+               "vidor_local": dict(wseed=31, vseed=6, n_tracklets=5, n_frames=700),
+               "vidor_x": dict(wseed=41, vseed=7, n_tracklets=4, n_frames=600),
+               "vidor_long": dict(config="vidor", wseed=21, vseed=10, n_tracklets=16, n_frames=2600)}
+# default (timing) initialisation: torch.manual_seed(0) + the module's own init, as bench.py uses it
+DEFAULT_INIT_CASES = {"vidor_default": dict(config="vidor", lens=[37, 128, 300, 512, 600], xseed=52)}
 
 
 def load_reference():
@@ -99,10 +106,15 @@ def loader_fixtures():
 def main():
     if "--loader-only" in sys.argv:
         return loader_fixtures()
-    loader_fixtures()
+    # --only name[,name...]: regenerate just these network / video fixtures (existing files of the others stay untouched)
+    only = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else None
+    if not only:
+        loader_fixtures()
     Ref = load_reference()
     torch.manual_seed(0)
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         cfg, ref, sd = build_ref(Ref, name, case["wseed"])
         mc = cfg["model_config"]
         feats = synth.pair_features(mc, case["lens"], case["xseed"])
@@ -122,8 +134,36 @@ def main():
                "schema": {k: list(v.shape) for k, v in sd.items()}}
         torch.save(fix, os.path.join(HERE, f"network_{name}.pt"))
         print(name, "network fixture:", fix["pred_logits"].shape, "logit std", float(fix["pred_logits"].std()))
+    for name, case in DEFAULT_INIT_CASES.items():
+        if only and name not in only:
+            continue
+        cfg = synth.load_config(case["config"])
+        mc = cfg["model_config"]
+        torch.manual_seed(0)
+        ours = MaskVRD(mc, "cpu")
+        sd = {k: v.detach().clone() for k, v in ours.state_dict().items()}
+        ref = Ref(mc, "cpu").eval()
+        ref.load_state_dict(sd, strict=True)
+        feats = synth.pair_features(mc, case["lens"], case["xseed"])
+        tpads = reference_padded_lengths(case["lens"], mc)
+        logits, masks = [], []
+        with torch.no_grad():
+            for f, t in zip(feats, tpads):
+                x = torch.zeros(1, f.shape[0], t)
+                x[0, :, : f.shape[1]] = f
+                m = (torch.arange(t) < f.shape[1])[None, None]
+                r = ref._mask_vrd(x, m)
+                logits.append(r["pred_logits"][0].clone())
+                masks.append(r["pred_masks"][0][:, : f.shape[1]].clone())
+        fix = {"config": case["config"], "lens": case["lens"], "tpads": tpads, "xseed": case["xseed"], "init": "torch.manual_seed(0)",
+               "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(feats),
+               "pred_logits": torch.stack(logits), "pred_masks": masks}
+        torch.save(fix, os.path.join(HERE, f"network_{name}.pt"))
+        print(name, "default-init network fixture: logit std", float(fix["pred_logits"].std()))
     for name, case in VIDEO_CASES.items():
-        cfg, ref, sd = build_ref(Ref, name, case["wseed"])
+        if only and name not in only:
+            continue
+        cfg, ref, sd = build_ref(Ref, case.get("config", name), case["wseed"])
         kw = {k: v for k, v in case.items() if k in ("n_tracklets", "n_frames")}
         video = synth.synthetic_video(cfg, case["vseed"], **kw)
         with torch.no_grad():
@@ -131,7 +171,7 @@ def main():
         lens = [int(f.shape[1]) for f in video["so_features_list"]]
         if out is not None:   # keep the fixture small: trajectories are stored as (n_frames, checksum) per triplet
             out["so_trajs"] = [[len(t[0]), float(torch.tensor(t).double().sum())] for t in out["so_trajs"]]
-        fix = {"config": name, **case, "n_pairs": len(lens), "lens": lens, "inputs_checksum": checksum(video["so_features_list"]),
+        fix = {"config": case.get("config", name), **case, "n_pairs": len(lens), "lens": lens, "inputs_checksum": checksum(video["so_features_list"]),
                "weights_checksum": checksum(sd.values()), "output": out}
         with open(os.path.join(HERE, f"video_{name}.json"), "w") as f:
             json.dump(fix, f)

@@ -133,3 +133,27 @@ def test_pair_table_merges_back_to_back_host_pairs_into_one_copy():
             L = f.shape[1]
             got = torch.from_numpy(stage[off:off + L * C * 4].view(np.float32).copy()).view(L, C).t()
             assert torch.equal(got, f)
+
+
+def test_eval_format_convertor_mirrors_reference_conversion():
+    """the per-video conversion of utils/evaluate.py:38-73 over eager lists and over LazyTrajs."""
+    import numpy as np
+    from vrdone_b200.eval_format import EvaluationFormatConvertor
+    from vrdone_b200.maskvrd import LazyTrajs
+    boxes = np.arange(40, dtype=np.float32).reshape(10, 4)
+    views = [(boxes[0:3], boxes[2:5]), (boxes[4:10], boxes[0:6])]
+    res = {"triplets": [[3, 7, 5], [1, 2, 3]], "triple_scores": [[.9, .5, .8], [.7, .6, .5]], "triple_scores_avg": [0.7333, 0.6],
+           "so_trajs": [[a.tolist(), b.tolist()] for a, b in views], "pred_durations": [[10, 13], [20, 26]], "so_tids": [[0, 1], [1, 0]]}
+    names = {i: f"e{i}" for i in range(10)}
+    preds = {i: f"p{i}" for i in range(10)}
+    conv = EvaluationFormatConvertor("vidor", names, preds)
+    out = conv.to_eval_format_pr("0001_3598080384", res)
+    assert list(out) == ["3598080384"]
+    r0 = out["3598080384"][0]
+    assert r0 == {"triplet": ["e3", "p7", "e5"], "duration": (10, 13), "score": 0.7333, "sub_traj": views[0][0].tolist(),
+                  "obj_traj": views[0][1].tolist()}
+    lazy = dict(res, so_trajs=LazyTrajs(views))
+    assert conv.to_eval_format_pr("0001_3598080384", lazy) == out
+    arr = EvaluationFormatConvertor("vidor", names, preds, trajs="array").to_eval_format_pr("0001_3598080384", lazy)["3598080384"]
+    assert arr[1]["sub_traj"] is views[1][0]
+    assert EvaluationFormatConvertor("vidvrd").to_eval_format_pr("ILSVRC2015_train_00005015", None) == {"ILSVRC2015_train_00005015": []}

@@ -13,9 +13,19 @@ pytestmark = pytest.mark.gpu
 
 NAMES = ["vidvrd", "vidor", "vidor_local", "vidor_x"]
 # Tolerances (relative to the tensor's max magnitude).  fp32 path: BASELINE.json asks for 1e-3 on logits and mask
-# probabilities.  bf16 path: operands of every GEMM are rounded to bf16 (8-bit mantissa, ~4e-3 relative per operand);
-# through ~30 chained GEMM+LN layers we allow 4e-2 on logits and 4e-2 absolute on mask probabilities.
-TOL = {"fp32": (1e-3, 1e-3), "bf16": (4e-2, 4e-2)}
+# probabilities.  bf16 path: operands of every GEMM are rounded to bf16 (8-bit mantissa, ~4e-3 relative per operand)
+# through ~30 chained GEMM+LN layers; the bound is <= 2x the largest error measured over the four stress-init fixtures on
+# a B200 (profiles/r2_parity.md lists the measured values per config).
+TOL = {"fp32": (1e-3, 1e-3), "bf16": (1.5e-2, 1.2e-2)}
+MEASURED = {}     # (test, case, precision) -> measured errors / rates, dumped to gpurun_out/parity_measured.json at session end
+
+
+def _record(key, **vals):
+    import json, os
+    MEASURED["/".join(key)] = {k: (round(float(v), 6) if isinstance(v, float) else v) for k, v in vals.items()}
+    os.makedirs(os.path.join(H.ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(H.ROOT, "gpurun_out", "parity_measured.json"), "w") as f:
+        json.dump(MEASURED, f, indent=1, sort_keys=True)
 
 
 def run_fixture(name, precision):
@@ -34,7 +44,18 @@ def test_network_matches_reference_golden(name, precision):
     fix, cfg, model, r = run_fixture(name, precision)
     tol_l, tol_m = TOL[precision]
     logits = r["logits"].cpu()
-    assert H.rel_err(logits, fix["pred_logits"]) < tol_l
+    err_l = H.rel_err(logits, fix["pred_logits"])
+    err_m = max(float((torch.sigmoid(m.t().cpu()) - torch.sigmoid(fix["pred_masks"][i])).abs().max()) for i, m in enumerate(r["masks"]))
+    k = cfg["inference_config"]["topk"]
+    ids_ref = torch.topk(torch.softmax(fix["pred_logits"], -1)[..., 1:], k, -1).indices + 1
+    flips = total = 0
+    for i, m in enumerate(r["masks"]):
+        a, b = torch.sigmoid(m.t().cpu()) > 0.5, torch.sigmoid(fix["pred_masks"][i]) > 0.5
+        flips += int((a != b).sum()); total += a.numel()
+    topk_mismatch = float((r["topk_ids"].cpu().long() != ids_ref).float().mean())
+    _record(("network", name, precision), logits_rel=err_l, mask_prob_abs=err_m, topk_mismatch_rate=topk_mismatch,
+            mask_flips=flips, mask_elems=total)
+    assert err_l < tol_l
     for i, m in enumerate(r["masks"]):
         pm, ref = torch.sigmoid(m.t().cpu()), torch.sigmoid(fix["pred_masks"][i])
         assert float((pm - ref).abs().max()) < tol_m, f"pair {i} (L={fix['lens'][i]})"
@@ -49,20 +70,51 @@ def test_network_matches_reference_golden(name, precision):
             nz = torch.nonzero(act[:, q]).flatten()
             exp = [int(nz[0]), int(nz[-1])] if nz.numel() else [-1, -1]
             assert r["first_last"][i, q].tolist() == exp
-    if precision == "fp32":   # and against the reference's own logits they agree wherever the reference is not borderline
-        ids_ref = torch.topk(torch.softmax(fix["pred_logits"], -1)[..., 1:], k, -1).indices + 1
-        assert float((r["topk_ids"].cpu().long() == ids_ref).float().mean()) > 0.995
-        flips = total = 0
-        for i, m in enumerate(r["masks"]):
-            a, b = torch.sigmoid(m.t().cpu()) > 0.5, torch.sigmoid(fix["pred_masks"][i]) > 0.5
-            flips += int((a != b).sum()); total += a.numel()
-        assert flips <= max(1, total // 2000)
+    # and against the reference's own logits they agree wherever the reference is not borderline (stress init: logit std ~0.6).
+    # BASELINE.md section 2 gives the reference's own bf16-vs-fp64 figures for comparison: 24 / 8181 mask flips (2.9e-3).
+    if precision == "fp32":
+        assert topk_mismatch < 0.005 and flips <= max(1, total // 2000)
+    else:
+        assert topk_mismatch < 0.06 and flips <= max(2, total // 250)
 
 
-@pytest.mark.parametrize("name", ["vidvrd", "vidor"])
-def test_forward_test_matches_reference_golden_video(name):
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_network_matches_reference_golden_default_init(precision):
+    """The timing initialisation of bench.py (torch.manual_seed(0), path scales 1e-4, near-constant class logits): logits and
+    mask probabilities against the reference; top-k order is noise at this init (the reference's own bf16
+    run mismatches 166 / 216 top-k entries against fp64), so only its rate is recorded."""
+    fix = H.network_fixture("vidor_default")
+    cfg = synth.load_config(fix["config"])
+    from vrdone_b200 import MaskVRD
+    torch.manual_seed(0)
+    model = MaskVRD(cfg["model_config"], "cpu").eval()
+    assert H.checksum(model.state_dict().values()) == pytest.approx(fix["weights_checksum"], rel=1e-12)
+    model._config_eval(cfg["inference_config"])
+    model.set_precision(precision).to("cuda")
+    feats = [f.cuda() for f in synth.pair_features(cfg["model_config"], fix["lens"], fix["xseed"])]
+    k = cfg["inference_config"]["topk"]
+    r = model.run_network(feats, fix["tpads"], k, want_masks=True)
+    logits = r["logits"].cpu()
+    err_l = H.rel_err(logits, fix["pred_logits"])
+    err_m = max(float((torch.sigmoid(m.t().cpu()) - torch.sigmoid(fix["pred_masks"][i])).abs().max()) for i, m in enumerate(r["masks"]))
+    ids_ref = torch.topk(torch.softmax(fix["pred_logits"], -1)[..., 1:], k, -1).indices + 1
+    flips = sum(int(((torch.sigmoid(m.t().cpu()) > 0.5) != (torch.sigmoid(fix["pred_masks"][i]) > 0.5)).sum()) for i, m in enumerate(r["masks"]))
+    _record(("network_default_init", "vidor", precision), logits_rel=err_l, mask_prob_abs=err_m,
+            topk_mismatch_rate=float((r["topk_ids"].cpu().long() != ids_ref).float().mean()), mask_flips=flips,
+            mask_elems=sum(m.numel() for m in r["masks"]))
+    tol_l, tol_m = TOL[precision]
+    assert err_l < tol_l and err_m < tol_m
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["vidvrd", "vidor", "vidor_local", "vidor_x", "vidor_long"])
+def test_forward_test_matches_reference_golden_video(name, precision):
+    """``model(input_data)`` against the result dict of the UNMODIFIED reference on the same seeded video (fixtures made by
+    tests/golden/make_golden.py): all four configs, plus a VidOR video with > max_so_pair pairs and long pairs (L > max_seq_len)
+    in every 200-pair slice.  fp32: ranked triplets identical apart from borderline ties; bf16: the agreement rate is
+    recorded and bounded from below (near-tied candidates swap ranks when logits move by ~1e-2)."""
     fix = H.video_fixture(name)
-    cfg, model, sd = H.seeded_model(name, fix["wseed"], precision="fp32")
+    cfg, model, sd = H.seeded_model(fix["config"], fix["wseed"], precision=precision)
     model.to("cuda")
     kw = {k: fix[k] for k in ("n_tracklets", "n_frames") if k in fix}
     video = synth.synthetic_video(cfg, fix["vseed"], **kw)
@@ -71,11 +123,21 @@ def test_forward_test_matches_reference_golden_video(name):
                  for k, v in video.items()}
     out = model(dev_video)
     ref = fix["output"]
-    assert len(out["triplets"]) == len(ref["triplets"])
     same = [a == b and c == d and e == f for a, b, c, d, e, f in
             zip(out["triplets"], ref["triplets"], out["pred_durations"], ref["pred_durations"], out["so_tids"], ref["so_tids"])]
-    assert np.mean(same) > 0.98, "ranked triplets differ from the reference beyond borderline ties"
-    assert np.allclose(np.array(out["triple_scores_avg"]), np.array(ref["triple_scores_avg"]), atol=2e-3)
+    # set agreement (order-free): a reference triplet counts as found when the same (tids, triplet, duration) is reported at all
+    key = lambda o, i: (tuple(o["so_tids"][i]), tuple(o["triplets"][i]), tuple(o["pred_durations"][i]))
+    ours_set = {key(out, i) for i in range(len(out["triplets"]))}
+    found = np.mean([key(ref, i) in ours_set for i in range(len(ref["triplets"]))])
+    score_err = float(np.abs(np.array(out["triple_scores_avg"])[: len(ref["triplets"])] - np.array(ref["triple_scores_avg"])[: len(out["triplets"])]).max())
+    _record(("forward_test", name, precision), n_triplets=len(out["triplets"]), n_ref=len(ref["triplets"]),
+            same_rank_rate=float(np.mean(same)), found_rate=float(found), ranked_score_abs=score_err)
+    assert len(out["triplets"]) == len(ref["triplets"])
+    if precision == "fp32":
+        assert np.mean(same) > 0.98, "ranked triplets differ from the reference beyond borderline ties"
+        assert score_err < 2e-3
+    else:
+        assert found > 0.85 and score_err < 1e-2
     for t, (n, chk), ok in zip(out["so_trajs"], ref["so_trajs"], same):
         if ok:
             assert len(t[0]) == n and abs(float(torch.tensor(t).double().sum()) - chk) < 1e-3 * max(1.0, abs(chk))
@@ -172,7 +234,7 @@ def test_native_schedule_equals_python_schedule(name, precision):
     n_native = model._ops.launches
     model.use_native = False
     b = model.run_network(feats, fix["tpads"], k, want_masks=True)
-    assert model._ops.launches - n_native == n_native - 0 or True     # launch counts are reported, not compared
+    assert model._ops.launches - n_native == n_native, "both schedules must issue the same number of launches"
     for key in ("logits", "topk_ids", "first_last", "topk_scores"):
         assert torch.equal(a[key], b[key]), key
     for ma, mb in zip(a["masks"], b["masks"]):
@@ -373,3 +435,68 @@ def test_forward_tracklets_with_duplicate_filter_matches_loader_then_forward(nam
     removed = {i for i, v in enumerate(item["valid_tracklets"]) if not v}
     assert removed and not any(s in removed or o in removed for s, o in b["so_tids"])
     assert unfiltered is not None
+
+
+def test_inputs_may_be_dropped_right_after_submit():
+    """host pair features are read by raw cudaMemcpyAsync calls that torch's pinned allocator knows nothing
+    about; ``submit()`` must keep them alive until the result is ready, because a ``for v in loader: submit(v)`` loop rebinds
+    ``v`` at once and the pinned blocks would be recycled (and refilled) under the DMA."""
+    import gc
+    import weakref
+    from vrdone_b200 import runner
+    cfg, model, sd = H.seeded_model("vidor", 21, precision="bf16")
+    model.to("cuda")
+    model.h2d_chunk_rows, model.h2d_edge_rows = 4096, 1024
+    base = synth.synthetic_video(cfg, 2, n_tracklets=9, n_frames=900)
+
+    def pinned_copy():
+        v = dict(base)
+        v["so_features_list"] = [t.t().contiguous().pin_memory().t() for t in base["so_features_list"]]
+        return v
+
+    expect = model(pinned_copy())
+    v = pinned_copy()
+    ref0 = weakref.ref(v["so_features_list"][0])
+    pending = model.submit(v)
+    del v
+    gc.collect()
+    assert ref0() is not None, "submit() must hold the host tensors until the copies have completed"
+    # recycle pinned memory aggressively while the DMA may still be running: same-sized blocks are handed out again at once
+    junk = [torch.full_like(t.t().contiguous(), float("nan")).pin_memory() for t in base["so_features_list"][:64]]
+    out = pending.result()
+    assert pending._keep is None       # ... and lets go of them once the result is out
+    del junk
+    keys = ("triplets", "triple_scores", "so_trajs", "pred_durations", "so_tids")
+    assert all(out[k] == expect[k] for k in keys)
+    # and through the pipelined loop with a generator that keeps no reference of its own
+    outs = list(runner.run_videos(model, (pinned_copy() for _ in range(3))))
+    assert all(o[k] == expect[k] for o in outs for k in keys)
+
+
+def test_lazy_trajs_and_eval_format_on_gpu():
+    """SURVEY 8f row 3 end to end on the device path: ``lazy_trajs`` results equal the eager ones, and the reference's
+    per-video conversion (utils/evaluate.py:38-73) consumes both."""
+    from vrdone_b200.eval_format import EvaluationFormatConvertor
+    from vrdone_b200.maskvrd import LazyTrajs
+    cfg, model, sd = H.seeded_model("vidor", 21, precision="bf16")
+    model.to("cuda")
+    video = synth.synthetic_video(cfg, 3, n_tracklets=6, n_frames=700, name="0001_3598080384")
+    dev_video = {k: ([t.cuda() for t in v] if isinstance(v, list) else (v.cuda() if torch.is_tensor(v) else v)) for k, v in video.items()}
+    eager = model(dev_video)
+    model.lazy_trajs = True
+    lazy = model(dev_video)
+    model.lazy_trajs = False
+    assert isinstance(lazy["so_trajs"], LazyTrajs) and isinstance(eager["so_trajs"], list)
+    for k in ("triplets", "triple_scores", "triple_scores_avg", "pred_durations", "so_tids"):
+        assert eager[k] == lazy[k]
+    assert lazy["so_trajs"] == eager["so_trajs"]
+    conv = EvaluationFormatConvertor("vidor")
+    a = conv.to_eval_format_pr(video["video_name"], eager)
+    b = conv.to_eval_format_pr(video["video_name"], lazy)
+    assert list(a) == ["3598080384"] and a == b
+    rel = a["3598080384"][0]
+    assert set(rel) == {"triplet", "duration", "score", "sub_traj", "obj_traj"}
+    assert len(rel["sub_traj"]) == rel["duration"][1] - rel["duration"][0] and len(rel["sub_traj"][0]) == 4
+    arr = EvaluationFormatConvertor("vidor", trajs="array").to_eval_format_pr(video["video_name"], lazy)["3598080384"]
+    assert all(np.array_equal(np.asarray(x["sub_traj"], dtype=np.float32), y["sub_traj"]) for x, y in zip(a["3598080384"], arr))
+    assert conv.to_eval_format_pr(video["video_name"], None) == {"3598080384": []}

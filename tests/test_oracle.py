@@ -30,18 +30,43 @@ def test_oracle_matches_golden_network(name):
             assert torch.all(out["pred_masks"][0][:, L:] == -10.0)
 
 
-def test_oracle_forward_test_matches_golden_video():
-    fix = H.video_fixture("vidvrd")
-    cfg, model, sd = H.seeded_model("vidvrd", fix["wseed"])
-    video = synth.synthetic_video(cfg, fix["vseed"])
+@pytest.mark.parametrize("name", ["vidvrd", "vidor_local", "vidor_x"])
+def test_oracle_forward_test_matches_golden_video(name):
+    fix = H.video_fixture(name)
+    cfg, model, sd = H.seeded_model(fix["config"], fix["wseed"])
+    kw = {k: fix[k] for k in ("n_tracklets", "n_frames") if k in fix}
+    video = synth.synthetic_video(cfg, fix["vseed"], **kw)
     assert [int(f.shape[1]) for f in video["so_features_list"]] == fix["lens"]
     out = O.forward_test(video, sd, cfg["model_config"], cfg["inference_config"])
     ref = fix["output"]
-    assert out["triplets"] == ref["triplets"]
-    assert out["pred_durations"] == ref["pred_durations"]
-    assert out["so_tids"] == ref["so_tids"]
-    assert [len(t[0]) for t in out["so_trajs"]] == [t[0] for t in ref["so_trajs"]]
+    if name == "vidvrd":
+        assert out["triplets"] == ref["triplets"]
+        assert out["pred_durations"] == ref["pred_durations"]
+        assert out["so_tids"] == ref["so_tids"]
+        assert [len(t[0]) for t in out["so_trajs"]] == [t[0] for t in ref["so_trajs"]]
+    else:       # batched oracle vs one-video reference call: candidates tied to ~1e-7 in the mean score may swap ranks
+        same = [a == b and c == d and e == f for a, b, c, d, e, f in
+                zip(out["triplets"], ref["triplets"], out["pred_durations"], ref["pred_durations"], out["so_tids"], ref["so_tids"])]
+        assert len(same) == len(ref["triplets"]) and sum(same) >= len(same) - 2
     assert torch.allclose(torch.tensor(out["triple_scores"]), torch.tensor(ref["triple_scores"]), atol=1e-5)
+
+
+def test_oracle_matches_golden_default_init():
+    fix = H.network_fixture("vidor_default")
+    cfg = synth.load_config(fix["config"])
+    mc = cfg["model_config"]
+    from vrdone_b200 import MaskVRD
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in MaskVRD(mc, "cpu").state_dict().items()}
+    assert H.checksum(sd.values()) == pytest.approx(fix["weights_checksum"], rel=1e-12)
+    feats = synth.pair_features(mc, fix["lens"], fix["xseed"])
+    with torch.no_grad():
+        for i in (0, len(feats) - 1):       # a short pair and a long one (T_pad 640)
+            x, m = O.pad_batch([feats[i]], fix["tpads"][i])
+            out = O.mask_vrd(x, m, sd, mc)
+            L = fix["lens"][i]
+            assert H.rel_err(out["pred_logits"][0], fix["pred_logits"][i]) < 2e-5
+            assert float((out["pred_masks"][0][:, :L] - fix["pred_masks"][i]).abs().max()) < 2e-5
 
 
 @pytest.mark.skipif(not H.have_reference(), reason="/root/reference not present (GPU box)")

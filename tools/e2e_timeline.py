@@ -2,7 +2,7 @@
 (CUDA events on the copy and compute streams) and when the host issued them."""
 import os, sys, time
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vrdone_b200 import MaskVRD, synth
 
 cfg = synth.load_config("vidor")

@@ -1,7 +1,7 @@
 """Where do Python GC pauses happen during forward_test? (GPU box)"""
 import gc, os, sys, time, traceback
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vrdone_b200 import MaskVRD, synth
 cfg = synth.load_config("vidor")
 dev = torch.device("cuda:0")

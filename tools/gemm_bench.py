@@ -1,4 +1,4 @@
-"""GEMM / kernel microbenchmarks on the B200 (CUDA events, inputs larger than L2).  Usage: python tools_gemm_bench.py [M]"""
+"""GEMM / kernel microbenchmarks on the B200 (CUDA events, inputs larger than L2).  Usage: python -m tools.gemm_bench [M]"""
 import sys
 
 import torch

@@ -1,4 +1,4 @@
-"""One GEMM shape, a few launches (for ncu).  Usage: python tools_gemm_one.py N K taps res(0/1) out(bf16|f32) act [M]"""
+"""One GEMM shape, a few launches (for ncu).  Usage: python -m tools.gemm_one N K taps res(0/1) out(bf16|f32) act [M]"""
 import sys
 import torch
 from vrdone_b200.cuda_ops import CudaOps

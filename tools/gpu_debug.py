@@ -1,5 +1,5 @@
 """GPU debug aid (not a test): compares engine intermediates ("taps") with the oracle's on a small case and prints
-where the first divergence appears.  Usage: python tools_gpu_debug.py [config] [fp32|bf16]"""
+where the first divergence appears.  Usage: python -m tools.gpu_debug [config] [fp32|bf16]"""
 import sys
 
 import torch

@@ -3,7 +3,7 @@ NUMA affinity of the GPU, and the chunk timeline of forward_test with pinned inp
 import os, sys, time
 import numpy as np
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vrdone_b200 import MaskVRD, synth
 
 def bw(label, fn, nbytes, reps=3):

@@ -1,5 +1,5 @@
 """Summarises an ncu launch list (--metrics gpu__time_duration.sum --csv) of bench.py: one device-resident forward, delimited by
-two consecutive pack kernels, grouped by kernel.  Usage: python tools_launch_summary.py gpurun_out/launches.csv [nth forward]"""
+two consecutive pack kernels, grouped by kernel.  Usage: python -m tools.launch_summary gpurun_out/launches.csv [nth forward]"""
 import collections
 import csv
 import re

@@ -1,11 +1,11 @@
-"""Turns the outputs of tools_gpu_final.sh (gpurun_out/) into the committed evidence under profiles/."""
+"""Turns the outputs of tools/gpu_final.sh (gpurun_out/) into the committed evidence under profiles/."""
 import csv
 import json
 import os
 import re
 import subprocess
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 
@@ -14,10 +14,10 @@ def last_json(name):
 
 
 def launch_files():
-    summary = subprocess.run(["python", os.path.join(ROOT, "tools_launch_summary.py"), os.path.join(G, "launches.csv"), "2"],
+    summary = subprocess.run(["python", os.path.join(ROOT, "tools/launch_summary.py"), os.path.join(G, "launches.csv"), "2"],
                              capture_output=True, text=True, check=True).stdout
     head = ("ncu --metrics gpu__time_duration.sum --clock-control none -c 3000, python bench.py --steps 1 --warmup 1 --videos 1 "
-            "--no-cpu-baseline (tools_gpu_final.sh)\nOne device-resident forward of the DEFAULT workload (video seed 0: 1298 pairs, "
+            "--no-cpu-baseline (tools/gpu_final.sh)\nOne device-resident forward of the DEFAULT workload (video seed 0: 1298 pairs, "
             "122 k valid frames), second pack kernel .. third pack kernel of the run.\n")
     open(os.path.join(P, "r1_launch_summary_default.txt"), "w").write(head + summary)
     lines = [l for l in open(os.path.join(G, "launches.csv")) if not l.startswith("==")]
@@ -47,7 +47,7 @@ def traffic():
     t = sum(v["gpu__time_duration.sum"][0] * tous[v["gpu__time_duration.sum"][1]] for v in per.values())
     out = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_tcgen05 "
                      "-s 236 -c 118, python bench.py --steps 1 --warmup 1 --videos 1 --no-cpu-baseline (third device-resident forward of the "
-                     "default workload, video seed 0: 1298 pairs; tools_gpu_final.sh)",
+                     "default workload, video seed 0: 1298 pairs; tools/gpu_final.sh)",
            "launches": len(per), "dram_bytes_read": rd, "dram_bytes_write": wr, "traffic_bytes_per_launch": (rd + wr) / len(per),
            "time_us_under_ncu": t}
     json.dump(out, open(os.path.join(P, "r1_gemm_traffic.json"), "w"), indent=1)
@@ -62,7 +62,7 @@ def bench_table():
     path = os.path.join(P, "r1_bench_configs.md")
     old = open(path).read()
     tail = old[old.index("\nTwo GPUs ("):] if "\nTwo GPUs (" in old else ""
-    out = ["# Round 1 — bench.py on one B200, all BASELINE.json configs (gpurun `tools_gpu_final.sh`, end of round)", "",
+    out = ["# Round 1 — bench.py on one B200, all BASELINE.json configs (gpurun `tools/gpu_final.sh`, end of round)", "",
            "`value` = pairs/s through `runner.run_videos` (two videos in flight) with pair features resident in HBM; `e2e` = the same loop with pinned HOST pair",
            "features (H2D inside); `tracklet api` = `forward_tracklets` with pinned host tracklet features (SURVEY 8f row 1); `blocking` = one `model(input)` call",
            "after the other (value / e2e); `lazy` = `model.lazy_trajs = True` (8f row 3; value / e2e); `net` = network only (no host decode); `frac` = tcgen05 GEMM",

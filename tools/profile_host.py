@@ -1,4 +1,4 @@
-"""Host-side profile of one forward (cProfile) + GPU/host time split.  Usage: python tools_profile_host.py [tracklets]"""
+"""Host-side profile of one forward (cProfile) + GPU/host time split.  Usage: python -m tools.profile_host [tracklets]"""
 import cProfile
 import pstats
 import sys

@@ -263,12 +263,9 @@ static int window_attn_tma_launch(const void* q, const void* k, const void* v, v
                                   cudaStream_t st) {
     constexpr int C = 512;
     constexpr int smem = 2 * (TILE + 2 * WIN_HALO) * C * (int)sizeof(T) + 16;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
     auto kern = window_attn_tma_kernel<T, C, HS, TILE>;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
-        attr_set = true;
-    }
+    if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
     const int total = streams * lay.R;    // R % 128 == 0, so TILE divides it
     kern<<<total / TILE, WARPS * 32, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)out, lay, w, total);
     return 0;
@@ -571,12 +568,9 @@ template <int HS, int NBUF>
 static int flash_launch(const void* q, const void* k, const void* v, void* out, long long ld, Lay lay, int n_head, int max_rows,
                         cudaStream_t st) {
     constexpr int smem = (1 + 2 * NBUF) * 64 * (HS + 8) * 2;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
     auto kern = flash_attn_bf16_kernel<HS, NBUF>;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
-        attr_set = true;
-    }
+    if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
     (void)max_rows;
     const dim3 grid((lay.R + 63) / 64, n_head);
     kern<<<grid, 128, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ld, lay);
@@ -781,12 +775,9 @@ __global__ void __launch_bounds__(WM_WARPS * 32, 2) window_attn_mma_kernel(const
 static int window_attn_mma_launch(const void* q, const void* k, const void* v, void* out, Lay lay, int w, int streams,
                                   cudaStream_t st) {
     constexpr int smem = WM_WARPS * 2 * (16 + 2 * (16 + 2 * WM_HALO)) * (64 + 8) * 2;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
     auto kern = window_attn_mma_kernel<8>;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
-        attr_set = true;
-    }
+    if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
     const int total = streams * lay.R;    // R % 128 == 0
     kern<<<total / (16 * WM_WARPS), WM_WARPS * 32, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                              (__nv_bfloat16*)out, lay, w, total);

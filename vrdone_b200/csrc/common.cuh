@@ -10,6 +10,29 @@
 #define VRD_EPS 1e-5f
 #define FULL_MASK 0xffffffffu
 
+// Per-device "done once" flags for host-side launchers: function attributes (max dynamic shared memory) and the SM count
+// belong to a DEVICE, not to the process -- a process that runs engines on two GPUs must set them on both.
+struct PerDeviceOnce {
+    bool done[64] = {false};
+    // true exactly once per device ordinal (and always for ordinals past the table: setting an attribute twice is harmless)
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+inline int device_sm_count() {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
+    if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev];
+}
+
 // One pyramid level of the varlen row layout (see vrdone_b200/layout.py).
 // seqinfo[i] = (first row, valid rows, first-pad-column-exists, 0); row_seq[r] = owning pair or -1.
 struct Lay {

@@ -548,8 +548,8 @@ bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int esi
 const char* gemm_tcgen05_error() { return g_err; }
 
 int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
-    static int num_sms = 0;
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once;      // the shared-memory attribute and the SM count belong to a device, not to the process
+    const int num_sms = device_sm_count();
     static const bool wide_ok = !(getenv("VRD_GEMM_WIDE") != nullptr && atoi(getenv("VRD_GEMM_WIDE")) == 0);   // A/B switch
     static const int dbg = getenv("VRD_GEMM_DBG") ? atoi(getenv("VRD_GEMM_DBG")) : 0;
     static int force_cg = -1;
@@ -581,11 +581,6 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
         return 1;
     }
     if (has_res && g.out_dtype != VRD_F32) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: residual needs an fp32 output"); return 1; }
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
     // CTA pairs whenever there are enough rows to keep every pair busy (the small query-decoder GEMMs keep one CTA per tile):
     // measured +6..10 % on the long-K GEMMs, +4..9 % on the K = 512 ones, neutral on the HBM-bound residual projections
     const int cg = force_cg == 1 ? 1 : ((force_cg == 2 || g.M >= 128 * 2 * 64) ? 2 : 1);
@@ -611,13 +606,11 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     const int smem = fixed + stages * stage_bytes;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-            cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
-            snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(max dynamic smem) failed");
-            return 1;
-        }
-        attr_set = true;
+    if (attr_once.first() &&
+        (cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+         cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)) {
+        snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(max dynamic smem) failed");
+        return 1;
     }
     const int wide = (!has_res && wide_ok && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) ? 1 : 0;
     EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R, wide, dbg};

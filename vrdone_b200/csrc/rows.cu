@@ -936,12 +936,7 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
 template <typename TO>
 static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const float* pre_b, const DwBranches& br, int streams,
                           cudaStream_t st) {
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int num_sms = device_sm_count();
     int mask = 0;
     for (int b = 0; b < br.n; ++b) mask |= (br.use_pre[b] ? 1 : 0) << b;
     static const int cfg = getenv("VRD_DW_CFG") ? atoi(getenv("VRD_DW_CFG")) : 2;   // 0: 8 warps x 32 rows, 1: 16 x 32, 2: 2 CTAs/SM of 8 x 16
@@ -953,8 +948,8 @@ static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const flo
 #define LAUNCH_NW(NB, MASK, NW, TILE) do { \
         auto kern = dwconv_ln_tile_kernel<TO, NB, MASK, NW, TILE>; \
         constexpr int smem = dwt_smem_bytes(MASK != 0 && MASK != ((1 << NB) - 1), TILE); \
-        static bool attr_set = false; \
-        if (!attr_set) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1; attr_set = true; } \
+        static PerDeviceOnce once; \
+        if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1; \
         kern<<<grid, NW * 32, smem, st>>>(x, lay, pre_g, pre_b, br, total); } while (0)
 #define LAUNCH(NB, MASK) do { if (cfg == 0) LAUNCH_NW(NB, MASK, 8, 32); else if (cfg == 1) LAUNCH_NW(NB, MASK, 16, 32); \
                                else LAUNCH_NW(NB, MASK, 8, 16); } while (0)

@@ -153,7 +153,7 @@ class CudaOps:
         if not torch.cuda.is_available():
             raise RuntimeError("vrdone_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         arch = self.lib.vrd_device_arch()
-        if arch < 100:
+        if arch != 100:      # the binary holds sm_100a code only (arch-specific: it does not run on sm_103 / sm_120 either)
             raise RuntimeError(f"vrdone_b200 kernels are built for sm_100a only; current device is sm_{arch}")
         self.launches = 0
         self._timing = None     # list of (op name, start event, end event, algorithmic flops) while profiling

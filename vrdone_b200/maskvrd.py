@@ -73,11 +73,16 @@ class PendingVideo:
     """A video whose copies and kernels are enqueued (``MaskVRD.submit``); ``result()`` waits for the read-back of the compact
     per-(pair, query) records and decodes them into the reference's output dict (or ``None``)."""
 
-    __slots__ = ("_model", "_host", "_event", "_input", "stats", "_done", "_out")
+    __slots__ = ("_model", "_host", "_event", "_input", "stats", "_done", "_out", "_keep")
 
-    def __init__(self, model, host, event, input_data, stats):
+    def __init__(self, model, host, event, input_data, stats, keep=None):
         self._model, self._host, self._event, self._input, self.stats = model, host, event, input_data, stats
         self._done, self._out = False, None
+        # Lifetime contract: host-resident pair features are read by raw cudaMemcpyAsync calls that torch's pinned-memory
+        # allocator does not know about, so the caller's tensors are referenced here until the read-back event (recorded after
+        # the last kernel that depends on those copies) has completed -- the caller may drop its own references right after
+        # ``submit()`` (a DataLoader(pin_memory=True) loop does exactly that).
+        self._keep = keep
 
     def result(self):
         if self._done:
@@ -94,7 +99,7 @@ class PendingVideo:
                                   packed[..., 2 * k:],                # [B, Q, 2] int32 first / last active frame
                                   self._input)
             self.stats.update(gpu_wait_ms=1e3 * (t1 - t0), decode_ms=1e3 * (time.perf_counter() - t1))
-        self._done, self._host, self._event, self._input = True, None, None, None
+        self._done, self._host, self._event, self._input, self._keep = True, None, None, None, None
         m.last_stats = self.stats
         return self._out
 
@@ -162,6 +167,8 @@ class MaskVRD(nn.Module):
         # measured best end to end (41.0 k pairs/s; three: 37.3 k, four: 33.8 k -- letting the copy engine run further ahead of
         # the kernels slows the whole pipeline down, so the depth stays at "one chunk being copied, one being computed")
         n_slots = int(config.get("h2d_staging_slots", os.environ.get("VRD_H2D_SLOTS", 2)))
+        if n_slots < 2:      # chunk i+1 is staged while chunk i is packed: one slot would be overwritten under the pack kernel
+            raise ValueError("h2d_staging_slots / VRD_H2D_SLOTS must be >= 2")
         self._staging = [None] * n_slots
         self._pack_done = [None] * n_slots
         self._stage_base = 0
@@ -516,7 +523,7 @@ class MaskVRD(nn.Module):
             small = self._stage_decode_inputs(input_data)
             host, ev = self._read_back(r, dev)
         stats = {"enqueue_ms": 1e3 * (time.perf_counter() - t0), **self._net_stats}
-        return PendingVideo(self, host, ev, small, stats)
+        return PendingVideo(self, host, ev, small, stats, keep=feats if desc["on_host"].any() else None)
 
     _DECODE_KEYS = ("sids", "oids", "traj_durations", "cat_ids", "cat_scores", "so_offset")
 

@@ -3,16 +3,24 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config vidor] [--precision bf16|fp32]
 
-A "step" is one pass of the hot path (``model(input_data)`` = network + heads epilogue + triplet decoding) over one
-synthetic VidOR-shaped video (tens of tracklets, every ordered pair with temporal overlap,
-feat_stride 4).  Prints ONE JSON line (rank 0).  For N > 1 launch with torchrun; every rank processes its own videos
-(weak scaling, no collective on the data path) and the time is the max over ranks.
+Workload (BASELINE.json configs[1]): a fixed, seeded SET of synthetic VidOR-shaped videos --
+frame counts F in {900, 1200, 1800, 3600} (.3/.4/.2/.1), N ~ U[20, 60] tracklets, every ordered pair with temporal overlap,
+feat_stride 4; the 3600-frame video carries pairs longer than max_seq_len (the reference's long-batch path, O(L^2) SOS
+attention).  A "step" is ONE PASS of ``model(input_data)`` (network + heads epilogue + ranking + triplet decoding) over every
+video of the set.  ``--tracklets T --frames F`` selects the fixed-shape round-1 workload instead.  Prints ONE JSON line
+(rank 0); details go to stderr.  For N > 1 launch with torchrun: every rank processes its own copy of the set (weak scaling,
+no collective on the data path), time = max over ranks.
 
-  value        whole-job pairs/s with the pair features already resident in HBM (CUDA events around the K steps)
-  e2e          the same through the public API with HOST (pinned) pair features: H2D copies + D2H of results inside
-  roofline     the tcgen05 GEMM kernel: algorithmic FLOPs of its launches / their CUDA-event durations vs the measured
-               bf16 peak in MEASURED_PEAKS.json (second pass over the same steps with per-launch events)
-  cpu_baseline the oracle port of the reference forward on the host cores, on a bounded sample of the same workload
+  value        whole-job pairs/s, pair features already resident in HBM (CUDA events around the K steps)
+  e2e          the same through the public API with HOST (pinned) pair features: H2D copies + D2H of results inside;
+               .blocking_value = the reference's eval loop (one blocking model(input_data) after the other);
+               .tracklet_api_value = MaskVRD.forward_tracklets with host tracklet features
+  roofline     dominant kernel (tcgen05 GEMM): algorithmic FLOPs of its launches / their CUDA-event durations vs the measured
+               bf16 peak; per-kernel time table; HBM fractions of the memory-bound kernels; attention TFLOP/s
+  parity       GPU outputs vs the oracle on the cpu_baseline sample (same pairs, same timing initialisation)
+  sweep        BASELINE config 5: a fixed set of distinct videos sharded by LPT over the ranks (strong scaling) through
+               runner.run_sharded + gather_object, inside the timed region
+  cpu_baseline the oracle port of the reference forward on the host cores, on a bounded random sample of the same workload
 """
 from __future__ import annotations
 
@@ -23,6 +31,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -37,37 +46,48 @@ UNIT = "pairs/s"
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--config", default="vidor", choices=list(synth.CONFIG_NAMES))
     p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    p.add_argument("--videos", type=int, default=2, help="distinct synthetic videos cycled through the steps")
-    p.add_argument("--tracklets", type=int, default=40)
-    p.add_argument("--frames", type=int, default=1200)
-    p.add_argument("--cpu-pairs", type=int, default=48, help="pairs in the bounded CPU-baseline sample")
+    p.add_argument("--set-videos", type=int, default=10, help="videos in the cfg2 set (one step = one pass over the set)")
+    p.add_argument("--set-seed", type=int, default=0)
+    p.add_argument("--tracklets", type=int, default=None, help="fixed-shape workload: tracklets per video (with --frames)")
+    p.add_argument("--frames", type=int, default=None)
+    p.add_argument("--videos", type=int, default=2, help="fixed-shape workload: distinct videos per step")
+    p.add_argument("--cpu-pairs", type=int, default=40, help="pairs in the bounded CPU-baseline sample")
+    p.add_argument("--sweep-videos", type=int, default=48, help="videos of the config-5 strong-scaling sweep (0: skip)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-extras", action="store_true", help="skip the blocking / tracklet / network-only / sweep legs")
     return p.parse_args()
 
 
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
 def peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) or the fallback B200_PROFILING.md states."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
-        return d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured"
-    return 1400.0, 1590.0, 6650.0, "fallback"
+        if all(k in d for k in ("bf16_tflops_sustained", "bf16_tflops", "hbm_gbs")):
+            return d["bf16_tflops_sustained"], d["bf16_tflops"], d["hbm_gbs"], "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"      # /opt/skills/guides/B200_PROFILING.md: 1.59 PF burst / ~1.4 sustained, 6.65 TB/s
 
 
-def gemm_traffic(args):
-    """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the 118 launches of one forward)
-    from the committed ncu capture of the DEFAULT workload; None for any other workload or precision."""
-    path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-    default = args.config == "vidor" and args.precision == "bf16" and args.tracklets == 40 and args.frames == 1200
-    if not (default and os.path.exists(path)):
-        return None
-    with open(path) as f:
-        return json.load(f)["traffic_bytes_per_launch"]
+def gemm_traffic(default_workload: bool):
+    """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one forward) from the
+    committed ncu capture of the default workload; None otherwise."""
+    for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if default_workload and os.path.exists(path):
+            with open(path) as f:
+                d = json.load(f)
+            return d["traffic_bytes_per_launch"], name
+    return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -116,30 +136,35 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def make_videos(cfg, args, rank):
-    vids = []
-    for v in range(args.videos):
-        # weak scaling: every rank works on its own copy of the SAME synthetic videos, so per-GPU work is identical for all N
-        vids.append(synth.synthetic_video(cfg, v, n_tracklets=args.tracklets, n_frames=args.frames))
-    return vids
+def video_specs(args):
+    """[(video seed, n_frames, n_tracklets)] of one step."""
+    if args.tracklets is not None or args.frames is not None:
+        return [(v, args.frames or 1200, args.tracklets or 40) for v in range(args.videos)]
+    return synth.cfg2_video_set(args.set_videos, args.set_seed)
+
+
+def workload_name(args, cfg):
+    st = cfg["dataset_config"]["feat_stride"]
+    if args.tracklets is not None or args.frames is not None:
+        return (f"{args.config}.yaml forward_test, synthetic VidOR-shaped videos: {args.tracklets or 40} tracklets x {args.frames or 1200} "
+                f"frames, feat_stride {st}, all ordered overlapping pairs; one step = {args.videos} videos")
+    return (f"{args.config}.yaml forward_test, SURVEY 8d cfg2 set: {args.set_videos} synthetic VidOR-shaped videos, F in "
+            f"{{900,1200,1800,3600}} frames (.3/.4/.2/.1), N ~ U[20,60] tracklets, feat_stride {st}, all ordered overlapping pairs "
+            f"(set seed {args.set_seed}); one step = one pass over the set")
 
 
 def to_device(video, dev):
     return {k: ([t.to(dev) for t in v] if isinstance(v, list) else (v.to(dev) if torch.is_tensor(v) else v)) for k, v in video.items()}
 
 
-def pin(video):
-    """Pinned host copy of the pair features, keeping the data loader's layout: a (C, L) view of an (L, C)-contiguous buffer
-    (reference vidor.py:708-711; DataLoader(pin_memory=True) preserves strides)."""
-    return {k: ([t.t().contiguous().pin_memory().t() if k == "so_features_list" else t for t in v] if isinstance(v, list) else v)
-            for k, v in video.items()}
-
-
-def pin_arena(video):
-    """The same pair features pinned in ONE arena per video, pairs back to back in token-major order (what a loader that
-    allocates a video's pinned memory once would hand over): back-to-back pairs are staged with one copy per chunk."""
+def pin_pairs(video):
+    """Pinned host copy of the pair features in the data loader's layout -- every pair a (C, L) view of its own (L, C)-contiguous
+    block (reference vidor.py:708-711; DataLoader(pin_memory=True) preserves strides) -- carved out of ONE pinned allocation per
+    video with a gap between pairs, so that pairs are NOT adjacent in memory and travel as one copy each, exactly like separately
+    pinned tensors (12 k cudaHostAlloc calls per set would only slow the benchmark's setup down)."""
     feats = video["so_features_list"]
-    total = sum(f.numel() for f in feats)
+    gap = 64                                                  # floats (256 bytes): keeps pairs from being coalesced into runs
+    total = sum(f.numel() + gap for f in feats)
     arena = torch.empty(total, dtype=torch.float32, pin_memory=True)
     views, pos = [], 0
     for f in feats:
@@ -147,28 +172,91 @@ def pin_arena(video):
         v = arena[pos:pos + L * C].view(L, C)
         v.copy_(f.t())
         views.append(v.t())
-        pos += L * C
+        pos += L * C + gap
     out = dict(video)
     out["so_features_list"] = views
     return out
 
 
-def cpu_baseline(cfg, video, n_pairs, threads):
-    """Oracle port of the reference forward on the host cores, on the first ``n_pairs`` pairs of a video."""
-    from oracle import maskvrd_oracle as O
-    from vrdone_b200 import MaskVRD
-    torch.set_num_threads(threads)
-    mc = cfg["model_config"]
-    torch.manual_seed(0)
-    sd = {k: v.detach().clone() for k, v in MaskVRD(mc, "cpu").state_dict().items()}
-    n = min(n_pairs, len(video["so_features_list"]))
+def sample_pairs(video, idx):
+    """``input_data`` restricted to the pairs ``idx`` (tracklet-level entries stay)."""
     sub = dict(video)
-    sub["so_features_list"] = video["so_features_list"][:n]
-    sub["sids"], sub["oids"], sub["so_offset"] = video["sids"][:n], video["oids"][:n], video["so_offset"][:n]
+    sub["so_features_list"] = [video["so_features_list"][i] for i in idx]
+    for k in ("sids", "oids", "so_offset"):
+        sub[k] = video[k][torch.as_tensor(idx, dtype=torch.long)]
+    return sub
+
+
+def cpu_sample(host_videos, n_pairs, seed):
+    """A bounded random sample of the workload for the CPU legs: ``n_pairs`` pairs drawn without replacement from the pairs of
+    ALL videos of the step, grouped by video (the oracle, like the reference, works video by video)."""
+    g = np.random.default_rng(seed)
+    owners = np.concatenate([np.full(len(v["sids"]), i) for i, v in enumerate(host_videos)])
+    local = np.concatenate([np.arange(len(v["sids"])) for v in host_videos])
+    pick = np.sort(g.choice(len(owners), size=min(n_pairs, len(owners)), replace=False))
+    return [(int(i), local[pick[owners[pick] == i]].tolist()) for i in np.unique(owners[pick])]
+
+
+def cpu_forward(cfg, sd, host_videos, sample, keep_outputs=False):
+    """Oracle port of the reference forward_test over a sample: ONE batched network pass over all sampled pairs (the reference
+    runs a slice of up to 200 pairs per network call, maskvrd.py:201-240; the oracle works in sub-batches of 16), then the
+    reference's candidate loop + ranking per video.  Returns (pairs, seconds, [(video, pair indices, logits, masks)])."""
+    from oracle import maskvrd_oracle as O
+    mc = cfg["model_config"]
+    subs = [(vi, idx, sample_pairs(host_videos[vi], idx)) for vi, idx in sample]
+    feats = [f for _, _, sub in subs for f in sub["so_features_list"]]
     t0 = time.perf_counter()
-    O.forward_test(sub, sd, mc, cfg["inference_config"])
+    with torch.no_grad():
+        logits, masks = O.network_outputs(feats, sd, mc)
+        pos = 0
+        for vi, idx, sub in subs:
+            O.decode_triplets(logits[pos:pos + len(idx)], masks[pos:pos + len(idx)], sub, cfg["inference_config"])
+            pos += len(idx)
     dt = time.perf_counter() - t0
-    return n / dt, n, dt
+    outs, pos = [], 0
+    if keep_outputs:
+        for vi, idx, sub in subs:
+            outs.append((vi, idx, logits[pos:pos + len(idx)], masks[pos:pos + len(idx)]))
+            pos += len(idx)
+    return len(feats), dt, outs
+
+
+def default_state_dict(mc):
+    from vrdone_b200 import MaskVRD
+    torch.manual_seed(0)
+    return {k: v.detach().clone() for k, v in MaskVRD(mc, "cpu").state_dict().items()}
+
+
+def parity_block(model, cfg, dev_videos, outs):
+    """GPU (benchmarked precision) vs oracle on the CPU sample: same pairs, same weights, the oracle's padded lengths."""
+    from oracle import maskvrd_oracle as O
+    mc = cfg["model_config"]
+    k = cfg["inference_config"]["topk"]
+    lmax = mmax = 0.0
+    ref_all, mis, tot_ids, flips, tot_m, n = [], 0, 0, 0, 0, 0
+    all_lens = [int(dev_videos[vi]["so_features_list"][i].shape[1]) for vi, idx, _, _ in outs for i in idx]
+    all_tpads = O.padded_lengths(all_lens, mc)         # the oracle padded the merged sample: long pairs to ITS longest pair
+    pos = 0
+    for vi, idx, logits, masks in outs:
+        feats = [dev_videos[vi]["so_features_list"][i] for i in idx]
+        r = model.run_network(feats, all_tpads[pos:pos + len(idx)], k, want_masks=True)
+        pos += len(idx)
+        torch.cuda.synchronize()
+        ref = torch.stack(logits)
+        got = r["logits"].cpu()
+        lmax = max(lmax, float((got - ref).abs().max()))
+        ref_all.append(ref)
+        ids_ref = torch.topk(torch.softmax(ref, -1)[..., 1:], k, -1).indices + 1
+        mis += int((r["topk_ids"].cpu().long() != ids_ref).sum()); tot_ids += ids_ref.numel()
+        for m, rm in zip(r["masks"], masks):
+            a, b = torch.sigmoid(m.t().cpu()), torch.sigmoid(rm)
+            mmax = max(mmax, float((a - b).abs().max()))
+            flips += int(((a > 0.5) != (b > 0.5)).sum()); tot_m += a.numel()
+        n += len(idx)
+    scale = max(float(torch.cat(ref_all).abs().max()), 1e-12)
+    return {"pairs": n, "logits_rel": lmax / scale, "mask_prob_abs": mmax, "topk_mismatch": mis, "topk_entries": tot_ids,
+            "mask_flips": flips, "mask_elems": tot_m, "init": "torch.manual_seed(0) default init (near-constant class logits: top-k order "
+            "is noise, BASELINE.md section 2: the reference's own bf16 run mismatches 166/216)", "vs": "oracle port, fp32"}
 
 
 def main():
@@ -177,24 +265,40 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = synth.load_config(args.config)
+    mc = cfg["model_config"]
     threads = os.cpu_count() or 1
-    workload = (f"{args.config}.yaml forward_test, synthetic VidOR-shaped videos: {args.tracklets} tracklets x {args.frames} frames, "
-                f"feat_stride {cfg['dataset_config']['feat_stride']}, all ordered overlapping pairs")
+    workload = workload_name(args, cfg)
+    specs = video_specs(args)
+    default_workload = (args.config == "vidor" and args.precision == "bf16" and args.tracklets is None and args.frames is None
+                        and args.set_videos == 10 and args.set_seed == 0)
 
     if args.impl == "reference":
+        # the reference's own CPU implementation of the path (oracle port: the reference is a Python package that cannot travel),
+        # all host threads, each step a fresh bounded random sample of the SAME workload
         if rank != 0:
             return
-        video = synth.synthetic_video(cfg, 0, n_tracklets=args.tracklets, n_frames=args.frames)
-        n = max(8, args.cpu_pairs // 2)
-        for _ in range(max(0, min(args.warmup, 1))):
-            cpu_baseline(cfg, video, n, threads)
+        torch.set_num_threads(threads)
+        st = cfg["dataset_config"].get("feat_stride", 1)
+        counts = [len(synth._overlapping_pairs(synth._tracklets(cfg, s, nt, nf)[2], st)) for s, nf, nt in specs]
+        sd = default_state_dict(mc)
+        n_step = max(8, args.cpu_pairs // 2)
+
+        def one_step(seed):     # only the sampled pairs' features are built (the full set is 11 GB)
+            sample = cpu_sample([{"sids": range(c)} for c in counts], n_step, seed)
+            vids = {vi: synth.synthetic_video(cfg, specs[vi][0], n_tracklets=specs[vi][2], n_frames=specs[vi][1], only_pairs=idx)
+                    for vi, idx in sample}
+            return cpu_forward(cfg, sd, vids, [(vi, list(range(len(idx)))) for vi, idx in sample])
+
+        for w in range(max(0, min(args.warmup, 1))):
+            one_step(1000 + w)
         tot_pairs = tot_t = 0.0
-        for _ in range(args.steps):
-            v, npairs, dt = cpu_baseline(cfg, video, n, threads)
-            tot_pairs += npairs
+        for s in range(args.steps):
+            n, dt, _ = one_step(s)
+            tot_pairs += n
             tot_t += dt
         val = tot_pairs / tot_t
-        sample = f"first {n} pairs of synthetic video seed 0 per step (reference padding: short pairs to max_seq_len)"
+        sample = (f"{n_step} pairs per step drawn at random (seeded, without replacement) from all pairs of the step's videos, padded as the "
+                  f"reference pads them (short pairs to max_seq_len, long pairs to the sample's longest)")
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -210,16 +314,28 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    model = MaskVRD(cfg["model_config"], dev).eval().to(dev)
+    model = MaskVRD(mc, dev).eval().to(dev)
     model._config_eval(cfg["inference_config"])
     model.set_precision(args.precision)
-    host_videos = make_videos(cfg, args, rank)
-    pinned = [pin(v) for v in host_videos]
-    dev_videos = [to_device(v, dev) for v in host_videos]
-    n_pairs = [len(v["sids"]) for v in host_videos]
-    flops = [runner.video_cost(args.config, [int(f.shape[1]) for f in v["so_features_list"]]) for v in host_videos]
-    frames = [sum(int(f.shape[1]) for f in v["so_features_list"]) for v in host_videos]
+    Q, topk = mc["predictor"]["num_queries"], cfg["inference_config"]["topk"]
+
+    t_setup = time.perf_counter()
+    host_videos, pinned, dev_videos = [], [], []
+    for s, nf, nt in specs:      # weak scaling: every rank works on its own copy of the SAME videos
+        v = synth.synthetic_video(cfg, s, n_tracklets=nt, n_frames=nf)
+        pv = pin_pairs(v)
+        pinned.append(pv)
+        dev_videos.append(to_device(pv, dev))
+        host_videos.append(pv)          # the pinned copy doubles as the host copy (CPU legs read it)
+        del v
+    lens_all = [[int(f.shape[1]) for f in v["so_features_list"]] for v in host_videos]
+    n_pairs = [len(l) for l in lens_all]
+    frames = [sum(l) for l in lens_all]
+    flops = [runner.video_cost(args.config, l) for l in lens_all]
     in_bytes = [sum(f.numel() * 4 for f in v["so_features_list"]) for v in host_videos]
+    long_pairs = [sum(1 for x in l if x > mc["max_seq_len"]) for l in lens_all]
+    log(f"[bench] rank {rank}: {len(specs)} videos, {sum(n_pairs)} pairs, {sum(frames)} valid frames, {sum(in_bytes) / 1e9:.2f} GB of pair "
+        f"features per step, {sum(flops) / 1e12:.1f} TFLOP per step; setup {time.perf_counter() - t_setup:.1f} s")
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -227,176 +343,186 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    gc_ms = [0.0]
-    gc_t0 = [0.0]
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
 
-    gc_gen = {}
+    step_ms = []
 
-    def gc_cb(phase, info):
-        if phase == "start":
-            gc_t0[0] = time.perf_counter()
-        else:
-            d = 1e3 * (time.perf_counter() - gc_t0[0])
-            gc_ms[0] += d
-            g = gc_gen.setdefault(info["generation"], [0, 0.0])
-            g[0] += 1
-            g[1] += d
-    import gc
-    gc.callbacks.append(gc_cb)
-    step_wall = []
-    free_ms = []
-
-    def timed(videos, steps, h2d, pipelined=True, dataset_config=None):
-        """K steps between two CUDA events.  ``pipelined``: through ``runner.run_videos`` (two videos in flight: the decode of
-        one overlaps the kernels of the next; every result is produced and dropped inside the timed region); otherwise one
-        synchronous ``model(v)`` call after the other, as the reference's eval loop does."""
+    def timed(videos, steps, pipelined=True, dataset_config=None):
+        """K steps (passes over ``videos``) between two CUDA events.  ``pipelined``: through ``runner.run_videos`` (two videos in
+        flight: the decode of one overlaps the kernels of the next; every result is produced and dropped inside the timed
+        region); otherwise one synchronous ``model(v)`` call after the other, as the reference's eval loop does.  Returns
+        (ms max over ranks, whole-job pairs)."""
         sync_all()
-        gc_ms[0] = 0.0
-        gc_gen.clear()
-        step_wall.clear()
-        free_ms.clear()
+        step_ms.clear()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pairs = 0
+        tw = time.perf_counter()
         if pipelined:
-            tw = time.perf_counter()
-            for out in runner.run_videos(model, (videos[s % len(videos)] for s in range(steps)), dataset_config=dataset_config):
-                del out     # dropping the ~2*10^5 Python objects of the result is part of the step
-                step_wall.append(round(1e3 * (time.perf_counter() - tw), 1))
-                tw = time.perf_counter()
-            pairs = sum(n_pairs[s % len(videos)] for s in range(steps))
+            n_v = len(videos)
+            for i, out in enumerate(runner.run_videos(model, (videos[j % n_v] for j in range(steps * n_v)), dataset_config=dataset_config)):
+                del out     # dropping the result's Python objects is part of the step
+                if (i + 1) % n_v == 0:
+                    step_ms.append(round(1e3 * (time.perf_counter() - tw), 1))
+                    tw = time.perf_counter()
         else:
             for s in range(steps):
-                v = videos[s % len(videos)]
+                for v in videos:
+                    # host-resident ``v``: the module moves the pair features (inside the timed region)
+                    out = model(v) if dataset_config is None else model.forward_tracklets(v, dataset_config)
+                    del out
+                step_ms.append(round(1e3 * (time.perf_counter() - tw), 1))
                 tw = time.perf_counter()
-                # h2d: ``v`` holds pinned HOST pair features; the module moves them (inside the timed region)
-                out = model(v) if dataset_config is None else model.forward_tracklets(v, dataset_config)
-                tm = time.perf_counter()
-                del out
-                step_wall.append(round(1e3 * (time.perf_counter() - tw), 1))
-                free_ms.append(round(1e3 * (time.perf_counter() - tm), 1))
-                pairs += n_pairs[s % len(videos)]
         e1.record()
         sync_all()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            p = torch.tensor([float(pairs)], device=dev)
-            dist.all_reduce(p, op=dist.ReduceOp.SUM)
-            ms, pairs = float(t), float(p)
-        return ms, pairs
+        return reduce_max(e0.elapsed_time(e1)), float(world * steps * sum(n_pairs))
 
-    def warm(videos, dataset_config=None):
+    def warm(videos, dataset_config=None, passes=None):
         """W untimed steps through BOTH loops: the pipelined one keeps two videos' pinned read-back / layout buffers alive at
         once, and the first cudaHostAlloc of those costs ~100 ms."""
-        for s in range(args.warmup):
-            v = videos[s % len(videos)]
-            model(v) if dataset_config is None else model.forward_tracklets(v, dataset_config)
-        for out in runner.run_videos(model, (videos[s % len(videos)] for s in range(max(args.warmup, 3))), dataset_config=dataset_config):
+        passes = args.warmup if passes is None else passes
+        for s in range(max(1, (passes + 1) // 2)):
+            for v in videos:
+                model(v) if dataset_config is None else model.forward_tracklets(v, dataset_config)
+        for out in runner.run_videos(model, (videos[j % len(videos)] for j in range(max(1, passes // 2) * len(videos))),
+                                     dataset_config=dataset_config):
             del out
 
+    ops = None
     warm(dev_videos)
     ops = model._ops
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ops.launches
-    ms, pairs = timed(dev_videos, args.steps, h2d=False)
+    ms, pairs = timed(dev_videos, args.steps)
     launches = ops.launches - l0
-    wall_pipe = list(step_wall)
+    steps_value = list(step_ms)
     host_pipe = {k: round(v, 2) for k, v in model.last_stats.items()}
-    ms_sync, pairs_sync = timed(dev_videos, args.steps, h2d=False, pipelined=False)
-    host_hbm = {k: round(v, 2) for k, v in model.last_stats.items()}
-    host_hbm["python_gc_ms_per_step"] = round(gc_ms[0] / args.steps, 2)
-    host_hbm["python_gc_by_generation"] = {str(k): [v[0], round(v[1], 1)] for k, v in gc_gen.items()}
-    host_hbm["forward_wall_ms_each_step"] = list(step_wall)
-    host_hbm["result_free_ms_each_step"] = list(free_ms)
     clocks = sampler.stop()
-    warm(pinned)                        # staging buffers, pinned upload blocks and the copy stream are created on first use
-    ms_e2e, pairs_e2e = timed(pinned, args.steps, h2d=True)
-    wall_pipe_e2e = list(step_wall)
-    host_pipe_e2e = {k: round(v, 2) for k, v in model.last_stats.items()}
-    ms_e2e_sync, pairs_e2e_sync = timed(pinned, args.steps, h2d=True, pipelined=False)
-    arena = [pin_arena(v) for v in host_videos]
-    warm(arena)
-    ms_arena, pairs_arena = timed(arena, args.steps, h2d=True)
-    del arena
-    host_e2e = {k: round(v, 2) for k, v in model.last_stats.items()}
-    host_e2e["forward_wall_ms_each_step"] = list(step_wall)
+    log(f"[bench] value: {pairs / ms * 1e3:.0f} pairs/s, {ms / args.steps:.1f} ms/step, per-step wall ms {steps_value}, host stats of the last "
+        f"video {host_pipe}")
 
-    # SURVEY 8f row 1: the same videos through the tracklet-level entry point (per-tracklet features cross PCIe once; the pair
-    # gather and the box geometry run on the device).  Reported beside the headline numbers, never instead of them.
-    trk_videos = []
-    for v in range(args.videos):
-        t = synth.synthetic_tracklet_video(cfg, v, n_tracklets=args.tracklets, n_frames=args.frames)
-        for key in ("visual_features_list", "clip_features_list", "bboxes_list"):
-            if key in t:
-                t[key] = [x.pin_memory() for x in t[key]]
-        trk_videos.append(t)
-    trk_bytes = [sum(x.numel() * 4 for key in ("visual_features_list", "clip_features_list", "bboxes_list") if key in t for x in t[key])
-                 for t in trk_videos]
-    warm(trk_videos, cfg["dataset_config"])
-    ms_trk, pairs_trk = timed(trk_videos, args.steps, h2d=True, dataset_config=cfg["dataset_config"])
-    ms_trk_sync, _ = timed(trk_videos, args.steps, h2d=True, pipelined=False, dataset_config=cfg["dataset_config"])
-    # SURVEY 8f row 3: the same loops with so_trajs returned as a lazy sequence (no eager per-frame box lists)
-    model.lazy_trajs = True
-    ms_lazy, pairs_lazy = timed(dev_videos, args.steps, h2d=False)
-    ms_lazy_e2e, _ = timed(pinned, args.steps, h2d=True)
-    model.lazy_trajs = False
+    warm(pinned)                        # staging buffers, pinned upload blocks and the copy streams are created on first use
+    ms_e2e, pairs_e2e = timed(pinned, args.steps)
+    steps_e2e = list(step_ms)
+    log(f"[bench] e2e: {pairs_e2e / ms_e2e * 1e3:.0f} pairs/s, per-step wall ms {steps_e2e}, host stats {model.last_stats}")
 
-    # network only (SURVEY 8d: the `_mask_vrd`-equivalent part, no triplet decode): kernels of all steps back to back
-    from vrdone_b200.layout import reference_padded_lengths
-    net_in = []
-    for v in dev_videos:
-        lens_v = [int(f.shape[1]) for f in v["so_features_list"]]
-        net_in.append((v["so_features_list"], reference_padded_lengths(lens_v, cfg["model_config"])))
-    for feats_v, tp_v in net_in:
-        model.run_network(feats_v, tp_v, model.topk)
-    sync_all()
-    net_sampler = ClockSampler(local_rank)       # this loop keeps the GPU at 100 % duty: power capping shows up here first
-    net_sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(args.steps):
-        feats_v, tp_v = net_in[s % len(net_in)]
-        model.run_network(feats_v, tp_v, model.topk)
-    e1.record()
-    sync_all()
-    net_clocks = net_sampler.stop()
-    ms_net = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_net], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_net = float(t)
-    pairs_net = world * sum(n_pairs[s % len(n_pairs)] for s in range(args.steps))
-    frames_net = world * sum(frames[s % len(frames)] for s in range(args.steps))
+    extras = not args.no_extras
+    e2e = {"value": pairs_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sum(in_bytes)),
+           "d2h_bytes_per_step": int(len(specs) * 4 * (4 + 6 * cfg["inference_config"]["n_max_pair"])),
+           "api": "runner.run_videos(model, videos): submit video i+1, then wait for + decode video i (two videos in flight; results "
+                  "identical to [model(v) for v in videos])"}
+    out_extra = {}
+    if extras:
+        ms_sync, pairs_sync = timed(dev_videos, args.steps, pipelined=False)
+        host_sync = {k: round(v, 2) for k, v in model.last_stats.items()}
+        ms_e2e_sync, pairs_e2e_sync = timed(pinned, args.steps, pipelined=False)
+        e2e["blocking_value"] = pairs_e2e_sync / (ms_e2e_sync * 1e-3)
+        out_extra["blocking_call"] = {"note": "one blocking model(input_data) call after the other (the reference's eval loop, eval.py:140-152)",
+                                      "value": pairs_sync / (ms_sync * 1e-3), "e2e": e2e["blocking_value"], "unit": UNIT}
+        log(f"[bench] blocking: {out_extra['blocking_call']}, host stats {host_sync}")
 
-    # roofline pass: the same steps with a CUDA-event pair around every launch of the dominant (GEMM) kernel
-    model.use_native = False        # same kernels, same order, issued one by one from Python so that each launch can be timed
+        # SURVEY 8f row 1: the same videos through the tracklet-level entry point (per-tracklet features cross PCIe once; the pair
+        # gather and the box geometry run on the device).  Reported beside the headline numbers, never instead of them.
+        trk_videos = []
+        for s, nf, nt in specs:
+            t = synth.synthetic_tracklet_video(cfg, s, n_tracklets=nt, n_frames=nf)
+            for key in ("visual_features_list", "clip_features_list", "bboxes_list"):
+                if key in t:
+                    t[key] = [x.pin_memory() for x in t[key]]
+            trk_videos.append(t)
+        trk_bytes = sum(x.numel() * 4 for t in trk_videos for key in ("visual_features_list", "clip_features_list", "bboxes_list") if key in t
+                        for x in t[key])
+        dc = cfg["dataset_config"]
+        warm(trk_videos, dc, passes=2)
+        ms_trk, pairs_trk = timed(trk_videos, args.steps, dataset_config=dc)
+        ms_trk_sync, _ = timed(trk_videos, args.steps, pipelined=False, dataset_config=dc)
+        e2e.update({"tracklet_api_value": pairs_trk / (ms_trk * 1e-3), "tracklet_api_blocking_value": pairs_trk / (ms_trk_sync * 1e-3),
+                    "tracklet_api_h2d_bytes_per_step": int(trk_bytes)})
+        log(f"[bench] tracklet api: {e2e['tracklet_api_value']:.0f} pairs/s pipelined, {e2e['tracklet_api_blocking_value']:.0f} blocking")
+        del trk_videos
+
+        # network only (SURVEY 8d: the `_mask_vrd`-equivalent part, no ranking / decode): kernels of all steps back to back
+        from vrdone_b200.layout import reference_padded_lengths
+        net_in = [(v["so_features_list"], reference_padded_lengths(l, mc)) for v, l in zip(dev_videos, lens_all)]
+        for feats_v, tp_v in net_in:
+            model.run_network(feats_v, tp_v, model.topk)
+        sync_all()
+        net_sampler = ClockSampler(local_rank)       # this loop keeps the GPU at 100 % duty: power capping shows up here first
+        net_sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(args.steps):
+            for feats_v, tp_v in net_in:
+                model.run_network(feats_v, tp_v, model.topk)
+        e1.record()
+        sync_all()
+        net_clocks = net_sampler.stop()
+        ms_net = reduce_max(e0.elapsed_time(e1))
+        out_extra["network_only"] = {"value": world * args.steps * sum(n_pairs) / (ms_net * 1e-3), "unit": UNIT,
+                                     "valid_frames_per_s": world * args.steps * sum(frames) / (ms_net * 1e-3),
+                                     "ms_per_step": ms_net / args.steps, "clocks": net_clocks}
+        log(f"[bench] network only: {out_extra['network_only']}")
+
+    # roofline pass: a CUDA-event pair around every launch (the per-operator Python schedule: same kernels, same order)
+    sustained, burst, hbm, src = peaks()
+    model.use_native = False
+    n_prof = min(args.steps, 2)
     ops.start_timing()
-    for s in range(args.steps):
-        model(dev_videos[s % len(dev_videos)])
+    for s in range(n_prof):
+        for v in dev_videos:
+            model(v)
     torch.cuda.synchronize(dev)
     prof = ops.stop_timing()
     model.use_native = True
-    sustained, burst, hbm, src = peaks()
-    gemm = prof.get("vrd_gemm", {"ms": 0.0, "flops": 0.0, "n": 0})
-    by_shape = {k.split(": ", 1)[1]: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["n"] / args.steps,
+    gemm = prof.get("vrd_gemm", {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+    by_shape = {k.split(": ", 1)[1]: {"ms_per_step": round(v["ms"] / n_prof, 3), "launches_per_step": round(v["n"] / n_prof, 1),
                                        "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)}
                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if ": " in k}
+    log("[bench] gemm by shape: " + json.dumps(by_shape))
     prof = {k: v for k, v in prof.items() if ": " not in k}
     total_ms = sum(p["ms"] for p in prof.values()) or 1.0
     ach = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
-    peak = sustained if args.precision == "bf16" else 75.0
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel" if args.precision == "bf16" else "gemm_simt_kernel",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": gemm_traffic(args),
-                "peak_source": f"{src} bf16 dense, sustained (burst {burst})" if args.precision == "bf16" else "nominal fp32 CUDA-core",
-                "launches": gemm["n"], "avg_launch_us": 1e3 * gemm["ms"] / max(1, gemm["n"]),
+    traffic, traffic_src = gemm_traffic(default_workload)
+    hbm_kernels = {k[4:]: {"ms_per_step": round(v["ms"] / n_prof, 3), "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 0),
+                           "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm, 3)}
+                   for k, v in prof.items() if v.get("bytes", 0.0) > 0 and k != "vrd_gemm" and v["ms"] > 0}
+    attn = prof.get("vrd_full_attn")
+    whole_tflops = args.steps * world * sum(flops) / (ms * 1e-3) / 1e12 / world      # per GPU
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach, "peak": sustained, "unit": "TFLOP/s",
+                "frac": ach / sustained, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": f"{src}: bf16 dense sustained {sustained} (burst {burst}) TFLOP/s, HBM copy {hbm} GB/s",
+                "launches_per_step": gemm["n"] / n_prof, "avg_launch_us": 1e3 * gemm["ms"] / max(1, gemm["n"]),
                 "share_of_step": gemm["ms"] / total_ms,
-                "per_kernel_ms": {k: round(v["ms"] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
-                "gemm_by_shape": by_shape,
-                "whole_path_algorithmic_tflops": sum(flops[s % len(flops)] for s in range(args.steps)) / (ms * 1e-3) / 1e12}
+                "per_kernel_ms": {k[4:]: round(v["ms"] / n_prof, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "hbm_kernels": hbm_kernels,
+                "whole_path_tflops_per_gpu": whole_tflops, "whole_path_frac": whole_tflops / sustained}
+    if attn is not None and attn["ms"] > 0:
+        roofline["full_attention"] = {"ms_per_step": round(attn["ms"] / n_prof, 3), "tflops": round(attn["flops"] / (attn["ms"] * 1e-3) / 1e12, 1),
+                                      "frac": round(attn["flops"] / (attn["ms"] * 1e-3) / 1e12 / sustained, 3)}
 
+    # BASELINE config 5: fixed set of distinct videos, sharded by LPT over the ranks, results gathered on rank 0 -- all timed
+    sweep = None
+    if extras and args.sweep_videos > 0:
+        sweep = run_sweep(args, cfg, model, dev, rank, world, sync_all, reduce_max)
+
+    parity = cpu = None
+    if not args.no_cpu_baseline and rank == 0:
+        torch.set_num_threads(threads)
+        sd = default_state_dict(mc)
+        sample = cpu_sample(host_videos, args.cpu_pairs, 12345)
+        n, dt, outs = cpu_forward(cfg, sd, host_videos, sample, keep_outputs=True)
+        cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n} pairs drawn at random (seeded) from all pairs of the step's videos, oracle port of forward_test ({dt:.1f} s)"}
+        parity = parity_block(model, cfg, dev_videos, outs)
+        parity["precision"] = args.precision
+
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -404,38 +530,84 @@ def main():
     out = {"metric": METRIC, "value": pairs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
-           "config": {"workload": workload, "pairs_per_step": n_pairs, "valid_frames_per_step": frames,
-                      "l2": "inputs larger than L2 (pair features of one video: %.2f GB)" % (in_bytes[0] / 1e9),
-                      "weights": "random init (torch.manual_seed(0))", "parallelism": f"dp{world} by video"},
-           "e2e": {"value": pairs_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sum(in_bytes) / len(in_bytes)),
-                   "d2h_bytes_per_step": int(sum(n * cfg["model_config"]["predictor"]["num_queries"] * (8 * cfg["inference_config"]["topk"] + 8)
-                                                 for n in n_pairs) / len(n_pairs))},
-           "e2e_arena": {"value": pairs_arena / (ms_arena * 1e-3), "unit": UNIT,
-                         "note": "as e2e, but every video's pair features pinned in ONE arena (pairs back to back): one copy per chunk"},
-           "e2e_tracklet_api": {"value": pairs_trk / (ms_trk * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sum(trk_bytes) / len(trk_bytes)),
-                                "note": "MaskVRD.forward_tracklets: host tracklet features in, triplets out (SURVEY 8f row 1)"},
-           "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-           "api": "runner.run_videos(model, videos): submit video i+1, then wait for + decode video i (two videos in flight)",
-           "sync_call": {"note": "one blocking model(input_data) call after the other (the reference's eval loop), no overlap of "
-                                 "host decode and device work",
-                         "value": pairs_sync / (ms_sync * 1e-3), "e2e": pairs_e2e_sync / (ms_e2e_sync * 1e-3),
-                         "e2e_tracklet_api": pairs_trk / (ms_trk_sync * 1e-3), "unit": UNIT},
-           "lazy_trajs": {"note": "model.lazy_trajs = True: so_trajs is a LazyTrajs sequence (SURVEY 8f row 3); same pipelined loops",
-                          "value": pairs_lazy / (ms_lazy * 1e-3), "e2e": pairs_lazy / (ms_lazy_e2e * 1e-3), "unit": UNIT},
-           "network_only": {"note": "run_network (everything up to the compact per-(pair, query) records, no host decode), HBM-resident",
-                            "value": pairs_net / (ms_net * 1e-3), "unit": UNIT, "valid_frames_per_s": frames_net / (ms_net * 1e-3),
-                            "ms_per_step": ms_net / args.steps, "clocks": net_clocks},
-           "valid_frames_per_s": world * sum(frames[s % len(frames)] for s in range(args.steps)) / (ms * 1e-3),
-           "step_wall_ms_pipelined": {"hbm_resident": wall_pipe, "e2e": wall_pipe_e2e},
-           "host_ms_last_step_pipelined": {"hbm_resident": host_pipe, "e2e": host_pipe_e2e},
-           "host_ms_last_step": host_hbm, "host_ms_last_step_e2e": host_e2e}
-    if not args.no_cpu_baseline:
-        v, n, dt = cpu_baseline(cfg, host_videos[0], args.cpu_pairs, threads)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"first {n} pairs of video 0 through the oracle port of forward_test ({dt:.1f} s)"}
+           "config": {"workload": workload, "videos_per_step": len(specs), "pairs_per_step": n_pairs, "long_pairs_per_step": long_pairs,
+                      "max_pair_len": max(max(l) for l in lens_all), "valid_frames_per_step": int(sum(frames)),
+                      "tflop_per_step": round(sum(flops) / 1e12, 2),
+                      "l2": "inputs larger than L2 (pair features of one step: %.2f GB)" % (sum(in_bytes) / 1e9),
+                      "weights": "random init (torch.manual_seed(0))", "parallelism": f"dp{world} by video",
+                      "step_wall_ms": {"value": steps_value, "e2e": steps_e2e}},
+           "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+           "valid_frames_per_s": world * args.steps * sum(frames) / (ms * 1e-3)}
+    out.update(out_extra)
+    if sweep is not None:
+        out["sweep"] = sweep
+    if parity is not None:
+        out["parity"] = parity
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sweep(args, cfg, model, dev, rank, world, sync_all, reduce_max):
+    """BASELINE config 5 (scaled stand-in: ``--sweep-videos`` distinct videos for the 835 of VidOR validation, drawn as cfg2):
+    strong scaling.  The videos are tracklet-level host inputs (the contract that scales: 11x fewer bytes than pair lists),
+    sharded longest-processing-time-first on the FLOP model, every rank runs the pipelined loop on its shard
+    (``runner.run_sharded``) and rank 0 gathers all results (``gather_object``); everything is inside the timed region."""
+    import torch.distributed as dist
+    dc = cfg["dataset_config"]
+    st = dc.get("feat_stride", 1)
+    specs = synth.cfg2_video_set(args.sweep_videos, args.set_seed + 7)
+    # costs need the durations only (cheap); features are generated for the rank's own shard
+    metas, costs, npairs = [], [], []
+    for s, nf, nt in specs:
+        _, _, durs, *_ = synth._tracklets(cfg, s, nt, nf, features=False, split_rng=True)
+        pr = synth._overlapping_pairs(durs, st)
+        lens = [len(range(0, min(durs[a][1], durs[b][1]) - max(durs[a][0], durs[b][0]), st)) for a, b in pr]
+        costs.append(runner.video_cost(args.config, lens))
+        npairs.append(len(lens))
+    shards = runner.shard_videos(costs, world)
+    videos = [None] * len(specs)
+    for i in shards[rank]:
+        s, nf, nt = specs[i]
+        t = synth.synthetic_tracklet_video(cfg, s, n_tracklets=nt, n_frames=nf, split_rng=True)
+        for key in ("visual_features_list", "clip_features_list", "bboxes_list"):
+            if key in t:
+                t[key] = [x.pin_memory() for x in t[key]]
+        videos[i] = t
+    for i in shards[rank][:2]:          # warm-up (buffers of this input kind)
+        model.forward_tracklets(videos[i], dc)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    res = runner.run_sharded(videos, costs, model=model, dataset_config=dc, gather=False)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    my_ms = e0.elapsed_time(e1)
+    tg = time.perf_counter()
+    merged = runner.gather_results(res)
+    gather_ms = 1e3 * (time.perf_counter() - tg)
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    sync_all()
+    ms_max = reduce_max(my_ms)
+    ms_sum = my_ms
+    if world > 1:
+        t = torch.tensor([my_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_sum = float(t)
+    wall_max = reduce_max(wall_ms)
+    if rank == 0:
+        assert len(merged) == len(specs)
+    n_trip = sum(len(r["triplets"]) for r in merged.values() if r is not None) if rank == 0 else 0
+    return {"config": f"BASELINE configs[4] scaled: {len(specs)} distinct cfg2 videos (stand-in for the 835 of VidOR validation), tracklet-level "
+                      f"host inputs, LPT shards over {world} rank(s), results gathered on rank 0",
+            "scaling": "strong", "videos": len(specs), "pairs": int(sum(npairs)), "value": sum(npairs) / (ms_max * 1e-3), "unit": UNIT,
+            "ms_device_max_over_ranks": ms_max, "imbalance_max_over_mean": ms_max / (ms_sum / world),
+            "cost_imbalance_lpt": max(sum(costs[i] for i in sh) for sh in shards) / (sum(costs) / world),
+            "gather_ms_rank0": gather_ms, "wall_ms_incl_gather_max_over_ranks": wall_max,
+            "value_incl_gather": sum(npairs) / (wall_max * 1e-3), "triplets_gathered": n_trip}
 
 
 if __name__ == "__main__":

@@ -29,7 +29,7 @@ extern "C" {
 #define VRD_ACT_NONE 0
 #define VRD_ACT_RELU 1
 #define VRD_ACT_GELU 2
-#define VRD_ABI_VERSION 2
+#define VRD_ABI_VERSION 3
 
 typedef void* vrd_stream_t; /* cudaStream_t */
 
@@ -140,6 +140,19 @@ int vrd_mask_logits(const float* mask_embed, int64_t ldm, const float* mask_feat
                     vrd_stream_t stream);
 int vrd_softmax_topk(const float* logits, int64_t ldl, int nrows, int n_cls, int topk, float* scores, int32_t* ids,
                      vrd_stream_t stream);
+
+/* k10, device-side compaction -- replaces the candidate loop, the mean-score ranking and the top-n_max_pair cut of
+ * MaskVRD.forward_test (maskvrd.py:262-328) on the outputs of vrd_softmax_topk / vrd_mask_logits.  Candidate
+ * c = (pair * Q + query) * topk + j is kept iff last >= 0 and (last - first) * feat_stride + 1 >= pred_min_frames; its score
+ * is ((cat_scores[sid] + topk_score) + cat_scores[oid]) / 3 in fp32; the n_max best (descending score, ties to the lower c)
+ * are written in rank order as records[i] = (c, score bits, predicate score bits, 1-based predicate id, first, last).
+ * sids / oids / so_offset [B] int64, cat_scores [N] fp32, traj_durations [N, 2] int64 are the reference's own per-video
+ * tensors (vidor.py:716-734) on the device.  header[0] = number of records, header[1] != 0 if a kept candidate violates the
+ * reference's assert 0 <= start, end <= overlap (maskvrd.py:297).  keys: scratch of B*Q*topk uint64.  n_max <= 1024. */
+int vrd_rank_triplets(const float* topk_scores, const int32_t* topk_ids, const int32_t* first_last, const int64_t* sids,
+                      const int64_t* oids, const float* cat_scores, const int64_t* traj_durations, const int64_t* so_offset, int B,
+                      int Q, int topk, int feat_stride, int pred_min_frames, int n_max, uint64_t* keys, int32_t* header,
+                      int32_t* records, vrd_stream_t stream);
 
 /* ---- native backbone schedule ------------------------------------------------------------------------------------
  * Replaces the per-operator Python schedule for MaskConvTransformerBackbone.forward + FPN1D_Fuse.forward

@@ -42,7 +42,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/vrdone_b200.h but not exported"
     assert declared == set(cuda_ops.exported_symbols())
-    assert cuda_ops.load_library().vrd_abi_version() == 2
+    assert cuda_ops.load_library().vrd_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -157,3 +157,60 @@ def test_eval_format_convertor_mirrors_reference_conversion():
     arr = EvaluationFormatConvertor("vidor", names, preds, trajs="array").to_eval_format_pr("0001_3598080384", lazy)["3598080384"]
     assert arr[1]["sub_traj"] is views[1][0]
     assert EvaluationFormatConvertor("vidvrd").to_eval_format_pr("ILSVRC2015_train_00005015", None) == {"ILSVRC2015_train_00005015": []}
+
+
+def emulate_rank_records(scores, cats, fl, video, stride, min_frames, n_max):
+    """numpy statement of csrc/rank.cu: keep filter, ((s + p) + o) / 3 in fp32, descending score with ties to the lower
+    candidate index, first n_max -> [4 + 6 n] int32 (header, records)."""
+    import numpy as np
+    B, Q, k = scores.shape
+    cs = video["cat_scores"].numpy().astype(np.float32)
+    sids, oids = video["sids"].numpy(), video["oids"].numpy()
+    first, last = fl[..., 0].astype(np.int64), fl[..., 1].astype(np.int64)
+    keep = (last >= 0) & ((last - first) * stride + 1 >= min_frames)
+    avg = ((cs[sids][:, None, None] + scores) + cs[oids][:, None, None]) / np.float32(3)
+    c = np.flatnonzero(np.broadcast_to(keep[:, :, None], avg.shape))
+    order = c[np.argsort(-avg.reshape(-1)[c], kind="stable")][:n_max]
+    rec = np.zeros((len(order), 6), dtype=np.int32)
+    rec[:, 0] = order.astype(np.uint32).view(np.int32)
+    rec[:, 1] = avg.reshape(-1)[order].view(np.int32)
+    rec[:, 2] = scores.reshape(-1)[order].view(np.int32)
+    rec[:, 3] = cats.reshape(-1)[order]
+    pq = order // k
+    rec[:, 4], rec[:, 5] = fl.reshape(-1, 2)[pq, 0], fl.reshape(-1, 2)[pq, 1]
+    return np.concatenate([np.array([len(order), 0, 0, 0], dtype=np.int32), rec.reshape(-1)])
+
+
+def test_ranked_decode_equals_dense_decode():
+    """The host half of the device-ranked path (``_decode_ranked`` on the records csrc/rank.cu specifies) must build the same
+    result dict as the dense numpy ranking ``_decode`` -- shared box lists, private box lists and lazy trajectories."""
+    import numpy as np
+    cfg = synth.load_config("vidor")
+    model = MaskVRD(cfg["model_config"], "cpu").eval()
+    model._config_eval(cfg["inference_config"])
+    video = synth.synthetic_video(cfg, 1, n_tracklets=10, n_frames=700)
+    B, Q, k = len(video["sids"]), cfg["model_config"]["predictor"]["num_queries"], model.topk
+    lens = np.array([int(f.shape[1]) for f in video["so_features_list"]])
+    g = np.random.default_rng(1)
+    scores = (g.integers(0, 64, (B, Q, k)) / 64).astype(np.float32)          # coarse values: many exact ties in the mean score
+    cats = g.integers(1, 51, (B, Q, k)).astype(np.int32)
+    first = (g.random((B, Q)) * lens[:, None] * 0.3).astype(np.int32)
+    last = np.minimum(lens[:, None] - 1, first + (g.random((B, Q)) * lens[:, None] * 0.7).astype(np.int32))
+    last[g.random((B, Q)) < 0.2] = -1                                         # queries without an active frame
+    fl = np.stack([np.where(last < 0, -1, first), last], -1).astype(np.int32)
+    dense = model._decode(scores, cats, fl, video)
+    packed = emulate_rank_records(scores, cats, fl, video, model.feat_stride, model.pred_min_frames, model.n_max_pair)
+    for private, lazy in ((False, False), (True, False), (False, True)):
+        model.private_box_lists, model.lazy_trajs = private, lazy
+        ranked = model._decode_ranked(packed, video)
+        for key in ("triplets", "triple_scores", "triple_scores_avg", "pred_durations", "so_tids"):
+            assert ranked[key] == dense[key], key
+        assert ranked["so_trajs"] == dense["so_trajs"]
+    model.private_box_lists = model.lazy_trajs = False
+    empty = packed.copy()
+    empty[0] = 0
+    assert model._decode_ranked(empty, video) is None
+    bad = packed.copy()
+    bad[1] = 1
+    with pytest.raises(AssertionError):
+        model._decode_ranked(bad, video)

@@ -16,7 +16,7 @@ NAMES = ["vidvrd", "vidor", "vidor_local", "vidor_x"]
 # probabilities.  bf16 path: operands of every GEMM are rounded to bf16 (8-bit mantissa, ~4e-3 relative per operand)
 # through ~30 chained GEMM+LN layers; the bound is <= 2x the largest error measured over the four stress-init fixtures on
 # a B200 (profiles/r2_parity.md lists the measured values per config).
-TOL = {"fp32": (1e-3, 1e-3), "bf16": (1.5e-2, 1.2e-2)}
+TOL = {"fp32": (1e-3, 1e-3), "bf16": (1.3e-2, 7e-3)}      # measured bf16 maxima: 6.6e-3 (logits), 3.5e-3 (mask probabilities)
 MEASURED = {}     # (test, case, precision) -> measured errors / rates, dumped to gpurun_out/parity_measured.json at session end
 
 
@@ -75,7 +75,9 @@ def test_network_matches_reference_golden(name, precision):
     if precision == "fp32":
         assert topk_mismatch < 0.005 and flips <= max(1, total // 2000)
     else:
-        assert topk_mismatch < 0.06 and flips <= max(2, total // 250)
+        # measured: top-k entries that differ from the reference's 1.0 % (vidor, k = 6 of 50) .. 6.1 % (vidvrd, k = 8 of 132);
+        # mask flips <= 1.0e-3 of the frames (the reference's own bf16 run: 2.9e-3)
+        assert topk_mismatch < 0.12 and flips <= max(2, total // 400)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -137,7 +139,9 @@ def test_forward_test_matches_reference_golden_video(name, precision):
         assert np.mean(same) > 0.98, "ranked triplets differ from the reference beyond borderline ties"
         assert score_err < 2e-3
     else:
-        assert found > 0.85 and score_err < 1e-2
+        # measured: every reference triplet is reported for 4 of the 5 videos (94.7 % for vidor_local), rank-for-rank agreement
+        # 68-94 % (near-tied candidates swap), mean scores of equal ranks within 2.2e-4
+        assert found > 0.9 and score_err < 1e-3
     for t, (n, chk), ok in zip(out["so_trajs"], ref["so_trajs"], same):
         if ok:
             assert len(t[0]) == n and abs(float(torch.tensor(t).double().sum()) - chk) < 1e-3 * max(1.0, abs(chk))
@@ -500,3 +504,45 @@ def test_lazy_trajs_and_eval_format_on_gpu():
     arr = EvaluationFormatConvertor("vidor", trajs="array").to_eval_format_pr(video["video_name"], lazy)["3598080384"]
     assert all(np.array_equal(np.asarray(x["sub_traj"], dtype=np.float32), y["sub_traj"]) for x, y in zip(a["3598080384"], arr))
     assert conv.to_eval_format_pr(video["video_name"], None) == {"3598080384": []}
+
+
+@pytest.mark.parametrize("name,kw", [("vidor", dict(n_tracklets=14, n_frames=900)), ("vidvrd", dict(n_tracklets=17, n_frames=150)),
+                                     ("vidor_x", dict(n_tracklets=6, n_frames=500))])
+def test_device_ranking_equals_host_ranking(name, kw):
+    """csrc/rank.cu (candidate filter, fp32 mean score, top-n_max_pair with ties to the earlier candidate) against the dense numpy
+    ranking of ``_decode`` on the same kernel outputs: identical result dicts, for device- and host-resident inputs, the tracklet
+    entry point, private / shared box lists, and the ``None`` result."""
+    cfg, model, sd = H.seeded_model(name, 21, precision="bf16")
+    model.to("cuda")
+    video = synth.synthetic_video(cfg, 5, **kw)
+    dev_video = {k: ([t.cuda() for t in v] if isinstance(v, list) else (v.cuda() if torch.is_tensor(v) else v)) for k, v in video.items()}
+    keys = ("triplets", "triple_scores", "triple_scores_avg", "so_trajs", "pred_durations", "so_tids")
+    model.device_rank = False
+    dense = model(dev_video)
+    model.device_rank = True
+    assert dense is not None and len(dense["triplets"]) == min(model.n_max_pair, len(dense["triplets"]))
+    for inp in (dev_video, video):
+        for private in (False, True):
+            model.private_box_lists = private
+            out = model(inp)
+            assert all(out[k] == dense[k] for k in keys)
+    model.private_box_lists = False
+    if name != "vidvrd":
+        trk = synth.synthetic_tracklet_video(cfg, 5, **kw)
+        model.device_rank = False
+        dense_t = model.forward_tracklets(trk, cfg["dataset_config"])
+        model.device_rank = True
+        out_t = model.forward_tracklets(trk, cfg["dataset_config"])
+        assert all(out_t[k] == dense_t[k] for k in keys)
+    # fewer kept candidates than n_max_pair, and none at all
+    model.n_max_pair = 1000
+    model.pred_min_frames = int(0.6 * max(int(f.shape[1]) for f in video["so_features_list"]) * cfg["inference_config"]["feat_stride"])
+    model.device_rank = False
+    few_dense = model(dev_video)
+    model.device_rank = True
+    few = model(dev_video)
+    assert (few is None) == (few_dense is None)
+    if few is not None:
+        assert len(few["triplets"]) < 1000 and all(few[k] == few_dense[k] for k in keys)
+    model.pred_min_frames = 10 ** 6
+    assert model(dev_video) is None

@@ -233,4 +233,18 @@ int vrd_softmax_topk(const float* logits, int64_t ldl, int nrows, int n_cls, int
     return check_launch("vrd_softmax_topk");
 }
 
+int vrd_rank_triplets(const float* topk_scores, const int32_t* topk_ids, const int32_t* first_last, const int64_t* sids,
+                      const int64_t* oids, const float* cat_scores, const int64_t* traj_durations, const int64_t* so_offset, int B,
+                      int Q, int topk, int feat_stride, int pred_min_frames, int n_max, uint64_t* keys, int32_t* header,
+                      int32_t* records, vrd_stream_t stream) {
+    if (!topk_scores || !topk_ids || !first_last || !sids || !oids || !cat_scores || !traj_durations || !so_offset || !keys || !header ||
+        !records)
+        return fail("vrd_rank_triplets: null argument");
+    if (vrd::rank_triplets(topk_scores, topk_ids, first_last, (const long long*)sids, (const long long*)oids, cat_scores,
+                           (const long long*)traj_durations, (const long long*)so_offset, B, Q, topk, feat_stride, pred_min_frames, n_max,
+                           (unsigned long long*)keys, header, records, (cudaStream_t)stream))
+        return fail("vrd_rank_triplets: need 1 <= n_max <= 1024 and B * Q * topk < 2^32 - 1");
+    return check_launch("vrd_rank_triplets");
+}
+
 }  // extern "C"

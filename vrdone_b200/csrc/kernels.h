@@ -55,6 +55,9 @@ int query_ln(const float* x, long long ldx, const float* g, const float* b, cons
 int mask_logits(const float* me, long long ldm, const float* mf, long long ldf, Lay lay, int Q, float* masks, long long ldk,
                 int* first_last, cudaStream_t st);
 int softmax_topk(const float* logits, long long ldl, int nrows, int n_cls, int topk, float* scores, int* ids, cudaStream_t st);
+int rank_triplets(const float* topk_scores, const int* topk_ids, const int* first_last, const long long* sids, const long long* oids,
+                  const float* cat_scores, const long long* durs, const long long* so_offset, int B, int Q, int topk, int feat_stride,
+                  int pred_min_frames, int n_max, unsigned long long* keys, int* header, int* records, cudaStream_t st);
 
 int window_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int n_head, int C, int w,
                 int streams, cudaStream_t st);

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "vrd_query_cross_attn": [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "vrd_mask_logits": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp],
     "vrd_softmax_topk": [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp],
+    "vrd_rank_triplets": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
 }
 
 
@@ -107,7 +108,7 @@ def load_library() -> C.CDLL:
     lib.vrd_predict.argtypes = [C.c_void_p, C.POINTER(PredictorCfg), C.POINTER(Level), C.POINTER(Level), C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vrd_predict.restype = C.c_int
-    if lib.vrd_abi_version() != 2:
+    if lib.vrd_abi_version() != 3:
         raise RuntimeError("libvrdone_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
@@ -158,6 +159,7 @@ class CudaOps:
         self.launches = 0
         self._timing = None     # list of (op name, start event, end event, algorithmic flops) while profiling
         self._last_flops = 0.0
+        self._last_bytes = 0.0       # algorithmic (compulsory) HBM bytes of the last op: valid rows only, each operand once
         self._last_tag = None
         self._stream_handle = C.c_void_p(0)
         self.bind_stream()
@@ -172,11 +174,12 @@ class CudaOps:
             def timed(*a, _fn=fn, _name=name, **k):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 self._last_flops = 0.0
+                self._last_bytes = 0.0
                 self._last_tag = None
                 e0.record()
                 r = _fn(*a, **k)
                 e1.record()
-                self._timing.append(("vrd_" + _name, e0, e1, self._last_flops, self._last_tag))
+                self._timing.append(("vrd_" + _name, e0, e1, self._last_flops, self._last_tag, self._last_bytes))
                 return r
             setattr(self, name, timed)
 
@@ -186,12 +189,13 @@ class CudaOps:
             if name in self.__dict__:
                 delattr(self, name)
         prof = {}
-        for name, e0, e1, fl, tag in self._timing:
+        for name, e0, e1, fl, tag, nbytes in self._timing:
             ms = e0.elapsed_time(e1)
             for key in ((name,) if tag is None else (name, name + ": " + tag)):
-                d = prof.setdefault(key, {"ms": 0.0, "flops": 0.0, "n": 0})
+                d = prof.setdefault(key, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
                 d["ms"] += ms
                 d["flops"] += fl
+                d["bytes"] += nbytes
                 d["n"] += 1
         self._timing = None
         return prof
@@ -259,6 +263,8 @@ class CudaOps:
     # -- ops ------------------------------------------------------------------------------------------------------
     def pack_pairs(self, ptrs, strides, lay, nv, nc, nbs, nbe, vis, clp, bso, bent, token_major=False):
         rs, si, R = self._lay(lay)
+        frames = int(lay.len.sum())
+        self._last_bytes = frames * (4.0 * (2 * nv + 2 * nc + nbs + 2 * nbe) + vis.element_size() * (2 * nv + 2 * nc) + 4.0 * 24)
         self._check(self.lib.vrd_pack_pairs(_p(ptrs), _p(strides), rs, si, R, lay.B, nv, nc, nbs, nbe, _p(vis), _p(clp),
                                             _dt(vis), _f32(bso), _f32(bent), int(token_major), self._stream()), "vrd_pack_pairs")
 
@@ -277,6 +283,8 @@ class CudaOps:
             rs, si, R = None, None, 0
         valid_rows = streams * int(lay.len.sum()) if lay is not None else M
         self._last_flops = 2.0 * valid_rows * N * K * taps     # algorithmic: valid rows only (no separators / tile padding)
+        self._last_bytes = valid_rows * (a.element_size() * K + out.element_size() * N + (4.0 * N if res1 is not None else 0.0)
+                                         + (4.0 * N if res2 is not None else 0.0)) + w.numel() * w.element_size()
         self._last_tag = (f"{'big' if M >= 16384 else 'small'} M, {taps}x{K}->{N} {'bf16' if out.dtype == torch.bfloat16 else 'f32'}"
                           f"{' gelu' if act == 2 else ''}{' +res' if res1 is not None else ''}")
         self._check(self.lib.vrd_gemm(ap, _dt(a), lda, _p(w), _f32(bias), op, _dt(out), ldo, M, N, K, taps, act, r1, ld1, r2, ld2,
@@ -287,6 +295,8 @@ class CudaOps:
         op, ldo = _mat(out)
         rows, Cc = x.shape
         rs, R = (lay.row_seq.data_ptr(), lay.R) if lay is not None else (None, 1)
+        valid = streams * int(lay.len.sum()) if lay is not None else rows
+        self._last_bytes = valid * Cc * float(x.element_size() + out.element_size())
         self._check(self.lib.vrd_layernorm(xp, _dt(x), ldx, _f32(g), _f32(b), op, _dt(out), ldo, rows, Cc, int(relu), rs, R,
                                            self._stream()), "vrd_layernorm")
 
@@ -313,6 +323,8 @@ class CudaOps:
         pg, pb = (pre if pre is not None else (None, None))
         ri, sii, Ri = self._lay(lay_in)
         ro, sio, Ro = self._lay(lay_out)
+        self._last_bytes = streams * x.shape[1] * (float(lay_in.len.sum()) * x.element_size()
+                                                  + float(lay_out.len.sum()) * n * branches[0][4].element_size())
         self._check(self.lib.vrd_dwconv_ln(xp, _dt(x), ldx, ri, sii, Ri, ro, sio, Ro, lay_in.B, stride, _f32(pg), _f32(pb), n, w,
                                            use_pre, g, b, outs, ldo, odt, x.shape[1], streams, self._stream()), "vrd_dwconv_ln")
 
@@ -320,6 +332,9 @@ class CudaOps:
         qp, ld = _mat(q)
         assert k.stride(0) == ld and v.stride(0) == ld and out.stride(0) == ld
         rs, si, R = self._lay(lay)
+        nl = lay.len.astype("float64")
+        self._last_bytes = streams * float(nl.sum()) * q.shape[1] * 4.0 * q.element_size()
+        self._last_flops = streams * 4.0 * q.shape[1] * float((nl * (2 * w + 1)).sum())      # <= 2w+1 keys per query (fewer at the edges)
         self._check(self.lib.vrd_window_attn(qp, _mat(k)[0], _mat(v)[0], _mat(out)[0], _dt(q), ld, rs, si, R, lay.B, n_head,
                                              q.shape[1], w, streams, self._stream()), "vrd_window_attn")
 
@@ -327,6 +342,9 @@ class CudaOps:
         qp, ld = _mat(q)
         assert k.stride(0) == ld and v.stride(0) == ld and out.stride(0) == ld
         rs, si, R = self._lay(lay)
+        nl = lay.len.astype("float64")
+        self._last_flops = 4.0 * q.shape[1] * float((nl * nl).sum())        # QK^T + PV over every (query, key) pair of a pair
+        self._last_bytes = float(nl.sum()) * q.shape[1] * 4.0 * q.element_size()
         self._check(self.lib.vrd_full_attn(qp, _mat(k)[0], _mat(v)[0], _mat(out)[0], _dt(q), ld, rs, si, R, lay.B, n_head,
                                            q.shape[1], lay.max_len, self._stream()), "vrd_full_attn")
 
@@ -335,6 +353,7 @@ class CudaOps:
         op, ldo = _mat(out)
         ri, sii, Ri = self._lay(lay_in)
         ro, sio, Ro = self._lay(lay_out)
+        self._last_bytes = 4.0 * x.shape[1] * (float(lay_in.len.sum()) + float(lay_out.len.sum()))
         self._check(self.lib.vrd_maxpool_skip(xp, ldx, ri, sii, Ri, ro, sio, Ro, lay_in.B, op, ldo, x.shape[1], self._stream()),
                     "vrd_maxpool_skip")
 
@@ -397,6 +416,19 @@ class CudaOps:
         assert ids.dtype == torch.int32 and scores.dtype == torch.float32 and ids.is_contiguous() and scores.is_contiguous()
         self._check(self.lib.vrd_softmax_topk(lp, ldl, nrows, n_cls, topk, scores.data_ptr(), ids.data_ptr(), self._stream()),
                     "vrd_softmax_topk")
+
+    def rank_triplets(self, scores, ids, first_last, sids, oids, cat_scores, durs, so_offset, feat_stride, pred_min_frames, n_max,
+                      keys, header, records):
+        """Device-side candidate filter + mean-score ranking + top-n_max cut (reference maskvrd.py:262-328); see vrd_rank_triplets."""
+        B, Q, k = scores.shape
+        assert scores.dtype == torch.float32 and ids.dtype == torch.int32 and first_last.dtype == torch.int32
+        assert all(t.dtype == torch.int64 and t.is_cuda and t.is_contiguous() for t in (sids, oids, durs, so_offset))
+        assert cat_scores.dtype == torch.float32 and keys.dtype == torch.int64 and keys.numel() >= B * Q * k
+        assert header.dtype == torch.int32 and header.numel() >= 4 and records.dtype == torch.int32 and records.numel() >= 6 * n_max
+        self._check(self.lib.vrd_rank_triplets(_p(scores), _p(ids), _p(first_last), _p(sids), _p(oids), _p(cat_scores), _p(durs),
+                                               _p(so_offset), B, Q, k, int(feat_stride), int(pred_min_frames), int(n_max), _p(keys),
+                                               _p(header), _p(records), self._stream()), "vrd_rank_triplets")
+        self.launches += 1       # two kernels: keys + select
 
 
 class NativeBackbone:

@@ -70,14 +70,16 @@ class LazyTrajs(Sequence):
 
 
 class PendingVideo:
-    """A video whose copies and kernels are enqueued (``MaskVRD.submit``); ``result()`` waits for the read-back of the compact
-    per-(pair, query) records and decodes them into the reference's output dict (or ``None``)."""
+    """A video whose copies and kernels are enqueued (``MaskVRD.submit``); ``result()`` waits for the read-back of the ranked
+    candidate records (or, with ``device_rank = False``, of the dense per-(pair, query) records) and builds the reference's
+    output dict (or ``None``)."""
 
-    __slots__ = ("_model", "_host", "_event", "_input", "stats", "_done", "_out", "_keep")
+    __slots__ = ("_model", "_host", "_event", "_input", "stats", "_done", "_out", "_keep", "_ranked", "_small_event")
 
-    def __init__(self, model, host, event, input_data, stats, keep=None):
+    def __init__(self, model, host, event, input_data, stats, keep=None, ranked=False, small_event=None):
         self._model, self._host, self._event, self._input, self.stats = model, host, event, input_data, stats
         self._done, self._out = False, None
+        self._ranked, self._small_event = ranked, small_event
         # Lifetime contract: host-resident pair features are read by raw cudaMemcpyAsync calls that torch's pinned-memory
         # allocator does not know about, so the caller's tensors are referenced here until the read-back event (recorded after
         # the last kernel that depends on those copies) has completed -- the caller may drop its own references right after
@@ -90,16 +92,26 @@ class PendingVideo:
         m = self._model
         t0 = time.perf_counter()
         if self._event is not None:
+            prep = None
+            if self._ranked:
+                # everything of the decode that does not depend on the results runs while the device still works
+                if self._small_event is not None:
+                    self._small_event.synchronize()
+                prep = m._decode_prepare(self._input, self._event)
+            tp = time.perf_counter()
             self._event.synchronize()
             t1 = time.perf_counter()
             packed = self._host.numpy()
-            k = m.topk
-            self._out = m._decode(packed[..., :k].view(np.float32),   # [B, Q, k] fp32 scores
-                                  packed[..., k:2 * k],               # [B, Q, k] int32, 1-based predicate ids
-                                  packed[..., 2 * k:],                # [B, Q, 2] int32 first / last active frame
-                                  self._input)
-            self.stats.update(gpu_wait_ms=1e3 * (t1 - t0), decode_ms=1e3 * (time.perf_counter() - t1))
-        self._done, self._host, self._event, self._input, self._keep = True, None, None, None, None
+            if self._ranked:
+                self._out = m._decode_ranked(packed, self._input, prep)
+            else:
+                k = m.topk
+                self._out = m._decode(packed[..., :k].view(np.float32),   # [B, Q, k] fp32 scores
+                                      packed[..., k:2 * k],               # [B, Q, k] int32, 1-based predicate ids
+                                      packed[..., 2 * k:],                # [B, Q, 2] int32 first / last active frame
+                                      self._input)
+            self.stats.update(prep_ms=1e3 * (tp - t0), gpu_wait_ms=1e3 * (t1 - tp), decode_ms=1e3 * (time.perf_counter() - t1))
+        self._done, self._host, self._event, self._input, self._keep, self._small_event = True, None, None, None, None, None
         m.last_stats = self.stats
         return self._out
 
@@ -153,6 +165,13 @@ class MaskVRD(nn.Module):
         self.gc_park_results = bool(config.get("gc_park_results", True))
         self.lazy_trajs = bool(config.get("lazy_trajs", False))           # so_trajs as a LazyTrajs sequence
         self.use_native = bool(config.get("use_native", True))            # C++ backbone schedule (csrc/engine.cu)
+        # candidate filter + mean-score ranking + top-n_max_pair cut on the device (csrc/rank.cu); False: dense records to the
+        # host and the same ranking in numpy (kept as the cross-check of the device path)
+        self.device_rank = bool(config.get("device_rank", True))
+        # so_trajs: per-frame [x1, y1, x2, y2] lists are built ONCE per tracklet and shared by the triplets that cover the frame
+        # (equal values, equal ``==`` / JSON; only in-place mutation of a box by a consumer would show).  True: fresh lists per
+        # triplet exactly as the reference's ``.tolist()`` (maskvrd.py:300-309) at ~4x the decode cost
+        self.private_box_lists = bool(config.get("private_box_lists", False))
         self._native = None
         # Copy streams used round-robin by chunk, chained by events so that chunks still cross PCIe in order.  One stream's queue
         # holds ~10^3 pending operations: with two videos (2 x ~1300 per-pair copies) in flight cudaMemcpyAsync blocked the host
@@ -410,8 +429,7 @@ class MaskVRD(nn.Module):
             cur = torch.cuda.current_stream(dev)
             if any_host:
                 chunks = self._chunks(lens, min(self.max_rows, self.h2d_chunk_rows), min(self.max_rows, self.h2d_edge_rows))
-                if self._copy_streams is None:
-                    self._copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, self.n_copy_streams))]
+                self._ensure_copy_streams(dev)
             else:
                 chunks = self._chunks(lens, self.max_rows)
             tA = time.perf_counter()
@@ -500,6 +518,57 @@ class MaskVRD(nn.Module):
         ev.record(torch.cuda.current_stream(dev))
         return host, ev
 
+    _RANK_KEYS = ("sids", "oids", "so_offset", "traj_durations")
+
+    def _stage_rank_inputs(self, small_src, dev, stream):
+        """The reference's per-video index tensors (sids, oids, so_offset, traj_durations: int64; cat_scores: fp32) on the
+        device for the ranking kernel.  Device tensors are used in place; host tensors travel as ONE pinned upload on ``stream``
+        (the copy stream when pair features come from the host: a small upload on the compute stream would stall its kernels
+        behind the bulk copies already queued on the copy engine).  Returns (dict, event or None)."""
+        if all(small_src[k].is_cuda for k in self._RANK_KEYS) and small_src["cat_scores"].is_cuda:
+            out = {k: small_src[k].to(torch.int64).contiguous() for k in self._RANK_KEYS}
+            out["cat_scores"] = small_src["cat_scores"].to(torch.float32).contiguous()
+            return out, None
+        parts = [small_src[k].detach().cpu().to(torch.int64).reshape(-1) for k in self._RANK_KEYS]
+        cs = small_src["cat_scores"].detach().cpu().to(torch.float32).reshape(-1)
+        sizes = [p.numel() for p in parts]
+        n64 = sum(sizes)
+        pin = torch.empty(n64 + (cs.numel() + 1) // 2, dtype=torch.int64, pin_memory=True)
+        torch.cat(parts, out=pin[:n64])
+        pin[n64:].view(torch.float32)[: cs.numel()] = cs
+        with torch.cuda.stream(stream):
+            d = pin.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        out, pos = {}, 0
+        for k, n in zip(self._RANK_KEYS, sizes):
+            out[k] = d[pos:pos + n]
+            pos += n
+        out["cat_scores"] = d[n64:].view(torch.float32)[: cs.numel()]
+        out["_buf"] = d
+        return out, ev
+
+    def _rank_and_read_back(self, r, rank_in, rank_ev, dev):
+        """Ranking kernels + asynchronous read-back of [4 + 6 * n_max_pair] int32 (header, records in rank order)."""
+        cur = torch.cuda.current_stream(dev)
+        if rank_ev is not None:
+            cur.wait_event(rank_ev)
+            if "_buf" in rank_in:
+                rank_in["_buf"].record_stream(cur)
+        B, Q, k = r["topk_scores"].shape
+        n_max = int(self.n_max_pair)
+        keys = torch.empty(B * Q * k, dtype=torch.int64, device=dev)
+        out = torch.empty(4 + 6 * n_max, dtype=torch.int32, device=dev)
+        self._ops.bind_stream()
+        self._ops.rank_triplets(r["topk_scores"], r["topk_ids"], r["first_last"], rank_in["sids"], rank_in["oids"], rank_in["cat_scores"],
+                                rank_in["traj_durations"], rank_in["so_offset"], self.feat_stride, self.pred_min_frames, n_max, keys,
+                                out[:4], out[4:])
+        host = torch.empty(out.shape, dtype=torch.int32, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        return host, ev
+
     @torch.no_grad()
     def submit(self, input_data) -> "PendingVideo":
         """First half of ``forward_test``: enqueue every copy and kernel of one video and the asynchronous read-back of its
@@ -517,30 +586,63 @@ class MaskVRD(nn.Module):
         if n_pairs == 0:                     # the loader hands on {} for such videos (vidor.py:652-653); nothing to rank
             return _NO_PAIRS
         desc = self._describe(feats)
+        any_host = bool(desc["on_host"].any())
         tpads = reference_padded_lengths(desc["shape"][:, 1].tolist(), self.config)
+        ranked = self.device_rank and self.n_max_pair <= 1024
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            # the small per-video tensors first: their device->host copies (decode inputs) finish long before the network does,
+            # and their host->device upload (ranking inputs) goes ahead of this video's bulk copies on the copy stream
+            small, small_ev = self._stage_decode_inputs(input_data, cur)
+            rank_in = rank_ev = None
+            if ranked:
+                if any_host:
+                    self._ensure_copy_streams(dev)
+                    up = self._copy_streams[self._copy_seq % len(self._copy_streams)]
+                    if self._copy_tail is not None:
+                        up.wait_event(self._copy_tail)
+                else:
+                    up = cur
+                rank_in, rank_ev = self._stage_rank_inputs(input_data, dev, up)
+                if up is cur:
+                    rank_ev = None
         r = self.run_network(feats, tpads, self.topk, desc=desc)
         with torch.cuda.device(dev):
-            small = self._stage_decode_inputs(input_data)
-            host, ev = self._read_back(r, dev)
+            if ranked:
+                host, ev = self._rank_and_read_back(r, rank_in, rank_ev, dev)
+            else:
+                host, ev = self._read_back(r, dev)
         stats = {"enqueue_ms": 1e3 * (time.perf_counter() - t0), **self._net_stats}
-        return PendingVideo(self, host, ev, small, stats, keep=feats if desc["on_host"].any() else None)
+        return PendingVideo(self, host, ev, small, stats, keep=feats if any_host else None, ranked=ranked, small_event=small_ev)
+
+    def _ensure_copy_streams(self, dev):
+        if self._copy_streams is None:
+            self._copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, self.n_copy_streams))]
 
     _DECODE_KEYS = ("sids", "oids", "traj_durations", "cat_ids", "cat_scores", "so_offset")
 
     @classmethod
-    def _stage_decode_inputs(cls, input_data):
+    def _stage_decode_inputs(cls, input_data, stream=None):
         """The small per-video tensors the decode reads (ids, durations, detection scores, boxes).  Device-resident ones are
-        read back asynchronously into pinned memory here, ahead of the result event: a blocking ``.cpu()`` inside the decode
-        would wait behind the kernels of the NEXT video when two videos are in flight."""
+        read back asynchronously into pinned memory here, ahead of the network: a blocking ``.cpu()`` inside the decode
+        would wait behind the kernels of the NEXT video when two videos are in flight.  Returns (dict of host tensors, event
+        after the last read-back or None when everything was on the host already)."""
+        n_dev = [0]
+
         def host(t):
             if not t.is_cuda:
                 return t
+            n_dev[0] += 1
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             h.copy_(t.detach(), non_blocking=True)
             return h
         out = {k: host(input_data[k]) for k in cls._DECODE_KEYS}
         out["bboxes_list"] = [host(b) for b in input_data["bboxes_list"]]
-        return out
+        ev = None
+        if n_dev[0] and stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return out, ev
 
     # ------------------------------------------------------------------------------------------------------------
     # SURVEY 8f row 1: tracklet-level input -- the data loader's pair construction on the device
@@ -634,6 +736,15 @@ class MaskVRD(nn.Module):
             up = self._trk_stream if host_in else cur
             tpads = reference_padded_lengths(lens, self.config)
             chunks = self._chunks(lens, self.max_rows)
+            ranked = self.device_rank and self.n_max_pair <= 1024
+            rank_in = rank_ev = None
+            if ranked:      # the ranking kernel's index tensors go first on the upload stream (small, ahead of the features)
+                rank_src = {"sids": torch.from_numpy(sids), "oids": torch.from_numpy(oids),
+                            "so_offset": torch.full((len(lens),), offset, dtype=torch.int64),
+                            "traj_durations": torch.from_numpy(durs_np), "cat_scores": data["cat_scores"].detach().cpu()}
+                rank_in, rank_ev = self._stage_rank_inputs(rank_src, dev, up)
+                if up is cur:
+                    rank_ev = None
             with torch.cuda.stream(up):
                 if boxes_all is None:
                     boxes_all = boxes_pin.to(dev, non_blocking=True)
@@ -665,16 +776,23 @@ class MaskVRD(nn.Module):
             else:
                 glay, e_top, mf = MergedLayout(lays, dev, self._ops.merge_layout), torch.cat(tops, 0), torch.cat(mfs, 0)
             r = (self._native.predict if self.use_native else eng.predict)(glay, e_top, mf, self.topk, False)
+            host_boxes_ready = boxes_host is not None
             if boxes_host is None:                                        # device-resident boxes: read the clamped copy back
                 boxes_pin = torch.empty(boxes_all.shape, dtype=torch.float32, pin_memory=True)
                 boxes_pin.copy_(boxes_all, non_blocking=True)
                 boxes_host = list(boxes_pin.split(n_frames.tolist()))
-            pairs = self._stage_decode_inputs({
-                "sids": torch.from_numpy(sids), "oids": torch.from_numpy(oids), "traj_durations": data["traj_durations"],
+            pairs, small_ev = self._stage_decode_inputs({
+                "sids": torch.from_numpy(sids), "oids": torch.from_numpy(oids), "traj_durations": torch.from_numpy(durs_np),
                 "cat_ids": data["cat_ids"], "cat_scores": data["cat_scores"],
-                "so_offset": torch.full((len(lens),), offset, dtype=torch.int64), "bboxes_list": boxes_host})
-            host, ev = self._read_back(r, dev)
-        return PendingVideo(self, host, ev, pairs, {"enqueue_ms": 1e3 * (time.perf_counter() - t0)})
+                "so_offset": torch.full((len(lens),), offset, dtype=torch.int64), "bboxes_list": boxes_host}, cur)
+            if boxes_host is not None and small_ev is None and not host_boxes_ready:
+                small_ev = torch.cuda.Event()
+                small_ev.record(cur)
+            if ranked:
+                host, ev = self._rank_and_read_back(r, rank_in, rank_ev, dev)
+            else:
+                host, ev = self._read_back(r, dev)
+        return PendingVideo(self, host, ev, pairs, {"enqueue_ms": 1e3 * (time.perf_counter() - t0)}, ranked=ranked, small_event=small_ev)
 
     def _filter_duplicates(self, boxes_dev, boxes_pin, base, durs_np, cat_ids, threshold: float, dev, cur):
         """the loader's duplicate-tracklet vIoU filter (dataloaders/vidor.py:583-641) on the device.  Runs on a
@@ -708,6 +826,100 @@ class MaskVRD(nn.Module):
         cur.wait_event(done)                                                # the pack kernel reads boxes_dev on the current stream
         done.synchronize()
         return valid_h.numpy().astype(bool), boxes_dev
+
+    def _decode_prepare(self, small, event=None):
+        """The part of the decode that does not depend on the results: numpy views of the per-video index tensors and -- while
+        the device still works (``event`` not complete) -- the per-tracklet box lists the trajectories are sliced from."""
+        sids, oids, durs, cat_ids, cat_scores, off = [small[k].numpy() for k in self._DECODE_KEYS]
+        prep = {"sids": sids.astype(np.int64, copy=False), "oids": oids.astype(np.int64, copy=False), "durs": durs.astype(np.int64, copy=False),
+                "cat_ids": cat_ids, "cat_scores": cat_scores.astype(np.float32, copy=False), "off": off.astype(np.int64, copy=False),
+                "boxes": small["bboxes_list"], "box_arrays": {}, "box_lists": {}}
+        if event is not None and not self.lazy_trajs and not self.private_box_lists:
+            gc_was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                for tid, b in enumerate(prep["boxes"]):
+                    if event.query():
+                        break                      # the results are there: convert the remaining tracklets only on demand
+                    prep["box_lists"][tid] = b.detach().numpy().tolist()
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
+        return prep
+
+    def _decode_ranked(self, packed, small, prep=None):
+        """Result dict from the ranked candidate records of ``vrd_rank_triplets`` ([4] header + [n, 6] records): only the
+        <= n_max_pair reported triplets are touched on the host (the reference's loop visits every candidate, maskvrd.py:262-328)."""
+        count, violated = int(packed[0]), int(packed[1])
+        assert not violated, "a predicted duration lies outside the pair's overlap (reference assert, maskvrd.py:297)"
+        if count == 0:
+            return None
+        if prep is None:
+            prep = self._decode_prepare(small)
+        sids, oids, durs, cat_ids, cat_scores, off = (prep[k] for k in ("sids", "oids", "durs", "cat_ids", "cat_scores", "off"))
+        rec = packed[4:4 + 6 * count].reshape(count, 6)
+        topk, stride = self.topk, self.feat_stride
+        c = rec[:, 0].view(np.uint32).astype(np.int64)
+        p = c // (topk * self._n_queries())
+        avg, pscore = rec[:, 1].view(np.float32), rec[:, 2].view(np.float32)
+        s, o = sids[p], oids[p]
+        so_start = np.maximum(durs[s, 0], durs[o, 0])
+        a = rec[:, 4].astype(np.int64) * stride + off[p]
+        b = rec[:, 5].astype(np.int64) * stride + off[p] + 1
+        out = {"triplets": np.stack([cat_ids[s], rec[:, 3], cat_ids[o]], 1).tolist(),
+               "triple_scores": np.stack([cat_scores[s], pscore, cat_scores[o]], 1).tolist(),
+               "triple_scores_avg": avg.tolist(), "so_trajs": None,
+               "pred_durations": np.stack([so_start + a, so_start + b], 1).tolist(), "so_tids": np.stack([s, o], 1).tolist()}
+        s0, o0 = (so_start - durs[s, 0] + a).tolist(), (so_start - durs[o, 0] + a).tolist()
+        n_fr = (b - a).tolist()
+        s_l, o_l = s.tolist(), o.tolist()
+        boxes, arrays, lists = prep["boxes"], prep["box_arrays"], prep["box_lists"]
+
+        def arr(tid):
+            x = arrays.get(tid)
+            if x is None:
+                x = arrays[tid] = boxes[tid].detach().numpy()
+            return x
+
+        gc_was_enabled = gc.isenabled()
+        gc.disable()        # the result is acyclic; see _decode for why the collector is paused and the objects are parked
+        try:
+            if self.lazy_trajs:
+                views = []
+                for i in range(count):
+                    st, ot = arr(s_l[i])[s0[i]: s0[i] + n_fr[i]], arr(o_l[i])[o0[i]: o0[i] + n_fr[i]]
+                    assert len(st) == len(ot) == n_fr[i]
+                    views.append((st, ot))
+                out["so_trajs"] = LazyTrajs(views)
+            elif self.private_box_lists:
+                trajs = []
+                for i in range(count):
+                    st, ot = arr(s_l[i])[s0[i]: s0[i] + n_fr[i]], arr(o_l[i])[o0[i]: o0[i] + n_fr[i]]
+                    assert len(st) == len(ot) == n_fr[i]
+                    trajs.append([st.tolist(), ot.tolist()])
+                out["so_trajs"] = trajs
+            else:
+                def full(tid):
+                    x = lists.get(tid)
+                    if x is None:
+                        x = lists[tid] = arr(tid).tolist()
+                    return x
+                trajs = []
+                for i in range(count):
+                    st, ot = full(s_l[i])[s0[i]: s0[i] + n_fr[i]], full(o_l[i])[o0[i]: o0[i] + n_fr[i]]
+                    assert len(st) == len(ot) == n_fr[i]
+                    trajs.append([st, ot])
+                out["so_trajs"] = trajs
+            if gc_was_enabled and self.gc_park_results and gc.get_freeze_count() < 100000:
+                gc.freeze()
+                gc.unfreeze()
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+        return out
+
+    def _n_queries(self) -> int:
+        return int(self.config["predictor"]["num_queries"])
 
     def _decode(self, scores, cats, fl, input_data):
         """Candidates in (pair, query, k) order -> durations -> min-length filter -> mean score ranking -> top n_max_pair.

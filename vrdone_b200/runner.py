@@ -56,21 +56,32 @@ def run_videos(model, videos: Iterable[dict], depth: int = 2, dataset_config: Op
         yield pending.popleft().result()
 
 
+def _rank_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def run_sharded(videos: Sequence[dict], costs: Sequence[float], fn: Optional[Callable[[dict], object]] = None, model=None,
-                dataset_config: Optional[dict] = None) -> Dict[int, object]:
+                dataset_config: Optional[dict] = None, gather: bool = True) -> Dict[int, object]:
     """Every rank processes its shard -- with ``fn(video)`` one video after the other, or with ``model`` through the pipelined
     ``run_videos`` loop (two videos in flight per GPU); rank 0 returns {video index: result} for all videos (other ranks:
-    their own).  Works with or without an initialised process group (world size 1)."""
+    their own; every rank with ``gather=False``, to be merged later with ``gather_results``).  Only the entries of a rank's
+    own shard of ``videos`` are touched.  Works with or without an initialised process group (world size 1)."""
     assert (fn is None) != (model is None), "give either fn or model"
-    if dist.is_available() and dist.is_initialized():
-        rank, world = dist.get_rank(), dist.get_world_size()
-    else:
-        rank, world = 0, 1
+    rank, world = _rank_world()
     mine = shard_videos(costs, world)[rank]
     if model is not None:
         local = dict(zip(mine, run_videos(model, (videos[i] for i in mine), dataset_config=dataset_config)))
     else:
         local = {i: fn(videos[i]) for i in mine}
+    return gather_results(local) if gather else local
+
+
+def gather_results(local: Dict[int, object]) -> Dict[int, object]:
+    """Host-side gather of the per-rank result dicts on rank 0 (``gather_object``: the results are Python lists; there is no
+    collective on the data path).  Other ranks get their own dict back."""
+    rank, world = _rank_world()
     if world == 1:
         return local
     gathered = [None] * world if rank == 0 else None

@@ -90,11 +90,32 @@ def _geometry(sb, ob, w, h):
     return rel, ent(sb), ent(ob)
 
 
-def _tracklets(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None):
+def cfg2_video_set(n_videos: int = 10, seed: int = 0):
+    """SURVEY.md section 8d cfg2 as a fixed, stratified video set: frame counts F in {900, 1200, 1800, 3600} in the proportions
+    .3 / .4 / .2 / .1 (exactly, for multiples of 10 videos -- a plain draw of 10 misses the 3600-frame videos, the only ones with
+    pairs longer than max_seq_len, 35 % of the time), tracklet counts N ~ U[20, 60].  Returns [(video seed, n_frames, n_tracklets)],
+    to be handed to ``synthetic_video`` / ``synthetic_tracklet_video``."""
+    g = torch.Generator().manual_seed(10007 * (seed + 1))
+    quota = [(900, .3), (1200, .4), (1800, .2), (3600, .1)]
+    frames: List[int] = []
+    for f, p in quota:
+        frames += [f] * int(round(p * n_videos))
+    while len(frames) < n_videos:
+        frames.append(1200)
+    frames = frames[:n_videos]
+    order = torch.randperm(n_videos, generator=g).tolist()
+    return [(1000 * (seed + 1) + i, frames[order[i]], int(torch.randint(20, 61, (1,), generator=g))) for i in range(n_videos)]
+
+
+def _tracklets(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None, features: bool = True, split_rng: bool = False):
     """Seeded per-tracklet data (durations, boxes, visual / CLIP features); the RNG is returned so that callers draw the
-    remaining per-video quantities in the historical order (the golden fixtures depend on it)."""
+    remaining per-video quantities in the historical order (the golden fixtures depend on it).  ``split_rng``: the features come
+    from a second generator, so that ``features=False`` (structure only: durations and boxes, for cost models) yields the same
+    durations as the full draw."""
     mc, dc = cfg["model_config"], cfg["dataset_config"]
     g = torch.Generator().manual_seed(seed)
+    gf = torch.Generator().manual_seed(seed + 0x5EED) if split_rng else g
+    assert features or split_rng, "structure-only draws need split_rng (the features share the structure's generator otherwise)"
     stride = dc.get("feat_stride", 1)
     clip = mc.get("with_clip_feature", False)
     vid_w, vid_h = 1280.0, 720.0
@@ -121,10 +142,16 @@ def _tracklets(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = No
         wh = 20 + 200 * torch.rand(length, 2, generator=g)
         xy = torch.rand(length, 2, generator=g) * (torch.tensor([vid_w, vid_h]) - wh - 2) + 1
         boxes.append(torch.cat([xy, xy + wh], 1))
-        vis.append(torch.randn(length, mc["visual_dim"], generator=g))
-        if clip:
-            clips.append(torch.randn(length, mc["clip_dim"], generator=g))
+        if features:
+            vis.append(torch.randn(length, mc["visual_dim"], generator=gf))
+            if clip:
+                clips.append(torch.randn(length, mc["clip_dim"], generator=gf))
     return g, n_tracklets, durs, boxes, vis, clips, (vid_w, vid_h)
+
+
+def pair_lengths(durs, stride):
+    """Sub-sampled lengths of the pairs ``_overlapping_pairs`` keeps, in the same order."""
+    return [len(range(0, min(durs[s][1], durs[o][1]) - max(durs[s][0], durs[o][0]), stride)) for s, o in _overlapping_pairs(durs, stride)]
 
 
 def _overlapping_pairs(durs, stride):
@@ -143,11 +170,12 @@ def _overlapping_pairs(durs, stride):
     return out
 
 
-def synthetic_tracklet_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None, name: str = None) -> dict:
+def synthetic_tracklet_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None, name: str = None,
+                             split_rng: bool = False) -> dict:
     """The same synthetic video as ``synthetic_video`` BEFORE the data loader's pair construction: the contract of the input of
     the reference's ``_val_getitem`` (dataloaders/vidor.py:556-571) with ``sids`` / ``oids`` already enumerated."""
     mc, dc = cfg["model_config"], cfg["dataset_config"]
-    g, n_tracklets, durs, boxes, vis, clips, wh = _tracklets(cfg, seed, n_tracklets, n_frames)
+    g, n_tracklets, durs, boxes, vis, clips, wh = _tracklets(cfg, seed, n_tracklets, n_frames, split_rng=split_rng)
     pairs = _overlapping_pairs(durs, dc.get("feat_stride", 1))
     n_cat = 35 if mc["num_classes"] > 100 else 80
     out = {
@@ -166,16 +194,20 @@ def synthetic_tracklet_video(cfg: dict, seed: int, n_tracklets: int = None, n_fr
     return out
 
 
-def synthetic_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None, name: str = None) -> dict:
+def synthetic_video(cfg: dict, seed: int, n_tracklets: int = None, n_frames: int = None, name: str = None, only_pairs=None) -> dict:
     """A synthetic ``input_data`` dict with the reference data loader's contract: every
-    ordered pair of tracklets with enough temporal overlap, features sub-sampled with ``feat_stride``."""
+    ordered pair of tracklets with enough temporal overlap, features sub-sampled with ``feat_stride``.  ``only_pairs``: keep
+    just these pair indices (same tensors as the full video's, without building the others: bounded CPU samples)."""
     mc, dc, ic = cfg["model_config"], cfg["dataset_config"], cfg["inference_config"]
     stride = dc.get("feat_stride", 1)
     clip = mc.get("with_clip_feature", False)
     g, n_tracklets, durs, boxes, vis, clips, (vid_w, vid_h) = _tracklets(cfg, seed, n_tracklets, n_frames)
     n_cat = 35 if mc["num_classes"] > 100 else 80
     sids, oids, feats, offs = [], [], [], []
-    for s, o in _overlapping_pairs(durs, stride):
+    only = None if only_pairs is None else set(int(i) for i in only_pairs)
+    for pi, (s, o) in enumerate(_overlapping_pairs(durs, stride)):
+        if only is not None and pi not in only:
+            continue
         a, b = max(durs[s][0], durs[o][0]), min(durs[s][1], durs[o][1])
         ss, os_ = a - durs[s][0], a - durs[o][0]
         sl_s = slice(ss, ss + b - a, stride)

@@ -258,3 +258,28 @@ def test_heads(ops, lays, Q, n_cls, topk):
     close(sc_g, sc_c, 1e-5, "topk scores")
     ref_ids = torch.topk(torch.softmax(logits[:B * Q, :n_cls], -1)[:, 1:], topk, -1).indices + 1
     assert torch.equal(id_g.cpu().long(), ref_ids)
+
+
+@pytest.mark.parametrize("scale", [0.5, 2.0])
+def test_full_attention_tcgen05_long_and_ragged(ops, scale):
+    """The tcgen05 / TMEM full-attention kernel (bf16, head_dim 64) on pairs from 1 frame to several query tiles and many key
+    blocks (online-softmax rescaling of the TMEM accumulator, partially filled key blocks, tiles that start anywhere in the
+    64-row scan blocks), against the fp32 emulation; larger score scale = peakier softmax = more rescaling."""
+    lens = [1, 2, 63, 64, 65, 127, 128, 129, 200, 31, 513, 7, 700, 256, 3, 90]
+    tp = [((l + 63) // 64) * 64 if l > 512 else 512 for l in lens]
+    tp = [max(t, 64) for t in tp]
+    lg, lc = PackLayout(lens, tp, 4, "cuda"), PackLayout(lens, tp, 4, "cpu")
+    R = lc.levels[0].R
+    q, k, v = [rnd((R, 512), s, scale if s < 3 else 1.0).to(torch.bfloat16) for s in (1, 2, 3)]
+    ref = torch.empty(R, 512, dtype=torch.bfloat16)
+    EmuOps().full_attn(q, k, v, ref, lc.levels[0], 8)
+    out = torch.full((R, 512), 5.0, dtype=torch.bfloat16, device="cuda")
+    ops.full_attn(q.cuda(), k.cuda(), v.cuda(), out, lg.levels[0], 8)
+    torch.cuda.synchronize()
+    valid = lc.levels[0].row_seq >= 0
+    close(out[valid], ref[valid], 1.5e-2, "full_attn tcgen05")
+    assert torch.all(out[~valid.cuda()] == 5.0), "separator rows must stay untouched"
+    # a second launch on the same inputs is bit-identical (no dependence on scheduling)
+    out2 = torch.full_like(out, 5.0)
+    ops.full_attn(q.cuda(), k.cuda(), v.cuda(), out2, lg.levels[0], 8)
+    assert torch.equal(out, out2)

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvrdone_b200.so")
-SOURCES = ["cabi.cu", "engine.cu", "rows.cu", "rank.cu", "viou.cu", "attention.cu", "gemm_simt.cu", "gemm_tcgen05.cu"]
+SOURCES = ["cabi.cu", "engine.cu", "rows.cu", "rank.cu", "viou.cu", "attention.cu", "attention_tc.cu", "gemm_simt.cu", "gemm_tcgen05.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
               "--use_fast_math=false", "-Xptxas", "-v"]
 

@@ -583,6 +583,12 @@ int full_attn(const void* q, const void* k, const void* v, void* out, int dt, lo
     if (lay.B > 65535 || max_len < 1) return 1;
     const int max_rows = max_len;   // longest pair of the level bounds the number of query tiles (blocks past a pair's end exit)
     if (dt == VRD_BF16) {
+        // head_dim 64: the tcgen05 / TMEM kernel (attention_tc.cu); VRD_FLASH=mma keeps the mma.sync kernel for A/B measurements
+        static const bool use_tc = !(getenv("VRD_FLASH") != nullptr && strcmp(getenv("VRD_FLASH"), "mma") == 0);
+        if (hs == 64 && use_tc) {
+            const int rc = full_attn_tcgen05(q, k, v, out, ld, lay, n_head, C, st);
+            if (rc != 1) return rc;
+        }
         if (hs == 64) return flash_launch<64, 2>(q, k, v, out, ld, lay, n_head, max_rows, st);
         if (hs == 128) return flash_launch<128, 1>(q, k, v, out, ld, lay, n_head, max_rows, st);
         return 1;

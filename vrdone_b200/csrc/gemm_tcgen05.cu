@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace vrd {
 
@@ -546,6 +547,11 @@ bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int esi
 }  // namespace
 
 const char* gemm_tcgen05_error() { return g_err; }
+
+bool make_tensor_map_2d(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int esize, long long rows, long long cols, long long ld,
+                        int box_rows, int box_cols, CUtensorMapSwizzle swz) {
+    return make_map(map, ptr, dt, esize, rows, cols, ld, box_rows, box_cols, swz);
+}
 
 int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     static PerDeviceOnce attr_once;      // the shared-memory attribute and the SM count belong to a device, not to the process

@@ -63,6 +63,8 @@ int window_attn(const void* q, const void* k, const void* v, void* out, int dt, 
                 int streams, cudaStream_t st);
 int full_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int n_head, int C,
               int max_len, cudaStream_t st);
+// tcgen05 / TMEM / TMA varlen attention (bf16, head_dim 64): 0 ok, 1 unsupported shape (caller falls back), 2 launch error
+int full_attn_tcgen05(const void* q, const void* k, const void* v, void* out, long long ld, Lay lay, int n_head, int C, cudaStream_t st);
 int query_self_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, int B, int Q, int n_head, int C,
                     cudaStream_t st);
 int query_cross_attn(const void* q, const void* k, const void* v, void* out, int dt, long long ld, Lay lay, int Q, int n_head,

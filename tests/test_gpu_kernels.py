@@ -85,7 +85,10 @@ def test_gemm_fp32(ops, lays, taps, act, res, corr, N, K):
     cu = lambda t: None if t is None else t.cuda()
     ops.gemm(a.cuda(), w.cuda(), out, bias=bias.cuda(), taps=taps, act=act, res1=cu(r1), res2=cu(r2), corr=cu(cv), lay=lg.levels[0],
              streams=streams)
-    close(out, ref, 2e-5, "gemm fp32")
+    # fp32 operands run on the tensor cores as 3 x bf16 split products (hi hi + lo hi + hi lo, fp32 accumulation): each operand keeps
+    # 16 mantissa bits, so a product carries ~2^-16 relative error instead of fp32's 2^-24 (N = 144 does not fit the MMA tile and
+    # takes the CUDA-core kernel)
+    close(out, ref, 6e-5, "gemm fp32")
 
 
 @pytest.mark.parametrize("dt", ["fp32", "bf16"])

@@ -36,7 +36,7 @@ constexpr int FA_SLOT_BYTES = FA_BM * FA_HS * 2;          // 16 KB: a Q tile, or
 constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;             // 16 KB
 constexpr int FA_THREADS = 192;
 constexpr int FA_TMEM_COLS = 256;          // S0 [0, 64), S1 [64, 128), O [128, 192)
-constexpr int FA_SMEM = 1024 + (2 + FA_SLOTS) * FA_SLOT_BYTES + FA_P_BYTES + 256;
+constexpr int FA_SMEM = 1024 + (2 + FA_SLOTS) * FA_SLOT_BYTES + FA_P_BYTES + 256 + 192 * 12;
 constexpr float FA_LOG2E = 1.4426950408889634f;
 
 struct FaItem { int row0, off, len, q0; };   // first layout row of the tile, pair's first row, pair length, tile's first row in the pair
@@ -51,31 +51,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Walks the items of this CTA in a fixed order; every role warp calls it with its own body so that all agree on the sequence.
-template <typename Body>
-__device__ __forceinline__ void fa_for_each_item(const Lay& lay, int n_head, int lane, Body&& body) {
-    const int n_units = (lay.R / 64) * n_head;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int b = u / n_head, h = u - b * n_head;
-        const int r0 = b * 64 + lane, r1 = r0 + 32;
-        const int p0 = lay.row_seq[r0], p1 = lay.row_seq[r1];
-        int4 i0 = make_int4(0, 0, 0, 0), i1 = make_int4(0, 0, 0, 0);
-        bool s0 = false, s1 = false;
-        if (p0 >= 0) { i0 = lay.seqinfo[p0]; s0 = ((r0 - i0.x) & (FA_BM - 1)) == 0; }
-        if (p1 >= 0) { i1 = lay.seqinfo[p1]; s1 = ((r1 - i1.x) & (FA_BM - 1)) == 0; }
-        unsigned m0 = __ballot_sync(FULL_MASK, s0), m1 = __ballot_sync(FULL_MASK, s1);
-        while (m0 | m1) {
-            const bool first = m0 != 0;
-            const int src = __ffs(first ? m0 : m1) - 1;
-            if (first) m0 &= m0 - 1; else m1 &= m1 - 1;
-            FaItem it;
-            it.off = __shfl_sync(FULL_MASK, first ? i0.x : i1.x, src);
-            it.len = __shfl_sync(FULL_MASK, first ? i0.y : i1.y, src);
-            it.row0 = b * 64 + src + (first ? 0 : 32);
-            it.q0 = it.row0 - it.off;
-            body(it, h);
-        }
-    }
+constexpr int FA_LIST = 192;                // query tiles a CTA collects per round (a 64-row block starts at most 32 tiles)
+
+// The query tiles that START in the 64-row block ``b``: appended to the CTA's shared-memory list by one warp.  A tile is
+// (first layout row, pair's first row, pair length).
+__device__ __forceinline__ void fa_scan_block(const Lay& lay, int b, int lane, int3* list, int* count) {
+    const int r0 = b * 64 + lane, r1 = r0 + 32;
+    const int p0 = lay.row_seq[r0], p1 = lay.row_seq[r1];
+    int4 i0 = make_int4(0, 0, 0, 0), i1 = make_int4(0, 0, 0, 0);
+    bool s0 = false, s1 = false;
+    if (p0 >= 0) { i0 = lay.seqinfo[p0]; s0 = ((r0 - i0.x) & (FA_BM - 1)) == 0; }
+    if (p1 >= 0) { i1 = lay.seqinfo[p1]; s1 = ((r1 - i1.x) & (FA_BM - 1)) == 0; }
+    const unsigned m0 = __ballot_sync(FULL_MASK, s0), m1 = __ballot_sync(FULL_MASK, s1);
+    const int n0 = __popc(m0), n = n0 + __popc(m1);
+    int base = 0;
+    if (lane == 0 && n > 0) base = atomicAdd(count, n);
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (s0) list[base + __popc(m0 & ((1u << lane) - 1))] = make_int3(r0, i0.x, i0.y);
+    if (s1) list[base + n0 + __popc(m1 & ((1u << lane) - 1))] = make_int3(r1, i1.x, i1.y);
 }
 
 __global__ void __launch_bounds__(FA_THREADS, 2)
@@ -95,6 +88,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     uint64_t* p_full = q_full + 6;             // softmax -> MMA: P_g in shared memory, S_g consumed, O rescaled
     uint64_t* pv_done = q_full + 7;            // MMA (commit) -> softmax: O accumulated through block g, P tile free
     uint32_t* tmem_slot = (uint32_t*)(q_full + 8);
+    int* list_count = (int*)(tmem_slot + 1);
+    int3* list = (int3*)(tmem_slot + 4);                           // [FA_LIST] query tiles of the current round
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -103,6 +98,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mbar_init(p_full, 4);
         mbar_init(pv_done, 1);
         mbar_fence_init();
+        *list_count = 0;
     }
     if (warp == 4) {
         tmem_alloc(tmem_slot, FA_TMEM_COLS);
@@ -114,11 +110,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + 2 * FA_BN;
 
-    if (warp == 4) {
-        // ---------------- TMA producer ----------------
-        int slot = 0; uint32_t phase = 0;
-        uint32_t n_item = 0;
-        fa_for_each_item(lay, n_head, lane, [&](const FaItem& it, int h) {
+    // per-role state (persists across rounds)
+    int slot = 0; uint32_t phase = 0;       // K/V ring position (producer and MMA issuer each keep their own copy)
+    uint32_t n_item = 0, g = 0;             // items / key blocks processed so far: barrier phase counters
+
+    // ---------------- TMA producer (warp 4) ----------------
+    auto producer_item = [&](const FaItem& it, int h) {
             if (lane == 0) {
                 const int n_kv = (it.len + FA_BN - 1) / FA_BN;
                 const int qb = n_item & 1;
@@ -136,16 +133,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
             ++n_item;
             __syncwarp();
-        });
-    } else if (warp == 5) {
-        // ---------------- MMA issuer ----------------
-        constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, false);
-        constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, FA_HS, true);      // V tile [keys, dims]: MN-major B
-        int slot = 0; uint32_t phase = 0;
-        uint32_t g = 0;                                                         // blocks completed so far (barrier phase counter)
-        uint32_t n_item = 0;
-        const uint64_t pdesc = make_smem_desc_sw128(smem_u32(p_tile));
-        fa_for_each_item(lay, n_head, lane, [&](const FaItem& it, int h) {
+    };
+    // ---------------- MMA issuer (warp 5) ----------------
+    constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, false);
+    constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, FA_HS, true);      // V tile [keys, dims]: MN-major B
+    const uint64_t pdesc = make_smem_desc_sw128(smem_u32(p_tile));
+    auto mma_item = [&](const FaItem& it, int h) {
             if (lane == 0) {
                 const int n_kv = (it.len + FA_BN - 1) / FA_BN;
                 const int qb = n_item & 1;
@@ -188,14 +181,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
             ++n_item;
             __syncwarp();
-        });
-    } else {
-        // ---------------- softmax warps: thread = query row ----------------
-        const int trow = warp * 32 + lane;                                      // row of the tile = TMEM lane
-        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-        const uint32_t p_row = smem_u32(p_tile) + (trow >> 3) * 1024 + (trow & 7) * 128;
-        uint32_t g = 0;
-        fa_for_each_item(lay, n_head, lane, [&](const FaItem& it, int h) {
+    };
+    // ---------------- softmax warps (0-3): thread = query row ----------------
+    const int trow = (warp & 3) * 32 + lane;                                    // row of the tile = TMEM lane
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t p_row = smem_u32(p_tile) + (trow >> 3) * 1024 + (trow & 7) * 128;
+    auto softmax_item = [&](const FaItem& it, int h) {
             const int n_kv = (it.len + FA_BN - 1) / FA_BN;
             float m = -INFINITY, l = 0.f;
             for (int j = 0; j < n_kv; ++j, ++g) {
@@ -275,7 +266,29 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     dst[c] = v;
                 }
             }
-        });
+    };
+
+    // Rounds: the six warps each scan one 64-row block of the layout for query-tile starts (one round of global-load latency for
+    // up to six blocks instead of two dependent loads in front of every item), then every role walks the same list.
+    const int n_blocks = lay.R / 64;
+    for (int base = blockIdx.x; base < n_blocks; base += 6 * gridDim.x) {
+        const int b = base + warp * gridDim.x;
+        if (b < n_blocks) fa_scan_block(lay, b, lane, list, list_count);
+        __syncthreads();
+        const int n_tiles = *list_count;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int3 tile = list[t];
+            FaItem it;
+            it.row0 = tile.x; it.off = tile.y; it.len = tile.z; it.q0 = tile.x - tile.y;
+            for (int h = 0; h < n_head; ++h) {
+                if (warp == 4) producer_item(it, h);
+                else if (warp == 5) mma_item(it, h);
+                else softmax_item(it, h);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *list_count = 0;
+        __syncthreads();
     }
     tc_fence_before();
     __syncthreads();
@@ -297,9 +310,9 @@ int full_attn_tcgen05(const void* q, const void* k, const void* v, void* out, lo
     if (!make_tensor_map_2d(&mv, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, lay.R, C, ld, FA_BN, FA_HS, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     static PerDeviceOnce once;
     if (once.first() && cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess) return 2;
-    const int n_units = (lay.R / 64) * n_head;
+    const int n_blocks = lay.R / 64;
     const int max_ctas = 2 * device_sm_count();
-    const int grid = n_units < max_ctas ? n_units : max_ctas;
+    const int grid = n_blocks < max_ctas ? n_blocks : max_ctas;
     flash_attn_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mk, mv, (__nv_bfloat16*)out, ld, lay, n_head);
     return 0;
 }

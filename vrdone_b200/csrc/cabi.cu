@@ -106,7 +106,9 @@ int vrd_gemm(const void* A, int a_dtype, int64_t lda, const void* W, const float
     if (a_dtype == VRD_BF16) {
         if (vrd::gemm_tcgen05_bf16(g, (cudaStream_t)stream) != 0) return fail(vrd::gemm_tcgen05_error());
     } else if (a_dtype == VRD_F32) {
-        if (vrd::gemm_simt_f32(g, (cudaStream_t)stream) != 0) return fail("vrd_gemm(fp32): K must be a multiple of 16 and lda of 4");
+        const int rc = vrd::gemm_f32(g, (cudaStream_t)stream);
+        if (rc == 2) return fail(vrd::gemm_tcgen05_error());
+        if (rc != 0) return fail("vrd_gemm(fp32): K must be a multiple of 16 and lda of 4");
     } else {
         return fail("vrd_gemm: bad a_dtype");
     }

@@ -134,4 +134,37 @@ __device__ __forceinline__ void row_normalize(float (&v)[NCH][4], int lane, cons
     }
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: two IEEE fp32 operations per issued instruction; results are bit-identical to
+// the scalar fma.rn / add.rn / mul.rn) for the issue-bound row kernels.  An f2 holds (lo, hi) = two consecutive channels. ----
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 f2_splat(float x) { f2 d; asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(x)); return d; }
+__device__ __forceinline__ void f2_unpack(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+__device__ __forceinline__ float f2_hsum(f2 a) { float lo, hi; f2_unpack(a, lo, hi); return lo + hi; }
+// four consecutive channels = two f2
+__device__ __forceinline__ void f2_lds(uint32_t addr, f2 (&v)[2]) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "r"(addr));
+}
+__device__ __forceinline__ void f2_sts(uint32_t addr, const f2 (&v)[2]) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(v[0]), "l"(v[1]) : "memory");
+}
+__device__ __forceinline__ void f2_ldg(const float* p, f2 (&v)[2]) {
+    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+__device__ __forceinline__ void f2_stg(float* p, const f2 (&v)[2]) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v[0], v[1]); }
+__device__ __forceinline__ void f2_stg(__nv_bfloat16* p, const f2 (&v)[2]) {
+    float a, b, c, d;
+    f2_unpack(v[0], a, b);
+    f2_unpack(v[1], c, d);
+    __nv_bfloat162 x = __floats2bfloat162_rn(a, b), y = __floats2bfloat162_rn(c, d);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&x);
+    t.y = *reinterpret_cast<uint32_t*>(&y);
+    *reinterpret_cast<uint2*>(p) = t;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

@@ -90,8 +90,8 @@ struct Run {
         if (l >= 0) { g.row_seq = L[l].row_seq; g.seqinfo = reinterpret_cast<const int4*>(L[l].seqinfo); g.R = L[l].R; }
         else { g.row_seq = nullptr; g.seqinfo = nullptr; g.R = 0; }
         if (W->cols != taps * a.cols || out.rows != a.rows || out.cols != W->rows) { error("gemm shape mismatch", wname); return; }
-        int rc = a.dt == VRD_BF16 ? vrd::gemm_tcgen05_bf16(g, st) : vrd::gemm_simt_f32(g, st);
-        if (rc != 0) { error(a.dt == VRD_BF16 ? vrd::gemm_tcgen05_error() : "gemm_simt: unsupported shape", wname); return; }
+        int rc = a.dt == VRD_BF16 ? vrd::gemm_tcgen05_bf16(g, st) : vrd::gemm_f32(g, st);
+        if (rc != 0) { error((a.dt == VRD_BF16 || rc == 2) ? vrd::gemm_tcgen05_error() : "gemm_simt: unsupported shape", wname); return; }
         check("gemm");
     }
 

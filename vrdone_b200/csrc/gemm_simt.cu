@@ -2,6 +2,8 @@
 // reference computes every conv in fp32, models/blocks.py:85-113, 46-61, 728-737).  D[M,N] = A[M,taps*K] * W[N,taps*K]^T
 // where, for taps == 3, K-slab d of row r is A[r + d - 1, :] (k=3 convolution over the token-major layout; the zero
 // separator rows of layout.py provide the zero padding).
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -104,6 +106,15 @@ int gemm_simt_f32(const GemmArgs& g, cudaStream_t st) {
     if (g.out_dtype == VRD_BF16) gemm_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(g);
     else gemm_simt_kernel<float><<<grid, 256, 0, st>>>(g);
     return 0;
+}
+
+int gemm_f32(const GemmArgs& g, cudaStream_t st) {
+    static const bool simt_only = getenv("VRD_FP32_GEMM") != nullptr && strcmp(getenv("VRD_FP32_GEMM"), "simt") == 0;
+    if (!simt_only) {
+        const int rc = gemm_tcgen05_f32split(g, st);
+        if (rc != 1) return rc;
+    }
+    return gemm_simt_f32(g, st);
 }
 
 }  // namespace vrd

@@ -251,7 +251,7 @@ template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, EpiArgs e, int K,
-                    int taps, int block_n, int stages) {
+                    int taps, int block_n, int stages, int split) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: stages of A, stages of W, epilogue staging boxes, barriers, bias / correction vectors
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -275,7 +275,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int n_tiles_n = e.N / block_n;
     const int n_tiles = ((e.M + BLOCK_M * CG - 1) / (BLOCK_M * CG)) * n_tiles_n;
     const int kb_per_tap = K / BLOCK_K;
-    const int num_kb = taps * kb_per_tap;
+    // split != 0: fp32 operands as bf16 pairs (hi, lo), A = [hi | lo] (2K columns), W = per tap [hi | lo]: three K-slabs per tap,
+    // A_hi W_hi + A_lo W_hi + A_hi W_lo (the 3 x bf16 product with fp32 accumulation; the lo x lo term, 2^-16 relative, is dropped)
+    const int num_kb = taps * kb_per_tap * (split ? 3 : 1);
 
     for (int i = threadIdx.x; i < e.N; i += NUM_THREADS) {
         s_bias[i] = (e.bias != nullptr) ? e.bias[i] : 0.f;
@@ -310,16 +312,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_wait(&empty[stage], phase ^ 1);
                     // the leader's barrier collects the bytes of both CTAs of a pair
                     if (cta_rank == 0) mbar_expect_tx(&full[stage], CG * (A_STAGE_BYTES + w_stage_bytes));
-                    const int tap = kb / kb_per_tap;
-                    const int ka = (kb - tap * kb_per_tap) * BLOCK_K;
+                    int tap, ka, wcol;
+                    if (split) {
+                        const int seg_all = kb / kb_per_tap;
+                        tap = seg_all / 3;
+                        const int seg = seg_all - 3 * tap;
+                        const int kk = (kb - seg_all * kb_per_tap) * BLOCK_K;
+                        ka = (seg == 1 ? K : 0) + kk;
+                        wcol = tap * 2 * K + (seg == 2 ? K : 0) + kk;
+                    } else {
+                        tap = kb / kb_per_tap;
+                        ka = (kb - tap * kb_per_tap) * BLOCK_K;
+                        wcol = kb * BLOCK_K;
+                    }
                     const int row = m0 + (taps == 3 ? tap - 1 : 0);
                     if constexpr (CG == 2) {
                         const uint32_t bar = mapa_shared(smem_u32(&full[stage]), 0);
                         tma_load_2d_cg2(smem_a + stage * A_STAGE_BYTES, &map_a, bar, ka, row);
-                        tma_load_2d_cg2(smem_w + stage * w_stage_bytes, &map_w, bar, kb * BLOCK_K, n0);
+                        tma_load_2d_cg2(smem_w + stage * w_stage_bytes, &map_w, bar, wcol, n0);
                     } else {
                         tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full[stage], ka, row);
-                        tma_load_2d(smem_w + stage * w_stage_bytes, &map_w, &full[stage], kb * BLOCK_K, n0);
+                        tma_load_2d(smem_w + stage * w_stage_bytes, &map_w, &full[stage], wcol, n0);
                     }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -553,7 +566,7 @@ bool make_tensor_map_2d(CUtensorMap* map, const void* ptr, CUtensorMapDataType d
     return make_map(map, ptr, dt, esize, rows, cols, ld, box_rows, box_cols, swz);
 }
 
-int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
+static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     static PerDeviceOnce attr_once;      // the shared-memory attribute and the SM count belong to a device, not to the process
     const int num_sms = device_sm_count();
     static const bool wide_ok = !(getenv("VRD_GEMM_WIDE") != nullptr && atoi(getenv("VRD_GEMM_WIDE")) == 0);   // A/B switch
@@ -591,8 +604,8 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     // measured +6..10 % on the long-K GEMMs, +4..9 % on the K = 512 ones, neutral on the HBM-bound residual projections
     const int cg = force_cg == 1 ? 1 : ((force_cg == 2 || g.M >= 128 * 2 * 64) ? 2 : 1);
     CUtensorMap map_a, map_w, map_out, map_res;
-    const long long kk = (long long)g.taps * g.K;
-    if (!make_map(&map_a, g.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    const long long kk = (long long)g.taps * g.K * (split ? 2 : 1);
+    if (!make_map(&map_a, g.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, split ? 2 * g.K : g.K, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (!make_map(&map_w, g.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, kk, kk, block_n / cg, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (g.out_dtype == VRD_BF16) {
         if (!make_map(&map_out, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
@@ -624,7 +637,7 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     const int max_groups = num_sms / cg;
     const int grid = cg * (n_tiles < max_groups ? n_tiles : max_groups);
     if (cg == 1) {
-        gemm_tcgen05_kernel<1><<<grid, NUM_THREADS, smem, st>>>(map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages);
+        gemm_tcgen05_kernel<1><<<grid, NUM_THREADS, smem, st>>>(map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages, split);
         return 0;
     }
     cudaLaunchConfig_t cfg = {};
@@ -639,11 +652,77 @@ int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages, split) != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "cluster launch of gemm_tcgen05_kernel<2> failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 1;
     }
     return 0;
+}
+
+int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) { return gemm_tcgen05_launch(g, st, 0); }
+
+// ---- fp32 operands on the tensor cores: 3 x bf16 split -------------------------------------------------------------------
+namespace {
+
+// x [rows, taps * K] fp32 (pitch ldx) -> out [rows, taps * 2K] bf16: per tap [hi(K) | lo(K)], hi = bf16(x), lo = bf16(x - hi)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, long long ldx, long long rows, int K, int taps,
+                                                         __nv_bfloat16* __restrict__ out) {
+    const int per_row = taps * K / 4;
+    const long long total = rows * per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / per_row;
+        const int c = (int)(i - r * per_row) * 4;
+        const int tap = c / K, k = c - tap * K;
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+        __nv_bfloat16* o = out + r * (2LL * taps * K) + (long long)tap * 2 * K + k;
+        uint2 hi, lo;
+        hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+        lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(o) = hi;
+        *reinterpret_cast<uint2*>(o + K) = lo;
+    }
+}
+
+struct Scratch { void* p = nullptr; size_t bytes = 0; };
+
+// grow-only device scratch; cudaFree synchronises the device, so kernels still reading the old block have finished
+void* scratch_get(Scratch& s, size_t need) {
+    if (s.bytes >= need) return s.p;
+    if (s.p != nullptr) cudaFree(s.p);
+    s.p = nullptr;
+    s.bytes = 0;
+    const size_t want = need + need / 4 + (1 << 20);
+    if (cudaMalloc(&s.p, want) != cudaSuccess) { s.p = nullptr; return nullptr; }
+    s.bytes = want;
+    return s.p;
+}
+
+}  // namespace
+
+// D = A W^T for fp32 A / W through the same tcgen05 kernel: both operands are split into bf16 (hi, lo) pairs by a streaming
+// kernel (scratch: 4 bytes per operand element) and multiplied as A_hi W_hi + A_lo W_hi + A_hi W_lo with fp32 accumulation in
+// TMEM -- relative error ~2^-16 per product instead of the 2^-9 of plain bf16 operands (SURVEY section 7 hard-part 3: tcgen05 has
+// no fp32 MMA).  Returns 1 when the shape does not fit the tensor-core kernel (the caller falls back to the CUDA-core GEMM).
+int gemm_tcgen05_f32split(const GemmArgs& g, cudaStream_t st) {
+    static Scratch sa[64], sw[64];
+    if (g.M % BLOCK_M != 0 || g.K % BLOCK_K != 0 || g.N % 64 != 0 || g.lda % 4 != 0 || ((uintptr_t)g.A & 15) != 0 || ((uintptr_t)g.W & 15) != 0)
+        return 1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 1;
+    const size_t a_bytes = (size_t)g.M * 2 * g.K * 2, w_bytes = (size_t)g.N * g.taps * 2 * g.K * 2;
+    __nv_bfloat16* a2 = (__nv_bfloat16*)scratch_get(sa[dev], a_bytes);
+    __nv_bfloat16* w2 = (__nv_bfloat16*)scratch_get(sw[dev], w_bytes);
+    if (a2 == nullptr || w2 == nullptr) { snprintf(g_err, sizeof g_err, "gemm_tcgen05_f32split: scratch allocation failed"); return 2; }
+    const int sms = device_sm_count();
+    split_bf16_kernel<<<sms * 8, 256, 0, st>>>((const float*)g.A, g.lda, g.M, g.K, 1, a2);
+    split_bf16_kernel<<<sms * 2, 256, 0, st>>>((const float*)g.W, (long long)g.taps * g.K, g.N, g.K, g.taps, w2);
+    GemmArgs h = g;
+    h.A = a2; h.lda = 2LL * g.K; h.W = w2;
+    return gemm_tcgen05_launch(h, st, 1) == 0 ? 0 : 2;
 }
 
 }  // namespace vrd

@@ -71,6 +71,10 @@ int query_cross_attn(const void* q, const void* k, const void* v, void* out, int
                      int C, cudaStream_t st);
 
 int gemm_simt_f32(const GemmArgs& a, cudaStream_t st);
+// fp32 operands on tcgen05 as 3 x bf16 split products (0 ok, 1 shape unsupported -> use gemm_simt_f32, 2 error: gemm_tcgen05_error())
+int gemm_tcgen05_f32split(const GemmArgs& a, cudaStream_t st);
+// the fp32 path's GEMM: tensor cores when the shape fits (VRD_FP32_GEMM=simt forces the CUDA-core kernel), else CUDA cores
+int gemm_f32(const GemmArgs& a, cudaStream_t st);
 int gemm_tcgen05_bf16(const GemmArgs& a, cudaStream_t st);   // returns non-zero + sets error text on failure
 const char* gemm_tcgen05_error();
 

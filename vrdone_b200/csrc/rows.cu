@@ -760,23 +760,28 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
             constexpr int NFULL = DWT_ROWS / DWT_WARPS, NREM = DWT_ROWS % DWT_WARPS;
             auto normalise = [&](auto nr_tag, int first) {
                 constexpr int NR = decltype(nr_tag)::value;
-                float v[NR][NCH][4];
+                f2 v[NR][NCH][2];
                 bool on[NR];
+                const uint32_t sx_base = (uint32_t)__cvta_generic_to_shared(sx) + lane * 16;
+                const uint32_t dst_base = (uint32_t)__cvta_generic_to_shared(MIXED ? s_nrm : sx) + lane * 16;
 #pragma unroll
                 for (int u = 0; u < NR; ++u) {
                     const int i = first + warp + u * DWT_WARPS;
                     const int p = r0 - 1 + i;
                     on[u] = p >= lo && p < hi;
-                    if (on[u]) load_row<float, NCH>(sx + i * C, lane, v[u]);
-                    else row_zero<NCH>(v[u]);
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        if (on[u]) f2_lds(sx_base + (uint32_t)i * C * 4 + j * 512, v[u][j]);
+                        else v[u][j][0] = v[u][j][1] = 0ull;
+                    }
                 }
                 float mean[NR], rstd[NR];
 #pragma unroll
                 for (int u = 0; u < NR; ++u) {
-                    float sm = 0.f;
+                    f2 sm = f2_add(v[u][0][0], v[u][0][1]);
 #pragma unroll
-                    for (int j = 0; j < NCH; ++j) sm += (v[u][j][0] + v[u][j][1]) + (v[u][j][2] + v[u][j][3]);
-                    mean[u] = sm;
+                    for (int j = 1; j < NCH; ++j) sm = f2_add(sm, f2_add(v[u][j][0], v[u][j][1]));
+                    mean[u] = f2_hsum(sm);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
@@ -785,12 +790,13 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
 #pragma unroll
                 for (int u = 0; u < NR; ++u) {
                     mean[u] *= (1.0f / C);
-                    float q = 0.f;
+                    const f2 mm = f2_splat(mean[u]);
+                    f2 q = 0ull;
 #pragma unroll
                     for (int j = 0; j < NCH; ++j)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { v[u][j][i] -= mean[u]; q = fmaf(v[u][j][i], v[u][j][i], q); }
-                    rstd[u] = q;
+                        for (int i = 0; i < 2; ++i) { v[u][j][i] = f2_sub(v[u][j][i], mm); q = f2_fma(v[u][j][i], v[u][j][i], q); }
+                    rstd[u] = f2_hsum(q);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
@@ -800,18 +806,23 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
                 for (int u = 0; u < NR; ++u) rstd[u] = rsqrtf(rstd[u] * (1.0f / C) + VRD_EPS);
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
-                    float g[4], be[4];
-                    ld4(pre_g + (j * 32 + lane) * 4, g);
-                    ld4(pre_b + (j * 32 + lane) * 4, be);
+                    f2 g[2], be[2];
+                    f2_ldg(pre_g + (j * 32 + lane) * 4, g);
+                    f2_ldg(pre_b + (j * 32 + lane) * 4, be);
 #pragma unroll
-                    for (int u = 0; u < NR; ++u)
+                    for (int u = 0; u < NR; ++u) {
+                        const f2 rs = f2_splat(rstd[u]);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) v[u][j][i] = v[u][j][i] * rstd[u] * g[i] + be[i];
+                        for (int i = 0; i < 2; ++i) v[u][j][i] = f2_fma(f2_mul(v[u][j][i], rs), g[i], be[i]);
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < NR; ++u) {
                     const int i = first + warp + u * DWT_WARPS;
-                    if (on[u]) store_row<float, NCH>((MIXED ? s_nrm : sx) + i * C, lane, v[u]);
+                    if (on[u]) {
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) f2_sts(dst_base + (uint32_t)i * C * 4 + j * 512, v[u][j]);
+                    }
                 }
             };
             normalise(std::integral_constant<int, NFULL>{}, 0);
@@ -852,32 +863,27 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
             for (int b = 0; b < NB; ++b) {
                 const bool pre = (PREMASK >> b) & 1;
                 const float* wb = br.w[b];
-                float y[DWT_RPW][NCH][4];
+                f2 y[DWT_RPW][NCH][2];
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
                     const int c = (j * 32 + lane) * 4;
-                    float w0[4], w1[4], w2[4];
-                    ld4(wb + c, w0); ld4(wb + C + c, w1); ld4(wb + 2 * C + c, w2);
-                    float a[NWIN][4];
+                    f2 w0[2], w1[2], w2[2];
+                    f2_ldg(wb + c, w0); f2_ldg(wb + C + c, w1); f2_ldg(wb + 2 * C + c, w2);
+                    f2 a[NWIN][2];
 #pragma unroll
-                    for (int w = 0; w < NWIN; ++w) {
-                        const uint32_t addr = (pre ? anrm[w] : araw[w]) + j * 512;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(a[w][0]), "=f"(a[w][1]), "=f"(a[w][2]), "=f"(a[w][3]) : "r"(addr));
-                    }
+                    for (int w = 0; w < NWIN; ++w) f2_lds((pre ? anrm[w] : araw[w]) + j * 512, a[w]);
 #pragma unroll
                     for (int u = 0; u < DWT_RPW; ++u)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) y[u][j][i] = fmaf(a[u + 2][i], w2[i], fmaf(a[u + 1][i], w1[i], a[u][i] * w0[i]));
+                        for (int i = 0; i < 2; ++i) y[u][j][i] = f2_fma(a[u + 2][i], w2[i], f2_fma(a[u + 1][i], w1[i], f2_mul(a[u][i], w0[i])));
                     if (pre && hib != 0) {                       // warp-uniform and rare (one row per padded pair)
-                        float bt[4];
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(bt[0]), "=f"(bt[1]), "=f"(bt[2]), "=f"(bt[3]) : "r"(beta_u + lane * 16 + j * 512));
+                        f2 bt[2];
+                        f2_lds(beta_u + lane * 16 + j * 512, bt);
 #pragma unroll
                         for (int u = 0; u < DWT_RPW; ++u)
                             if ((hib >> u) & 1) {
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) y[u][j][i] = fmaf(bt[i], w2[i], y[u][j][i]);   // the tap read 0 above
+                                for (int i = 0; i < 2; ++i) y[u][j][i] = f2_fma(bt[i], w2[i], y[u][j][i]);   // the tap read 0 above
                             }
                     }
                 }
@@ -885,10 +891,10 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
                 float mean[DWT_RPW], rstd[DWT_RPW];
 #pragma unroll
                 for (int u = 0; u < DWT_RPW; ++u) {
-                    float sm = 0.f;
+                    f2 sm = f2_add(y[u][0][0], y[u][0][1]);
 #pragma unroll
-                    for (int j = 0; j < NCH; ++j) sm += (y[u][j][0] + y[u][j][1]) + (y[u][j][2] + y[u][j][3]);
-                    mean[u] = sm;
+                    for (int j = 1; j < NCH; ++j) sm = f2_add(sm, f2_add(y[u][j][0], y[u][j][1]));
+                    mean[u] = f2_hsum(sm);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
@@ -897,12 +903,13 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
 #pragma unroll
                 for (int u = 0; u < DWT_RPW; ++u) {
                     mean[u] *= (1.0f / C);
-                    float q = 0.f;
+                    const f2 mm = f2_splat(mean[u]);
+                    f2 q = 0ull;
 #pragma unroll
                     for (int j = 0; j < NCH; ++j)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { y[u][j][i] -= mean[u]; q = fmaf(y[u][j][i], y[u][j][i], q); }
-                    rstd[u] = q;
+                        for (int i = 0; i < 2; ++i) { y[u][j][i] = f2_sub(y[u][j][i], mm); q = f2_fma(y[u][j][i], y[u][j][i], q); }
+                    rstd[u] = f2_hsum(q);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
@@ -912,19 +919,25 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
                 for (int u = 0; u < DWT_RPW; ++u) rstd[u] = rsqrtf(rstd[u] * (1.0f / C) + VRD_EPS);
 #pragma unroll
                 for (int j = 0; j < NCH; ++j) {
-                    float g[4], be[4];
-                    ld4(br.g[b] + (j * 32 + lane) * 4, g);
-                    ld4(br.b[b] + (j * 32 + lane) * 4, be);
+                    f2 g[2], be[2];
+                    f2_ldg(br.g[b] + (j * 32 + lane) * 4, g);
+                    f2_ldg(br.b[b] + (j * 32 + lane) * 4, be);
 #pragma unroll
-                    for (int u = 0; u < DWT_RPW; ++u)
+                    for (int u = 0; u < DWT_RPW; ++u) {
+                        const f2 rs = f2_splat(rstd[u]);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) y[u][j][i] = y[u][j][i] * rstd[u] * g[i] + be[i];
+                        for (int i = 0; i < 2; ++i) y[u][j][i] = f2_fma(f2_mul(y[u][j][i], rs), g[i], be[i]);
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < DWT_RPW; ++u) {
                     TO* o = (TO*)br.out[b] + (long long)(r0 + rr0 + u) * br.ldo[b];
-                    if (live[u]) store_row<TO, NCH>(o, lane, y[u]);        // warp-uniform
-                    else zero_row<TO, NCH>(o, lane);                        // separator rows -> 0
+                    if (live[u]) {                                          // warp-uniform
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) f2_stg(o + (j * 32 + lane) * 4, y[u][j]);
+                    } else {
+                        zero_row<TO, NCH>(o, lane);                         // separator rows -> 0
+                    }
                 }
             }
         }

@@ -29,7 +29,7 @@ extern "C" {
 #define VRD_ACT_NONE 0
 #define VRD_ACT_RELU 1
 #define VRD_ACT_GELU 2
-#define VRD_ABI_VERSION 3
+#define VRD_ABI_VERSION 4
 
 typedef void* vrd_stream_t; /* cudaStream_t */
 
@@ -102,9 +102,12 @@ int vrd_dwconv_ln(const void* x, int x_dtype, int64_t ldx, const int32_t* row_se
 int vrd_window_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, const int32_t* row_seq,
                     const int32_t* seqinfo, int R, int B, int n_head, int C, int w, int streams, vrd_stream_t stream);
 
-/* k5 -- full attention inside each pair (local_transformer.py:170-183); max_len = longest pair of the level. */
+/* k5 -- full attention inside each pair (local_transformer.py:170-183); max_len = longest pair of the level.  attn_tiles
+ * (optional, may be NULL): int32x4 (first row, pair's first row, pair length, 0) per 128-row query tile of every pair, longest
+ * pairs first (vrdone_b200/layout.py) -- with it the bf16 / head_dim 64 case runs on the tcgen05 / TMEM kernel. */
 int vrd_full_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, const int32_t* row_seq,
-                  const int32_t* seqinfo, int R, int B, int n_head, int C, int max_len, vrd_stream_t stream);
+                  const int32_t* seqinfo, int R, int B, int n_head, int C, int max_len, const int32_t* attn_tiles, int n_attn_tiles,
+                  vrd_stream_t stream);
 
 /* k7 -- MaxPool1d(3, 2, 1) skip path of the stride-2 blocks (blocks.py:1040-1046, 1074). fp32, C = 512. */
 int vrd_maxpool_skip(const float* x, int64_t ldx, const int32_t* row_seq_in, const int32_t* seqinfo_in, int R_in,
@@ -167,6 +170,8 @@ typedef struct {
     const int32_t* row_seq; /* device, R entries */
     const int32_t* seqinfo; /* device, B x 4 */
     int32_t R, B, max_len;
+    int32_t n_attn_tiles;       /* level 0 only (0 elsewhere): query tiles of vrd_full_attn */
+    const int32_t* attn_tiles;  /* device, n_attn_tiles x 4, or NULL */
 } vrd_level_t;
 typedef struct vrd_engine vrd_engine_t;
 

@@ -42,7 +42,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/vrdone_b200.h but not exported"
     assert declared == set(cuda_ops.exported_symbols())
-    assert cuda_ops.load_library().vrd_abi_version() == 3
+    assert cuda_ops.load_library().vrd_abi_version() == 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

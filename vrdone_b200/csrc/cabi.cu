@@ -158,8 +158,11 @@ int vrd_window_attn(const void* q, const void* k, const void* v, void* out, int 
 }
 
 int vrd_full_attn(const void* q, const void* k, const void* v, void* out, int dtype, int64_t ld, const int32_t* row_seq,
-                  const int32_t* seqinfo, int R, int B, int n_head, int C, int max_len, vrd_stream_t stream) {
+                  const int32_t* seqinfo, int R, int B, int n_head, int C, int max_len, const int32_t* attn_tiles, int n_attn_tiles,
+                  vrd_stream_t stream) {
     Lay l = make_lay(row_seq, seqinfo, R, B);
+    l.tiles = reinterpret_cast<const int4*>(attn_tiles);
+    l.n_tiles = attn_tiles != nullptr ? n_attn_tiles : 0;
     if (vrd::full_attn(q, k, v, out, dtype, ld, l, n_head, C, max_len, (cudaStream_t)stream))
         return fail("vrd_full_attn: needs head_dim in {64, 128} and B <= 65535");
     return check_launch("vrd_full_attn");

@@ -40,6 +40,8 @@ struct Lay {
     const int4* __restrict__ seqinfo;
     int R;   // rows per stream (multiple of 128)
     int B;   // pairs
+    const int4* __restrict__ tiles = nullptr;   // level 0, optional: query tiles of the full-attention kernel (layout.py), longest first
+    int n_tiles = 0;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -55,7 +55,9 @@ struct Run {
 
     bool dry() const { return A->dry; }
     Lay lay(int l) const {
-        Lay x; x.row_seq = L[l].row_seq; x.seqinfo = reinterpret_cast<const int4*>(L[l].seqinfo); x.R = L[l].R; x.B = L[l].B; return x;
+        Lay x; x.row_seq = L[l].row_seq; x.seqinfo = reinterpret_cast<const int4*>(L[l].seqinfo); x.R = L[l].R; x.B = L[l].B;
+        x.tiles = reinterpret_cast<const int4*>(L[l].attn_tiles); x.n_tiles = L[l].attn_tiles != nullptr ? L[l].n_attn_tiles : 0;
+        return x;
     }
     void error(const char* what, const std::string& name) {
         if (!fail) snprintf(E->err, sizeof E->err, "%s: %s", what, name.c_str());

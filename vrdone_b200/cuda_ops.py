@@ -34,7 +34,7 @@ _SIGNATURES = {
     "vrd_dwconv_ln": [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
                       _vp, _i32, _i32, _i32, _vp],
     "vrd_window_attn": [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
-    "vrd_full_attn": [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "vrd_full_attn": [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "vrd_maxpool_skip": [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp],
     "vrd_fpn_top": [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "vrd_fpn_level": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
@@ -54,7 +54,8 @@ class ModelCfg(C.Structure):
 
 
 class Level(C.Structure):
-    _fields_ = [("row_seq", C.c_void_p), ("seqinfo", C.c_void_p), ("R", C.c_int32), ("B", C.c_int32), ("max_len", C.c_int32)]
+    _fields_ = [("row_seq", C.c_void_p), ("seqinfo", C.c_void_p), ("R", C.c_int32), ("B", C.c_int32), ("max_len", C.c_int32),
+                ("n_attn_tiles", C.c_int32), ("attn_tiles", C.c_void_p)]
 
 
 _ENGINE_SYMBOLS = ["vrd_engine_last_error", "vrd_engine_create", "vrd_engine_destroy", "vrd_engine_launches",
@@ -108,7 +109,7 @@ def load_library() -> C.CDLL:
     lib.vrd_predict.argtypes = [C.c_void_p, C.POINTER(PredictorCfg), C.POINTER(Level), C.POINTER(Level), C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vrd_predict.restype = C.c_int
-    if lib.vrd_abi_version() != 3:
+    if lib.vrd_abi_version() != 4:
         raise RuntimeError("libvrdone_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
@@ -345,8 +346,10 @@ class CudaOps:
         nl = lay.len.astype("float64")
         self._last_flops = 4.0 * q.shape[1] * float((nl * nl).sum())        # QK^T + PV over every (query, key) pair of a pair
         self._last_bytes = float(nl.sum()) * q.shape[1] * 4.0 * q.element_size()
+        tiles = getattr(lay, "tiles", None)
         self._check(self.lib.vrd_full_attn(qp, _mat(k)[0], _mat(v)[0], _mat(out)[0], _dt(q), ld, rs, si, R, lay.B, n_head,
-                                           q.shape[1], lay.max_len, self._stream()), "vrd_full_attn")
+                                           q.shape[1], lay.max_len, _p(tiles), lay.n_tiles if tiles is not None else 0,
+                                           self._stream()), "vrd_full_attn")
 
     def maxpool_skip(self, x, lay_in, lay_out, out):
         xp, ldx = _mat(x)
@@ -473,6 +476,9 @@ class NativeBackbone:
         for i, lv in enumerate(lay.levels):
             arr[i].row_seq, arr[i].seqinfo = lv.row_seq.data_ptr(), lv.seqinfo.data_ptr()
             arr[i].R, arr[i].B, arr[i].max_len = lv.R, lv.B, lv.max_len
+            tiles = getattr(lv, "tiles", None)
+            arr[i].n_attn_tiles = lv.n_tiles if tiles is not None else 0
+            arr[i].attn_tiles = tiles.data_ptr() if tiles is not None and lv.n_tiles > 0 else None
         return arr
 
     def _fail(self, what):
@@ -528,6 +534,7 @@ class NativeBackbone:
         def level(lv):
             x = Level()
             x.row_seq, x.seqinfo, x.R, x.B, x.max_len = lv.row_seq.data_ptr(), lv.seqinfo.data_ptr(), lv.R, lv.B, lv.max_len
+            x.n_attn_tiles, x.attn_tiles = 0, None
             return x
         l0, lt = level(lay.levels[0]), level(lay.levels[-1])
         B, Q, pc = lay.B, self.Q, self.pcfg

@@ -55,6 +55,10 @@ class LevelLayout:
         self.max_len = int(length.max())
         self.row_seq: torch.Tensor = None   # int32 [R]
         self.seqinfo: torch.Tensor = None   # int32 [B, 4]
+        # level 0 only: the query tiles of the full-attention kernel, (first row, pair's first row, pair length, 0) per 128-row tile
+        # of every pair, sorted by pair length (longest first: a static round-robin over this list balances the persistent CTAs)
+        self.tiles: torch.Tensor = None     # int32 [n_tiles, 4]
+        self.n_tiles = 0
 
     @property
     def B(self) -> int:
@@ -94,6 +98,8 @@ class PackLayout:
             lev = LevelLayout(l, off.astype(np.int32), ll.astype(np.int32), haspad, rows)
             self.levels.append(lev)
             host += [row_seq, info.reshape(-1)]
+        host.append(self._attention_tiles(self.levels[0]))
+        self.levels[0].n_tiles = host[-1].size // 4
         self._host = host
         self.n_words = sum(h.size for h in host)      # int32 words; every piece is a multiple of 4 words (16 bytes)
         self.total_frames = int(lens.sum())
@@ -105,6 +111,22 @@ class PackLayout:
                 self.bind(flat.to(device, non_blocking=True))
             else:
                 self.bind(torch.from_numpy(np.concatenate(host)))
+
+    ATTN_TILE = 128
+
+    @classmethod
+    def _attention_tiles(cls, lev: "LevelLayout") -> np.ndarray:
+        """int32 [n_tiles * 4]: (first layout row of the tile, pair's first row, pair length, 0), longest pairs first."""
+        ln, off = lev.len.astype(np.int64), lev.off.astype(np.int64)
+        n_t = (ln + cls.ATTN_TILE - 1) // cls.ATTN_TILE
+        pair = np.repeat(np.arange(len(ln)), n_t)
+        t_in_pair = np.arange(int(n_t.sum())) - np.repeat(np.cumsum(n_t) - n_t, n_t)
+        order = np.argsort(-ln[pair], kind="stable")
+        tiles = np.zeros((len(pair), 4), dtype=np.int32)
+        tiles[:, 0] = (off[pair] + cls.ATTN_TILE * t_in_pair)[order]
+        tiles[:, 1] = off[pair][order]
+        tiles[:, 2] = ln[pair][order]
+        return tiles.reshape(-1)
 
     def host_words(self, out: np.ndarray) -> None:
         """Write the int32 image of all levels into ``out`` (n_words elements)."""
@@ -118,6 +140,8 @@ class PackLayout:
             pos += lev.R
             lev.seqinfo = dev[pos:pos + 4 * self.B].view(self.B, 4)
             pos += 4 * self.B
+        l0 = self.levels[0]
+        l0.tiles = dev[pos:pos + 4 * l0.n_tiles].view(l0.n_tiles, 4)
 
 
 class MergedLayout:

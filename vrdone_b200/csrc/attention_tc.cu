@@ -4,20 +4,23 @@
 // 1 / sqrt(hs) scale is folded into the query projection.
 //
 // Work item = (pair, head, query tile of 128 rows aligned to the pair's first row): results do not depend on where a pair's rows
-// sit in the layout.  Keys / values stream in blocks of 64 rows.  Per block:
-//     S[128, 64]  = Q K_j^T          tcgen05.mma (M 128, N 64, K 64: 4 instructions), accumulator in TMEM columns [0, 64) / [64, 128)
-//     softmax     thread = query row: tcgen05.ld of its 64 scores, running max / sum in registers (no shuffles), P = exp2(.) as bf16
-//                 into a 128-byte-swizzled shared-memory tile; when the running max of any row of the warp grew, the O
-//                 accumulator is rescaled in TMEM (tcgen05.ld / .st) -- exact online softmax, no approximation threshold
-//     O[128, 64] += P V_j            tcgen05.mma with V as an MN-major B operand straight from its TMA tile, accumulator in
-//                 TMEM columns [128, 192)
-// One CTA = 6 warps: 4 softmax warps (TMEM lane quarters 0-3), one TMA producer warp (two Q buffers alternating between items and
-// a ring of three K/V slots: the next item's tiles arrive while this one is computed), one MMA issuer warp.  S is double
-// buffered in TMEM, so Q K_{j+1}^T (and the first S of the next item) is issued while the softmax warps still work on block j.
-// TWO co-resident CTAs per SM (97 KB of shared memory and 256 TMEM columns each) hide what is left of the serial
-// QK -> softmax -> PV chain.  Persistent grid: CTA c takes items c, c + grid, ... of the layout's query-tile list (layout.py:
-// one entry per 128-row tile of every pair, longest pairs first) x heads.
+// sit in the layout.  Keys / values stream in blocks of 64 rows.  Per block g:
+//     S_g[128, 64]  = Q K^T          tcgen05.mma (SS: M 128, N 64, K 64 = 4 instructions), accumulator in TMEM buffer g & 1
+//     softmax        thread = (query row, part of the 64 keys): tcgen05.ld of its scores, running max / sum in registers,
+//                    P = exp2(.) rounded to bf16 and stored with tcgen05.st into TMEM buffer g & 1 (two keys per 32-bit column,
+//                    the layout tcgen05.mma expects for an A operand in tensor memory)
+//     O[128, 64]   += P V            tcgen05.mma (TS: A = P from TMEM, B = V as an MN-major operand straight from its TMA tile)
+// The running maximum is exact but lazy: the accumulator rows are rescaled (tcgen05.ld / .st of O) only when a row outgrew its
+// maximum by more than 2^8, so the softmax warps wait for the tensor core only then and at item boundaries.
+//
+// One CTA: softmax warps (NSPLIT per TMEM lane quarter, 64 / NSPLIT keys each) + one TMA producer warp (two Q buffers alternating
+// between items, a ring of K/V slots: the next item's tiles arrive while this one is computed) + one MMA issuer warp, software-
+// pipelined over the flat block sequence: S_{g+1} (also across an item boundary) is issued before the wait for P_g.  TMEM (256
+// columns): S0 S1 (64 + 64), O (64), P0 P1 (32 + 32).  Two co-resident CTAs per SM.  Persistent grid: CTA c takes items c,
+// c + grid, ... of the layout's query-tile list (layout.py: one entry per 128-row tile of every pair, LONGEST pairs first -- a
+// long pair's tile costs 10 x a short one's, and any assignment by position leaves most CTAs idle behind a few) x heads.
 // Separator rows of the output are not written (the consumer is a projection GEMM whose epilogue zeroes them).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -31,15 +34,12 @@ using namespace tc;
 constexpr int FA_BM = 128;                 // query rows per item (UMMA M)
 constexpr int FA_BN = 64;                  // keys per block (UMMA N of S, K of P V)
 constexpr int FA_HS = 64;                  // head dim
-constexpr int FA_SLOTS = 3;                // K/V ring
+constexpr int FA_SLOTS = 4;                // K/V ring
 constexpr int FA_SLOT_BYTES = FA_BM * FA_HS * 2;          // 16 KB: a Q tile, or K (8 KB) + V (8 KB) of one block
-constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;             // 16 KB
-constexpr int FA_THREADS = 192;
-constexpr int FA_TMEM_COLS = 256;          // S0 [0, 64), S1 [64, 128), O [128, 192)
-constexpr int FA_SMEM = 1024 + (2 + FA_SLOTS) * FA_SLOT_BYTES + FA_P_BYTES + 256;
+constexpr int FA_TMEM_COLS = 256;
+constexpr int FA_TM_S = 0, FA_TM_O = 128, FA_TM_P = 192;  // S0 S1 | O | P0 P1
+constexpr int FA_SMEM = 1024 + (2 + FA_SLOTS) * FA_SLOT_BYTES + 256 + 3 * 2 * FA_BM * 4;
 constexpr float FA_LOG2E = 1.4426950408889634f;
-
-struct FaItem { int row0, off, len, q0; };   // first layout row of the tile, pair's first row, pair length, tile's first row in the pair
 
 __device__ __forceinline__ float ex2f(float x) {
     float y;
@@ -50,34 +50,95 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
+    if constexpr (N == 64) { tmem_ld32(taddr, r); tmem_ld32(taddr + 32, r + 32); }
+    else if constexpr (N == 32) tmem_ld32(taddr, r);
+    else tmem_ld16(taddr, r);
+}
+template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r) {
+    if constexpr (N == 64) { tmem_st32(taddr, r); tmem_st32(taddr + 32, r + 32); }
+    else if constexpr (N == 32) tmem_st32(taddr, r);
+    else tmem_st16(taddr, r);
+}
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
+// Every role walks the same flat sequence of key blocks: item i = (query tile i / n_head, head i % n_head) of the layout's tile
+// list for i = blockIdx.x, blockIdx.x + gridDim.x, ...; per item its blocks of 64 keys.  The next item's tile is fetched one
+// item ahead.
+struct FaCursor {
+    const int4* tiles; int n_items, n_head, stride, i, h, j, n_kv; int4 tile, pre;
+    __device__ __forceinline__ void fetch() {
+        const int nx = i + stride;
+        if (nx < n_items) pre = __ldg(tiles + nx / n_head);
+    }
+    __device__ __forceinline__ void start(const int4* t, int n_tiles, int nh, int first, int step) {
+        tiles = t; n_items = n_tiles * nh; n_head = nh; stride = step; i = first; j = 0; h = 0; n_kv = 1;
+        if (i < n_items) { tile = __ldg(t + i / nh); h = i % nh; n_kv = (tile.z + FA_BN - 1) / FA_BN; fetch(); }
+    }
+    __device__ __forceinline__ bool valid() const { return i < n_items; }
+    __device__ __forceinline__ bool last_of_item() const { return j == n_kv - 1; }
+    __device__ __forceinline__ void next() {
+        if (++j == n_kv) {
+            j = 0;
+            i += stride;
+            if (i < n_items) { tile = pre; h = i % n_head; n_kv = (tile.z + FA_BN - 1) / FA_BN; fetch(); }
+        }
+    }
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__((4 * NSPLIT + 2) * 32, 2)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, long long ld, Lay lay, int n_head) {
+    constexpr int N_SOFTMAX = 4 * NSPLIT;                          // softmax warps; then the producer warp and the MMA warp
+    constexpr int HC = FA_BN / NSPLIT;                             // keys (and output dims) per softmax thread
     extern __shared__ __align__(1024) uint8_t fa_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)fa_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* q_tiles = smem;                                       // [2] Q tiles, alternating between items
     uint8_t* ring = smem + 2 * FA_SLOT_BYTES;                      // [FA_SLOTS] K | V blocks
-    uint8_t* p_tile = ring + FA_SLOTS * FA_SLOT_BYTES;
-    uint64_t* bars = (uint64_t*)(p_tile + FA_P_BYTES);
+    uint64_t* bars = (uint64_t*)(ring + FA_SLOTS * FA_SLOT_BYTES);
     uint64_t* full = bars;                     // [FA_SLOTS]  TMA -> MMA
     uint64_t* empty = bars + FA_SLOTS;         // [FA_SLOTS]  MMA (commit) -> TMA
     uint64_t* q_full = bars + 2 * FA_SLOTS;    // [2]
     uint64_t* q_empty = q_full + 2;            // [2]
     uint64_t* s_full = q_full + 4;             // [2] MMA (commit) -> softmax: S of block g in TMEM buffer g & 1
-    uint64_t* p_full = q_full + 6;             // softmax -> MMA: P_g in shared memory, S_g consumed, O rescaled
-    uint64_t* pv_done = q_full + 7;            // MMA (commit) -> softmax: O accumulated through block g, P tile free
+    uint64_t* p_full = q_full + 6;             // softmax -> MMA: P_g in TMEM buffer g & 1, S_g consumed, O rescaled if need be
+    uint64_t* pv_done = q_full + 7;            // MMA (commit) -> softmax: O accumulated through block g, P buffer g & 1 free
     uint32_t* tmem_slot = (uint32_t*)(q_full + 8);
+    float* xch = (float*)(tmem_slot + 4);      // [3][NSPLIT][FA_BM]: partial row maxima (two block parities) and row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < FA_SLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); }
-        mbar_init(p_full, 4);
+        mbar_init(p_full, N_SOFTMAX);
         mbar_init(pv_done, 1);
         mbar_fence_init();
     }
-    if (warp == 4) {
+    if (warp == N_SOFTMAX) {
         tmem_alloc(tmem_slot, FA_TMEM_COLS);
         if (lane == 0) { prefetch_tensormap(&map_q); prefetch_tensormap(&map_k); prefetch_tensormap(&map_v); }
     }
@@ -85,37 +146,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + 2 * FA_BN;
+    const uint32_t tmem_o = tmem_base + FA_TM_O;
 
-    // Every role walks the same flat sequence of key blocks: item i = (query tile i / n_head, head i % n_head) of the layout's tile
-    // list for i = blockIdx.x, blockIdx.x + gridDim.x, ...; per item its blocks of 64 keys.  The list is sorted by pair length
-    // (longest first), so this static round-robin hands every CTA the same mix of long and short items (a long pair's tile
-    // costs 10 x a short one's: any assignment by position in the layout leaves most CTAs idle behind a few).  g counts blocks,
-    // n_item counts items: they carry the barrier phases.  The next item's tile is fetched one item ahead.
-    struct Cursor {
-        const int4* tiles; int n_items, n_head, stride, i, h, j, n_kv; int4 tile, pre;
-        __device__ __forceinline__ void fetch() {
-            const int nx = i + stride;
-            if (nx < n_items) pre = __ldg(tiles + nx / n_head);
-        }
-        __device__ __forceinline__ void start(const int4* t, int n_tiles, int nh, int first, int step) {
-            tiles = t; n_items = n_tiles * nh; n_head = nh; stride = step; i = first; j = 0;
-            if (i < n_items) { tile = __ldg(t + i / nh); h = i % nh; n_kv = (tile.z + FA_BN - 1) / FA_BN; fetch(); }
-        }
-        __device__ __forceinline__ bool valid() const { return i < n_items; }
-        __device__ __forceinline__ bool last_of_item() const { return j == n_kv - 1; }
-        __device__ __forceinline__ void next() {
-            if (++j == n_kv) {
-                j = 0;
-                i += stride;
-                if (i < n_items) { tile = pre; h = i % n_head; n_kv = (tile.z + FA_BN - 1) / FA_BN; fetch(); }
-            }
-        }
-    };
-    uint32_t g = 0, n_item = 0;
+    uint32_t g = 0, n_item = 0;             // key blocks / items processed so far: they carry the barrier phases
 
-    // ---------------- TMA producer (warp 4, one lane) ----------------
-    auto produce = [&](Cursor c) {
+    // ---------------- TMA producer (one lane) ----------------
+    auto produce = [&](FaCursor c) {
         for (; c.valid(); c.next(), ++g) {
             if (c.j == 0) {
                 const int qb = n_item & 1;
@@ -133,15 +169,14 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
     };
 
-    // ---------------- MMA issuer (warp 5, one lane) ----------------
-    // Software-pipelined over the flat block sequence: S of block g + 1 (also across an item boundary) is issued before the
-    // wait for P of block g, so the softmax warps find their next scores ready.  S buffer (g + 1) & 1 was last read by the
-    // softmax of block g - 1, which arrived on p_full before PV_{g-1} was issued by this thread: free by program order.
+    // ---------------- MMA issuer (one lane) ----------------
+    // S buffer (g + 1) & 1 was last read by the softmax of block g - 1, which arrived on p_full before PV_{g-1} was issued by this
+    // thread: free by program order.  The same holds for the P buffers (written by the softmax warps only after pv_done of the
+    // block that last read them).
     constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, false);
     constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, FA_HS, true);      // V tile [keys, dims]: MN-major B
-    const uint64_t pdesc = make_smem_desc_sw128(smem_u32(p_tile));
     uint32_t n_item_qk = 0;                                                 // items whose first S has been issued
-    auto issue_qk = [&](const Cursor& c, uint32_t gg) {
+    auto issue_qk = [&](const FaCursor& c, uint32_t gg) {
         if (c.j == 0) {
             mbar_wait(&q_full[n_item_qk & 1], (n_item_qk >> 1) & 1);
             ++n_item_qk;
@@ -152,27 +187,28 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tc_fence_after();
         const uint64_t qdesc = make_smem_desc_sw128(smem_u32(q_tiles + qb * FA_SLOT_BYTES));
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(ring + slot * FA_SLOT_BYTES));
-        const uint32_t tmem_s = tmem_base + (gg & 1) * FA_BN;
+        const uint32_t tmem_s = tmem_base + FA_TM_S + (gg & 1) * FA_BN;
 #pragma unroll
         for (int k = 0; k < FA_HS / 16; ++k) umma_f16_ss(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[gg & 1]);
         if (c.last_of_item()) umma_commit(&q_empty[qb]);                    // the Q tile is free once the last S of the item is done
     };
-    auto mma = [&](Cursor c) {
+    auto mma = [&](FaCursor c) {
         if (!c.valid()) return;
-        Cursor nx = c;
+        FaCursor nx = c;
         issue_qk(c, g);
         nx.next();
         for (; c.valid(); ++g) {
             if (nx.valid()) issue_qk(nx, g + 1);
             mbar_wait(p_full, g & 1);
             tc_fence_after();
-            // O += P V : A = P [128 x 64 keys] K-major (+32 bytes per 16 keys), B = V [64 keys x 64 dims] MN-major
-            // (+16 key rows = 2048 bytes per step)
+            // O += P V : A = P_g from TMEM (16 keys = 8 columns per step), B = V [64 keys x 64 dims] MN-major (+16 key rows =
+            // 2048 bytes per step)
             const int slot = g % FA_SLOTS;
             const uint64_t vdesc = make_smem_desc_sw128(smem_u32(ring + slot * FA_SLOT_BYTES + FA_SLOT_BYTES / 2));
+            const uint32_t tmem_p = tmem_base + FA_TM_P + (g & 1) * (FA_BN / 2);
 #pragma unroll
-            for (int k = 0; k < FA_BN / 16; ++k) umma_f16_ss(tmem_o, pdesc + 2 * k, vdesc + 128 * k, idesc_o, (c.j | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < FA_BN / 16; ++k) umma_f16_ts(tmem_o, tmem_p + 8 * k, vdesc + 128 * k, idesc_o, (c.j | k) != 0 ? 1u : 0u);
             umma_commit(&empty[slot]);
             umma_commit(pv_done);
             c = nx;
@@ -180,22 +216,33 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
     };
 
-    // ---------------- softmax warps (0-3): thread = query row ----------------
-    const int trow = (warp & 3) * 32 + lane;                                    // row of the tile = TMEM lane
-    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t p_row = smem_u32(p_tile) + (trow >> 3) * 1024 + (trow & 7) * 128;
+    // ---------------- softmax warps ----------------
+    // NSPLIT == 2: warps q and q + 4 share TMEM lane quarter q and split the block's keys (and the output dims); the halves of a
+    // row agree on the running maximum through shared memory and a 64-thread named barrier per block, their partial row sums
+    // meet once per item.
+    const int quarter = warp & 3, part = (warp >> 2) % NSPLIT;
+    const int trow = quarter * 32 + lane;                                       // row of the tile = TMEM lane
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    const uint32_t col0 = part * HC;
+    auto pair_sync = [&]() { if constexpr (NSPLIT > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * NSPLIT) : "memory"); };
     // O / l -> bf16 -> global for the rows of a finished item (valid query rows only); the caller has waited for its last PV
     auto epilogue = [&](int row0, int len, int q0, int h, float l) {
-        uint32_t orr[FA_HS];
-        tmem_ld32(tmem_o + lane_sel, orr);
-        tmem_ld32(tmem_o + lane_sel + 32, orr + 32);
+        uint32_t orr[HC];
+        tmem_ld_n<HC>(tmem_o + lane_sel + col0, orr);
+        if constexpr (NSPLIT > 1) {
+            float* xl = xch + 2 * NSPLIT * FA_BM;
+            xl[part * FA_BM + trow] = l;
+            pair_sync();
+            l += xl[(part ^ 1) * FA_BM + trow];
+        }
         tmem_ld_wait();
         tc_fence_before();                   // orders these TMEM reads before the next item's first PV (released through p_full)
+        pair_sync();                         // the partner has read this thread's sum before the next item overwrites it
         if (q0 + trow < len) {
             const float inv = 1.0f / l;
-            uint4* dst = reinterpret_cast<uint4*>(out + (long long)(row0 + trow) * ld + h * FA_HS);
+            uint4* dst = reinterpret_cast<uint4*>(out + (long long)(row0 + trow) * ld + h * FA_HS + col0);
 #pragma unroll
-            for (int c8 = 0; c8 < FA_HS / 8; ++c8) {
+            for (int c8 = 0; c8 < HC / 8; ++c8) {
                 uint4 v;
                 v.x = pack_bf16x2(__uint_as_float(orr[8 * c8]) * inv, __uint_as_float(orr[8 * c8 + 1]) * inv);
                 v.y = pack_bf16x2(__uint_as_float(orr[8 * c8 + 2]) * inv, __uint_as_float(orr[8 * c8 + 3]) * inv);
@@ -205,35 +252,48 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
         }
     };
-    auto softmax = [&](Cursor c) {
+    auto softmax = [&](FaCursor c) {
         float m = -INFINITY, l = 0.f;
         bool have_prev = false;
         int pv_row0 = 0, pv_len = 0, pv_q0 = 0, pv_h = 0;
         float pv_l = 1.f;
+        uint32_t pv_waited = 0;              // pv_done phases [0, pv_waited) are known to be complete
+        auto wait_pv = [&](uint32_t upto) {  // blocks < upto have been accumulated into O (and their P buffers are free)
+            if (upto > pv_waited) {
+                mbar_wait(pv_done, (upto - 1) & 1);
+                tc_fence_after();
+                pv_waited = upto;
+            }
+        };
         for (; c.valid(); c.next(), ++g) {
             mbar_wait(&s_full[g & 1], (g >> 1) & 1);
             tc_fence_after();
-            const uint32_t tmem_s = tmem_base + (g & 1) * FA_BN + lane_sel;
-            uint32_t sr[FA_BN];
-            tmem_ld32(tmem_s, sr);
-            tmem_ld32(tmem_s + 32, sr + 32);
+            uint32_t sr[HC];
+            tmem_ld_n<HC>(tmem_base + FA_TM_S + (g & 1) * FA_BN + lane_sel + col0, sr);
             if (c.j == 0) { m = -INFINITY; l = 0.f; }
-            const int nk = c.tile.z - c.j * FA_BN;                              // valid keys of this block (>= 1)
+            const int nk = c.tile.z - c.j * FA_BN - (int)col0;                  // valid keys among this thread's columns (may be <= 0)
             tmem_ld_wait();
             float mx = -INFINITY;
-            if (nk >= FA_BN) {
+            if (nk >= HC) {
 #pragma unroll
-                for (int i = 0; i < FA_BN; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+                for (int i = 0; i < HC; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
             } else {
 #pragma unroll
-                for (int i = 0; i < FA_BN; ++i) {
+                for (int i = 0; i < HC; ++i) {
                     if (i >= nk) sr[i] = 0xff800000u;                           // -inf: keys past the end of the pair
                     mx = fmaxf(mx, __uint_as_float(sr[i]));
                 }
             }
+            if constexpr (NSPLIT > 1) {
+                float* xm = xch + (g & 1) * NSPLIT * FA_BM;
+                xm[part * FA_BM + trow] = mx;
+                pair_sync();
+                mx = fmaxf(mx, xm[(part ^ 1) * FA_BM + trow]);                  // the row's maximum over all 64 keys (finite: >= 1 valid key)
+            }
             // Lazy rescaling (exact arithmetic, fewer TMEM round trips): the running maximum only moves when some row of the warp
             // outgrew it by more than 2^8 -- until then P = exp2(s - m_old) <= 256 and the sums stay well inside fp32 / bf16
-            // range; the final division by l uses the same m, so the result is the softmax either way.
+            // range; the final division by l uses the same m, so the result is the softmax either way.  All parts of a row see
+            // the same mx and m, hence take the same decision.
             const bool first = c.j == 0;
             const bool grow = first || __any_sync(FULL_MASK, (mx - m) * FA_LOG2E > 8.0f);
             float alpha = 1.0f;
@@ -242,42 +302,39 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 alpha = ex2f((m - m_new) * FA_LOG2E);                           // 0 for the first block (m = -inf)
                 m = m_new;
             }
-            if (g > 0) {
-                mbar_wait(pv_done, (g - 1) & 1);                                // O holds every earlier block; the P tile is free
-                tc_fence_after();
-            }
             if (first) {
-                if (have_prev) epilogue(pv_row0, pv_len, pv_q0, pv_h, pv_l);    // deferred: its last PV ran behind this block's S phase
-            } else if (grow) {                                                  // rescale the accumulator rows
-                uint32_t orr[FA_HS];
-                tmem_ld32(tmem_o + lane_sel, orr);
-                tmem_ld32(tmem_o + lane_sel + 32, orr + 32);
+                if (have_prev) {                                                // deferred: its last PV ran behind this block's S phase
+                    wait_pv(g);
+                    epilogue(pv_row0, pv_len, pv_q0, pv_h, pv_l);
+                }
+            } else if (grow) {                                                  // rescale this thread's part of the accumulator row
+                wait_pv(g);
+                uint32_t orr[HC];
+                tmem_ld_n<HC>(tmem_o + lane_sel + col0, orr);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < FA_HS; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
-                tmem_st32(tmem_o + lane_sel, orr);
-                tmem_st32(tmem_o + lane_sel + 32, orr + 32);
-                tmem_st_wait();
+                for (int i = 0; i < HC; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                tmem_st_n<HC>(tmem_o + lane_sel + col0, orr);
             }
             const float ms = m * FA_LOG2E;
-            float sum = 0.f;
-            const int n_chunks = (min(nk, FA_BN) + 7) >> 3;                     // chunks of 8 keys that hold a valid key (warp-uniform)
+            float sum0 = 0.f, sum1 = 0.f;
+            uint32_t pr[HC / 2];
 #pragma unroll
-            for (int c8 = 0; c8 < FA_BN / 8; ++c8) {
-                // 16-byte chunk c8 of row r sits at chunk c8 ^ (r & 7) (128-byte swizzle, as TMA / the MMA descriptor expect)
-                const uint32_t addr = p_row + ((uint32_t)(c8 ^ (trow & 7)) << 4);
-                if (c8 < n_chunks) {
-                    float p[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { p[i] = ex2f(fmaf(__uint_as_float(sr[8 * c8 + i]), FA_LOG2E, -ms)); sum += p[i]; }
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(p[0], p[1])),
-                                 "r"(pack_bf16x2(p[2], p[3])), "r"(pack_bf16x2(p[4], p[5])), "r"(pack_bf16x2(p[6], p[7])) : "memory");
-                } else {                                                        // keys past the pair: P = 0 (V rows there belong to others)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
-                }
+            for (int i = 0; i < HC; i += 4) {                                   // masked keys: exp2(-inf) = 0 exactly
+                const float p0 = ex2f(fmaf(__uint_as_float(sr[i]), FA_LOG2E, -ms)), p1 = ex2f(fmaf(__uint_as_float(sr[i + 1]), FA_LOG2E, -ms));
+                const float p2 = ex2f(fmaf(__uint_as_float(sr[i + 2]), FA_LOG2E, -ms)), p3 = ex2f(fmaf(__uint_as_float(sr[i + 3]), FA_LOG2E, -ms));
+                sum0 += p0 + p1;
+                sum1 += p2 + p3;
+                pr[i / 2] = pack_bf16x2(p0, p1);
+                pr[i / 2 + 1] = pack_bf16x2(p2, p3);
             }
-            l = l * alpha + sum;
-            fence_async_smem();              // P: generic-proxy writes -> visible to the tensor core's async proxy
+            // P buffer g & 1 was read by PV_{g-2}.  The wait names phase g - 1 (PV of the previous block, which ran behind the
+            // exponentials above and has normally completed): a parity wait must never name a phase two behind the barrier --
+            // with phases g - 2 and g - 1 both complete it would be taken for phase g, which needs this warp's own arrival.
+            if (g >= 1) wait_pv(g);
+            tmem_st_n<HC / 2>(tmem_base + FA_TM_P + (g & 1) * (FA_BN / 2) + lane_sel + col0 / 2, pr);
+            l = l * alpha + (sum0 + sum1);
+            tmem_st_wait();                  // P (and a rescaled O) are in tensor memory
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
@@ -286,24 +343,36 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 pv_row0 = c.tile.x; pv_len = c.tile.z; pv_q0 = c.tile.x - c.tile.y; pv_h = c.h; pv_l = l;
             }
         }
-        if (have_prev) {                                                        // the round's last item
-            mbar_wait(pv_done, (g - 1) & 1);
-            tc_fence_after();
+        if (have_prev) {                                                        // the CTA's last item
+            wait_pv(g);
             epilogue(pv_row0, pv_len, pv_q0, pv_h, pv_l);
         }
     };
 
-    Cursor c;
+    FaCursor c;
     c.start(lay.tiles, lay.n_tiles, n_head, blockIdx.x, gridDim.x);
-    if (warp == 4) { if (lane == 0) produce(c); }
-    else if (warp == 5) { if (lane == 0) mma(c); }
+    if (warp == N_SOFTMAX) { if (lane == 0) produce(c); }
+    else if (warp == N_SOFTMAX + 1) { if (lane == 0) mma(c); }
     else softmax(c);
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == N_SOFTMAX) {
         tc_fence_after();
         tmem_dealloc(tmem_base, FA_TMEM_COLS);
     }
+}
+
+template <int NSPLIT>
+int fa_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, void* out, long long ld, Lay lay, int n_head,
+              cudaStream_t st) {
+    static PerDeviceOnce once;
+    auto kern = flash_attn_tc_kernel<NSPLIT>;
+    if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess) return 2;
+    const int n_items = lay.n_tiles * n_head;
+    const int max_ctas = 2 * device_sm_count();
+    const int grid = n_items < max_ctas ? n_items : max_ctas;
+    kern<<<grid, (4 * NSPLIT + 2) * 32, FA_SMEM, st>>>(mq, mk, mv, (__nv_bfloat16*)out, ld, lay, n_head);
+    return 0;
 }
 
 }  // namespace
@@ -316,13 +385,8 @@ int full_attn_tcgen05(const void* q, const void* k, const void* v, void* out, lo
     if (!make_tensor_map_2d(&mq, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, lay.R, C, ld, FA_BM, FA_HS, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     if (!make_tensor_map_2d(&mk, k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, lay.R, C, ld, FA_BN, FA_HS, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     if (!make_tensor_map_2d(&mv, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, lay.R, C, ld, FA_BN, FA_HS, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
-    static PerDeviceOnce once;
-    if (once.first() && cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess) return 2;
-    const int n_items = lay.n_tiles * n_head;
-    const int max_ctas = 2 * device_sm_count();
-    const int grid = n_items < max_ctas ? n_items : max_ctas;
-    flash_attn_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mk, mv, (__nv_bfloat16*)out, ld, lay, n_head);
-    return 0;
+    static const int nsplit = getenv("VRD_FA_SPLIT") ? atoi(getenv("VRD_FA_SPLIT")) : 1;      // A/B switch: softmax warps per lane quarter
+    return nsplit == 1 ? fa_launch<1>(mq, mk, mv, out, ld, lay, n_head, st) : fa_launch<2>(mq, mk, mv, out, ld, lay, n_head, st);
 }
 
 }  // namespace vrd

@@ -273,17 +273,18 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             if (c.j == 0) { m = -INFINITY; l = 0.f; }
             const int nk = c.tile.z - c.j * FA_BN - (int)col0;                  // valid keys among this thread's columns (may be <= 0)
             tmem_ld_wait();
-            float mx = -INFINITY;
-            if (nk >= HC) {
+            if (nk < HC) {
 #pragma unroll
-                for (int i = 0; i < HC; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
-            } else {
-#pragma unroll
-                for (int i = 0; i < HC; ++i) {
+                for (int i = 0; i < HC; ++i)
                     if (i >= nk) sr[i] = 0xff800000u;                           // -inf: keys past the end of the pair
-                    mx = fmaxf(mx, __uint_as_float(sr[i]));
-                }
             }
+            float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};        // four independent chains (a single one is 64 dependent ops)
+#pragma unroll
+            for (int i = 0; i < HC; i += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) mxa[u] = fmaxf(mxa[u], __uint_as_float(sr[i + u]));
+            }
+            float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
             if constexpr (NSPLIT > 1) {
                 float* xm = xch + (g & 1) * NSPLIT * FA_BM;
                 xm[part * FA_BM + trow] = mx;

@@ -946,13 +946,238 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// dwconv_ln_bw ("branch warps"): same staging as dwconv_ln_tile, different division of labour.  ncu on dwconv_ln_tile: the
+// shared-memory / L1 data pipe is 63-72 % busy while issue slots (35 %) and DRAM (28-39 %) idle, and MORE THAN HALF of its
+// wavefronts are the per-channel parameters (three conv taps, LayerNorm gamma / beta: 10 KB per branch) that every warp
+// re-reads from L1 for every two rows.  Here a warp belongs to ONE branch for the lifetime of the persistent CTA and keeps that
+// branch's 5 x 16 parameters per lane in registers: parameter traffic disappears, what is left per output row is the window
+// (32 wavefronts per branch) and the one-off pre-LayerNorm pass.  WPB warps per branch; a warp walks over row pairs of the tile.
+// One CTA per SM (the parameters cost 80 registers), 32-row tiles.
+// ------------------------------------------------------------------------------------------------------------
+template <typename TO, int NB, int PREMASK, int WPB, int TILE>
+__global__ void __launch_bounds__(NB * WPB * 32, 1) dwconv_ln_bw_kernel(const float* __restrict__ x, Lay lay,
+                                                                         const float* __restrict__ pre_g,
+                                                                         const float* __restrict__ pre_b, DwBranches br,
+                                                                         int total_rows) {
+    constexpr int NCH = 4, C = 512;
+    constexpr int DWT_ROWS = TILE + 2, NW = NB * WPB;
+    constexpr int PAIRS_PER_WARP = TILE / 2 / WPB;
+    static_assert(TILE % (2 * WPB) == 0, "row pairs must divide evenly over a branch's warps");
+    constexpr bool ANY_PRE = PREMASK != 0;
+    constexpr bool ALL_PRE = PREMASK == ((1 << NB) - 1);
+    constexpr bool MIXED = ANY_PRE && !ALL_PRE;
+    extern __shared__ __align__(128) uint8_t dwt_smem[];
+    float* sx_all = reinterpret_cast<float*>(dwt_smem);          // [2][DWT_ROWS][C]; row i <-> physical row r0 - 1 + i
+    float* s_nrm = sx_all + 2 * DWT_ROWS * C;                    // [DWT_ROWS][C] (MIXED only)
+    float* s_zero = s_nrm + (MIXED ? DWT_ROWS * C : 0);          // [C] zeros: taps outside the pair
+    float* s_beta = s_zero + C;                                  // [C] LN_pre bias: the first pad column
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + C);    // [2]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = warp / WPB, sub = warp - b * WPB;              // this warp's branch, and its index among the branch's warps
+    const bool pre = (PREMASK >> b) & 1;
+    const int n_tiles = total_rows / TILE;
+    const uint32_t bar_u = (uint32_t)__cvta_generic_to_shared(bars);
+    auto issue = [&](int tile, int buf) {                         // one thread: stage the rows of `tile` into buffer `buf`
+        const int r0 = tile * TILE;
+        const int lo = max(r0 - 1, 0), hi = min(r0 + TILE + 1, total_rows);
+        const uint32_t bytes = (uint32_t)(hi - lo) * C * 4;
+        const uint32_t bb = bar_u + 8 * buf;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(sx_all + buf * DWT_ROWS * C + (lo - (r0 - 1)) * C)),
+                       "l"(x + (long long)lo * C), "r"(bytes), "r"(bb) : "memory");
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    }
+    for (int i = threadIdx.x; i < C; i += NW * 32) {
+        s_zero[i] = 0.f;
+        s_beta[i] = ANY_PRE ? pre_b[i] : 0.f;
+    }
+    // the branch's parameters, resident in registers: lane owns channels (j * 32 + lane) * 4 .. + 3 of every 128-channel chunk j
+    f2 w0[NCH][2], w1[NCH][2], w2[NCH][2], gm[NCH][2], bt[NCH][2];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        f2_ldg(br.w[b] + c, w0[j]); f2_ldg(br.w[b] + C + c, w1[j]); f2_ldg(br.w[b] + 2 * C + c, w2[j]);
+        f2_ldg(br.g[b] + c, gm[j]); f2_ldg(br.b[b] + c, bt[j]);
+    }
+    TO* const out_b = (TO*)br.out[b];
+    const long long ldo_b = br.ldo[b];
+    __syncthreads();                                             // barriers initialised before anyone polls them
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        float* sx = sx_all + buf * DWT_ROWS * C;
+        const float* sn = MIXED ? s_nrm : sx;                    // where the normalised rows live
+        const int r0 = tile * TILE;
+        const int lo = max(r0 - 1, 0), hi = min(r0 + TILE + 1, total_rows);
+        if (threadIdx.x == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1);   // freed by the trailing sync
+        {
+            const uint32_t parity = (it >> 1) & 1;
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar_u + 8 * buf), "r"(parity) : "memory");
+            }
+        }
+        if (ANY_PRE) {
+            // every warp of the CTA normalises its share of the staged rows once (rows i = warp, warp + NW, ...)
+            const uint32_t sx_base = (uint32_t)__cvta_generic_to_shared(sx) + lane * 16;
+            const uint32_t dst_base = (uint32_t)__cvta_generic_to_shared(MIXED ? s_nrm : sx) + lane * 16;
+            for (int i = warp; i < DWT_ROWS; i += NW) {
+                const int p = r0 - 1 + i;
+                if (p < lo || p >= hi) continue;                 // warp-uniform
+                f2 v[NCH][2];
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) f2_lds(sx_base + (uint32_t)i * C * 4 + j * 512, v[j]);
+                f2 sm = f2_add(v[0][0], v[0][1]);
+#pragma unroll
+                for (int j = 1; j < NCH; ++j) sm = f2_add(sm, f2_add(v[j][0], v[j][1]));
+                const float mean = warp_sum(f2_hsum(sm)) * (1.0f / C);
+                const f2 mm = f2_splat(mean);
+                f2 q = 0ull;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) { v[j][e] = f2_sub(v[j][e], mm); q = f2_fma(v[j][e], v[j][e], q); }
+                const f2 rs = f2_splat(rsqrtf(warp_sum(f2_hsum(q)) * (1.0f / C) + VRD_EPS));
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    f2 g[2], be[2];
+                    f2_ldg(pre_g + (j * 32 + lane) * 4, g);
+                    f2_ldg(pre_b + (j * 32 + lane) * 4, be);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) v[j][e] = f2_fma(f2_mul(v[j][e], rs), g[e], be[e]);
+                    f2_sts(dst_base + (uint32_t)i * C * 4 + j * 512, v[j]);
+                }
+            }
+            __syncthreads();
+        }
+        {
+            const uint32_t sx_u = (uint32_t)__cvta_generic_to_shared(sx), sn_u = (uint32_t)__cvta_generic_to_shared(sn);
+            const uint32_t zero_u = (uint32_t)__cvta_generic_to_shared(s_zero), beta_u = (uint32_t)__cvta_generic_to_shared(s_beta);
+            const uint32_t src_u = pre ? sn_u : sx_u;
+#pragma unroll 1
+            for (int pp = 0; pp < PAIRS_PER_WARP; ++pp) {
+                const int rr0 = 2 * (sub * PAIRS_PER_WARP + pp);                     // first of the two output rows, within the tile
+                uint32_t awin[4];
+                int wseq[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int grow = r0 + rr0 - 1 + w;
+                    int seq = -1;
+                    if (grow >= 0 && grow < total_rows) seq = lay.row_seq[grow % lay.R];
+                    wseq[w] = seq;
+                    awin[w] = (seq >= 0 ? src_u + (uint32_t)(rr0 + w) * C * 4 : zero_u) + lane * 16;
+                }
+                bool live[2];
+                uint32_t hib = 0;                                // bit u: tap +1 of output row u is a first pad column
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    live[u] = wseq[u + 1] >= 0;
+                    if (pre && live[u] && wseq[u + 2] < 0 && lay.seqinfo[wseq[u + 1]].z != 0) hib |= 1u << u;
+                }
+                f2 y[2][NCH][2];
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    f2 a[4][2];
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) f2_lds(awin[w] + j * 512, a[w]);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) y[u][j][e] = f2_fma(a[u + 2][e], w2[j][e], f2_fma(a[u + 1][e], w1[j][e], f2_mul(a[u][e], w0[j][e])));
+                    if (hib != 0) {                              // warp-uniform and rare (one row per padded pair)
+                        f2 pb[2];
+                        f2_lds(beta_u + lane * 16 + j * 512, pb);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+                            if ((hib >> u) & 1) {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) y[u][j][e] = f2_fma(pb[e], w2[j][e], y[u][j][e]);   // the tap read 0 above
+                            }
+                    }
+                }
+                float mean[2], rstd[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    f2 sm = f2_add(y[u][0][0], y[u][0][1]);
+#pragma unroll
+                    for (int j = 1; j < NCH; ++j) sm = f2_add(sm, f2_add(y[u][j][0], y[u][j][1]));
+                    mean[u] = f2_hsum(sm);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) mean[u] += __shfl_xor_sync(FULL_MASK, mean[u], o);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    mean[u] *= (1.0f / C);
+                    const f2 mm = f2_splat(mean[u]);
+                    f2 q = 0ull;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) { y[u][j][e] = f2_sub(y[u][j][e], mm); q = f2_fma(y[u][j][e], y[u][j][e], q); }
+                    rstd[u] = f2_hsum(q);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) rstd[u] += __shfl_xor_sync(FULL_MASK, rstd[u], o);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const f2 rs = f2_splat(rsqrtf(rstd[u] * (1.0f / C) + VRD_EPS));
+                    TO* o = out_b + (long long)(r0 + rr0 + u) * ldo_b;
+                    if (live[u]) {                                          // warp-uniform
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) y[u][j][e] = f2_fma(f2_mul(y[u][j][e], rs), gm[j][e], bt[j][e]);
+                            f2_stg(o + (j * 32 + lane) * 4, y[u][j]);
+                        }
+                    } else {
+                        zero_row<TO, NCH>(o, lane);                         // separator rows -> 0
+                    }
+                }
+            }
+        }
+        if constexpr (ALL_PRE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before the next TMA fill
+        __syncthreads();                                         // this buffer may be refilled from now on
+    }
+}
+
 template <typename TO>
 static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const float* pre_b, const DwBranches& br, int streams,
                           cudaStream_t st) {
     const int num_sms = device_sm_count();
     int mask = 0;
     for (int b = 0; b < br.n; ++b) mask |= (br.use_pre[b] ? 1 : 0) << b;
-    static const int cfg = getenv("VRD_DW_CFG") ? atoi(getenv("VRD_DW_CFG")) : 2;   // 0: 8 warps x 32 rows, 1: 16 x 32, 2: 2 CTAs/SM of 8 x 16
+    static const int cfg = getenv("VRD_DW_CFG") ? atoi(getenv("VRD_DW_CFG")) : 2;   // 0: 8 warps x 32 rows, 1: 16 x 32, 2: 2 CTAs/SM of 8 x 16, 3: branch warps
+    if (cfg == 3) {
+        constexpr int TILE = 32;
+        const int total = streams * lay.R;
+        const int n_tiles = total / TILE;
+        const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+#define LAUNCH_BW(NB, MASK, WPB) do { \
+        auto kern = dwconv_ln_bw_kernel<TO, NB, MASK, WPB, TILE>; \
+        constexpr int smem = dwt_smem_bytes(MASK != 0 && MASK != ((1 << NB) - 1), TILE); \
+        static PerDeviceOnce once; \
+        if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1; \
+        kern<<<grid, NB * WPB * 32, smem, st>>>(x, lay, pre_g, pre_b, br, total); } while (0)
+        if (br.n == 3 && mask == 7) LAUNCH_BW(3, 7, 4);
+        else if (br.n == 3 && mask == 3) LAUNCH_BW(3, 3, 4);
+        else if (br.n == 2 && mask == 0) LAUNCH_BW(2, 0, 8);
+        else if (br.n == 1 && mask == 1) LAUNCH_BW(1, 1, 16);
+        else return 1;
+#undef LAUNCH_BW
+        return 0;
+    }
     const int tile_rows = cfg == 2 ? 16 : 32;
     const int total = streams * lay.R;
     const int n_tiles = total / tile_rows;

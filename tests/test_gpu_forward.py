@@ -134,13 +134,16 @@ def test_forward_test_matches_reference_golden_video(name, precision):
     score_err = float(np.abs(np.array(out["triple_scores_avg"])[: len(ref["triplets"])] - np.array(ref["triple_scores_avg"])[: len(out["triplets"])]).max())
     _record(("forward_test", name, precision), n_triplets=len(out["triplets"]), n_ref=len(ref["triplets"]),
             same_rank_rate=float(np.mean(same)), found_rate=float(found), ranked_score_abs=score_err)
-    assert len(out["triplets"]) == len(ref["triplets"])
     if precision == "fp32":
+        assert len(out["triplets"]) == len(ref["triplets"])
         assert np.mean(same) > 0.98, "ranked triplets differ from the reference beyond borderline ties"
         assert score_err < 2e-3
     else:
         # measured: every reference triplet is reported for 4 of the 5 videos (94.7 % for vidor_local), rank-for-rank agreement
         # 68-94 % (near-tied candidates swap), mean scores of equal ranks within 2.2e-4
+        # below n_max_pair the NUMBER of triplets is the number of candidates that pass pred_min_frames: a mask flip at a duration's
+        # edge (bf16: ~1e-3 of the frames) moves it by one
+        assert abs(len(out["triplets"]) - len(ref["triplets"])) <= max(1, len(ref["triplets"]) // 50)
         assert found > 0.9 and score_err < 1e-3
     for t, (n, chk), ok in zip(out["so_trajs"], ref["so_trajs"], same):
         if ok:

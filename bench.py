@@ -64,7 +64,8 @@ def parse():
 
 
 def log(*a):
-    print(*a, file=sys.stderr, flush=True)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(*a, file=sys.stderr, flush=True)
 
 
 def peaks():
@@ -312,7 +313,18 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout at the first communicator: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     torch.manual_seed(0)
     model = MaskVRD(mc, dev).eval().to(dev)
     model._config_eval(cfg["inference_config"])
@@ -511,7 +523,7 @@ def main():
         sweep = run_sweep(args, cfg, model, dev, rank, world, sync_all, reduce_max)
 
     parity = cpu = None
-    if not args.no_cpu_baseline and rank == 0:
+    if not args.no_cpu_baseline and rank == 0 and world == 1:      # the CPU legs run at N = 1 only (torchrun pins OMP to one thread)
         torch.set_num_threads(threads)
         sd = default_state_dict(mc)
         sample = cpu_sample(host_videos, args.cpu_pairs, 12345)

@@ -33,8 +33,29 @@ class _FakeModel:
         def result(self):
             return _fake_forward(self.video)
 
+    lazy_trajs = False
+
+    class _PendingTrajs(_Pending):
+        """A result that carries ``so_trajs`` the way MaskVRD does: nested lists, or LazyTrajs when ``lazy_trajs`` is on."""
+
+        def __init__(self, video, lazy):
+            super().__init__(video)
+            self.lazy = lazy
+
+        def result(self):
+            import numpy as np
+            from vrdone_b200.maskvrd import LazyTrajs
+            out = _fake_forward(self.video)
+            boxes = np.arange(4 * 12, dtype=np.float32).reshape(12, 4) + len(self.video["lens"])
+            views = [(boxes[0:3], boxes[2:5]), (boxes[4:12], boxes[0:8])]
+            out["so_trajs"] = LazyTrajs(views) if self.lazy else [[a.tolist(), b.tolist()] for a, b in views]
+            return out
+
+    def __init__(self, with_trajs=False):
+        self.with_trajs = with_trajs
+
     def submit(self, video):
-        return self._Pending(video)
+        return self._PendingTrajs(video, self.lazy_trajs) if self.with_trajs else self._Pending(video)
 
 
 def _worker(rank, world, port, q):
@@ -44,8 +65,14 @@ def _worker(rank, world, port, q):
     costs = [runner.video_cost("vidor", v["lens"]) for v in vids]
     out = runner.run_sharded(vids, costs, _fake_forward)
     piped = runner.run_sharded(vids, costs, model=_FakeModel())
+    m = _FakeModel(with_trajs=True)
+    lazy = runner.run_sharded(vids, costs, model=m)                # trajectories travel as LazyTrajs (float32 arrays)
+    assert m.lazy_trajs is False                                   # ... and the model's own setting is restored
     if rank == 0:
-        q.put((out, piped))
+        from vrdone_b200.maskvrd import LazyTrajs
+        assert all(isinstance(r["so_trajs"], LazyTrajs) for r in lazy.values())
+        lazy = {i: dict(r, so_trajs=r["so_trajs"].materialise()) for i, r in lazy.items()}
+        q.put((out, piped, lazy))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -73,11 +100,12 @@ def test_two_rank_gloo_matches_single_rank():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    merged, piped = q.get(timeout=120)
+    merged, piped, lazy = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert merged == single and piped == single
+    assert lazy == runner.run_sharded(vids, costs, model=_FakeModel(with_trajs=True))      # one rank: plain nested lists
     assert runner.run_sharded(vids, costs, model=_FakeModel()) == single
 
 

@@ -63,16 +63,25 @@ def _rank_world():
 
 
 def run_sharded(videos: Sequence[dict], costs: Sequence[float], fn: Optional[Callable[[dict], object]] = None, model=None,
-                dataset_config: Optional[dict] = None, gather: bool = True) -> Dict[int, object]:
+                dataset_config: Optional[dict] = None, gather: bool = True, lazy_transport: bool = True) -> Dict[int, object]:
     """Every rank processes its shard -- with ``fn(video)`` one video after the other, or with ``model`` through the pipelined
     ``run_videos`` loop (two videos in flight per GPU); rank 0 returns {video index: result} for all videos (other ranks:
     their own; every rank with ``gather=False``, to be merged later with ``gather_results``).  Only the entries of a rank's
-    own shard of ``videos`` are touched.  Works with or without an initialised process group (world size 1)."""
+    own shard of ``videos`` are touched.  Works with or without an initialised process group (world size 1).
+    ``lazy_transport`` (multi-rank runs with ``model``): ``so_trajs`` travels as a ``LazyTrajs`` of float32 box arrays instead
+    of nested Python lists -- pickling 10^7 Python floats per rank cost more than the forward itself (measured: 1.4 s for 24
+    videos) -- and compares / indexes like the reference's lists on arrival (``.materialise()`` for the lists themselves)."""
     assert (fn is None) != (model is None), "give either fn or model"
     rank, world = _rank_world()
     mine = shard_videos(costs, world)[rank]
     if model is not None:
-        local = dict(zip(mine, run_videos(model, (videos[i] for i in mine), dataset_config=dataset_config)))
+        was_lazy = getattr(model, "lazy_trajs", False)
+        if lazy_transport and world > 1:
+            model.lazy_trajs = True
+        try:
+            local = dict(zip(mine, run_videos(model, (videos[i] for i in mine), dataset_config=dataset_config)))
+        finally:
+            model.lazy_trajs = was_lazy
     else:
         local = {i: fn(videos[i]) for i in mine}
     return gather_results(local) if gather else local

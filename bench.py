@@ -590,6 +590,9 @@ def run_sweep(args, cfg, model, dev, rank, world, sync_all, reduce_max):
         videos[i] = t
     for i in shards[rank][:2]:          # warm-up (buffers of this input kind)
         model.forward_tracklets(videos[i], dc)
+    tw = time.perf_counter()
+    runner.gather_results({})           # warm-up of the gather path (NCCL sets up its send/recv channels on first use)
+    gather_warm_ms = 1e3 * (time.perf_counter() - tw)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -618,7 +621,7 @@ def run_sweep(args, cfg, model, dev, rank, world, sync_all, reduce_max):
             "scaling": "strong", "videos": len(specs), "pairs": int(sum(npairs)), "value": sum(npairs) / (ms_max * 1e-3), "unit": UNIT,
             "ms_device_max_over_ranks": ms_max, "imbalance_max_over_mean": ms_max / (ms_sum / world),
             "cost_imbalance_lpt": max(sum(costs[i] for i in sh) for sh in shards) / (sum(costs) / world),
-            "gather_ms_rank0": gather_ms, "wall_ms_incl_gather_max_over_ranks": wall_max,
+            "gather_ms_rank0": gather_ms, "gather_first_use_ms_rank0": gather_warm_ms, "wall_ms_incl_gather_max_over_ranks": wall_max,
             "value_incl_gather": sum(npairs) / (wall_max * 1e-3), "triplets_gathered": n_trip}
 
 

@@ -206,6 +206,22 @@ def test_ranked_decode_equals_dense_decode():
         for key in ("triplets", "triple_scores", "triple_scores_avg", "pred_durations", "so_tids"):
             assert ranked[key] == dense[key], key
         assert ranked["so_trajs"] == dense["so_trajs"]
+        if lazy:
+            # transport form of the multi-GPU gather: one array of the covered tracklet rows + (start, rows) per slice, built
+            # from the known origin of the views (_pack_refs) or by inspecting them (_pack_views); both arrive as equal lists
+            import pickle
+            from vrdone_b200.maskvrd import LazyTrajs, _pack_views
+            lt = ranked["so_trajs"]
+            assert lt._refs is not None
+            back = pickle.loads(pickle.dumps(lt))
+            assert isinstance(back, LazyTrajs) and back == dense["so_trajs"]
+            flat_r, refs_r = lt.__reduce__()[1]
+            flat_v, refs_v = _pack_views(lt._views)
+            slices = sum(len(a) + len(b) for a, b in lt._views)
+            assert len(flat_r) < slices and len(flat_v) < slices           # shared tracklet rows travel once
+            assert pickle.loads(pickle.dumps(LazyTrajs(lt._views))) == dense["so_trajs"]
+            odd = LazyTrajs([(np.arange(8, dtype=np.float64).reshape(2, 4), np.ones((2, 4), np.float32))])
+            assert pickle.loads(pickle.dumps(odd)).materialise() == [[[[0, 1, 2, 3], [4, 5, 6, 7]], [[1.0] * 4] * 2]]
     model.private_box_lists = model.lazy_trajs = False
     empty = packed.copy()
     empty[0] = 0

@@ -37,11 +37,14 @@ class LazyTrajs(Sequence):
     views without any conversion.  Enabled with ``model.lazy_trajs = True`` (config key ``lazy_trajs``); off by default so that
     ``forward`` returns plain lists exactly as the reference does."""
 
-    __slots__ = ("_views", "_cache")
+    __slots__ = ("_views", "_cache", "_refs")
 
-    def __init__(self, views):
+    def __init__(self, views, refs=None):
         self._views = views                  # [(subject (n, 4) float32 array, object (n, 4) float32 array)]
         self._cache = {}
+        # optional: where the views come from -- (root arrays, root index [2n], first row [2n], rows [2n]) in view order
+        # (subject, object, subject, ...) -- so that the transport form is built without inspecting 2n arrays
+        self._refs = refs
 
     def __len__(self):
         return len(self._views)
@@ -61,10 +64,9 @@ class LazyTrajs(Sequence):
         return item
 
     def __reduce__(self):
-        # transport form (multi-GPU gather): the (n, 4) float32 slices themselves, not nested Python lists (10-100 x smaller
-        # and faster to pickle); pickling copies just the slices, not the per-tracklet arrays they view
-        import numpy as _np
-        return (LazyTrajs, ([(_np.ascontiguousarray(a), _np.ascontiguousarray(b)) for a, b in self._views],))
+        # transport form (multi-GPU gather): ONE float32 array + (start, length) per slice -- not nested Python lists (10^7
+        # floats per rank) and not 2 x n_triplets small arrays (numpy's per-array pickle overhead, ~10 us each way)
+        return (_lazy_trajs_from_packed, _pack_refs(*self._refs) if self._refs is not None else _pack_views(self._views))
 
     def materialise(self):
         """The reference's format: a list of ``[subject_boxes, object_boxes]`` nested lists."""
@@ -77,6 +79,69 @@ class LazyTrajs(Sequence):
 
     def __repr__(self):
         return f"LazyTrajs({len(self)} triplets)"
+
+
+def _pack_refs(roots, root_idx, start, rows):
+    """``_pack_views`` for views whose origin is known: one copy of the covered row range per root array."""
+    lo = np.full(len(roots), np.iinfo(np.int64).max, dtype=np.int64)
+    hi = np.zeros(len(roots), dtype=np.int64)
+    np.minimum.at(lo, root_idx, start)
+    np.maximum.at(hi, root_idx, start + rows)
+    used = hi > 0
+    lo[~used] = 0
+    base = np.cumsum(hi - lo) - (hi - lo)
+    pieces = [roots[k][lo[k]: hi[k]] for k in np.nonzero(used)[0].tolist()]
+    flat = np.concatenate(pieces, axis=0) if pieces else np.zeros((0, 4), np.float32)
+    return flat, np.stack([base[root_idx] + start - lo[root_idx], rows], 1)
+
+
+def _pack_views(views):
+    """``(flat [rows, 4] float32, refs [2 * n, 2] int64 (start row, rows))`` for the slices of a ``LazyTrajs``.  Slices that
+    view the same per-tracklet box array (the normal case: <= 200 triplets over a few dozen tracklets) are sent as ONE copy
+    of the row range they cover together, so the transported bytes are bounded by the video's tracklet boxes (about a quarter
+    of the slices laid end to end); anything else (own arrays, other dtypes / strides) is appended as it is."""
+    parts = [a for pair in views for a in pair]
+    refs = np.zeros((len(parts), 2), dtype=np.int64)
+    roots = {}                       # id(root array) -> [root, lowest row, highest row + 1, [(part index, first row)]]
+    loose = []
+    for i, a in enumerate(parts):
+        r = a
+        while isinstance(r.base, np.ndarray):
+            r = r.base
+        ok = (r is not a and a.dtype == np.float32 and r.dtype == np.float32 and r.ndim == 2 and a.ndim == 2 and a.shape[1] == 4
+              and r.shape[1] == 4 and r.flags.c_contiguous and a.flags.c_contiguous)
+        if ok:
+            off = a.__array_interface__["data"][0] - r.__array_interface__["data"][0]
+            ok = off >= 0 and off % 16 == 0 and off // 16 + len(a) <= len(r)
+        if not ok:
+            loose.append(i)
+            continue
+        row = off // 16
+        e = roots.get(id(r))
+        if e is None:
+            roots[id(r)] = [r, row, row + len(a), [(i, row)]]
+        else:
+            e[1], e[2] = min(e[1], row), max(e[2], row + len(a))
+            e[3].append((i, row))
+    pieces, base = [], 0
+    for r, lo, hi, users in roots.values():
+        pieces.append(r[lo:hi])
+        for i, row in users:
+            refs[i] = (base + row - lo, len(parts[i]))
+        base += hi - lo
+    for i in loose:
+        a = np.ascontiguousarray(parts[i], dtype=np.float32).reshape(-1, 4)
+        pieces.append(a)
+        refs[i] = (base, len(a))
+        base += len(a)
+    flat = np.concatenate(pieces, axis=0) if pieces else np.zeros((0, 4), np.float32)
+    return flat, refs
+
+
+def _lazy_trajs_from_packed(flat, refs):
+    """Inverse of ``LazyTrajs.__reduce__``: views into the one transported array."""
+    r = refs.tolist()
+    return LazyTrajs([(flat[r[i][0]: r[i][0] + r[i][1]], flat[r[i + 1][0]: r[i + 1][0] + r[i + 1][1]]) for i in range(0, len(r), 2)])
 
 
 class PendingVideo:
@@ -900,7 +965,15 @@ class MaskVRD(nn.Module):
                     st, ot = arr(s_l[i])[s0[i]: s0[i] + n_fr[i]], arr(o_l[i])[o0[i]: o0[i] + n_fr[i]]
                     assert len(st) == len(ot) == n_fr[i]
                     views.append((st, ot))
-                out["so_trajs"] = LazyTrajs(views)
+                refs = None
+                if count and all(x.dtype == np.float32 and x.ndim == 2 and x.shape[1] == 4 for x in arrays.values()):
+                    tids = sorted(arrays)
+                    slot = np.zeros(max(tids) + 1, dtype=np.int64)
+                    slot[tids] = np.arange(len(tids))
+                    refs = ([arrays[t] for t in tids], slot[np.stack([s, o], 1).reshape(-1)],
+                            np.stack([so_start - durs[s, 0] + a, so_start - durs[o, 0] + a], 1).reshape(-1).astype(np.int64),
+                            np.repeat((b - a).astype(np.int64), 2))
+                out["so_trajs"] = LazyTrajs(views, refs)
             elif self.private_box_lists:
                 trajs = []
                 for i in range(count):

@@ -94,10 +94,10 @@ def gather_results(local: Dict[int, object]) -> Dict[int, object]:
     if world == 1:
         return local
     gathered = [None] * world if rank == 0 else None
-    dist.gather_object(local, gathered, dst=0)
+    dist.gather_object(local if rank != 0 else None, gathered, dst=0)      # rank 0's own results need no pickling round trip
     if rank != 0:
         return local
-    merged: Dict[int, object] = {}
-    for part in gathered:
+    merged: Dict[int, object] = dict(local)
+    for part in gathered[1:]:
         merged.update(part)
     return merged

@@ -37,6 +37,10 @@ int vrd_abi_version(void);
 const char* vrd_last_error(void);
 /* compute capability major*10+minor of the current device (100 on B200); <0 on error */
 int vrd_device_arch(void);
+/* experiment switches of the launchers ("pdl": programmatic dependent launch on / off, "dw_cfg": dwconv_ln_tile variant); the
+ * defaults come from the environment (VRD_PDL, VRD_DW_CFG).  Returns the previous value, <0 for an unknown name.  No reference
+ * counterpart: it exists so that one process can A/B a switch on the same inputs. */
+int vrd_set_option(const char* name, int value);
 
 /* a0 -- replaces utils.dict_to_device for the pair features (eval.py:144, utils/misc.py:98-112): n asynchronous
  * host->device copies on `stream` (the copy engine; src[i] HOST pointers, pinned for true asynchrony) of bytes[i] bytes to

@@ -22,6 +22,8 @@ constexpr int WARPS = 8;
 template <typename T, int NCH, int LPH>
 __global__ void window_attn_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                                    T* __restrict__ out, long long ld, Lay lay, int w, int streams) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int MAXK = 9;
     const int lane = threadIdx.x & 31;
     const int grow = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -139,6 +141,8 @@ template <typename T, int C, int HS, int TILE>
 __global__ void __launch_bounds__(WARPS * 32) window_attn_tma_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                                      const T* __restrict__ v, T* __restrict__ out, Lay lay, int w,
                                                                      int total_rows) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int VEC = Vec16<T>::N, NV = C / (32 * VEC), LPH = HS / VEC, MAXK = 2 * WIN_HALO + 1;
     constexpr int ROWS = TILE + 2 * WIN_HALO;
     extern __shared__ __align__(128) uint8_t win_smem[];
@@ -267,7 +271,7 @@ static int window_attn_tma_launch(const void* q, const void* k, const void* v, v
     auto kern = window_attn_tma_kernel<T, C, HS, TILE>;
     if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
     const int total = streams * lay.R;    // R % 128 == 0, so TILE divides it
-    kern<<<total / TILE, WARPS * 32, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)out, lay, w, total);
+    launch_k(kern, dim3(total / TILE), dim3(WARPS * 32), smem, st, (const T*)q, (const T*)k, (const T*)v, (T*)out, lay, w, total);
     return 0;
 }
 
@@ -283,7 +287,7 @@ static int window_attn_simt(const void* q, const void* k, const void* v, void* o
     }
     const int grid = (streams * lay.R + WARPS - 1) / WARPS;
 #define LAUNCH(T, LPH) \
-    window_attn_kernel<T, 4, LPH><<<grid, WARPS * 32, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay, w, streams)
+    launch_k(window_attn_kernel<T, 4, LPH>, dim3(grid), dim3(WARPS * 32), 0, st, (const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay, w, streams)
     if (hs == 64) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 16); else LAUNCH(float, 16); }
     else if (hs == 128) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 32); else LAUNCH(float, 32); }
     else return 1;
@@ -299,6 +303,8 @@ static int window_attn_simt(const void* q, const void* k, const void* v, void* o
 template <typename T, int HS>
 __global__ void __launch_bounds__(128) full_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                         const T* __restrict__ v, T* __restrict__ out, long long ld, Lay lay) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int TPQ = HS / 32;
     constexpr int QPB = 128 / TPQ;
     constexpr int KT = 32;
@@ -399,6 +405,8 @@ template <int HS, int NBUF>
 __global__ void __launch_bounds__(128, HS == 64 ? 4 : 1) flash_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                               const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
                                                               long long ld, Lay lay) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int BM = 64, BN = 64, LDS = HS + 8, KSTEPS = HS / 16, DBLK = HS / 8, CPR = HS / 8;   // CPR: 16-byte chunks per row
     extern __shared__ __align__(16) uint8_t fa_smem[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);
@@ -573,7 +581,7 @@ static int flash_launch(const void* q, const void* k, const void* v, void* out, 
     if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
     (void)max_rows;
     const dim3 grid((lay.R + 63) / 64, n_head);
-    kern<<<grid, 128, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ld, lay);
+    launch_k(kern, dim3(grid), dim3(128), smem, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ld, lay);
     return 0;
 }
 
@@ -594,7 +602,7 @@ int full_attn(const void* q, const void* k, const void* v, void* out, int dt, lo
         return 1;
     }
 #define LAUNCH(T, HS) \
-    full_attn_kernel<T, HS><<<dim3((max_rows + (128 / (HS / 32)) - 1) / (128 / (HS / 32)), n_head, lay.B), 128, 0, st>>>( \
+    launch_k(full_attn_kernel<T, HS>, dim3(dim3((max_rows + (128 / (HS / 32)) - 1) / (128 / (HS / 32)), n_head, lay.B)), dim3(128), 0, st,  \
         (const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay)
     if (hs == 64) LAUNCH(float, 64);
     else if (hs == 128) LAUNCH(float, 128);
@@ -622,6 +630,8 @@ template <int NH>
 __global__ void __launch_bounds__(WM_WARPS * 32, 2) window_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                                            const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
                                                                            Lay lay, int w, int total_rows) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int HS = 64, BM = 16, KR = BM + 2 * WM_HALO, LDS = HS + 8, CPR = HS / 8, C = NH * HS;
     constexpr int STAGE = (BM + 2 * KR) * LDS;          // elements per pipeline stage: Q, K, V
     extern __shared__ __align__(16) uint8_t wm_smem[];
@@ -785,7 +795,7 @@ static int window_attn_mma_launch(const void* q, const void* k, const void* v, v
     auto kern = window_attn_mma_kernel<8>;
     if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
     const int total = streams * lay.R;    // R % 128 == 0
-    kern<<<total / (16 * WM_WARPS), WM_WARPS * 32, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+    launch_k(kern, dim3(total / (16 * WM_WARPS)), dim3(WM_WARPS * 32), smem, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                                                              (__nv_bfloat16*)out, lay, w, total);
     return 0;
 }
@@ -807,6 +817,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) query_self_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                               const T* __restrict__ v, T* __restrict__ out, long long ld,
                                                               int Q, int n_head) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int D = 256, MAXQ = 12, MAXH = 8;
     // sk rows are padded by four words: in the score phase consecutive threads read the SAME column of consecutive key rows
     // (a 1 KB row pitch would put all of them on one bank)
@@ -851,10 +863,10 @@ int query_self_attn(const void* q, const void* k, const void* v, void* out, int 
                     cudaStream_t st) {
     if (C != 256 || Q > 12 || n_head > 8 || B < 1) return 1;
     if (dt == VRD_BF16)
-        query_self_attn_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+        launch_k(query_self_attn_kernel<__nv_bfloat16>, dim3(B), dim3(256), 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
                                                                  (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ld, Q, n_head);
     else
-        query_self_attn_kernel<float><<<B, 256, 0, st>>>((const float*)q, (const float*)k, (const float*)v, (float*)out, ld, Q, n_head);
+        launch_k(query_self_attn_kernel<float>, dim3(B), dim3(256), 0, st, (const float*)q, (const float*)k, (const float*)v, (float*)out, ld, Q, n_head);
     return 0;
 }
 
@@ -868,6 +880,8 @@ template <typename T, int HS>
 __global__ void __launch_bounds__(256) query_cross_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                                const T* __restrict__ v, T* __restrict__ out, long long ld,
                                                                Lay lay, int Q, int n_head) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int D = 256, MAXQ = 12, DPL = HS / 32;
     __shared__ __align__(16) float sq[MAXQ][D];
     const int pair = blockIdx.x;
@@ -945,7 +959,7 @@ int query_cross_attn(const void* q, const void* k, const void* v, void* out, int
     if (C != 256 || Q > 12) return 1;
     const int hs = C / n_head;
 #define LAUNCH(T, HS) \
-    query_cross_attn_kernel<T, HS><<<lay.B, 256, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay, Q, n_head)
+    launch_k(query_cross_attn_kernel<T, HS>, dim3(lay.B), dim3(256), 0, st, (const T*)q, (const T*)k, (const T*)v, (T*)out, ld, lay, Q, n_head)
     if (hs == 32) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 32); else LAUNCH(float, 32); }
     else if (hs == 64) { if (dt == VRD_BF16) LAUNCH(__nv_bfloat16, 64); else LAUNCH(float, 64); }
     else return 1;

@@ -131,6 +131,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     float* xch = (float*)(tmem_slot + 4);      // [3][NSPLIT][FA_BM]: partial row maxima (two block parities) and row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < FA_SLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); }
@@ -147,6 +148,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + FA_TM_O;
+    pdl_wait();                             // q / k / v and the tile list are the previous kernels' outputs: nothing of them was touched above
 
     uint32_t g = 0, n_item = 0;             // key blocks / items processed so far: they carry the barrier phases
 
@@ -372,7 +374,7 @@ int fa_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& m
     const int n_items = lay.n_tiles * n_head;
     const int max_ctas = 2 * device_sm_count();
     const int grid = n_items < max_ctas ? n_items : max_ctas;
-    kern<<<grid, (4 * NSPLIT + 2) * 32, FA_SMEM, st>>>(mq, mk, mv, (__nv_bfloat16*)out, ld, lay, n_head);
+    launch_k(kern, dim3(grid), dim3((4 * NSPLIT + 2) * 32), FA_SMEM, st, mq, mk, mv, (__nv_bfloat16*)out, ld, lay, n_head);
     return 0;
 }
 

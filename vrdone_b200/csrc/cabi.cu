@@ -29,9 +29,31 @@ Lay make_lay(const int32_t* row_seq, const int32_t* seqinfo, int R, int B) {
 }
 }  // namespace
 
+VrdOptions& vrd_options() {
+    static VrdOptions o = [] {
+        VrdOptions d;
+        d.pdl = (getenv("VRD_PDL") != nullptr && atoi(getenv("VRD_PDL")) == 0) ? 0 : 1;
+        d.dw_cfg = getenv("VRD_DW_CFG") != nullptr ? atoi(getenv("VRD_DW_CFG")) : 2;
+        return d;
+    }();
+    return o;
+}
+
 extern "C" {
 
 int vrd_abi_version(void) { return VRD_ABI_VERSION; }
+
+int vrd_set_option(const char* name, int value) {
+    if (name == nullptr) return -1;
+    VrdOptions& o = vrd_options();
+    int* slot = nullptr;
+    if (strcmp(name, "pdl") == 0) slot = &o.pdl;
+    else if (strcmp(name, "dw_cfg") == 0) slot = &o.dw_cfg;
+    if (slot == nullptr) { fail("vrd_set_option: unknown option"); return -1; }
+    const int old = *slot;
+    *slot = value;
+    return old;
+}
 const char* vrd_last_error(void) { return t_err; }
 
 int vrd_device_arch(void) {

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdlib>
+#include <utility>
 
 #define VRD_F32 0
 #define VRD_BF16 1
@@ -31,6 +33,37 @@ inline int device_sm_count() {
     if (dev < 0 || dev >= 64) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
     if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
     return sms[dev];
+}
+
+// ---- programmatic dependent launch (PDL).  Every kernel launched through launch_k() starts with pdl_trigger(); ... pdl_wait():
+// the trigger lets the NEXT kernel of the stream be launched (its CTAs become resident as SM resources free up and run their
+// prologue) while this one still runs; pdl_wait() blocks until the PREVIOUS kernel has completed and its memory is visible, and
+// must precede the first access to anything an earlier kernel wrote.  Launch latency and prologues (barrier init, TMEM
+// allocation, parameter loads) then overlap the previous kernel's tail: the forward is ~2400 short launches per step.
+// Without the launch attribute (VRD_PDL=0, or a plain <<<>>> launch) both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Experiment switches shared by the launchers (defined in cabi.cu): initialised from the environment on first use
+// (VRD_PDL, VRD_DW_CFG), changeable at run time through vrd_set_option() so that one process can A/B them on the same inputs.
+struct VrdOptions {
+    int pdl;        // 1: kernels are launched with programmatic stream serialization (default), 0: plain stream order
+    int dw_cfg;     // dwconv_ln_tile variant (see rows.cu)
+};
+VrdOptions& vrd_options();
+inline bool pdl_enabled() { return vrd_options().pdl != 0; }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // One pyramid level of the varlen row layout (see vrdone_b200/layout.py).

@@ -253,6 +253,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, EpiArgs e, int K,
                     int taps, int block_n, int stages, int split) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_trigger();                                    // the next kernel of the stream may be launched (it waits for this one in its own pdl_wait)
     // carve: stages of A, stages of W, epilogue staging boxes, barriers, bias / correction vectors
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int w_stage_bytes = (block_n / CG) * BLOCK_K * 2;       // each CTA of a pair holds block_n / CG rows of the W tile
@@ -279,6 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // A_hi W_hi + A_lo W_hi + A_hi W_lo (the 3 x bf16 product with fp32 accumulation; the lo x lo term, 2^-16 relative, is dropped)
     const int num_kb = taps * kb_per_tap * (split ? 3 : 1);
 
+    // weights only (bias, pad-column correction: constant during a forward), so this may run before pdl_wait()
     for (int i = threadIdx.x; i < e.N; i += NUM_THREADS) {
         s_bias[i] = (e.bias != nullptr) ? e.bias[i] : 0.f;
         s_corr[i] = (e.corr != nullptr) ? e.corr[i] : 0.f;
@@ -301,6 +303,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation, bias staging) overlapped the previous kernel's tail; activations, residuals
+    // and layout arrays are only touched from here on
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -637,7 +642,11 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     const int max_groups = num_sms / cg;
     const int grid = cg * (n_tiles < max_groups ? n_tiles : max_groups);
     if (cg == 1) {
-        gemm_tcgen05_kernel<1><<<grid, NUM_THREADS, smem, st>>>(map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages, split);
+        if (launch_k(gemm_tcgen05_kernel<1>, dim3(grid), dim3(NUM_THREADS), smem, st, map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n,
+                     stages, split) != cudaSuccess) {
+            snprintf(g_err, sizeof g_err, "launch of gemm_tcgen05_kernel<1> failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return 1;
+        }
         return 0;
     }
     cudaLaunchConfig_t cfg = {};
@@ -645,13 +654,15 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages, split) != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "cluster launch of gemm_tcgen05_kernel<2> failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 1;
@@ -667,6 +678,8 @@ namespace {
 // x [rows, taps * K] fp32 (pitch ldx) -> out [rows, taps * 2K] bf16: per tap [hi(K) | lo(K)], hi = bf16(x), lo = bf16(x - hi)
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, long long ldx, long long rows, int K, int taps,
                                                          __nv_bfloat16* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int per_row = taps * K / 4;
     const long long total = rows * per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -718,8 +731,8 @@ int gemm_tcgen05_f32split(const GemmArgs& g, cudaStream_t st) {
     __nv_bfloat16* w2 = (__nv_bfloat16*)scratch_get(sw[dev], w_bytes);
     if (a2 == nullptr || w2 == nullptr) { snprintf(g_err, sizeof g_err, "gemm_tcgen05_f32split: scratch allocation failed"); return 2; }
     const int sms = device_sm_count();
-    split_bf16_kernel<<<sms * 8, 256, 0, st>>>((const float*)g.A, g.lda, g.M, g.K, 1, a2);
-    split_bf16_kernel<<<sms * 2, 256, 0, st>>>((const float*)g.W, (long long)g.taps * g.K, g.N, g.K, g.taps, w2);
+    launch_k(split_bf16_kernel, dim3(sms * 8), dim3(256), 0, st, (const float*)g.A, g.lda, (long long)g.M, g.K, 1, a2);
+    launch_k(split_bf16_kernel, dim3(sms * 2), dim3(256), 0, st, (const float*)g.W, (long long)g.taps * g.K, (long long)g.N, g.K, g.taps, w2);
     GemmArgs h = g;
     h.A = a2; h.lda = 2LL * g.K; h.W = w2;
     return gemm_tcgen05_launch(h, st, 1) == 0 ? 0 : 2;

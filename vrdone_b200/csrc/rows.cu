@@ -305,6 +305,8 @@ template <typename TI, typename TO, int NCH>
 __global__ void layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, TO* __restrict__ out, long long ldo, int rows, int relu,
                                  const int* __restrict__ row_seq, int R) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * LN_RPW;
     if (row0 >= rows) return;
@@ -338,9 +340,9 @@ static int layernorm_t(const void* x, long long ldx, const float* g, const float
                        int C, int relu, const int* row_seq, int R, cudaStream_t st) {
     const int grid = (rows + WARPS * LN_RPW - 1) / (WARPS * LN_RPW);
     if (C == 512)
-        layernorm_kernel<TI, TO, 4><<<grid, WARPS * 32, 0, st>>>((const TI*)x, ldx, g, b, (TO*)out, ldo, rows, relu, row_seq, R);
+        launch_k(layernorm_kernel<TI, TO, 4>, dim3(grid), dim3(WARPS * 32), 0, st, (const TI*)x, ldx, g, b, (TO*)out, ldo, rows, relu, row_seq, R);
     else if (C == 256)
-        layernorm_kernel<TI, TO, 2><<<grid, WARPS * 32, 0, st>>>((const TI*)x, ldx, g, b, (TO*)out, ldo, rows, relu, row_seq, R);
+        launch_k(layernorm_kernel<TI, TO, 2>, dim3(grid), dim3(WARPS * 32), 0, st, (const TI*)x, ldx, g, b, (TO*)out, ldo, rows, relu, row_seq, R);
     else
         return 1;
     return 0;
@@ -437,6 +439,8 @@ __global__ void small_conv_kernel(const float* __restrict__ x, int cin, const fl
                                   const float* __restrict__ bias, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, int relu, TO* __restrict__ out, long long ldo, int rows,
                                   const int* __restrict__ row_seq, int R) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int N = NCH * 128;
     const int lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * SC_RPW;
@@ -493,9 +497,9 @@ int small_conv(const float* x, int cin, const float* wt, const float* bias, cons
     if (N != 512 || cin > 8) return 1;
     const int grid = (rows + WARPS * SC_RPW - 1) / (WARPS * SC_RPW);
     if (odt == VRD_BF16)
-        small_conv_kernel<__nv_bfloat16, 4><<<grid, WARPS * 32, 0, st>>>(x, cin, wt, bias, g, b, relu, (__nv_bfloat16*)out, ldo, rows, row_seq, R);
+        launch_k(small_conv_kernel<__nv_bfloat16, 4>, dim3(grid), dim3(WARPS * 32), 0, st, x, cin, wt, bias, g, b, relu, (__nv_bfloat16*)out, ldo, rows, row_seq, R);
     else
-        small_conv_kernel<float, 4><<<grid, WARPS * 32, 0, st>>>(x, cin, wt, bias, g, b, relu, (float*)out, ldo, rows, row_seq, R);
+        launch_k(small_conv_kernel<float, 4>, dim3(grid), dim3(WARPS * 32), 0, st, x, cin, wt, bias, g, b, relu, (float*)out, ldo, rows, row_seq, R);
     return 0;
 }
 
@@ -527,6 +531,8 @@ template <typename TI, typename TO, int NCH, int STRIDE, int NB, int PREMASK>
 __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_kernel(const TI* __restrict__ x, long long ldx, Lay lin, Lay lout,
                                                                  const float* __restrict__ pre_g, const float* __restrict__ pre_b,
                                                                  DwBranches br, int streams) {
+    pdl_trigger();
+    pdl_wait();
     constexpr bool ANY_PRE = PREMASK != 0;
     constexpr bool ANY_RAW = PREMASK != ((1 << NB) - 1);
     constexpr int C = NCH * 128;
@@ -701,6 +707,8 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
                                                                            const float* __restrict__ pre_g,
                                                                            const float* __restrict__ pre_b, DwBranches br,
                                                                            int total_rows) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NCH = 4, C = 512;
     constexpr int DWT_TILE = TILE, DWT_ROWS = TILE + 2, DWT_WARPS = NW, DWT_RPW = TILE / NW;
     constexpr bool ANY_PRE = PREMASK != 0;
@@ -960,6 +968,8 @@ __global__ void __launch_bounds__(NB * WPB * 32, 1) dwconv_ln_bw_kernel(const fl
                                                                          const float* __restrict__ pre_g,
                                                                          const float* __restrict__ pre_b, DwBranches br,
                                                                          int total_rows) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NCH = 4, C = 512;
     constexpr int DWT_ROWS = TILE + 2, NW = NB * WPB;
     constexpr int PAIRS_PER_WARP = TILE / 2 / WPB;
@@ -1152,13 +1162,291 @@ __global__ void __launch_bounds__(NB * WPB * 32, 1) dwconv_ln_bw_kernel(const fl
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// dwconv_ln_qr ("quarter-row warps", VRD_DW_CFG=4): same arithmetic per element as dwconv_ln_tile, different ownership.  ncu on
+// dwconv_ln_tile: the shared-memory / L1 data pipe is 63-72 % busy and more than half of its ~280 wavefronts per row are the
+// per-channel parameters (three conv taps, LayerNorm gamma / beta of three branches) re-read for every two rows, the rest is the
+// stencil window re-read per branch.  Here a lane owns FOUR channels (a warp: one 128-channel quarter of a row), so the parameters
+// of ALL branches fit in registers (20 per branch) for the lifetime of the persistent CTA, and a warp walks DOWN a strip of
+// QR_S rows with the stencil window in registers: every staged row is read once for the pre-LayerNorm statistics and once for the
+// window (~70 wavefronts per row instead of ~280).  The price is that a LayerNorm row is spread over four warps: the post-conv
+// statistics (sum and sum of squares per row and branch, one pass) of two rows at a time are reduced inside each warp through a
+// transposition in shared memory (12 conflict-free stores, then 24 lanes add 16 values each), exchanged between the four warps
+// behind a 128-thread named barrier, finished by one lane per (row, branch) and broadcast by shuffles.  The four warps of a group form an independent pipeline (own TMA double
+// buffer, own mbarriers, own named barrier): NG groups per CTA drift out of phase and cover each other's dependent chains
+// (TMA wait -> statistics -> barrier -> conv -> exchange -> normalise), which dwconv_ln_tile needed two CTAs per SM for.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int QR_S = 8;                 // output rows per strip
+constexpr int QR_ROWS = QR_S + 2;       // staged rows per strip (one halo row on either side)
+constexpr int QR_NG = 4;                // groups of four warps per CTA
+
+constexpr int qr_smem_bytes(int ng) {
+    // per group: two TMA buffers of QR_ROWS rows, (mean, rstd) and the row codes of a strip (double-buffered), the exchange
+    // buffer of two batches (12 values x 4 quarters each), two mbarriers, four per-warp transposition scratches of 12 x 36 floats
+    return ng * (2 * QR_ROWS * 512 * 4 + 2 * QR_ROWS * 8 + 2 * QR_ROWS * 4 + 2 * 12 * 4 * 4 + 16 + 4 * 12 * 36 * 4) + 128;
+}
+
+template <typename TO, int NB, int PREMASK, int NG>
+__global__ void __launch_bounds__(NG * 128, 1) dwconv_ln_qr_kernel(const float* __restrict__ x, Lay lay,
+                                                                    const float* __restrict__ pre_g,
+                                                                    const float* __restrict__ pre_b, DwBranches br,
+                                                                    int total_rows) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int C = 512;
+    constexpr bool ANY_PRE = PREMASK != 0;
+    constexpr bool ANY_RAW = PREMASK != ((1 << NB) - 1);
+    constexpr int NV = 2 * NB * 2;                                // values exchanged per batch of two rows
+    extern __shared__ __align__(128) uint8_t qr_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = warp >> 2, wq = warp & 3;                       // group, channel quarter
+    const int gt = threadIdx.x & 127;                             // thread index inside the group
+    float* s_rows = reinterpret_cast<float*>(qr_smem) + (size_t)g * 2 * QR_ROWS * C;                  // [2][QR_ROWS][C]
+    constexpr int AUX = 2 * QR_ROWS * 8 + 2 * QR_ROWS * 4 + 2 * 12 * 4 * 4 + 16 + 4 * 12 * 36 * 4;
+    uint8_t* aux = qr_smem + (size_t)NG * 2 * QR_ROWS * C * 4 + (size_t)g * AUX;
+    float2* s_stats = reinterpret_cast<float2*>(aux);                                               // [2][QR_ROWS]
+    int* s_code = reinterpret_cast<int*>(aux + 2 * QR_ROWS * 8);                                     // [2][QR_ROWS]
+    float* s_part = reinterpret_cast<float*>(aux + 2 * QR_ROWS * 8 + 2 * QR_ROWS * 4);               // [2][12][4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 2 * QR_ROWS * 8 + 2 * QR_ROWS * 4 + 2 * 12 * 4 * 4);   // [2]
+    float* s_scr = reinterpret_cast<float*>(aux + 2 * QR_ROWS * 8 + 2 * QR_ROWS * 4 + 2 * 12 * 4 * 4 + 16) + wq * 12 * 36;   // [12][36], this warp's
+    const uint32_t bar_u = (uint32_t)__cvta_generic_to_shared(bars);
+    const uint32_t rows_u = (uint32_t)__cvta_generic_to_shared(s_rows);
+    const int n_strips = total_rows / QR_S;
+    const int strip0 = blockIdx.x * NG + g, strip_step = gridDim.x * NG;
+
+    auto issue = [&](int strip, int buf) {                         // one thread of the group: stage the rows of `strip`
+        const int r0 = strip * QR_S;
+        const int lo = max(r0 - 1, 0), hi = min(r0 + QR_S + 1, total_rows);
+        const uint32_t bytes = (uint32_t)(hi - lo) * C * 4;
+        const uint32_t b = bar_u + 8 * buf;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(rows_u + (uint32_t)((buf * QR_ROWS + (lo - (r0 - 1))) * C * 4)),
+                       "l"(x + (long long)lo * C), "r"(bytes), "r"(b) : "memory");
+    };
+    if (gt == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (strip0 < n_strips) issue(strip0, 0);
+    }
+    // the parameters of every branch for this lane's four channels, resident in registers
+    const int c0 = wq * 128 + lane * 4;
+    f2 w0[NB][2], w1[NB][2], w2[NB][2], gm[NB][2], bt[NB][2], pg[2], pb[2];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        f2_ldg(br.w[b] + c0, w0[b]); f2_ldg(br.w[b] + C + c0, w1[b]); f2_ldg(br.w[b] + 2 * C + c0, w2[b]);
+        f2_ldg(br.g[b] + c0, gm[b]); f2_ldg(br.b[b] + c0, bt[b]);
+    }
+    if constexpr (ANY_PRE) { f2_ldg(pre_g + c0, pg); f2_ldg(pre_b + c0, pb); }
+    else { pg[0] = pg[1] = pb[0] = pb[1] = 0ull; }
+    __syncthreads();                                               // barriers initialised before anyone polls them
+
+    int it = 0;
+    for (int strip = strip0; strip < n_strips; strip += strip_step, ++it) {
+        const int buf = it & 1;
+        const int r0 = strip * QR_S;
+        const int lo = max(r0 - 1, 0), hi = min(r0 + QR_S + 1, total_rows);
+        // every warp of the group has passed the last exchange barrier of the previous strip: its rows (buffer buf ^ 1) are dead
+        if (gt == 0 && strip + strip_step < n_strips) issue(strip + strip_step, buf ^ 1);
+        {
+            const uint32_t parity = (it >> 1) & 1;
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar_u + 8 * buf), "r"(parity) : "memory");
+            }
+        }
+        const uint32_t sx_u = rows_u + (uint32_t)(buf * QR_ROWS * C * 4);
+        float2* stats = s_stats + buf * QR_ROWS;
+        int* code = s_code + buf * QR_ROWS;
+        // ---- phase 1: row codes (bit 0: the row belongs to a pair, bit 1: that pair has a first pad column) and the
+        //      pre-LayerNorm statistics of every staged row (two-pass, as dwconv_ln_tile)
+        if (wq == 0 && lane < QR_ROWS) {
+            const int p = r0 - 1 + lane;
+            int cd = 0;
+            if (p >= lo && p < hi) {
+                const int seq = lay.row_seq[p % lay.R];
+                if (seq >= 0) cd = 1 | (lay.seqinfo[seq].z != 0 ? 2 : 0);
+            }
+            code[lane] = cd;
+        }
+        if constexpr (ANY_PRE) {
+            f2 v[3][4][2];
+            bool on[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int i = wq + 4 * u;
+                const int p = r0 - 1 + i;
+                on[u] = i < QR_ROWS && p >= lo && p < hi;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (on[u]) f2_lds(sx_u + (uint32_t)i * C * 4 + j * 512 + lane * 16, v[u][j]);
+                    else v[u][j][0] = v[u][j][1] = 0ull;
+                }
+            }
+            float mean[3], rstd[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                f2 sm = f2_add(v[u][0][0], v[u][0][1]);
+#pragma unroll
+                for (int j = 1; j < 4; ++j) sm = f2_add(sm, f2_add(v[u][j][0], v[u][j][1]));
+                mean[u] = f2_hsum(sm);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < 3; ++u) mean[u] += __shfl_xor_sync(FULL_MASK, mean[u], o);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                mean[u] *= (1.0f / C);
+                const f2 mm = f2_splat(mean[u]);
+                f2 q = 0ull;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) { const f2 d = f2_sub(v[u][j][e], mm); q = f2_fma(d, d, q); }
+                rstd[u] = f2_hsum(q);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < 3; ++u) rstd[u] += __shfl_xor_sync(FULL_MASK, rstd[u], o);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int i = wq + 4 * u;
+                if (lane == 0 && i < QR_ROWS) stats[i] = make_float2(mean[u], rsqrtf(rstd[u] * (1.0f / C) + VRD_EPS));
+            }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+
+        // ---- phase 2: walk down the strip, two output rows per batch (fully unrolled: the window rotates by renaming)
+        f2 wn[QR_ROWS][2], wr[QR_ROWS][2];                        // staged rows of the strip, this lane's channels: normalised / raw
+        int wc[QR_ROWS];
+        auto fetch = [&](int i) {
+            const int cd = code[i];
+            wc[i] = cd;
+            // rows outside a pair (separators, padding, rows past the ends) contribute zeros: multiply by the row's 0 / 1 flag
+            // instead of branching (the staged bytes are finite: separator rows are zero rows, out-of-range rows are never read)
+            f2 raw[2] = {0ull, 0ull};
+            if (cd & 1) f2_lds(sx_u + (uint32_t)(i * C * 4 + c0 * 4), raw);
+            wr[i][0] = raw[0]; wr[i][1] = raw[1];
+            wn[i][0] = wn[i][1] = 0ull;
+            if constexpr (ANY_PRE) {
+                if (cd & 1) {
+                    const float2 st = stats[i];
+                    const f2 mm = f2_splat(st.x), rs = f2_splat(st.y);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) wn[i][e] = f2_fma(f2_mul(f2_sub(raw[e], mm), rs), pg[e], pb[e]);
+                }
+            }
+        };
+        TO* optr[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) optr[b] = (TO*)br.out[b] + (long long)r0 * br.ldo[b] + c0;
+        fetch(0);
+        fetch(1);
+#pragma unroll
+        for (int k = 0; k < QR_S / 2; ++k) {
+            fetch(2 * k + 2);
+            fetch(2 * k + 3);
+            f2 y[2][NB][2];
+            bool live[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = 2 * k + u;                           // window rows i, i + 1, i + 2; output row = staged row i + 1
+                live[u] = (wc[i + 1] & 1) != 0;
+                // tap +1 of the last row of a padded pair reads the first pad column, whose LN_pre value is the bias
+                const bool hib = ANY_PRE && live[u] && (wc[i + 2] & 1) == 0 && (wc[i + 1] & 2) != 0;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const bool pre = (PREMASK >> b) & 1;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const f2 a0 = pre ? wn[i][e] : wr[i][e];
+                        const f2 a1 = pre ? wn[i + 1][e] : wr[i + 1][e];
+                        f2 a2 = pre ? wn[i + 2][e] : wr[i + 2][e];
+                        if (pre && hib) a2 = pb[e];
+                        y[u][b][e] = f2_fma(a2, w2[b][e], f2_fma(a1, w1[b][e], f2_mul(a0, w0[b][e])));
+                    }
+                    s_scr[((u * NB + b) * 2) * 36 + lane] = f2_hsum(f2_add(y[u][b][0], y[u][b][1]));
+                    s_scr[((u * NB + b) * 2 + 1) * 36 + lane] = f2_hsum(f2_fma(y[u][b][1], y[u][b][1], f2_mul(y[u][b][0], y[u][b][0])));
+                }
+            }
+            __syncwarp();
+            float* part = s_part + (k & 1) * 48;
+            if (lane < 2 * NV) {                                   // lane = (value, half): 16 of the warp's 32 partial sums
+                const float4* q = reinterpret_cast<const float4*>(s_scr + (lane >> 1) * 36 + (lane & 1) * 16);
+                const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+                float t = (((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w))) +
+                          (((q2.x + q2.y) + (q2.z + q2.w)) + ((q3.x + q3.y) + (q3.z + q3.w)));
+                t += __shfl_xor_sync((2 * NV >= 32) ? FULL_MASK : ((1u << (2 * NV)) - 1u), t, 1);
+                if ((lane & 1) == 0) part[(lane >> 1) * 4 + wq] = t;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+            // lane j < 2 NB finishes (row u, branch b) = j: totals over the four quarters, mean and 1 / std (one-pass variance)
+            float mj = 0.f, nj = 0.f;                              // 1 / std and -mean / std
+            if (lane < 2 * NB) {
+                const float4 s1 = *reinterpret_cast<const float4*>(part + (2 * lane) * 4);
+                const float4 s2 = *reinterpret_cast<const float4*>(part + (2 * lane + 1) * 4);
+                const float mean = ((s1.x + s1.y) + (s1.z + s1.w)) * (1.0f / C);
+                const float var = fmaxf(((s2.x + s2.y) + (s2.z + s2.w)) * (1.0f / C) - mean * mean, 0.f);
+                mj = rsqrtf(var + VRD_EPS);
+                nj = -mean * mj;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                f2 rs[NB], ms[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    rs[b] = f2_splat(__shfl_sync(FULL_MASK, mj, u * NB + b));
+                    ms[b] = f2_splat(__shfl_sync(FULL_MASK, nj, u * NB + b));
+                }
+                if (live[u]) {                                     // warp-uniform
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        f2 o[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) o[e] = f2_fma(f2_fma(y[u][b][e], rs[b], ms[b]), gm[b][e], bt[b][e]);
+                        f2_stg(optr[b], o);
+                    }
+                } else {                                           // separator rows -> 0
+                    const f2 z[2] = {0ull, 0ull};
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) f2_stg(optr[b], z);
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) optr[b] += br.ldo[b];
+            }
+        }
+    }
+}
+
 template <typename TO>
 static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const float* pre_b, const DwBranches& br, int streams,
                           cudaStream_t st) {
     const int num_sms = device_sm_count();
     int mask = 0;
     for (int b = 0; b < br.n; ++b) mask |= (br.use_pre[b] ? 1 : 0) << b;
-    static const int cfg = getenv("VRD_DW_CFG") ? atoi(getenv("VRD_DW_CFG")) : 2;   // 0: 8 warps x 32 rows, 1: 16 x 32, 2: 2 CTAs/SM of 8 x 16, 3: branch warps
+    const int cfg = vrd_options().dw_cfg;   // 0: 8 warps x 32 rows, 1: 16 x 32, 2: 2 CTAs/SM of 8 x 16, 3: branch warps, 4: quarter-row warps
+    if (cfg == 4) {
+        const int total = streams * lay.R;
+        const int n_strips = total / QR_S;
+#define LAUNCH_QR(NB, MASK, NG) do { \
+        auto kern = dwconv_ln_qr_kernel<TO, NB, MASK, NG>; \
+        constexpr int smem = qr_smem_bytes(NG); \
+        static PerDeviceOnce once; \
+        if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1; \
+        const int need = (n_strips + NG - 1) / NG; \
+        launch_k(kern, dim3(need < num_sms ? need : num_sms), dim3(NG * 128), smem, st, x, lay, pre_g, pre_b, br, total); } while (0)
+        if (br.n == 3 && mask == 7) LAUNCH_QR(3, 7, QR_NG);
+        else if (br.n == 3 && mask == 3) LAUNCH_QR(3, 3, QR_NG);
+        else if (br.n == 2 && mask == 0) LAUNCH_QR(2, 0, QR_NG);
+        else if (br.n == 1 && mask == 1) LAUNCH_QR(1, 1, QR_NG);
+        else return 1;
+#undef LAUNCH_QR
+        return 0;
+    }
     if (cfg == 3) {
         constexpr int TILE = 32;
         const int total = streams * lay.R;
@@ -1169,7 +1457,7 @@ static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const flo
         constexpr int smem = dwt_smem_bytes(MASK != 0 && MASK != ((1 << NB) - 1), TILE); \
         static PerDeviceOnce once; \
         if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1; \
-        kern<<<grid, NB * WPB * 32, smem, st>>>(x, lay, pre_g, pre_b, br, total); } while (0)
+        launch_k(kern, dim3(grid), dim3(NB * WPB * 32), smem, st, x, lay, pre_g, pre_b, br, total); } while (0)
         if (br.n == 3 && mask == 7) LAUNCH_BW(3, 7, 4);
         else if (br.n == 3 && mask == 3) LAUNCH_BW(3, 3, 4);
         else if (br.n == 2 && mask == 0) LAUNCH_BW(2, 0, 8);
@@ -1188,7 +1476,7 @@ static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const flo
         constexpr int smem = dwt_smem_bytes(MASK != 0 && MASK != ((1 << NB) - 1), TILE); \
         static PerDeviceOnce once; \
         if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1; \
-        kern<<<grid, NW * 32, smem, st>>>(x, lay, pre_g, pre_b, br, total); } while (0)
+        launch_k(kern, dim3(grid), dim3(NW * 32), smem, st, x, lay, pre_g, pre_b, br, total); } while (0)
 #define LAUNCH(NB, MASK) do { if (cfg == 0) LAUNCH_NW(NB, MASK, 8, 32); else if (cfg == 1) LAUNCH_NW(NB, MASK, 16, 32); \
                                else LAUNCH_NW(NB, MASK, 8, 16); } while (0)
     if (br.n == 3 && mask == 7) LAUNCH(3, 7);
@@ -1209,7 +1497,7 @@ static int dwconv_ln_mask(const void* x, long long ldx, Lay lin, Lay lout, const
     const int runs = streams * ((lout.R + DW_RUN - 1) / DW_RUN);
     const int grid = (runs + DW_WARPS - 1) / DW_WARPS;
 #define LAUNCH(NB, MASK) \
-    dwconv_ln_kernel<TI, TO, NCH, STRIDE, NB, MASK><<<grid, DW_WARPS * 32, 0, st>>>((const TI*)x, ldx, lin, lout, pre_g, pre_b, br, streams)
+    launch_k(dwconv_ln_kernel<TI, TO, NCH, STRIDE, NB, MASK>, dim3(grid), dim3(DW_WARPS * 32), 0, st, (const TI*)x, ldx, lin, lout, pre_g, pre_b, br, streams)
     if (br.n == 3 && mask == 7) LAUNCH(3, 7);
     else if (br.n == 3 && mask == 3) LAUNCH(3, 3);
     else if (br.n == 2 && mask == 0) LAUNCH(2, 0);
@@ -1240,6 +1528,8 @@ int dwconv_ln(const void* x, int xdt, long long ldx, Lay lin, Lay lout, int stri
 template <int NCH>
 __global__ void maxpool_skip_kernel(const float* __restrict__ x, long long ldx, Lay lin, Lay lout, float* __restrict__ out,
                                     long long ldo) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (r >= lout.R) return;
@@ -1277,7 +1567,7 @@ __global__ void maxpool_skip_kernel(const float* __restrict__ x, long long ldx, 
 
 int maxpool_skip(const float* x, long long ldx, Lay lin, Lay lout, float* out, long long ldo, int C, cudaStream_t st) {
     if (C != 512) return 1;
-    maxpool_skip_kernel<4><<<(lout.R + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(x, ldx, lin, lout, out, ldo);
+    launch_k(maxpool_skip_kernel<4>, dim3((lout.R + WARPS - 1) / WARPS), dim3(WARPS * 32), 0, st, x, ldx, lin, lout, out, ldo);
     return 0;
 }
 
@@ -1288,6 +1578,8 @@ int maxpool_skip(const float* x, long long ldx, Lay lin, Lay lout, float* out, l
 __global__ void fpn_top_kernel(const float* __restrict__ x, long long ldx, Lay lay, const float* __restrict__ pre_g,
                                const float* __restrict__ pre_b, const float* __restrict__ wt, const float* __restrict__ g,
                                const float* __restrict__ b, float* __restrict__ out, long long ldo) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NCH = 4;
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -1344,7 +1636,7 @@ __global__ void fpn_top_kernel(const float* __restrict__ x, long long ldx, Lay l
 
 int fpn_top(const float* x, long long ldx, Lay lay, const float* pre_g, const float* pre_b, const float* wt, const float* g,
             const float* b, float* out, long long ldo, cudaStream_t st) {
-    fpn_top_kernel<<<(lay.R + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(x, ldx, lay, pre_g, pre_b, wt, g, b, out, ldo);
+    launch_k(fpn_top_kernel, dim3((lay.R + WARPS - 1) / WARPS), dim3(WARPS * 32), 0, st, x, ldx, lay, pre_g, pre_b, wt, g, b, out, ldo);
     return 0;
 }
 
@@ -1353,6 +1645,8 @@ __global__ void fpn_level_kernel(const float* __restrict__ cur, long long ldc, c
                                  Lay lay, Lay lup, const float* __restrict__ lat_g, const float* __restrict__ lat_b,
                                  const float* __restrict__ beta_up, const float* __restrict__ w, const float* __restrict__ g,
                                  const float* __restrict__ b, float* __restrict__ out, long long ldo) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NCH = 2;
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -1402,7 +1696,7 @@ __global__ void fpn_level_kernel(const float* __restrict__ cur, long long ldc, c
 int fpn_level(const float* cur, long long ldc, const float* yup, long long ldu, Lay lay, Lay lup, const float* lat_g,
               const float* lat_b, const float* beta_up, const float* w, const float* g, const float* b, float* out,
               long long ldo, cudaStream_t st) {
-    fpn_level_kernel<<<(lay.R + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(cur, ldc, yup, ldu, lay, lup, lat_g, lat_b, beta_up, w,
+    launch_k(fpn_level_kernel, dim3((lay.R + WARPS - 1) / WARPS), dim3(WARPS * 32), 0, st, cur, ldc, yup, ldu, lay, lup, lat_g, lat_b, beta_up, w,
                                                                            g, b, out, ldo);
     return 0;
 }
@@ -1411,6 +1705,8 @@ int fpn_level(const float* cur, long long ldc, const float* yup, long long ldu, 
 __global__ void mask_features_kernel(const float* __restrict__ y, long long ldy, Lay lay, const float* __restrict__ beta,
                                      const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                                      long long ldo) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NCH = 2;
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -1445,7 +1741,7 @@ __global__ void mask_features_kernel(const float* __restrict__ y, long long ldy,
 
 int mask_features(const float* y, long long ldy, Lay lay, const float* beta, const float* w, const float* bias, float* out,
                   long long ldo, cudaStream_t st) {
-    mask_features_kernel<<<(lay.R + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(y, ldy, lay, beta, w, bias, out, ldo);
+    launch_k(mask_features_kernel, dim3((lay.R + WARPS - 1) / WARPS), dim3(WARPS * 32), 0, st, y, ldy, lay, beta, w, bias, out, ldo);
     return 0;
 }
 
@@ -1457,6 +1753,8 @@ __global__ void query_ln_kernel(const float* __restrict__ x, long long ldx, cons
                                 const float* __restrict__ b, const float* __restrict__ pos, int Q, int nrows, int total_rows,
                                 const float* __restrict__ dw, const float* __restrict__ g2, const float* __restrict__ b2,
                                 TO* __restrict__ out, long long ldo) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NCH = 2;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -1495,9 +1793,9 @@ int query_ln(const float* x, long long ldx, const float* g, const float* b, cons
     if (C != 256) return 1;
     const int grid = (total_rows + WARPS - 1) / WARPS;
     if (odt == VRD_BF16)
-        query_ln_kernel<__nv_bfloat16><<<grid, WARPS * 32, 0, st>>>(x, ldx, g, b, pos, Q, nrows, total_rows, dw, g2, b2, (__nv_bfloat16*)out, ldo);
+        launch_k(query_ln_kernel<__nv_bfloat16>, dim3(grid), dim3(WARPS * 32), 0, st, x, ldx, g, b, pos, Q, nrows, total_rows, dw, g2, b2, (__nv_bfloat16*)out, ldo);
     else
-        query_ln_kernel<float><<<grid, WARPS * 32, 0, st>>>(x, ldx, g, b, pos, Q, nrows, total_rows, dw, g2, b2, (float*)out, ldo);
+        launch_k(query_ln_kernel<float>, dim3(grid), dim3(WARPS * 32), 0, st, x, ldx, g, b, pos, Q, nrows, total_rows, dw, g2, b2, (float*)out, ldo);
     return 0;
 }
 
@@ -1508,6 +1806,8 @@ int query_ln(const float* x, long long ldx, const float* g, const float* b, cons
 // sigmoid(logit) > 0.5 evaluated in fp32 exactly as the reference does (maskvrd.py:287), NOT logit > 0.
 __global__ void mask_logits_kernel(const float* __restrict__ me, long long ldm, const float* __restrict__ mf, long long ldf,
                                    Lay lay, int Q, float* __restrict__ masks, long long ldk, int* __restrict__ first_last) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NCH = 2;
     constexpr int MAXQ = 16;
     __shared__ int s_first[MAXQ], s_last[MAXQ];
@@ -1550,13 +1850,15 @@ __global__ void mask_logits_kernel(const float* __restrict__ me, long long ldm, 
 int mask_logits(const float* me, long long ldm, const float* mf, long long ldf, Lay lay, int Q, float* masks, long long ldk,
                 int* first_last, cudaStream_t st) {
     if (Q > 16) return 1;
-    mask_logits_kernel<<<lay.B, WARPS * 32, 0, st>>>(me, ldm, mf, ldf, lay, Q, masks, ldk, first_last);
+    launch_k(mask_logits_kernel, dim3(lay.B), dim3(WARPS * 32), 0, st, me, ldm, mf, ldf, lay, Q, masks, ldk, first_last);
     return 0;
 }
 
 // One warp per (pair, query): softmax over n_cls logits, then top-k of classes 1..n_cls-1 (ties -> lower class id).
 __global__ void softmax_topk_kernel(const float* __restrict__ logits, long long ldl, int nrows, int n_cls, int topk,
                                     float* __restrict__ scores, int* __restrict__ ids) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int PER = 8;   // up to 256 classes
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -1606,7 +1908,7 @@ __global__ void softmax_topk_kernel(const float* __restrict__ logits, long long 
 
 int softmax_topk(const float* logits, long long ldl, int nrows, int n_cls, int topk, float* scores, int* ids, cudaStream_t st) {
     if (n_cls > 256 || topk >= n_cls) return 1;
-    softmax_topk_kernel<<<(nrows + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(logits, ldl, nrows, n_cls, topk, scores, ids);
+    launch_k(softmax_topk_kernel, dim3((nrows + WARPS - 1) / WARPS), dim3(WARPS * 32), 0, st, logits, ldl, nrows, n_cls, topk, scores, ids);
     return 0;
 }
 

@@ -22,6 +22,7 @@ _vp, _i32, _i64, _f32p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p
 _SIGNATURES = {
     "vrd_abi_version": [],
     "vrd_device_arch": [],
+    "vrd_set_option": [C.c_char_p, _i32],
     "vrd_h2d_pairs": [_vp, _vp, _vp, _vp, _i32, _vp],
     "vrd_merge_layout": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "vrd_upload": [_vp, _vp, _i64, _vp],
@@ -164,6 +165,13 @@ class CudaOps:
         self._last_tag = None
         self._stream_handle = C.c_void_p(0)
         self.bind_stream()
+
+    def set_option(self, name: str, value: int) -> int:
+        """Experiment switches of the launchers ("pdl", "dw_cfg"); returns the previous value."""
+        old = self.lib.vrd_set_option(name.encode(), int(value))
+        if old < 0:
+            raise ValueError(f"vrd_set_option: unknown option {name!r}")
+        return old
 
     # -- per-launch CUDA-event timing (bench.py roofline pass) --------------------------------------------------------
     def start_timing(self):

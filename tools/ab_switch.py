@@ -45,8 +45,10 @@ def timed(reps=2):
 
 run_once()
 ops = model._ops
-configs = [("base pdl=0 dw=2", {"pdl": 0, "dw_cfg": 2}), ("pdl=1 dw=2", {"pdl": 1, "dw_cfg": 2}), ("pdl=1 dw=4", {"pdl": 1, "dw_cfg": 4}),
-           ("pdl=0 dw=4", {"pdl": 0, "dw_cfg": 4})]
+configs = [("base: spec=0 pdl=0 dw=2", {"gemm_spec": 0, "pdl": 0, "dw_cfg": 2}), ("spec=1", {"gemm_spec": 1, "pdl": 0, "dw_cfg": 2}),
+           ("spec=1 pdl=1", {"gemm_spec": 1, "pdl": 1, "dw_cfg": 2}), ("spec=1 dw=4", {"gemm_spec": 1, "pdl": 0, "dw_cfg": 4})]
+if len(sys.argv) > 3 and sys.argv[3] == "short":
+    configs = configs[:2]
 res = {name: [] for name, _ in configs}
 ref = None
 for r in range(rounds):
@@ -56,15 +58,16 @@ for r in range(rounds):
         run_once()
         res[name].append(round(timed(), 3))
 out = {"pairs": pairs, "videos": order, "ms_per_pass": res, "best": {k: min(v) for k, v in res.items()}}
-# chunk size: L2 residency against launch count
-ops.set_option("pdl", 1)
+ops.set_option("pdl", 0)
 ops.set_option("dw_cfg", 2)
-mr = {}
-for rows in (196608, 98304, 49152, 37888, 24576):
-    model.max_rows = rows
-    run_once()
-    mr[rows] = round(min(timed(), timed()), 3)
-out["max_rows_ms"] = mr
+# the specialised GEMM epilogues do the same arithmetic: bit-identical logits
+outs = {}
+for sp in (0, 1):
+    ops.set_option("gemm_spec", sp)
+    r = model.run_network(vids[0][0], vids[0][1], model.topk)
+    torch.cuda.synchronize()
+    outs[sp] = r["logits"].float().clone()
+out["gemm_spec_bit_identical"] = bool(torch.equal(outs[0], outs[1]))
 # numerical agreement of the two dwconv variants on the first video
 model.max_rows = 196608
 outs = {}

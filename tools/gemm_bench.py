@@ -13,6 +13,7 @@ shapes = [  # (name, N, K, taps, res, out dtype, act)
     ("fuse0 1024->512 gelu bf16", 512, 1024, 1, 0, torch.bfloat16, 2),
     ("qkv 512->512 bf16", 512, 512, 1, 0, torch.bfloat16, 0),
     ("proj 512->512 +res f32", 512, 512, 1, 1, torch.float32, 0),
+    ("proj 512->512 +res +res2 f32", 512, 512, 1, 2, torch.float32, 0),
     ("mlp0 512->2048 gelu bf16", 2048, 512, 1, 0, torch.bfloat16, 2),
     ("mlp3 2048->512 +res f32", 512, 2048, 1, 1, torch.float32, 0),
     ("lat 512->256 f32", 256, 512, 1, 0, torch.float32, 0),
@@ -24,19 +25,20 @@ for name, N, K, taps, res, odt, act in shapes:
     w = (torch.randn(N, taps * K, device="cuda") * K ** -0.5).to(torch.bfloat16)
     bias = torch.randn(N, device="cuda")
     r1 = torch.randn(M, N, device="cuda") if res else None
+    r2 = torch.randn(M, N, device="cuda") if res == 2 else None
     out = torch.empty(M, N, dtype=odt, device="cuda")
     for _ in range(3):
-        ops.gemm(a, w, out, bias=bias, taps=taps, act=act, res1=r1)
+        ops.gemm(a, w, out, bias=bias, taps=taps, act=act, res1=r1, res2=r2)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 10
     e0.record()
     for _ in range(n):
-        ops.gemm(a, w, out, bias=bias, taps=taps, act=act, res1=r1)
+        ops.gemm(a, w, out, bias=bias, taps=taps, act=act, res1=r1, res2=r2)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     fl = 2.0 * M * N * K * taps
-    by = M * K * 2 + M * N * out.element_size() + (M * N * 4 if res else 0)
+    by = M * K * 2 + M * N * out.element_size() + M * N * 4 * res
     print(f"{name:28s} {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s  {by/ms/1e6:8.1f} GB/s (compulsory)")
-    del a, w, out, r1
+    del a, w, out, r1, r2

@@ -32,8 +32,9 @@ Lay make_lay(const int32_t* row_seq, const int32_t* seqinfo, int R, int B) {
 VrdOptions& vrd_options() {
     static VrdOptions o = [] {
         VrdOptions d;
-        d.pdl = (getenv("VRD_PDL") != nullptr && atoi(getenv("VRD_PDL")) == 0) ? 0 : 1;
+        d.pdl = (getenv("VRD_PDL") != nullptr && atoi(getenv("VRD_PDL")) != 0) ? 1 : 0;   // measured slower: off by default
         d.dw_cfg = getenv("VRD_DW_CFG") != nullptr ? atoi(getenv("VRD_DW_CFG")) : 2;
+        d.gemm_spec = (getenv("VRD_GEMM_SPEC") != nullptr && atoi(getenv("VRD_GEMM_SPEC")) == 0) ? 0 : 1;
         return d;
     }();
     return o;
@@ -49,6 +50,7 @@ int vrd_set_option(const char* name, int value) {
     int* slot = nullptr;
     if (strcmp(name, "pdl") == 0) slot = &o.pdl;
     else if (strcmp(name, "dw_cfg") == 0) slot = &o.dw_cfg;
+    else if (strcmp(name, "gemm_spec") == 0) slot = &o.gemm_spec;
     if (slot == nullptr) { fail("vrd_set_option: unknown option"); return -1; }
     const int old = *slot;
     *slot = value;

@@ -48,6 +48,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 struct VrdOptions {
     int pdl;        // 1: kernels are launched with programmatic stream serialization (default), 0: plain stream order
     int dw_cfg;     // dwconv_ln_tile variant (see rows.cu)
+    int gemm_spec;  // 1: specialised tcgen05 GEMM epilogues (default), 0: the generic run-time-flag epilogue for every launch
 };
 VrdOptions& vrd_options();
 inline bool pdl_enabled() { return vrd_options().pdl != 0; }

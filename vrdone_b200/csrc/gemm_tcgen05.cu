@@ -237,7 +237,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int m) {
 struct EpiArgs {
     const float* bias; int out_dtype;
     int M, N, act, has_res;
-    const float* res2; long long ldr2;      // second residual: row-strided loads (only the SOS output projection uses it)
+    const float* res2; long long ldr2;      // second residual (only the SOS output projection uses it): boxes through map_res2, like res1
     const float* corr; const int* row_seq; const int4* seqinfo; int R;
     int wide;                               // bf16 output without residual: [32 x 64] store boxes (map in the map_res slot)
     int dbg;                                // timing experiments only (wrong results): 1 = no TMA stores, 2 = nothing after the TMEM load
@@ -247,11 +247,20 @@ struct EpiArgs {
 // tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A but only HALF of the W tile, and keeps its 128 accumulator
 // rows in its own TMEM, so the shared-memory fill per FLOP (the L2 -> SM traffic that bounds the K = 512 GEMMs) drops by a third.
 // Only the leader CTA (rank 0) issues MMAs; its commits arrive on the barriers of both CTAs.
-template <int CG>
+// MODE: the epilogue's feature flags are run-time values in EPI_GENERIC and compile-time constants in the specialised modes (the
+// same arithmetic on the same registers: results are bit-identical).  ncu on the generic epilogue of a K = 512 GEMM: 208 executed
+// instructions per 32-column chunk, of which 32 FADD + 16 F2FP + 8 LDS + 4 STS + 1 LDTM do the work and ~120 are LDC / ISETP / BRA /
+// BSSY chains re-deciding the flags (warp cycles per issued instruction 10-14: two epilogue warps per scheduler hide nothing), so
+// the epilogue, not the tensor pipe, paced these GEMMs.  BN != 0 fixes the tile width (the chunk loop unrolls).
+enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_F32_RES = 3 };
+
+template <int CG, int MODE, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, EpiArgs e, int K,
-                    int taps, int block_n, int stages, int split) {
+                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+                    const __grid_constant__ CUtensorMap map_res2, EpiArgs e, int K,
+                    int taps, int block_n_rt, int stages, int split) {
+    const int block_n = BN != 0 ? BN : block_n_rt;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_trigger();                                    // the next kernel of the stream may be launched (it waits for this one in its own pdl_wait)
     // carve: stages of A, stages of W, epilogue staging boxes, barriers, bias / correction vectors
@@ -262,7 +271,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint8_t* smem_a = smem;
     uint8_t* smem_w = smem + stages * A_STAGE_BYTES;
     uint8_t* staging = smem_w + stages * w_stage_bytes;          // 1024-aligned: every stage size is a multiple of 1024
-    uint64_t* bars = (uint64_t*)(staging + STAGING_TOTAL);
+    uint8_t* staging2 = staging + STAGING_TOTAL;                 // second-residual boxes (only carved when there is one)
+    uint64_t* bars = (uint64_t*)(staging + (e.res2 != nullptr ? 2 : 1) * STAGING_TOTAL);
     uint64_t* full = bars;                           // [MAX_STAGES]
     uint64_t* empty = bars + MAX_STAGES;             // [MAX_STAGES]
     uint64_t* tfull = bars + 2 * MAX_STAGES;         // [2]
@@ -373,17 +383,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else if (warp >= EPI_WARP0) {
-        const int ew = warp - EPI_WARP0;
-        const int wq = warp & 3;                         // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                        // which half of the tile's columns
-        const int n_ch = block_n / (2 * CHUNK);          // chunks of 32 columns per warp and tile (<= 2 when has_res)
-        const bool out_bf16 = e.out_dtype == VRD_BF16;
-        const uint32_t s_bias_u = smem_u32(s_bias);
+        constexpr bool GEN = MODE == EPI_GENERIC;
+        const bool out_bf16 = GEN ? (e.out_dtype == VRD_BF16) : (MODE == EPI_BF16 || MODE == EPI_BF16_GELU);
         // bf16 outputs without a residual: two 32-column chunks share one [32 x 64] box (128-byte rows, same 4 KB as an fp32
         // [32 x 32] box) and ONE TMA store -- the TMA unit handles requests at a fixed rate, and with 32 small store boxes
         // per 128 x 256 tile on top of the 16 operand loads it, not the tensor pipe, set the pace of the K = 512 GEMMs
-        const bool wide = e.wide != 0;
+        const bool wide = GEN ? (e.wide != 0) : (MODE == EPI_BF16 || MODE == EPI_BF16_GELU);
+        const bool has_res = GEN ? (e.has_res != 0) : (MODE == EPI_F32_RES);
+        const int act = GEN ? e.act : (MODE == EPI_BF16_GELU ? 2 : 0);
+        const bool has_res2 = GEN && e.res2 != nullptr;
+        const bool has_corr = GEN && e.corr != nullptr;
+        const int dbg = GEN ? e.dbg : 0;
+        const int ew = warp - EPI_WARP0;
+        const int wq = warp & 3;                         // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                        // which half of the tile's columns
+        const int n_ch = block_n / (2 * CHUNK);          // chunks of 32 columns per warp and tile (<= 2 when has_res and K is short)
+        const uint32_t s_bias_u = smem_u32(s_bias);
         uint8_t* my_stage = staging + ew * 2 * STAGING_BYTES;
+        uint8_t* my_stage2 = staging2 + ew * 2 * STAGING_BYTES;
         uint64_t* my_resbar = resbar + 2 * ew;
         int it = 0;
         uint32_t box_cnt = 0;                            // boxes alternate across chunks AND tiles (no-residual path)
@@ -398,18 +415,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int rl = row % e.R;
                 const int seq = e.row_seq[rl];
                 valid = seq >= 0;
-                if (valid && e.corr != nullptr) {
+                if (valid && has_corr) {
                     const int4 si = e.seqinfo[seq];
                     add_corr = (si.z != 0) && (rl - si.x == si.y - 1);
                 }
             }
-            if (e.has_res) {
+            if (has_res) {
                 // the residual boxes do not depend on the accumulator: fetch them while the MMAs of this tile still run
                 if (lane == 0) {
                     bulk_wait_read<0>();                 // the previous tile's stores have read both staging boxes
                     for (int c = 0; c < min(n_ch, 2); ++c) {
-                        mbar_expect_tx(&my_resbar[c], STAGING_BYTES);
+                        mbar_expect_tx(&my_resbar[c], has_res2 ? 2 * STAGING_BYTES : STAGING_BYTES);
                         tma_load_2d(my_stage + c * STAGING_BYTES, &map_res, &my_resbar[c], col0 + c * CHUNK, row0);
+                        if (has_res2) tma_load_2d(my_stage2 + c * STAGING_BYTES, &map_res2, &my_resbar[c], col0 + c * CHUNK, row0);
                     }
                 }
                 __syncwarp();
@@ -417,15 +435,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + as * ACC_STAGE_COLS + half * (block_n / 2);
-            for (int c = 0; c < n_ch; ++c) {
-                const int box_i = e.has_res ? (c & 1) : (wide ? (int)((box_cnt >> 1) & 1) : (int)(box_cnt & 1));
+            uint32_t acc[CHUNK];
+            tmem_ld32(taddr, acc);                        // chunk c + 1 is always in flight while chunk c is processed
+            auto chunk = [&](const int c) {
+                const int box_i = has_res ? (c & 1) : (wide ? (int)((box_cnt >> 1) & 1) : (int)(box_cnt & 1));
                 const bool box_first = !wide || (c & 1) == 0, box_last = !wide || (c & 1) == 1;
                 ++box_cnt;
                 uint8_t* box = my_stage + box_i * STAGING_BYTES;
                 const uint32_t box_u = smem_u32(box);
-                uint32_t acc[CHUNK];
-                tmem_ld32(taddr + c * CHUNK, acc);
-                if (e.has_res) {
+                if (has_res) {
                     // box c & 1 is filled once (n_ch <= 2) or twice (n_ch == 4, long-K tiles) per tile
                     mbar_wait(&my_resbar[c & 1], n_ch <= 2 ? (it & 1) : ((c >> 1) & 1));
                 } else if (box_first) {
@@ -433,15 +451,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     __syncwarp();
                 }
                 tmem_ld_wait();
-                if (c == n_ch - 1) {                     // accumulator fully read: hand the TMEM stage back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[as]), 0));   // the leader issues the MMAs
-                        else mbar_arrive(&tempty[as]);
-                    }
-                }
-                if (e.dbg & 2) continue;
                 const int n = col0 + c * CHUNK;
                 float v[CHUNK];
 #pragma unroll
@@ -452,18 +461,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bi.z;
                     v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + bi.w;
                 }
+                if (c + 1 < n_ch) {
+                    tmem_ld32(taddr + (c + 1) * CHUNK, acc);
+                } else {                                 // accumulator fully read: hand the TMEM stage back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[as]), 0));   // the leader issues the MMAs
+                        else mbar_arrive(&tempty[as]);
+                    }
+                }
+                if (dbg & 2) return;
                 if (add_corr) {
 #pragma unroll
                     for (int i = 0; i < CHUNK; ++i) v[i] += s_corr[n + i];
                 }
-                if (e.act == 1) {
+                if (act == 1) {
 #pragma unroll
                     for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.f);
-                } else if (e.act == 2 && !out_bf16) {
+                } else if (act == 2 && !out_bf16) {
 #pragma unroll
                     for (int i = 0; i < CHUNK; ++i) v[i] = gelu_fast(v[i]);
                 }
-                if (e.has_res) {
+                if (has_res) {
                     // residual box: 128-byte rows, 16-byte chunk j of row r stored at chunk j ^ (r & 7) (TMA SWIZZLE_128B)
 #pragma unroll
                     for (int j = 0; j < CHUNK / 4; ++j) {
@@ -471,10 +491,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
                     }
                 }
-                if (e.res2 != nullptr && valid) {
-                    const float4* p2 = reinterpret_cast<const float4*>(e.res2 + (long long)row * e.ldr2 + n);
+                if (has_res2) {
+                    // second residual box, same layout.  (Row-strided global loads here -- one L1 wavefront per row -- made the SOS
+                    // output projections 44 % slower than the single-residual ones: 247 vs 171 us at equal shapes.)
+                    const uint32_t box2_u = smem_u32(my_stage2 + (c & 1) * STAGING_BYTES);
 #pragma unroll
-                    for (int j = 0; j < CHUNK / 4; ++j) { const float4 t = p2[j]; v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
+                    for (int j = 0; j < CHUNK / 4; ++j) {
+                        const float4 r = lds128(box2_u + lane * 128 + ((j ^ (lane & 7)) << 4));
+                        v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                    }
                 }
                 if (!valid) {
 #pragma unroll
@@ -485,7 +510,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < CHUNK / 8; ++j) {
                         uint4 pk;
-                        if (e.act == 2) {        // GELU GEMMs have no residual: the activation is the last step (gelu(0) = 0)
+                        if (act == 2) {          // GELU GEMMs have no residual: the activation is the last step (gelu(0) = 0)
                             pk.x = gelu_pair_bf16(v[8 * j], v[8 * j + 1]); pk.y = gelu_pair_bf16(v[8 * j + 2], v[8 * j + 3]);
                             pk.z = gelu_pair_bf16(v[8 * j + 4], v[8 * j + 5]); pk.w = gelu_pair_bf16(v[8 * j + 6], v[8 * j + 7]);
                         } else {
@@ -503,21 +528,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         sts128(box_u + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
                 }
-                if (!box_last) continue;                 // the second chunk of a wide box completes it
+                if (!box_last) return;                   // the second chunk of a wide box completes it
                 fence_async_smem();                      // make the generic-proxy writes visible to the TMA engine
                 __syncwarp();
                 if (lane == 0) {
-                    if (!(e.dbg & 1)) {
+                    if (!(dbg & 1)) {
                         if (wide) tma_store_2d(&map_res, box_u, n - CHUNK, row0);   // map_res carries the [32 x 64] bf16 box map
                         else tma_store_2d(&map_out, box_u, n, row0);
                     }
                     bulk_commit();
-                    if (e.has_res && c + 2 < n_ch) {     // refill this box with the residual of chunk c + 2 (tiles with long K only:
+                    if (has_res && c + 2 < n_ch) {       // refill this box with the residual of chunk c + 2 (tiles with long K only:
                         bulk_wait_read<0>();             // the MMAs of the next tile hide this latency)
-                        mbar_expect_tx(&my_resbar[c & 1], STAGING_BYTES);
+                        mbar_expect_tx(&my_resbar[c & 1], has_res2 ? 2 * STAGING_BYTES : STAGING_BYTES);
                         tma_load_2d(box, &map_res, &my_resbar[c & 1], col0 + (c + 2) * CHUNK, row0);
+                        if (has_res2)
+                            tma_load_2d(my_stage2 + (c & 1) * STAGING_BYTES, &map_res2, &my_resbar[c & 1], col0 + (c + 2) * CHUNK, row0);
                     }
                 }
+            };
+            if constexpr (BN != 0) {
+#pragma unroll
+                for (int c = 0; c < BN / (2 * CHUNK); ++c) chunk(c);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < n_ch; ++c) chunk(c);
             }
         }
         if (lane == 0) bulk_wait_all();                  // all output boxes written before the CTA retires
@@ -529,6 +563,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
+}
+
+typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, EpiArgs, int, int,
+                           int, int, int);
+
+GemmKernel pick_kernel(int cg, int mode, int bn) {
+#define VRD_PICK(M, B) (cg == 1 ? (GemmKernel)gemm_tcgen05_kernel<1, M, B> : (GemmKernel)gemm_tcgen05_kernel<2, M, B>)
+    if (mode == EPI_GENERIC && bn == 0) return VRD_PICK(EPI_GENERIC, 0);
+    if (mode == EPI_BF16 && bn == 256) return VRD_PICK(EPI_BF16, 256);
+    if (mode == EPI_BF16_GELU && bn == 256) return VRD_PICK(EPI_BF16_GELU, 256);
+    if (mode == EPI_F32_RES && bn == 128) return VRD_PICK(EPI_F32_RES, 128);
+    if (mode == EPI_F32_RES && bn == 256) return VRD_PICK(EPI_F32_RES, 256);
+#undef VRD_PICK
+    return nullptr;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -576,6 +624,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     const int num_sms = device_sm_count();
     static const bool wide_ok = !(getenv("VRD_GEMM_WIDE") != nullptr && atoi(getenv("VRD_GEMM_WIDE")) == 0);   // A/B switch
     static const int dbg = getenv("VRD_GEMM_DBG") ? atoi(getenv("VRD_GEMM_DBG")) : 0;
+    const bool spec_ok = vrd_options().gemm_spec != 0;   // A/B switch: 0 = every launch through the generic epilogue
     static int force_cg = -1;
     if (force_cg < 0) { const char* v = getenv("VRD_GEMM_CG"); force_cg = v ? atoi(v) : 0; }
     if (g.M % BLOCK_M != 0 || g.K % BLOCK_K != 0 || g.N % 64 != 0 || g.lda % 8 != 0 || ((uintptr_t)g.A & 15) != 0) {
@@ -608,7 +657,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     // CTA pairs whenever there are enough rows to keep every pair busy (the small query-decoder GEMMs keep one CTA per tile):
     // measured +6..10 % on the long-K GEMMs, +4..9 % on the K = 512 ones, neutral on the HBM-bound residual projections
     const int cg = force_cg == 1 ? 1 : ((force_cg == 2 || g.M >= 128 * 2 * 64) ? 2 : 1);
-    CUtensorMap map_a, map_w, map_out, map_res;
+    CUtensorMap map_a, map_w, map_out, map_res, map_res2;
     const long long kk = (long long)g.taps * g.K * (split ? 2 : 1);
     if (!make_map(&map_a, g.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, split ? 2 * g.K : g.K, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (!make_map(&map_w, g.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, kk, kk, block_n / cg, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
@@ -625,24 +674,46 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     } else {
         map_res = map_out;
     }
+    if (g.res2 != nullptr) {
+        if (!make_map(&map_res2, g.res2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldr2, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    } else {
+        map_res2 = map_res;
+    }
     const int stage_bytes = A_STAGE_BYTES + (block_n / cg) * BLOCK_K * 2;
-    const int fixed = 1024 + STAGING_TOTAL + 1024 + 2 * MAX_N * 4;   // alignment slack, staging, barriers, bias + corr
+    const int fixed = 1024 + (g.res2 != nullptr ? 2 : 1) * STAGING_TOTAL + 1024 + 2 * MAX_N * 4;   // alignment slack, staging, barriers, bias + corr
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: tile does not fit in shared memory (N=%d, residuals=%d)", g.N, has_res + (g.res2 != nullptr)); return 1; }
     const int smem = fixed + stages * stage_bytes;
-    if (attr_once.first() &&
-        (cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-         cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess)) {
-        snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(max dynamic smem) failed");
-        return 1;
+    if (attr_once.first()) {
+        for (int c = 1; c <= 2; ++c)
+            for (int m = 0; m < 4; ++m)
+                for (int bn = 0; bn <= 256; bn += 128) {
+                    GemmKernel k = pick_kernel(c, m, bn);
+                    if (k != nullptr && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+                        snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(max dynamic smem) failed");
+                        return 1;
+                    }
+                }
     }
     const int wide = (!has_res && wide_ok && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) ? 1 : 0;
     EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R, wide, dbg};
+    // specialised epilogues for the shapes that carry the forward (q / k / v and other bf16 projections, the GELU MLP-up GEMMs, the
+    // fp32 residual projections); everything else (ReLU, pad correction, second residual, narrow tiles, experiments) stays generic
+    int mode = EPI_GENERIC, bn_ct = 0;
+    if (spec_ok && dbg == 0 && g.corr == nullptr && g.res2 == nullptr) {
+        if (wide && block_n == 256 && g.act == 0) { mode = EPI_BF16; bn_ct = 256; }
+        else if (wide && block_n == 256 && g.act == 2) { mode = EPI_BF16_GELU; bn_ct = 256; }
+        // the fp32 residual projections are HBM-bound: the specialised epilogue measured -2 % on them (gemm_spec = 2 selects it)
+        else if (vrd_options().gemm_spec == 2 && has_res && g.act == 0 && (block_n == 128 || block_n == 256)) { mode = EPI_F32_RES; bn_ct = block_n; }
+    }
+    GemmKernel kern = pick_kernel(cg, mode, bn_ct);
+    if (kern == nullptr) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: no kernel for cg=%d mode=%d bn=%d", cg, mode, bn_ct); return 1; }
     const int n_tiles = ((g.M + BLOCK_M * cg - 1) / (BLOCK_M * cg)) * (g.N / block_n);
     const int max_groups = num_sms / cg;
     const int grid = cg * (n_tiles < max_groups ? n_tiles : max_groups);
     if (cg == 1) {
-        if (launch_k(gemm_tcgen05_kernel<1>, dim3(grid), dim3(NUM_THREADS), smem, st, map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n,
+        if (launch_k(kern, dim3(grid), dim3(NUM_THREADS), smem, st, map_a, map_w, map_out, map_res, map_res2, e, g.K, g.taps, block_n,
                      stages, split) != cudaSuccess) {
             snprintf(g_err, sizeof g_err, "launch of gemm_tcgen05_kernel<1> failed: %s", cudaGetErrorString(cudaGetLastError()));
             return 1;
@@ -663,7 +734,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    if (cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, map_a, map_w, map_out, map_res, e, g.K, g.taps, block_n, stages, split) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, kern, map_a, map_w, map_out, map_res, map_res2, e, g.K, g.taps, block_n, stages, split) != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "cluster launch of gemm_tcgen05_kernel<2> failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 1;
     }

@@ -636,7 +636,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     if (g.res2 != nullptr && !has_res) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: res2 without res1"); return 1; }
     int block_n;
     if (has_res) {   // two 32-column chunks per epilogue warp (both residual boxes prefetched), four when K is long enough to hide
-        if (g.N % 256 == 0 && g.taps * g.K >= 1024) block_n = 256;
+        if (g.N % 256 == 0 && g.taps * g.K >= 1024 && g.res2 == nullptr) block_n = 256;   // a second residual doubles the staging boxes
         else if (g.N % 128 == 0) block_n = 128;
         else if (g.N <= 128) block_n = g.N;
         else { snprintf(g_err, sizeof g_err, "gemm_tcgen05: N=%d with a residual must be <= 128 or a multiple of 128", g.N); return 1; }

@@ -1428,7 +1428,10 @@ static int dwconv_ln_tile(const float* x, Lay lay, const float* pre_g, const flo
     const int num_sms = device_sm_count();
     int mask = 0;
     for (int b = 0; b < br.n; ++b) mask |= (br.use_pre[b] ? 1 : 0) << b;
-    const int cfg = vrd_options().dw_cfg;   // 0: 8 warps x 32 rows, 1: 16 x 32, 2: 2 CTAs/SM of 8 x 16, 3: branch warps, 4: quarter-row warps
+    // 0: 8 warps x 32 rows, 1: 16 x 32, 2: 2 CTAs/SM of 8 x 16, 3: branch warps, 4: quarter-row warps, 5: quarter-row warps for the
+    // launches with two or three branches (measured 9 % faster there, 5 % slower on the single-branch launch), tiles otherwise
+    int cfg = vrd_options().dw_cfg;
+    if (cfg == 5) cfg = br.n >= 2 ? 4 : 2;
     if (cfg == 4) {
         const int total = streams * lay.R;
         const int n_strips = total / QR_S;

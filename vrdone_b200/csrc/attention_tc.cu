@@ -34,11 +34,17 @@ using namespace tc;
 constexpr int FA_BM = 128;                 // query rows per item (UMMA M)
 constexpr int FA_BN = 64;                  // keys per block (UMMA N of S, K of P V)
 constexpr int FA_HS = 64;                  // head dim
-constexpr int FA_SLOTS = 4;                // K/V ring
 constexpr int FA_SLOT_BYTES = FA_BM * FA_HS * 2;          // 16 KB: a Q tile, or K (8 KB) + V (8 KB) of one block
-constexpr int FA_TMEM_COLS = 256;
-constexpr int FA_TM_S = 0, FA_TM_O = 128, FA_TM_P = 192;  // S0 S1 | O | P0 P1
-constexpr int FA_SMEM = 1024 + (2 + FA_SLOTS) * FA_SLOT_BYTES + 256 + 3 * 2 * FA_BM * 4;
+// Two configurations (template parameter NCTA = co-resident CTAs per SM):
+//   NCTA 2  TMEM 256 columns: S0 S1 | O | P0 P1, four K/V slots; S_{g+1} is computed while the softmax of block g runs.
+//   NCTA 3  TMEM 128 columns: S | O with P ALIASED onto the first 32 columns of S (the scores are in registers by the time P is
+//           written), two K/V slots; QK -> softmax -> PV of a CTA are strictly serial, and THREE such streams share the SM.  The
+//           kernel is bound by the latency of one block's chain (ncu: issue slots 47 %, the softmax warps wait or do bookkeeping
+//           70 % of their time), so a third independent stream pays more than overlapping QK inside a stream.
+template <int NCTA> struct FaCfg;
+template <> struct FaCfg<2> { static constexpr int SLOTS = 4, TMEM_COLS = 256, TM_S = 0, TM_O = 128, TM_P = 192, S_BUFS = 2; };
+template <> struct FaCfg<3> { static constexpr int SLOTS = 2, TMEM_COLS = 128, TM_S = 0, TM_O = 64, TM_P = 0, S_BUFS = 1; };
+template <int NCTA> constexpr int fa_smem() { return 1024 + (2 + FaCfg<NCTA>::SLOTS) * FA_SLOT_BYTES + 256 + 3 * 2 * FA_BM * 4; }
 constexpr float FA_LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -89,14 +95,25 @@ template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const
 // list for i = blockIdx.x, blockIdx.x + gridDim.x, ...; per item its blocks of 64 keys.  The next item's tile is fetched one
 // item ahead.
 struct FaCursor {
-    const int4* tiles; int n_items, n_head, stride, i, h, j, n_kv; int4 tile, pre;
+    const int4* tiles; int n_items, n_head, nh_shift, stride, i, h, j, n_kv; int4 tile, pre;
+    // i / n_head and i % n_head: a shift and a mask when the head count is a power of two (it is 8 in every config; the integer
+    // division cost ~40 instructions per item on the softmax warps' critical path, and an item is only ~2 key blocks long)
+    __device__ __forceinline__ int tile_of(int it) const { return nh_shift >= 0 ? (it >> nh_shift) : it / n_head; }
+    __device__ __forceinline__ int head_of(int it) const { return nh_shift >= 0 ? (it & (n_head - 1)) : it % n_head; }
+    // three scalar loads, not one 128-bit load: the vector load lands in four consecutive temporaries and the moves into `pre`
+    // waited for it on the spot (2 % of all stall samples sat on that move), scalar loads go straight to their registers and the
+    // latency stays hidden until the next item starts
     __device__ __forceinline__ void fetch() {
         const int nx = i + stride;
-        if (nx < n_items) pre = __ldg(tiles + nx / n_head);
+        if (nx < n_items) {
+            const int* p = reinterpret_cast<const int*>(tiles + tile_of(nx));
+            pre.x = __ldg(p); pre.y = __ldg(p + 1); pre.z = __ldg(p + 2);
+        }
     }
     __device__ __forceinline__ void start(const int4* t, int n_tiles, int nh, int first, int step) {
         tiles = t; n_items = n_tiles * nh; n_head = nh; stride = step; i = first; j = 0; h = 0; n_kv = 1;
-        if (i < n_items) { tile = __ldg(t + i / nh); h = i % nh; n_kv = (tile.z + FA_BN - 1) / FA_BN; fetch(); }
+        nh_shift = (nh & (nh - 1)) == 0 ? 31 - __clz(nh) : -1;
+        if (i < n_items) { tile = __ldg(t + tile_of(i)); h = head_of(i); n_kv = (tile.z + FA_BN - 1) / FA_BN; fetch(); }
     }
     __device__ __forceinline__ bool valid() const { return i < n_items; }
     __device__ __forceinline__ bool last_of_item() const { return j == n_kv - 1; }
@@ -104,15 +121,19 @@ struct FaCursor {
         if (++j == n_kv) {
             j = 0;
             i += stride;
-            if (i < n_items) { tile = pre; h = i % n_head; n_kv = (tile.z + FA_BN - 1) / FA_BN; fetch(); }
+            if (i < n_items) { tile = pre; h = head_of(i); n_kv = (tile.z + FA_BN - 1) / FA_BN; fetch(); }
         }
     }
 };
 
-template <int NSPLIT>
-__global__ void __launch_bounds__((4 * NSPLIT + 2) * 32, 2)
+template <int NSPLIT, int NCTA>
+__global__ void __launch_bounds__((4 * NSPLIT + 2) * 32, NCTA)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                     const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, long long ld, Lay lay, int n_head) {
+                     const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, long long ld, Lay lay, int n_head,
+                     int fa_serial_safe) {
+    using Cfg = FaCfg<NCTA>;
+    constexpr int FA_SLOTS = Cfg::SLOTS, FA_TMEM_COLS = Cfg::TMEM_COLS, FA_TM_S = Cfg::TM_S, FA_TM_O = Cfg::TM_O, FA_TM_P = Cfg::TM_P;
+    constexpr bool SERIAL = Cfg::S_BUFS == 1;                      // one S buffer: no QK lookahead, P aliased onto S
     constexpr int N_SOFTMAX = 4 * NSPLIT;                          // softmax warps; then the producer warp and the MMA warp
     constexpr int HC = FA_BN / NSPLIT;                             // keys (and output dims) per softmax thread
     extern __shared__ __align__(1024) uint8_t fa_smem_raw[];
@@ -189,10 +210,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tc_fence_after();
         const uint64_t qdesc = make_smem_desc_sw128(smem_u32(q_tiles + qb * FA_SLOT_BYTES));
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(ring + slot * FA_SLOT_BYTES));
-        const uint32_t tmem_s = tmem_base + FA_TM_S + (gg & 1) * FA_BN;
+        const uint32_t tmem_s = tmem_base + FA_TM_S + (SERIAL ? 0 : (gg & 1) * FA_BN);
 #pragma unroll
         for (int k = 0; k < FA_HS / 16; ++k) umma_f16_ss(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[gg & 1]);
+        umma_commit(&s_full[SERIAL ? 0 : (gg & 1)]);
         if (c.last_of_item()) umma_commit(&q_empty[qb]);                    // the Q tile is free once the last S of the item is done
     };
     auto mma = [&](FaCursor c) {
@@ -201,18 +222,24 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         issue_qk(c, g);
         nx.next();
         for (; c.valid(); ++g) {
-            if (nx.valid()) issue_qk(nx, g + 1);
+            // one S buffer: S_{g+1} overwrites the columns P_g lives in, so it is issued behind PV_g (the tensor core executes a
+            // CTA's MMAs in issue order); with two buffers it is issued now and runs beside the softmax of block g
+            if (!SERIAL && nx.valid()) issue_qk(nx, g + 1);
             mbar_wait(p_full, g & 1);
             tc_fence_after();
             // O += P V : A = P_g from TMEM (16 keys = 8 columns per step), B = V [64 keys x 64 dims] MN-major (+16 key rows =
             // 2048 bytes per step)
             const int slot = g % FA_SLOTS;
             const uint64_t vdesc = make_smem_desc_sw128(smem_u32(ring + slot * FA_SLOT_BYTES + FA_SLOT_BYTES / 2));
-            const uint32_t tmem_p = tmem_base + FA_TM_P + (g & 1) * (FA_BN / 2);
+            const uint32_t tmem_p = tmem_base + FA_TM_P + (SERIAL ? 0 : (g & 1) * (FA_BN / 2));
 #pragma unroll
             for (int k = 0; k < FA_BN / 16; ++k) umma_f16_ts(tmem_o, tmem_p + 8 * k, vdesc + 128 * k, idesc_o, (c.j | k) != 0 ? 1u : 0u);
             umma_commit(&empty[slot]);
             umma_commit(pv_done);
+            if (SERIAL && nx.valid()) {
+                if (fa_serial_safe) { mbar_wait(pv_done, g & 1); tc_fence_after(); }   // experiment: do not rely on issue order
+                issue_qk(nx, g + 1);
+            }
             c = nx;
             nx.next();
         }
@@ -254,6 +281,30 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
         }
     };
+    // the same in two halves of 32 dims: the 3-CTA configuration lives in 96 registers
+    auto epilogue_halves = [&](int row0, int len, int q0, int h, float l) {
+        const float inv = 1.0f / l;
+        const bool store = q0 + trow < len;
+        uint4* dst = reinterpret_cast<uint4*>(out + (long long)(row0 + trow) * ld + h * FA_HS);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t orr[32];
+            tmem_ld32(tmem_o + lane_sel + 32 * hf, orr);
+            tmem_ld_wait();
+            if (store) {
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint4 v;
+                    v.x = pack_bf16x2(__uint_as_float(orr[8 * c8]) * inv, __uint_as_float(orr[8 * c8 + 1]) * inv);
+                    v.y = pack_bf16x2(__uint_as_float(orr[8 * c8 + 2]) * inv, __uint_as_float(orr[8 * c8 + 3]) * inv);
+                    v.z = pack_bf16x2(__uint_as_float(orr[8 * c8 + 4]) * inv, __uint_as_float(orr[8 * c8 + 5]) * inv);
+                    v.w = pack_bf16x2(__uint_as_float(orr[8 * c8 + 6]) * inv, __uint_as_float(orr[8 * c8 + 7]) * inv);
+                    dst[4 * hf + c8] = v;
+                }
+            }
+        }
+        tc_fence_before();                   // orders these TMEM reads before the next item's first PV (released through p_full)
+    };
     auto softmax = [&](FaCursor c) {
         float m = -INFINITY, l = 0.f;
         bool have_prev = false;
@@ -268,10 +319,14 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
         };
         for (; c.valid(); c.next(), ++g) {
-            mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+            if constexpr (SERIAL) mbar_wait(&s_full[0], g & 1); else mbar_wait(&s_full[g & 1], (g >> 1) & 1);
             tc_fence_after();
+            if constexpr (SERIAL) {
+                // S_g was issued behind the previous item's last PV: O is final.  Written out before the scores are loaded (registers).
+                if (c.j == 0 && have_prev) { pv_waited = g; epilogue_halves(pv_row0, pv_len, pv_q0, pv_h, pv_l); }
+            }
             uint32_t sr[HC];
-            tmem_ld_n<HC>(tmem_base + FA_TM_S + (g & 1) * FA_BN + lane_sel + col0, sr);
+            tmem_ld_n<HC>(tmem_base + FA_TM_S + (SERIAL ? 0 : (g & 1) * FA_BN) + lane_sel + col0, sr);
             if (c.j == 0) { m = -INFINITY; l = 0.f; }
             const int nk = c.tile.z - c.j * FA_BN - (int)col0;                  // valid keys among this thread's columns (may be <= 0)
             tmem_ld_wait();
@@ -306,21 +361,54 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 m = m_new;
             }
             if (first) {
-                if (have_prev) {                                                // deferred: its last PV ran behind this block's S phase
+                if (!SERIAL && have_prev) {                                     // deferred: its last PV ran behind this block's S phase
                     wait_pv(g);
                     epilogue(pv_row0, pv_len, pv_q0, pv_h, pv_l);
                 }
             } else if (grow) {                                                  // rescale this thread's part of the accumulator row
-                wait_pv(g);
-                uint32_t orr[HC];
-                tmem_ld_n<HC>(tmem_o + lane_sel + col0, orr);
-                tmem_ld_wait();
+                if constexpr (SERIAL) {
+                    pv_waited = g;                                              // S_g complete => PV_{g-1} complete (issue order)
 #pragma unroll
-                for (int i = 0; i < HC; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
-                tmem_st_n<HC>(tmem_o + lane_sel + col0, orr);
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint32_t orr[16];
+                        tmem_ld16(tmem_o + lane_sel + 16 * q4, orr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                        tmem_st16(tmem_o + lane_sel + 16 * q4, orr);
+                    }
+                } else {
+                    wait_pv(g);
+                    uint32_t orr[HC];
+                    tmem_ld_n<HC>(tmem_o + lane_sel + col0, orr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < HC; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                    tmem_st_n<HC>(tmem_o + lane_sel + col0, orr);
+                }
             }
             const float ms = m * FA_LOG2E;
             float sum0 = 0.f, sum1 = 0.f;
+            if constexpr (SERIAL) {
+                // P_g replaces S_g in place (its columns 0 .. 31): every score of the row is in registers by now, and PV_{g-1} has
+                // completed (S_g was issued behind it).  Two halves of 32 keys keep the live registers down.
+                pv_waited = g;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t pr[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const int k0 = 32 * hf + i;
+                        const float p0 = ex2f(fmaf(__uint_as_float(sr[k0]), FA_LOG2E, -ms)), p1 = ex2f(fmaf(__uint_as_float(sr[k0 + 1]), FA_LOG2E, -ms));
+                        const float p2 = ex2f(fmaf(__uint_as_float(sr[k0 + 2]), FA_LOG2E, -ms)), p3 = ex2f(fmaf(__uint_as_float(sr[k0 + 3]), FA_LOG2E, -ms));
+                        sum0 += p0 + p1;
+                        sum1 += p2 + p3;
+                        pr[i / 2] = pack_bf16x2(p0, p1);
+                        pr[i / 2 + 1] = pack_bf16x2(p2, p3);
+                    }
+                    tmem_st16(tmem_base + FA_TM_P + lane_sel + 16 * hf, pr);
+                }
+            } else {
             uint32_t pr[HC / 2];
 #pragma unroll
             for (int i = 0; i < HC; i += 4) {                                   // masked keys: exp2(-inf) = 0 exactly
@@ -336,6 +424,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             // with phases g - 2 and g - 1 both complete it would be taken for phase g, which needs this warp's own arrival.
             if (g >= 1) wait_pv(g);
             tmem_st_n<HC / 2>(tmem_base + FA_TM_P + (g & 1) * (FA_BN / 2) + lane_sel + col0 / 2, pr);
+            }
             l = l * alpha + (sum0 + sum1);
             tmem_st_wait();                  // P (and a rescaled O) are in tensor memory
             tc_fence_before();
@@ -348,7 +437,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         if (have_prev) {                                                        // the CTA's last item
             wait_pv(g);
-            epilogue(pv_row0, pv_len, pv_q0, pv_h, pv_l);
+            if constexpr (SERIAL) epilogue_halves(pv_row0, pv_len, pv_q0, pv_h, pv_l);
+            else epilogue(pv_row0, pv_len, pv_q0, pv_h, pv_l);
         }
     };
 
@@ -365,16 +455,18 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
 }
 
-template <int NSPLIT>
+template <int NSPLIT, int NCTA>
 int fa_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, void* out, long long ld, Lay lay, int n_head,
               cudaStream_t st) {
     static PerDeviceOnce once;
-    auto kern = flash_attn_tc_kernel<NSPLIT>;
-    if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM) != cudaSuccess) return 2;
+    auto kern = flash_attn_tc_kernel<NSPLIT, NCTA>;
+    constexpr int smem = fa_smem<NCTA>();
+    if (once.first() && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 2;
     const int n_items = lay.n_tiles * n_head;
-    const int max_ctas = 2 * device_sm_count();
+    const int max_ctas = NCTA * device_sm_count();
     const int grid = n_items < max_ctas ? n_items : max_ctas;
-    launch_k(kern, dim3(grid), dim3((4 * NSPLIT + 2) * 32), FA_SMEM, st, mq, mk, mv, (__nv_bfloat16*)out, ld, lay, n_head);
+    static const int safe = getenv("VRD_FA_SAFE") ? atoi(getenv("VRD_FA_SAFE")) : 0;
+    launch_k(kern, dim3(grid), dim3((4 * NSPLIT + 2) * 32), smem, st, mq, mk, mv, (__nv_bfloat16*)out, ld, lay, n_head, safe);
     return 0;
 }
 
@@ -389,7 +481,9 @@ int full_attn_tcgen05(const void* q, const void* k, const void* v, void* out, lo
     if (!make_tensor_map_2d(&mk, k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, lay.R, C, ld, FA_BN, FA_HS, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     if (!make_tensor_map_2d(&mv, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, lay.R, C, ld, FA_BN, FA_HS, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     static const int nsplit = getenv("VRD_FA_SPLIT") ? atoi(getenv("VRD_FA_SPLIT")) : 1;      // A/B switch: softmax warps per lane quarter
-    return nsplit == 1 ? fa_launch<1>(mq, mk, mv, out, ld, lay, n_head, st) : fa_launch<2>(mq, mk, mv, out, ld, lay, n_head, st);
+    static const int ncta = getenv("VRD_FA_CTAS") ? atoi(getenv("VRD_FA_CTAS")) : 2;          // A/B switch: co-resident CTAs per SM (2 | 3)
+    if (ncta == 3) return fa_launch<1, 3>(mq, mk, mv, out, ld, lay, n_head, st);
+    return nsplit == 1 ? fa_launch<1, 2>(mq, mk, mv, out, ld, lay, n_head, st) : fa_launch<2, 2>(mq, mk, mv, out, ld, lay, n_head, st);
 }
 
 }  // namespace vrd

@@ -12,7 +12,8 @@ from typing import Optional
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvrdone_b200.so")
+# VRD_LIB_PATH: A/B experiments against another build of the same ABI (tools/); the product loads the in-tree library
+_LIB_PATH = os.environ.get("VRD_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvrdone_b200.so")
 _lib = None
 
 F32, BF16 = 0, 1

@@ -22,7 +22,6 @@ constexpr int WARPS = 8;
 template <typename T, int NCH, int LPH>
 __global__ void window_attn_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                                    T* __restrict__ out, long long ld, Lay lay, int w, int streams) {
-    pdl_trigger();
     pdl_wait();
     constexpr int MAXK = 9;
     const int lane = threadIdx.x & 31;
@@ -141,7 +140,6 @@ template <typename T, int C, int HS, int TILE>
 __global__ void __launch_bounds__(WARPS * 32) window_attn_tma_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                                      const T* __restrict__ v, T* __restrict__ out, Lay lay, int w,
                                                                      int total_rows) {
-    pdl_trigger();
     pdl_wait();
     constexpr int VEC = Vec16<T>::N, NV = C / (32 * VEC), LPH = HS / VEC, MAXK = 2 * WIN_HALO + 1;
     constexpr int ROWS = TILE + 2 * WIN_HALO;
@@ -303,7 +301,6 @@ static int window_attn_simt(const void* q, const void* k, const void* v, void* o
 template <typename T, int HS>
 __global__ void __launch_bounds__(128) full_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                         const T* __restrict__ v, T* __restrict__ out, long long ld, Lay lay) {
-    pdl_trigger();
     pdl_wait();
     constexpr int TPQ = HS / 32;
     constexpr int QPB = 128 / TPQ;
@@ -405,7 +402,6 @@ template <int HS, int NBUF>
 __global__ void __launch_bounds__(128, HS == 64 ? 4 : 1) flash_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                               const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
                                                               long long ld, Lay lay) {
-    pdl_trigger();
     pdl_wait();
     constexpr int BM = 64, BN = 64, LDS = HS + 8, KSTEPS = HS / 16, DBLK = HS / 8, CPR = HS / 8;   // CPR: 16-byte chunks per row
     extern __shared__ __align__(16) uint8_t fa_smem[];
@@ -630,7 +626,6 @@ template <int NH>
 __global__ void __launch_bounds__(WM_WARPS * 32, 2) window_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                                            const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
                                                                            Lay lay, int w, int total_rows) {
-    pdl_trigger();
     pdl_wait();
     constexpr int HS = 64, BM = 16, KR = BM + 2 * WM_HALO, LDS = HS + 8, CPR = HS / 8, C = NH * HS;
     constexpr int STAGE = (BM + 2 * KR) * LDS;          // elements per pipeline stage: Q, K, V
@@ -817,7 +812,6 @@ template <typename T>
 __global__ void __launch_bounds__(256) query_self_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                               const T* __restrict__ v, T* __restrict__ out, long long ld,
                                                               int Q, int n_head) {
-    pdl_trigger();
     pdl_wait();
     constexpr int D = 256, MAXQ = 12, MAXH = 8;
     // sk rows are padded by four words: in the score phase consecutive threads read the SAME column of consecutive key rows
@@ -880,7 +874,6 @@ template <typename T, int HS>
 __global__ void __launch_bounds__(256) query_cross_attn_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                                const T* __restrict__ v, T* __restrict__ out, long long ld,
                                                                Lay lay, int Q, int n_head) {
-    pdl_trigger();
     pdl_wait();
     constexpr int D = 256, MAXQ = 12, DPL = HS / 32;
     __shared__ __align__(16) float sq[MAXQ][D];

@@ -152,7 +152,6 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     float* xch = (float*)(tmem_slot + 4);      // [3][NSPLIT][FA_BM]: partial row maxima (two block parities) and row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < FA_SLOTS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); }

@@ -32,7 +32,7 @@ Lay make_lay(const int32_t* row_seq, const int32_t* seqinfo, int R, int B) {
 VrdOptions& vrd_options() {
     static VrdOptions o = [] {
         VrdOptions d;
-        d.pdl = (getenv("VRD_PDL") != nullptr && atoi(getenv("VRD_PDL")) != 0) ? 1 : 0;   // measured slower: off by default
+        d.pdl = (getenv("VRD_PDL") != nullptr && atoi(getenv("VRD_PDL")) == 0) ? 0 : 1;
         d.dw_cfg = getenv("VRD_DW_CFG") != nullptr ? atoi(getenv("VRD_DW_CFG")) : 2;
         d.gemm_spec = (getenv("VRD_GEMM_SPEC") != nullptr && atoi(getenv("VRD_GEMM_SPEC")) == 0) ? 0 : 1;
         return d;

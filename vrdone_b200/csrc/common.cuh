@@ -35,14 +35,18 @@ inline int device_sm_count() {
     return sms[dev];
 }
 
-// ---- programmatic dependent launch (PDL).  Every kernel launched through launch_k() starts with pdl_trigger(); ... pdl_wait():
-// the trigger lets the NEXT kernel of the stream be launched (its CTAs become resident as SM resources free up and run their
-// prologue) while this one still runs; pdl_wait() blocks until the PREVIOUS kernel has completed and its memory is visible, and
-// must precede the first access to anything an earlier kernel wrote.  Launch latency and prologues (barrier init, TMEM
-// allocation, parameter loads) then overlap the previous kernel's tail: the forward is ~2400 short launches per step.
-// Without the launch attribute (VRD_PDL=0, or a plain <<<>>> launch) both instructions are no-ops.
+// ---- programmatic dependent launch (PDL).  Kernels launched through launch_k() carry the programmatic-stream-serialization
+// attribute and start with pdl_wait(): the NEXT kernel of the stream is launched (its CTAs become resident as SM resources free
+// up and run their prologue: barrier init, TMEM allocation, parameter loads) when every CTA of this one has exited or called
+// pdl_launch_dependents(); pdl_wait() blocks until the PREVIOUS kernel has completed and its memory is visible, and must precede
+// the first access to anything an earlier kernel wrote.  Measured on the ~2400 launches per step of the forward (network-only
+// time of four cfg2 videos, tools/ab_switch.py): releasing the dependents EARLY -- griddepcontrol.launch_dependents at the top
+// of every kernel -- was 2-3 % SLOWER than plain stream order, releasing them when a persistent GEMM CTA starts its last tile
+// 1-2 % slower, and no explicit release at all (the implicit one at CTA exit: only launch latency and the prologue overlap the
+// previous kernel's tail) ~1 % faster.  No kernel calls pdl_launch_dependents(); it stays for experiments.
+// Without the launch attribute (VRD_PDL=0) both instructions are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Experiment switches shared by the launchers (defined in cabi.cu): initialised from the environment on first use
 // (VRD_PDL, VRD_DW_CFG), changeable at run time through vrd_set_option() so that one process can A/B them on the same inputs.
 struct VrdOptions {

@@ -262,7 +262,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     int taps, int block_n_rt, int stages, int split) {
     const int block_n = BN != 0 ? BN : block_n_rt;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    pdl_trigger();                                    // the next kernel of the stream may be launched (it waits for this one in its own pdl_wait)
     // carve: stages of A, stages of W, epilogue staging boxes, barriers, bias / correction vectors
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int w_stage_bytes = (block_n / CG) * BLOCK_K * 2;       // each CTA of a pair holds block_n / CG rows of the W tile
@@ -749,7 +748,6 @@ namespace {
 // x [rows, taps * K] fp32 (pitch ldx) -> out [rows, taps * 2K] bf16: per tap [hi(K) | lo(K)], hi = bf16(x), lo = bf16(x - hi)
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, long long ldx, long long rows, int K, int taps,
                                                          __nv_bfloat16* __restrict__ out) {
-    pdl_trigger();
     pdl_wait();
     const int per_row = taps * K / 4;
     const long long total = rows * per_row;

@@ -305,7 +305,6 @@ template <typename TI, typename TO, int NCH>
 __global__ void layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, TO* __restrict__ out, long long ldo, int rows, int relu,
                                  const int* __restrict__ row_seq, int R) {
-    pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * LN_RPW;
@@ -439,7 +438,6 @@ __global__ void small_conv_kernel(const float* __restrict__ x, int cin, const fl
                                   const float* __restrict__ bias, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, int relu, TO* __restrict__ out, long long ldo, int rows,
                                   const int* __restrict__ row_seq, int R) {
-    pdl_trigger();
     pdl_wait();
     constexpr int N = NCH * 128;
     const int lane = threadIdx.x & 31;
@@ -531,7 +529,6 @@ template <typename TI, typename TO, int NCH, int STRIDE, int NB, int PREMASK>
 __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_kernel(const TI* __restrict__ x, long long ldx, Lay lin, Lay lout,
                                                                  const float* __restrict__ pre_g, const float* __restrict__ pre_b,
                                                                  DwBranches br, int streams) {
-    pdl_trigger();
     pdl_wait();
     constexpr bool ANY_PRE = PREMASK != 0;
     constexpr bool ANY_RAW = PREMASK != ((1 << NB) - 1);
@@ -707,7 +704,6 @@ __global__ void __launch_bounds__(NW * 32, 32 / TILE) dwconv_ln_tile_kernel(cons
                                                                            const float* __restrict__ pre_g,
                                                                            const float* __restrict__ pre_b, DwBranches br,
                                                                            int total_rows) {
-    pdl_trigger();
     pdl_wait();
     constexpr int NCH = 4, C = 512;
     constexpr int DWT_TILE = TILE, DWT_ROWS = TILE + 2, DWT_WARPS = NW, DWT_RPW = TILE / NW;
@@ -968,7 +964,6 @@ __global__ void __launch_bounds__(NB * WPB * 32, 1) dwconv_ln_bw_kernel(const fl
                                                                          const float* __restrict__ pre_g,
                                                                          const float* __restrict__ pre_b, DwBranches br,
                                                                          int total_rows) {
-    pdl_trigger();
     pdl_wait();
     constexpr int NCH = 4, C = 512;
     constexpr int DWT_ROWS = TILE + 2, NW = NB * WPB;
@@ -1191,7 +1186,6 @@ __global__ void __launch_bounds__(NG * 128, 1) dwconv_ln_qr_kernel(const float* 
                                                                     const float* __restrict__ pre_g,
                                                                     const float* __restrict__ pre_b, DwBranches br,
                                                                     int total_rows) {
-    pdl_trigger();
     pdl_wait();
     constexpr int C = 512;
     constexpr bool ANY_PRE = PREMASK != 0;
@@ -1531,7 +1525,6 @@ int dwconv_ln(const void* x, int xdt, long long ldx, Lay lin, Lay lout, int stri
 template <int NCH>
 __global__ void maxpool_skip_kernel(const float* __restrict__ x, long long ldx, Lay lin, Lay lout, float* __restrict__ out,
                                     long long ldo) {
-    pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -1581,7 +1574,6 @@ int maxpool_skip(const float* x, long long ldx, Lay lin, Lay lout, float* out, l
 __global__ void fpn_top_kernel(const float* __restrict__ x, long long ldx, Lay lay, const float* __restrict__ pre_g,
                                const float* __restrict__ pre_b, const float* __restrict__ wt, const float* __restrict__ g,
                                const float* __restrict__ b, float* __restrict__ out, long long ldo) {
-    pdl_trigger();
     pdl_wait();
     constexpr int NCH = 4;
     const int lane = threadIdx.x & 31;
@@ -1648,7 +1640,6 @@ __global__ void fpn_level_kernel(const float* __restrict__ cur, long long ldc, c
                                  Lay lay, Lay lup, const float* __restrict__ lat_g, const float* __restrict__ lat_b,
                                  const float* __restrict__ beta_up, const float* __restrict__ w, const float* __restrict__ g,
                                  const float* __restrict__ b, float* __restrict__ out, long long ldo) {
-    pdl_trigger();
     pdl_wait();
     constexpr int NCH = 2;
     const int lane = threadIdx.x & 31;
@@ -1708,7 +1699,6 @@ int fpn_level(const float* cur, long long ldc, const float* yup, long long ldu, 
 __global__ void mask_features_kernel(const float* __restrict__ y, long long ldy, Lay lay, const float* __restrict__ beta,
                                      const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                                      long long ldo) {
-    pdl_trigger();
     pdl_wait();
     constexpr int NCH = 2;
     const int lane = threadIdx.x & 31;
@@ -1756,7 +1746,6 @@ __global__ void query_ln_kernel(const float* __restrict__ x, long long ldx, cons
                                 const float* __restrict__ b, const float* __restrict__ pos, int Q, int nrows, int total_rows,
                                 const float* __restrict__ dw, const float* __restrict__ g2, const float* __restrict__ b2,
                                 TO* __restrict__ out, long long ldo) {
-    pdl_trigger();
     pdl_wait();
     constexpr int NCH = 2;
     const int lane = threadIdx.x & 31;
@@ -1809,7 +1798,6 @@ int query_ln(const float* x, long long ldx, const float* g, const float* b, cons
 // sigmoid(logit) > 0.5 evaluated in fp32 exactly as the reference does (maskvrd.py:287), NOT logit > 0.
 __global__ void mask_logits_kernel(const float* __restrict__ me, long long ldm, const float* __restrict__ mf, long long ldf,
                                    Lay lay, int Q, float* __restrict__ masks, long long ldk, int* __restrict__ first_last) {
-    pdl_trigger();
     pdl_wait();
     constexpr int NCH = 2;
     constexpr int MAXQ = 16;
@@ -1860,7 +1848,6 @@ int mask_logits(const float* me, long long ldm, const float* mf, long long ldf, 
 // One warp per (pair, query): softmax over n_cls logits, then top-k of classes 1..n_cls-1 (ties -> lower class id).
 __global__ void softmax_topk_kernel(const float* __restrict__ logits, long long ldl, int nrows, int n_cls, int topk,
                                     float* __restrict__ scores, int* __restrict__ ids) {
-    pdl_trigger();
     pdl_wait();
     constexpr int PER = 8;   // up to 256 classes
     const int lane = threadIdx.x & 31;

@@ -1,4 +1,4 @@
-"""Turns the outputs of tools/gpu_final_r2.sh (gpurun_out/f_*) into the committed evidence under profiles/r2_*."""
+"""Turns the outputs of tools/gpu_final_r2b.sh (gpurun_out/f_*) into the committed evidence under profiles/r2_*."""
 import collections
 import csv
 import json
@@ -44,7 +44,7 @@ def launch_files():
         d[0] += 1
         d[1] += us
     tot = sum(us for _, us, _ in sel)
-    head = (f"ncu --metrics gpu__time_duration.sum --clock-control none -s 14500 -c 7500 --csv, {CMD} (tools/gpu_final_r2.sh)\n"
+    head = (f"ncu --metrics gpu__time_duration.sum --clock-control none -s 14500 -c 7500 --csv, {CMD} (tools/gpu_final_r2b.sh)\n"
             f"{len(sel)} consecutive launches from the first pack kernel of the capture window on: about three passes over the 10-video cfg2 set (the window "
             f"falls into bench.py's host-input passes, whose videos are chunked finer: more pack / merge launches per pass than the device-resident "
             f"passes) ({tot / 1e3:.1f} ms; "
@@ -69,7 +69,7 @@ def traffic():
     wr = sum(v["dram__bytes_write.sum"][0] * tob[v["dram__bytes_write.sum"][1]] for v in per.values())
     t = sum(us_of(str(v["gpu__time_duration.sum"][0]), v["gpu__time_duration.sum"][1]) for v in per.values())
     out = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_tcgen05 "
-                     f"-s 2652 -c 1326, {CMD} (the GEMM launches of one pass over the 10-video cfg2 set; tools/gpu_final_r2.sh)",
+                     f"-s 2652 -c 1326, {CMD} (the GEMM launches of one pass over the 10-video cfg2 set; tools/gpu_final_r2b.sh)",
            "launches": len(per), "dram_bytes_read": rd, "dram_bytes_write": wr, "traffic_bytes_per_launch": (rd + wr) / len(per),
            "traffic_bytes_per_step": rd + wr, "time_us_under_ncu": t}
     json.dump(out, open(os.path.join(P, "r2_gemm_traffic.json"), "w"), indent=1)
@@ -85,7 +85,7 @@ def bench_table():
              "python bench.py --config vidvrd --tracklets 6 --frames 150 --videos 4 --steps 20 --warmup 3 --cpu-pairs 30 --sweep-videos 0"),
             ("vidor, round-1 workload (40 tracklets x 1200 frames, 2 videos per step)", "f_bench_r1workload.json",
              "python bench.py --tracklets 40 --frames 1200 --videos 2 --steps 10 --warmup 3 --no-cpu-baseline --sweep-videos 0")]
-    out = ["# Round 2 -- bench.py on one B200, all BASELINE.json configs (gpurun `tools/gpu_final_r2.sh`)", "",
+    out = ["# Round 2 -- bench.py on one B200, all BASELINE.json configs (gpurun `tools/gpu_final_r2b.sh`, end of round 2)", "",
            "`value` = pairs/s through `runner.run_videos` (two videos in flight), pair features resident in HBM; `e2e` = the same loop with pinned HOST",
            "pair features (H2D inside); `blocking` = one `model(input)` call after the other (value / e2e); `tracklet api` = `forward_tracklets` with",
            "pinned host tracklet features (pipelined / blocking); `net` = network only; `gemm frac` = tcgen05 GEMM TFLOP/s over the measured sustained",
@@ -120,7 +120,7 @@ def bench_table():
     two = os.path.join(G, "r2_bench_2gpu.json")
     if os.path.exists(two):
         t = last_json("r2_bench_2gpu.json")
-        out += ["", f"Two GPUs (`gpurun --gpus 2`, torchrun, --steps 3 --warmup 2, earlier build of this round): value {t['value']:,.0f}, e2e {t['e2e']['value']:,.0f}, "
+        out += ["", f"Two GPUs (`gpurun --gpus 2`, torchrun, --steps 3 --warmup 2, same build): value {t['value']:,.0f}, e2e {t['e2e']['value']:,.0f}, "
                 f"tracklet api {t['e2e']['tracklet_api_value']:,.0f} pairs/s; sweep {json.dumps(t.get('sweep'))}"]
     gs = r.get("gemm_by_shape")
     open(os.path.join(P, "r2_bench_configs.md"), "w").write("\n".join(out) + "\n")

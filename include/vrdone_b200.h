@@ -41,6 +41,7 @@ int vrd_device_arch(void);
  * defaults come from the environment (VRD_PDL, VRD_DW_CFG).  Returns the previous value, <0 for an unknown name.  No reference
  * counterpart: it exists so that one process can A/B a switch on the same inputs. */
 int vrd_set_option(const char* name, int value);
+int vrd_get_option(const char* name);   /* current value, <0 for an unknown name; also "gemm_spec", "embed_ln" */
 
 /* a0 -- replaces utils.dict_to_device for the pair features (eval.py:144, utils/misc.py:98-112): n asynchronous
  * host->device copies on `stream` (the copy engine; src[i] HOST pointers, pinned for true asynchrony) of bytes[i] bytes to
@@ -85,6 +86,14 @@ int vrd_pack_pairs(const void* pair_ptrs, const int64_t* pair_strides, const int
 int vrd_gemm(const void* A, int a_dtype, int64_t lda, const void* W, const float* bias, void* out, int out_dtype, int64_t ldo,
              int M, int N, int K, int taps, int act, const float* res1, int64_t ldr1, const float* res2, int64_t ldr2,
              const float* corr, const int32_t* row_seq, const int32_t* seqinfo, int R, vrd_stream_t stream);
+
+/* k1 + k6 fused -- the embedding convs followed by their channel LayerNorm and ReLU (backbones.py:184-197 with blocks.py:143-158):
+ * out[M, 512] (bf16) = [relu](LN_channels(A * W^T + bias [+ corr on the last row of padded pairs])) * row validity.  bf16 operands
+ * only (tcgen05 path), N must be 512: the tile spans the row, the statistics are taken on the fp32 accumulator in tensor memory and
+ * the fp32 conv output never reaches HBM.  Same operand conventions as vrd_gemm. */
+int vrd_gemm_ln(const void* A, int64_t lda, const void* W, const float* bias, const float* corr, const float* gamma, const float* beta,
+                int relu, void* out, int64_t ldo, int M, int N, int K, int taps, const int32_t* row_seq, const int32_t* seqinfo, int R,
+                vrd_stream_t stream);
 
 /* k6 -- channel LayerNorm (blocks.py:143-158) [+ReLU]; C in {256, 512}; separator rows -> 0 when row_seq != NULL. */
 int vrd_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,

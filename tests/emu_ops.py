@@ -86,6 +86,28 @@ class EmuOps:
             acc = acc * self._valid_rows(lay, streams)[:, None]
         out.copy_(acc.to(out.dtype))
 
+    def gemm_ln(self, a, w, out, ln, bias=None, taps=1, corr=None, relu=False, lay=None, streams=1):
+        """Conv-as-GEMM with the channel LayerNorm (+ ReLU) as its epilogue: the fp32 accumulator is normalised, never stored."""
+        self.calls.append("gemm_ln")
+        M, K = a.shape
+        af = a.float()
+        if taps == 3:
+            z = torch.zeros(1, K)
+            af = torch.cat([torch.cat([z, af[:-1]]), af, torch.cat([af[1:], z])], 1)   # rows r-1, r, r+1
+        acc = af @ w.float().t()
+        if bias is not None:
+            acc = acc + bias
+        if corr is not None:
+            for s, i, r0, L, hp in self._seqs(lay, streams):
+                if hp:
+                    acc[r0 + L - 1] += corr
+        y = _ln_rows(acc, ln[0], ln[1])
+        if relu:
+            y = F.relu(y)
+        if lay is not None:
+            y = y * self._valid_rows(lay, streams)[:, None]
+        out.copy_(y.to(out.dtype))
+
     def layernorm(self, x, g, b, out, relu=False, lay=None, streams=1):
         self.calls.append("layernorm")
         y = _ln_rows(x, g, b)

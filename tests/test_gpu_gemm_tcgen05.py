@@ -105,3 +105,33 @@ def test_gemm_bf16_cta_pairs(ops, taps, act, res, corr, N, K, odt):
     err = float((out.float().cpu() - ref).abs().max())
     tol = 2e-3 if odt == torch.float32 else 2e-2
     assert err <= tol * float(ref.abs().max()), f"max abs err {err:.3e} vs scale {float(ref.abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("taps,K,relu,corr,big", [(3, 1024, True, True, False), (3, 512, True, True, True), (1, 512, False, False, False),
+                                                  (1, 256, True, False, True)])
+def test_gemm_layernorm_epilogue(ops, taps, K, relu, corr, big):
+    """The embedding convs with their channel LayerNorm + ReLU as the GEMM's epilogue (N = 512, the tile spans the row), against the
+    CPU emulation; ``big``: enough rows for the CTA-pair variant (M >= 16384)."""
+    lens = LENS * 12 if big else LENS
+    tpads = TPADS * 12 if big else TPADS
+    lg, lc = PackLayout(lens, tpads, 4, "cuda"), PackLayout(lens, tpads, 4, "cpu")
+    streams, N = 2, 512
+    M = streams * lc.levels[0].R
+    assert (M >= 16384) == big
+    a = rnd((M, K), 1).to(torch.bfloat16)
+    a[(lc.levels[0].row_seq < 0).repeat(streams)] = 0
+    w = rnd((N, taps * K), 2, K ** -0.5).to(torch.bfloat16)
+    bias, gm, be = rnd((N,), 3), rnd((N,), 7) * 0.2 + 1, rnd((N,), 8)
+    cv = rnd((N,), 6) if corr else None
+    ref = torch.empty(M, N, dtype=torch.bfloat16)
+    EmuOps().gemm_ln(a, w, ref, (gm, be), bias=bias, taps=taps, corr=cv, relu=relu, lay=lc.levels[0], streams=streams)
+    out = torch.full((M, N), 3.0, dtype=torch.bfloat16, device="cuda")
+    ops.gemm_ln(a.cuda(), w.cuda(), out, (gm.cuda(), be.cuda()), bias=bias.cuda(), taps=taps, corr=None if cv is None else cv.cuda(),
+                relu=relu, lay=lg.levels[0], streams=streams)
+    torch.cuda.synchronize()
+    ref = ref.float()
+    err = float((out.float().cpu() - ref).abs().max())
+    assert err <= 2e-2 * float(ref.abs().max()), f"max abs err {err:.3e} vs scale {float(ref.abs().max()):.3e}"
+    # separator rows are written as zeros
+    sep = (lc.levels[0].row_seq < 0).repeat(streams)
+    assert float(out.float().cpu()[sep].abs().max()) == 0.0

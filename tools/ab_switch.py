@@ -47,6 +47,8 @@ run_once()
 ops = model._ops
 configs = [("base: spec=0 pdl=0 dw=2", {"gemm_spec": 0, "pdl": 0, "dw_cfg": 2}), ("spec=1", {"gemm_spec": 1, "pdl": 0, "dw_cfg": 2}),
            ("spec=1 pdl=1", {"gemm_spec": 1, "pdl": 1, "dw_cfg": 2}), ("spec=1 dw=4", {"gemm_spec": 1, "pdl": 0, "dw_cfg": 4}), ("spec=1 dw=5", {"gemm_spec": 1, "pdl": 0, "dw_cfg": 5})]
+if len(sys.argv) > 3 and sys.argv[3] == "one":
+    configs = [("default", {})]
 if len(sys.argv) > 3 and sys.argv[3] == "pdl":
     configs = [configs[1], configs[2]]
 if len(sys.argv) > 3 and sys.argv[3] == "dw":

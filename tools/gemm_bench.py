@@ -10,6 +10,8 @@ M = int(sys.argv[1]) if len(sys.argv) > 1 else 98304
 shapes = [  # (name, N, K, taps, res, out dtype, act)
     ("embd0 3x1024->512 f32", 512, 1024, 3, 0, torch.float32, 0),
     ("embd1 3x512->512 f32", 512, 512, 3, 0, torch.float32, 0),
+    ("embd0 3x1024->512 +ln bf16", 512, 1024, 3, 0, torch.bfloat16, -1),
+    ("embd1 3x512->512 +ln bf16", 512, 512, 3, 0, torch.bfloat16, -1),
     ("fuse0 1024->512 gelu bf16", 512, 1024, 1, 0, torch.bfloat16, 2),
     ("qkv 512->512 bf16", 512, 512, 1, 0, torch.bfloat16, 0),
     ("proj 512->512 +res f32", 512, 512, 1, 1, torch.float32, 0),
@@ -27,14 +29,19 @@ for name, N, K, taps, res, odt, act in shapes:
     r1 = torch.randn(M, N, device="cuda") if res else None
     r2 = torch.randn(M, N, device="cuda") if res == 2 else None
     out = torch.empty(M, N, dtype=odt, device="cuda")
+    if act < 0:      # LayerNorm + ReLU epilogue (the tile spans the 512-channel row)
+        gm, be = torch.rand(N, device="cuda") + 0.5, torch.randn(N, device="cuda")
+        run = lambda: ops.gemm_ln(a, w, out, (gm, be), bias=bias, taps=taps, relu=True)
+    else:
+        run = lambda: ops.gemm(a, w, out, bias=bias, taps=taps, act=act, res1=r1, res2=r2)
     for _ in range(3):
-        ops.gemm(a, w, out, bias=bias, taps=taps, act=act, res1=r1, res2=r2)
+        run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 10
     e0.record()
     for _ in range(n):
-        ops.gemm(a, w, out, bias=bias, taps=taps, act=act, res1=r1, res2=r2)
+        run()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n

@@ -34,7 +34,8 @@ VrdOptions& vrd_options() {
         VrdOptions d;
         d.pdl = (getenv("VRD_PDL") != nullptr && atoi(getenv("VRD_PDL")) == 0) ? 0 : 1;
         d.dw_cfg = getenv("VRD_DW_CFG") != nullptr ? atoi(getenv("VRD_DW_CFG")) : 2;
-        d.gemm_spec = (getenv("VRD_GEMM_SPEC") != nullptr && atoi(getenv("VRD_GEMM_SPEC")) == 0) ? 0 : 1;
+        d.gemm_spec = getenv("VRD_GEMM_SPEC") != nullptr ? atoi(getenv("VRD_GEMM_SPEC")) : 1;
+        d.embed_ln = (getenv("VRD_EMBED_LN") != nullptr && atoi(getenv("VRD_EMBED_LN")) == 0) ? 0 : 1;
         return d;
     }();
     return o;
@@ -44,17 +45,28 @@ extern "C" {
 
 int vrd_abi_version(void) { return VRD_ABI_VERSION; }
 
-int vrd_set_option(const char* name, int value) {
-    if (name == nullptr) return -1;
+static int* option_slot(const char* name) {
+    if (name == nullptr) return nullptr;
     VrdOptions& o = vrd_options();
-    int* slot = nullptr;
-    if (strcmp(name, "pdl") == 0) slot = &o.pdl;
-    else if (strcmp(name, "dw_cfg") == 0) slot = &o.dw_cfg;
-    else if (strcmp(name, "gemm_spec") == 0) slot = &o.gemm_spec;
+    if (strcmp(name, "pdl") == 0) return &o.pdl;
+    if (strcmp(name, "dw_cfg") == 0) return &o.dw_cfg;
+    if (strcmp(name, "gemm_spec") == 0) return &o.gemm_spec;
+    if (strcmp(name, "embed_ln") == 0) return &o.embed_ln;
+    return nullptr;
+}
+
+int vrd_set_option(const char* name, int value) {
+    int* slot = option_slot(name);
     if (slot == nullptr) { fail("vrd_set_option: unknown option"); return -1; }
     const int old = *slot;
     *slot = value;
     return old;
+}
+
+int vrd_get_option(const char* name) {
+    const int* slot = option_slot(name);
+    if (slot == nullptr) { fail("vrd_get_option: unknown option"); return -1; }
+    return *slot;
 }
 const char* vrd_last_error(void) { return t_err; }
 
@@ -137,6 +149,22 @@ int vrd_gemm(const void* A, int a_dtype, int64_t lda, const void* W, const float
         return fail("vrd_gemm: bad a_dtype");
     }
     return check_launch("vrd_gemm");
+}
+
+int vrd_gemm_ln(const void* A, int64_t lda, const void* W, const float* bias, const float* corr, const float* gamma, const float* beta,
+                int relu, void* out, int64_t ldo, int M, int N, int K, int taps, const int32_t* row_seq, const int32_t* seqinfo, int R,
+                vrd_stream_t stream) {
+    if (taps != 1 && taps != 3) return fail("vrd_gemm_ln: taps must be 1 or 3");
+    if (gamma == nullptr || beta == nullptr) return fail("vrd_gemm_ln: gamma and beta are required");
+    if (corr != nullptr && row_seq == nullptr) return fail("vrd_gemm_ln: corr needs a layout");
+    vrd::GemmArgs g;
+    g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.out = out; g.out_dtype = VRD_BF16; g.ldo = ldo;
+    g.M = M; g.N = N; g.K = K; g.taps = taps; g.act = 0;
+    g.res1 = nullptr; g.ldr1 = 0; g.res2 = nullptr; g.ldr2 = 0; g.corr = corr;
+    g.row_seq = row_seq; g.seqinfo = reinterpret_cast<const int4*>(seqinfo); g.R = R;
+    g.ln_gamma = gamma; g.ln_beta = beta; g.ln_relu = relu;
+    if (vrd::gemm_tcgen05_bf16(g, (cudaStream_t)stream) != 0) return fail(vrd::gemm_tcgen05_error());
+    return check_launch("vrd_gemm_ln");
 }
 
 int vrd_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,

@@ -53,6 +53,7 @@ struct VrdOptions {
     int pdl;        // 1: kernels are launched with programmatic stream serialization (default), 0: plain stream order
     int dw_cfg;     // dwconv_ln_tile variant (see rows.cu)
     int gemm_spec;  // 1: specialised tcgen05 GEMM epilogues (default), 0: the generic run-time-flag epilogue for every launch
+    int embed_ln;   // 1: LayerNorm + ReLU of the embedding convs as the GEMM's epilogue on the bf16 path (default), 0: separate launch
 };
 VrdOptions& vrd_options();
 inline bool pdl_enabled() { return vrd_options().pdl != 0; }

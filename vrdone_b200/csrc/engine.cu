@@ -79,7 +79,8 @@ struct Run {
 
     // out = act(a * W^T + bias [+corr]) + res1 + res2 with the layout of level l (or none when l < 0)
     void gemm(const Mat& a, const std::string& wname, const Mat& out, int l, int taps = 1, int act = 0, const Mat* res1 = nullptr,
-              const Mat* res2 = nullptr, const float* corr = nullptr) {
+              const Mat* res2 = nullptr, const float* corr = nullptr, const float* ln_g = nullptr, const float* ln_b = nullptr,
+              int ln_relu = 0) {
         const Weight* W = find(wname + ".W");
         if (fail || dry()) return;
         vrd::GemmArgs g;
@@ -89,6 +90,7 @@ struct Run {
         g.res1 = res1 ? (const float*)res1->p : nullptr; g.ldr1 = res1 ? res1->ld : 0;
         g.res2 = res2 ? (const float*)res2->p : nullptr; g.ldr2 = res2 ? res2->ld : 0;
         g.corr = corr;
+        g.ln_gamma = ln_g; g.ln_beta = ln_b; g.ln_relu = ln_relu;
         if (l >= 0) { g.row_seq = L[l].row_seq; g.seqinfo = reinterpret_cast<const int4*>(L[l].seqinfo); g.R = L[l].R; }
         else { g.row_seq = nullptr; g.seqinfo = nullptr; g.R = 0; }
         if (W->cols != taps * a.cols || out.rows != a.rows || out.cols != W->rows) { error("gemm shape mismatch", wname); return; }
@@ -212,12 +214,20 @@ struct Run {
         const int C = E->cfg.embd_dim, n_conv = E->cfg.n_conv;
         const long long rows = 2LL * L[0].R;
         const size_t mark = A->top;
+        const bool fuse = adt == VRD_BF16 && C == 512 && vrd_options().embed_ln != 0;   // LayerNorm + ReLU as the GEMM's epilogue
         for (int i = 0; i < n_conv; ++i) {
-            Mat e = A->alloc(rows, C, VRD_F32);
             const std::string cn = "backbone." + conv + "." + std::to_string(i);
+            const std::string nn = "backbone." + norm + "." + std::to_string(i);
+            if (fuse) {
+                Mat nx = (i == n_conv - 1) ? out : A->alloc(rows, C, adt);
+                gemm(x, cn, nx, 0, 3, 0, nullptr, nullptr, F(cn + ".corr", false), F(nn + ".g"), F(nn + ".be"), 1);
+                x = nx;
+                continue;
+            }
+            Mat e = A->alloc(rows, C, VRD_F32);
             gemm(x, cn, e, 0, 3, 0, nullptr, nullptr, F(cn + ".corr", false));
             Mat nx = (i == n_conv - 1) ? out : A->alloc(rows, C, adt);
-            layernorm(e, "backbone." + norm + "." + std::to_string(i), nx, true, 0);
+            layernorm(e, nn, nx, true, 0);
             x = nx;
         }
         A->top = mark;

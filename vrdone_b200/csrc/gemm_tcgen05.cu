@@ -241,6 +241,7 @@ struct EpiArgs {
     const float* corr; const int* row_seq; const int4* seqinfo; int R;
     int wide;                               // bf16 output without residual: [32 x 64] store boxes (map in the map_res slot)
     int dbg;                                // timing experiments only (wrong results): 1 = no TMA stores, 2 = nothing after the TMEM load
+    const float* ln_g; const float* ln_b; int ln_relu;   // EPI_LN: channel LayerNorm (+ ReLU) over the N = 512 outputs of a row
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of two SMs of one TPC) shares a 256 x BN tile through
@@ -252,7 +253,12 @@ struct EpiArgs {
 // instructions per 32-column chunk, of which 32 FADD + 16 F2FP + 8 LDS + 4 STS + 1 LDTM do the work and ~120 are LDC / ISETP / BRA /
 // BSSY chains re-deciding the flags (warp cycles per issued instruction 10-14: two epilogue warps per scheduler hide nothing), so
 // the epilogue, not the tensor pipe, paced these GEMMs.  BN != 0 fixes the tile width (the chunk loop unrolls).
-enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_F32_RES = 3 };
+// EPI_LN (BN = 512): the tile spans the whole 512-channel row, so the epilogue owns complete rows and applies the channel LayerNorm
+// (+ ReLU) of the embedding convs itself (reference blocks.py:143-158 after the k = 3 convs of backbones.py:184-197): the fp32
+// conv output never reaches HBM and the standalone layernorm launch disappears.  The accumulator takes all 512 TMEM columns (two
+// N = 256 instructions per K step), so main loop and epilogue of a CTA alternate instead of overlapping -- these GEMMs have K = 1536
+// or 3072, the epilogue is ~5-10 % of a tile.
+enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_F32_RES = 3, EPI_LN = 4 };
 
 template <int CG, int MODE, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -271,7 +277,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint8_t* smem_w = smem + stages * A_STAGE_BYTES;
     uint8_t* staging = smem_w + stages * w_stage_bytes;          // 1024-aligned: every stage size is a multiple of 1024
     uint8_t* staging2 = staging + STAGING_TOTAL;                 // second-residual boxes (only carved when there is one)
-    uint64_t* bars = (uint64_t*)(staging + (e.res2 != nullptr ? 2 : 1) * STAGING_TOTAL);
+    constexpr bool LNM = MODE == EPI_LN;                         // one staging box per epilogue warp, the 512-column accumulator
+    static_assert(!LNM || BN == 512, "EPI_LN needs the full row in one tile");
+    uint64_t* bars = (uint64_t*)(staging + (LNM ? STAGING_TOTAL / 2 : (e.res2 != nullptr ? 2 : 1) * STAGING_TOTAL));
     uint64_t* full = bars;                           // [MAX_STAGES]
     uint64_t* empty = bars + MAX_STAGES;             // [MAX_STAGES]
     uint64_t* tfull = bars + 2 * MAX_STAGES;         // [2]
@@ -280,6 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t* tmem_slot = (uint32_t*)(resbar + 2 * EPI_WARPS);
     float* s_bias = (float*)(tmem_slot + 4);         // [MAX_N]
     float* s_corr = s_bias + MAX_N;                  // [MAX_N]
+    float* s_xch = s_corr + MAX_N;                   // EPI_LN: [2 tile parities][2 column halves][128 rows][sum, sum of squares]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_n = e.N / block_n;
@@ -293,6 +302,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int i = threadIdx.x; i < e.N; i += NUM_THREADS) {
         s_bias[i] = (e.bias != nullptr) ? e.bias[i] : 0.f;
         s_corr[i] = (e.corr != nullptr) ? e.corr[i] : 0.f;
+        if constexpr (LNM) { s_bias[512 + i] = e.ln_g[i]; s_bias[1024 + i] = e.ln_b[i]; }   // N = 512: gamma, beta behind the bias
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -343,10 +353,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if constexpr (CG == 2) {
                         const uint32_t bar = mapa_shared(smem_u32(&full[stage]), 0);
                         tma_load_2d_cg2(smem_a + stage * A_STAGE_BYTES, &map_a, bar, ka, row);
-                        tma_load_2d_cg2(smem_w + stage * w_stage_bytes, &map_w, bar, wcol, n0);
+                        if constexpr (LNM) {   // two boxes of 128 W rows: this CTA's share of output channels [0, 256) and of [256, 512)
+                            tma_load_2d_cg2(smem_w + stage * w_stage_bytes, &map_w, bar, wcol, cta_rank * 128);
+                            tma_load_2d_cg2(smem_w + stage * w_stage_bytes + w_stage_bytes / 2, &map_w, bar, wcol, 256 + cta_rank * 128);
+                        } else {
+                            tma_load_2d_cg2(smem_w + stage * w_stage_bytes, &map_w, bar, wcol, n0);
+                        }
                     } else {
                         tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full[stage], ka, row);
-                        tma_load_2d(smem_w + stage * w_stage_bytes, &map_w, &full[stage], wcol, n0);
+                        if constexpr (LNM) {
+                            tma_load_2d(smem_w + stage * w_stage_bytes, &map_w, &full[stage], wcol, 0);
+                            tma_load_2d(smem_w + stage * w_stage_bytes + w_stage_bytes / 2, &map_w, &full[stage], wcol, 256);
+                        } else {
+                            tma_load_2d(smem_w + stage * w_stage_bytes, &map_w, &full[stage], wcol, n0);
+                        }
                     }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -354,12 +374,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else if (warp == 1) {
         if (lane == 0 && cta_rank == 0) {
-            const uint32_t idesc = make_idesc(block_n, BLOCK_M * CG);
+            const uint32_t idesc = make_idesc(LNM ? 256 : block_n, BLOCK_M * CG);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
+                const int as = LNM ? 0 : (it & 1);                       // EPI_LN: one accumulator stage of 512 columns
+                const uint32_t aphase = LNM ? (it & 1) : ((it >> 1) & 1);
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * ACC_STAGE_COLS;
@@ -373,6 +393,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
                         if constexpr (CG == 2) umma_bf16_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                         else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (LNM) {   // output channels [256, 512): the second half of the W stage, accumulator columns 256 ..
+                            const uint64_t bdesc2 = make_smem_desc(smem_u32(smem_w + stage * w_stage_bytes + w_stage_bytes / 2));
+                            if constexpr (CG == 2) umma_bf16_cg2(tmem_d + 256, adesc + 2 * k, bdesc2 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            else umma_bf16(tmem_d + 256, adesc + 2 * k, bdesc2 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
                     if constexpr (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
@@ -381,6 +406,136 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if constexpr (CG == 2) umma_commit_cg2(&tfull[as]); else umma_commit(&tfull[as]);   // accumulator stage complete
             }
         }
+    } else if (warp >= EPI_WARP0 && LNM) {
+        // ---- EPI_LN: thread = row; the two warps of a TMEM lane quarter own 256 columns each.  Pass 1: sum and sum of squares of
+        // v = acc + bias (+ pad correction) over the warp's columns, exchanged with the partner warp through shared memory behind a
+        // 64-thread named barrier.  Pass 2 (the accumulator is read again, nothing is kept in registers): normalise, gamma / beta,
+        // ReLU, bf16, [32 x 64] staging box, TMA store.
+        const int ew = warp - EPI_WARP0;
+        const int wq = warp & 3;
+        const int half = ew >> 2;
+        const uint32_t s_bias_u = smem_u32(s_bias);
+        uint8_t* box = staging + ew * STAGING_BYTES;
+        const uint32_t box_u = smem_u32(box);
+        int it = 0;
+        for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+            const int m0 = tile * (BLOCK_M * CG) + cta_rank * BLOCK_M;
+            const int row0 = m0 + wq * 32, row = row0 + lane;
+            bool valid = row < e.M, add_corr = false;
+            if (e.row_seq != nullptr && valid) {
+                const int rl = row % e.R;
+                const int seq = e.row_seq[rl];
+                valid = seq >= 0;
+                if (valid && e.corr != nullptr) {
+                    const int4 si = e.seqinfo[seq];
+                    add_corr = (si.z != 0) && (rl - si.x == si.y - 1);
+                }
+            }
+            mbar_wait(&tfull[0], it & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + half * 256;
+            uint32_t acc[CHUNK];
+            float s1 = 0.f, s2 = 0.f;
+            tmem_ld32(taddr, acc);
+#pragma unroll 2
+            for (int c = 0; c < 8; ++c) {
+                tmem_ld_wait();
+                const int n = half * 256 + c * CHUNK;
+                float v[CHUNK];
+#pragma unroll
+                for (int i = 0; i < CHUNK / 4; ++i) {
+                    const float4 bi = lds128_ro(s_bias_u + (uint32_t)(n + 4 * i) * 4);
+                    v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + bi.x;
+                    v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + bi.y;
+                    v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bi.z;
+                    v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + bi.w;
+                }
+                tmem_ld32(taddr + ((c + 1) & 7) * CHUNK, acc);      // the next chunk; after the last one: chunk 0 of pass 2
+                if (add_corr) {
+#pragma unroll
+                    for (int i = 0; i < CHUNK; ++i) v[i] += s_corr[n + i];
+                }
+                float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < CHUNK; i += 2) {
+                    a0 += v[i]; a1 += v[i + 1];
+                    q0 = fmaf(v[i], v[i], q0); q1 = fmaf(v[i + 1], v[i + 1], q1);
+                }
+                s1 += a0 + a1;
+                s2 += q0 + q1;
+            }
+            float* xs = s_xch + (it & 1) * 512;
+            *reinterpret_cast<float2*>(xs + (half * 128 + wq * 32 + lane) * 2) = make_float2(s1, s2);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
+            const float2 xa = *reinterpret_cast<const float2*>(xs + (wq * 32 + lane) * 2);
+            const float2 xb = *reinterpret_cast<const float2*>(xs + (128 + wq * 32 + lane) * 2);
+            const float mean = (xa.x + xb.x) * (1.0f / 512.f);
+            const float var = fmaxf((xa.y + xb.y) * (1.0f / 512.f) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + VRD_EPS);
+            const float nmr = -mean * rstd;
+#pragma unroll 2
+            for (int c = 0; c < 8; ++c) {
+                if ((c & 1) == 0) {
+                    if (lane == 0) bulk_wait_read<0>();      // the previous store has read this warp's box
+                    __syncwarp();
+                }
+                tmem_ld_wait();
+                const int n = half * 256 + c * CHUNK;
+                float v[CHUNK];
+#pragma unroll
+                for (int i = 0; i < CHUNK / 4; ++i) {
+                    const float4 bi = lds128_ro(s_bias_u + (uint32_t)(n + 4 * i) * 4);
+                    v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + bi.x;
+                    v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + bi.y;
+                    v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + bi.z;
+                    v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + bi.w;
+                }
+                if (c + 1 < 8) {
+                    tmem_ld32(taddr + (c + 1) * CHUNK, acc);
+                } else {                                     // accumulator read twice: hand the TMEM back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[0]), 0));
+                        else mbar_arrive(&tempty[0]);
+                    }
+                }
+                if (add_corr) {
+#pragma unroll
+                    for (int i = 0; i < CHUNK; ++i) v[i] += s_corr[n + i];
+                }
+#pragma unroll
+                for (int i = 0; i < CHUNK / 4; ++i) {
+                    const float4 gi = lds128_ro(s_bias_u + (uint32_t)(512 + n + 4 * i) * 4);
+                    const float4 be = lds128_ro(s_bias_u + (uint32_t)(1024 + n + 4 * i) * 4);
+                    v[4 * i + 0] = fmaf(fmaf(v[4 * i + 0], rstd, nmr), gi.x, be.x);
+                    v[4 * i + 1] = fmaf(fmaf(v[4 * i + 1], rstd, nmr), gi.y, be.y);
+                    v[4 * i + 2] = fmaf(fmaf(v[4 * i + 2], rstd, nmr), gi.z, be.z);
+                    v[4 * i + 3] = fmaf(fmaf(v[4 * i + 3], rstd, nmr), gi.w, be.w);
+                }
+                if (e.ln_relu) {
+#pragma unroll
+                    for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < CHUNK; ++i) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < CHUNK / 8; ++j)          // 128-byte rows: chunk jj of row r stored at chunk jj ^ (r & 7) (TMA SWIZZLE_128B)
+                    sts128(box_u + lane * 128 + (((j + 4 * (c & 1)) ^ (lane & 7)) << 4), pack2(v[8 * j], v[8 * j + 1]),
+                           pack2(v[8 * j + 2], v[8 * j + 3]), pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+                if ((c & 1) == 1) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_res, box_u, n - CHUNK, row0);   // map_res carries the [32 x 64] bf16 box map
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all();
     } else if (warp >= EPI_WARP0) {
         constexpr bool GEN = MODE == EPI_GENERIC;
         const bool out_bf16 = GEN ? (e.out_dtype == VRD_BF16) : (MODE == EPI_BF16 || MODE == EPI_BF16_GELU);
@@ -574,6 +729,7 @@ GemmKernel pick_kernel(int cg, int mode, int bn) {
     if (mode == EPI_BF16_GELU && bn == 256) return VRD_PICK(EPI_BF16_GELU, 256);
     if (mode == EPI_F32_RES && bn == 128) return VRD_PICK(EPI_F32_RES, 128);
     if (mode == EPI_F32_RES && bn == 256) return VRD_PICK(EPI_F32_RES, 256);
+    if (mode == EPI_LN && bn == 512) return VRD_PICK(EPI_LN, 512);
 #undef VRD_PICK
     return nullptr;
 }
@@ -633,8 +789,15 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     }
     const bool has_res = g.res1 != nullptr;
     if (g.res2 != nullptr && !has_res) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: res2 without res1"); return 1; }
+    const bool ln = g.ln_gamma != nullptr;
+    if (ln && (g.N != 512 || g.out_dtype != VRD_BF16 || has_res || g.act != 0 || g.ln_beta == nullptr || split)) {
+        snprintf(g_err, sizeof g_err, "gemm_tcgen05: the LayerNorm epilogue needs N = 512, a bf16 output, no residual and no activation");
+        return 1;
+    }
     int block_n;
-    if (has_res) {   // two 32-column chunks per epilogue warp (both residual boxes prefetched), four when K is long enough to hide
+    if (ln) {
+        block_n = 512;
+    } else if (has_res) {   // two 32-column chunks per epilogue warp (both residual boxes prefetched), four when K is long enough to hide
         if (g.N % 256 == 0 && g.taps * g.K >= 1024 && g.res2 == nullptr) block_n = 256;   // a second residual doubles the staging boxes
         else if (g.N % 128 == 0) block_n = 128;
         else if (g.N <= 128) block_n = g.N;
@@ -659,7 +822,8 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     CUtensorMap map_a, map_w, map_out, map_res, map_res2;
     const long long kk = (long long)g.taps * g.K * (split ? 2 : 1);
     if (!make_map(&map_a, g.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, split ? 2 * g.K : g.K, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    if (!make_map(&map_w, g.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, kk, kk, block_n / cg, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    // EPI_LN: two boxes of block_n / (2 cg) W rows per stage (output channels [0, 256) and [256, 512))
+    if (!make_map(&map_w, g.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, kk, kk, ln ? block_n / (2 * cg) : block_n / cg, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (g.out_dtype == VRD_BF16) {
         if (!make_map(&map_out, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     } else {
@@ -667,7 +831,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     }
     if (has_res) {
         if (!make_map(&map_res, g.res1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldr1, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    } else if (wide_ok && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) {
+    } else if ((wide_ok || ln) && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) {
         // no residual: the slot carries the [32 rows x 64 cols] box map of the wide bf16 epilogue
         if (!make_map(&map_res, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, 2 * CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     } else {
@@ -679,15 +843,17 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
         map_res2 = map_res;
     }
     const int stage_bytes = A_STAGE_BYTES + (block_n / cg) * BLOCK_K * 2;
-    const int fixed = 1024 + (g.res2 != nullptr ? 2 : 1) * STAGING_TOTAL + 1024 + 2 * MAX_N * 4;   // alignment slack, staging, barriers, bias + corr
+    // alignment slack, staging, barriers, bias + corr (EPI_LN: one box per epilogue warp, + the statistics exchange buffer)
+    const int fixed = ln ? 1024 + STAGING_TOTAL / 2 + 1024 + 2 * MAX_N * 4 + 4096
+                         : 1024 + (g.res2 != nullptr ? 2 : 1) * STAGING_TOTAL + 1024 + 2 * MAX_N * 4;
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: tile does not fit in shared memory (N=%d, residuals=%d)", g.N, has_res + (g.res2 != nullptr)); return 1; }
     const int smem = fixed + stages * stage_bytes;
     if (attr_once.first()) {
         for (int c = 1; c <= 2; ++c)
-            for (int m = 0; m < 4; ++m)
-                for (int bn = 0; bn <= 256; bn += 128) {
+            for (int m = 0; m < 5; ++m)
+                for (int bn = 0; bn <= 512; bn += 128) {
                     GemmKernel k = pick_kernel(c, m, bn);
                     if (k != nullptr && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
                         snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(max dynamic smem) failed");
@@ -696,11 +862,14 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
                 }
     }
     const int wide = (!has_res && wide_ok && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) ? 1 : 0;
-    EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R, wide, dbg};
+    EpiArgs e{g.bias, g.out_dtype, g.M, g.N, g.act, has_res ? 1 : 0, g.res2, g.ldr2, g.corr, g.row_seq, g.seqinfo, g.R, wide, dbg,
+              g.ln_gamma, g.ln_beta, g.ln_relu};
     // specialised epilogues for the shapes that carry the forward (q / k / v and other bf16 projections, the GELU MLP-up GEMMs, the
     // fp32 residual projections); everything else (ReLU, pad correction, second residual, narrow tiles, experiments) stays generic
     int mode = EPI_GENERIC, bn_ct = 0;
-    if (spec_ok && dbg == 0 && g.corr == nullptr && g.res2 == nullptr) {
+    if (ln) {
+        mode = EPI_LN; bn_ct = 512;
+    } else if (spec_ok && dbg == 0 && g.corr == nullptr && g.res2 == nullptr) {
         if (wide && block_n == 256 && g.act == 0) { mode = EPI_BF16; bn_ct = 256; }
         else if (wide && block_n == 256 && g.act == 2) { mode = EPI_BF16_GELU; bn_ct = 256; }
         // the fp32 residual projections are HBM-bound: the specialised epilogue measured -2 % on them (gemm_spec = 2 selects it)

@@ -25,6 +25,8 @@ struct GemmArgs {
     const float* res2; long long ldr2;
     const float* corr;                 // optional [N] vector added (before the activation) on the last row of pairs with haspad
     const int* row_seq; const int4* seqinfo; int R;   // optional layout: separator rows are written as zeros
+    // optional channel LayerNorm (+ ReLU) of the N = 512 outputs in the epilogue (tcgen05 bf16 path only; bf16 output, no residual)
+    const float* ln_gamma = nullptr; const float* ln_beta = nullptr; int ln_relu = 0;
 };
 
 void pack_pairs(const void* ptrs, const long long* strides, Lay lay, int nv, int nc, int nbs, int nbe, void* vis, void* clip,

@@ -24,6 +24,7 @@ _SIGNATURES = {
     "vrd_abi_version": [],
     "vrd_device_arch": [],
     "vrd_set_option": [C.c_char_p, _i32],
+    "vrd_get_option": [C.c_char_p],
     "vrd_h2d_pairs": [_vp, _vp, _vp, _vp, _i32, _vp],
     "vrd_merge_layout": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "vrd_upload": [_vp, _vp, _i64, _vp],
@@ -31,6 +32,7 @@ _SIGNATURES = {
     "vrd_pack_pairs": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
     "vrd_gemm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp,
                  _vp, _i32, _vp],
+    "vrd_gemm_ln": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "vrd_layernorm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _vp],
     "vrd_small_conv": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp],
     "vrd_dwconv_ln": [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
@@ -144,7 +146,7 @@ def _f32(t: Optional[torch.Tensor]):
     return _p(t)
 
 
-_OP_NAMES = frozenset(["pack_pairs", "gemm", "layernorm", "small_conv", "dwconv_ln", "window_attn", "full_attn", "maxpool_skip",
+_OP_NAMES = frozenset(["pack_pairs", "gemm", "gemm_ln", "layernorm", "small_conv", "dwconv_ln", "window_attn", "full_attn", "maxpool_skip",
                        "fpn_top", "fpn_level", "mask_features", "query_ln", "query_self_attn", "query_cross_attn", "mask_logits",
                        "softmax_topk"])
 
@@ -174,6 +176,12 @@ class CudaOps:
             raise ValueError(f"vrd_set_option: unknown option {name!r}")
         return old
 
+    def get_option(self, name: str) -> int:
+        v = self.lib.vrd_get_option(name.encode())
+        if v < 0:
+            raise ValueError(f"vrd_get_option: unknown option {name!r}")
+        return v
+
     # -- per-launch CUDA-event timing (bench.py roofline pass) --------------------------------------------------------
     def start_timing(self):
         """Wrap every op of this instance with a CUDA-event pair (instance attributes shadow the class methods)."""
@@ -189,7 +197,9 @@ class CudaOps:
                 e0.record()
                 r = _fn(*a, **k)
                 e1.record()
-                self._timing.append(("vrd_" + _name, e0, e1, self._last_flops, self._last_tag, self._last_bytes))
+                # the GEMM with the LayerNorm epilogue is the same kernel: it is accounted with the GEMMs
+                self._timing.append(("vrd_" + ("gemm" if _name == "gemm_ln" else _name), e0, e1, self._last_flops, self._last_tag,
+                                     self._last_bytes))
                 return r
             setattr(self, name, timed)
 
@@ -299,6 +309,27 @@ class CudaOps:
                           f"{' gelu' if act == 2 else ''}{' +res' if res1 is not None else ''}")
         self._check(self.lib.vrd_gemm(ap, _dt(a), lda, _p(w), _f32(bias), op, _dt(out), ldo, M, N, K, taps, act, r1, ld1, r2, ld2,
                                       _f32(corr), rs, si, R, self._stream()), "vrd_gemm")
+
+    def gemm_ln(self, a, w, out, ln, bias=None, taps=1, corr=None, relu=False, lay=None, streams=1):
+        """out (bf16) = [relu](LayerNorm_channels(a @ w.T + bias [+ corr])): the conv-as-GEMM of an embedding layer with its
+        LayerNorm + ReLU as the epilogue (N = 512)."""
+        ap, lda = _mat(a)
+        op, ldo = _mat(out)
+        M, K = a.shape
+        N = w.shape[0]
+        assert a.dtype == torch.bfloat16 and w.dtype == a.dtype and out.dtype == torch.bfloat16
+        assert w.is_contiguous() and w.shape[1] == taps * K and out.shape == (M, N)
+        if lay is not None:
+            assert M == streams * lay.R
+            rs, si, R = self._lay(lay)
+        else:
+            rs, si, R = None, None, 0
+        valid_rows = streams * int(lay.len.sum()) if lay is not None else M
+        self._last_flops = 2.0 * valid_rows * N * K * taps
+        self._last_bytes = valid_rows * (2.0 * K + 2.0 * N) + w.numel() * 2.0
+        self._last_tag = f"{'big' if M >= 16384 else 'small'} M, {taps}x{K}->{N} bf16 +ln"
+        self._check(self.lib.vrd_gemm_ln(ap, lda, _p(w), _f32(bias), _f32(corr), _f32(ln[0]), _f32(ln[1]), int(relu), op, ldo, M, N, K,
+                                         taps, rs, si, R, self._stream()), "vrd_gemm_ln")
 
     def layernorm(self, x, g, b, out, relu=False, lay=None, streams=1):
         xp, ldx = _mat(x)

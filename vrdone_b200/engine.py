@@ -171,6 +171,13 @@ class Engine:
         bucket = (rows + ROW_BUCKET - 1) // ROW_BUCKET * ROW_BUCKET
         return torch.empty(bucket, cols, dtype=dtype, device=self.device)[:rows]
 
+    @property
+    def fuse_embed_ln(self) -> bool:
+        """LayerNorm + ReLU of the embedding convs as the GEMM's epilogue (the launcher option ``embed_ln``, shared with the native
+        schedule so that both run the same kernels); kernel providers without options (the CPU emulation of the tests) fuse."""
+        get = getattr(self.ops, "get_option", None)
+        return hasattr(self.ops, "gemm_ln") and (get is None or get("embed_ln") != 0)
+
     def _W(self, name):
         return self.w.t[name]
 
@@ -251,12 +258,18 @@ class Engine:
         n_conv = self.mc["backbone_arch"][0]
         rows = 2 * lay0.R
         for i in range(n_conv):
-            e = self._buf(rows, C, torch.float32)
             corr = self._b(f"backbone.{conv}.{i}.corr")
-            self._gemm(x, f"backbone.{conv}.{i}", e, lay0, 2, taps=3, corr=corr)
-            x = out if i == n_conv - 1 else self._buf(rows, C, self.adt)
-            ops.layernorm(e, self._W(f"backbone.{norm}.{i}.g"), self._W(f"backbone.{norm}.{i}.be"), x, relu=True,
-                          lay=lay0, streams=2)
+            nx = out if i == n_conv - 1 else self._buf(rows, C, self.adt)
+            ln = (self._W(f"backbone.{norm}.{i}.g"), self._W(f"backbone.{norm}.{i}.be"))
+            if self.fuse_embed_ln and self.adt == torch.bfloat16 and C == 512:
+                # bf16 path: LayerNorm + ReLU are the GEMM's epilogue (the tile spans the 512-channel row); no fp32 conv output
+                ops.gemm_ln(x, self._W(f"backbone.{conv}.{i}.W"), nx, ln, bias=self._b(f"backbone.{conv}.{i}.b"), taps=3, corr=corr,
+                            relu=True, lay=lay0, streams=2)
+            else:
+                e = self._buf(rows, C, torch.float32)
+                self._gemm(x, f"backbone.{conv}.{i}", e, lay0, 2, taps=3, corr=corr)
+                ops.layernorm(e, ln[0], ln[1], nx, relu=True, lay=lay0, streams=2)
+            x = nx
         return out
 
     # -- full network ---------------------------------------------------------------------------

@@ -302,7 +302,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int i = threadIdx.x; i < e.N; i += NUM_THREADS) {
         s_bias[i] = (e.bias != nullptr) ? e.bias[i] : 0.f;
         s_corr[i] = (e.corr != nullptr) ? e.corr[i] : 0.f;
-        if constexpr (LNM) { s_bias[512 + i] = e.ln_g[i]; s_bias[1024 + i] = e.ln_b[i]; }   // N = 512: gamma, beta behind the bias
+        if constexpr (LNM) {                                                                // N = 512: gamma, beta behind the bias
+            s_bias[512 + i] = e.ln_g != nullptr ? e.ln_g[i] : 1.f;
+            s_bias[1024 + i] = e.ln_g != nullptr ? e.ln_b[i] : 0.f;
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -436,9 +439,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + half * 256;
             uint32_t acc[CHUNK];
             float s1 = 0.f, s2 = 0.f;
+            const bool do_ln = e.ln_g != nullptr;    // false: experiment, a plain bf16 GEMM on 512-column tiles (A is read once)
             tmem_ld32(taddr, acc);
 #pragma unroll 2
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < (do_ln ? 8 : 0); ++c) {
                 tmem_ld_wait();
                 const int n = half * 256 + c * CHUNK;
                 float v[CHUNK];
@@ -464,15 +468,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 s1 += a0 + a1;
                 s2 += q0 + q1;
             }
-            float* xs = s_xch + (it & 1) * 512;
-            *reinterpret_cast<float2*>(xs + (half * 128 + wq * 32 + lane) * 2) = make_float2(s1, s2);
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
-            const float2 xa = *reinterpret_cast<const float2*>(xs + (wq * 32 + lane) * 2);
-            const float2 xb = *reinterpret_cast<const float2*>(xs + (128 + wq * 32 + lane) * 2);
-            const float mean = (xa.x + xb.x) * (1.0f / 512.f);
-            const float var = fmaxf((xa.y + xb.y) * (1.0f / 512.f) - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + VRD_EPS);
-            const float nmr = -mean * rstd;
+            float rstd = 1.f, nmr = 0.f;
+            if (do_ln) {
+                float* xs = s_xch + (it & 1) * 512;
+                *reinterpret_cast<float2*>(xs + (half * 128 + wq * 32 + lane) * 2) = make_float2(s1, s2);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
+                const float2 xa = *reinterpret_cast<const float2*>(xs + (wq * 32 + lane) * 2);
+                const float2 xb = *reinterpret_cast<const float2*>(xs + (128 + wq * 32 + lane) * 2);
+                const float mean = (xa.x + xb.x) * (1.0f / 512.f);
+                const float var = fmaxf((xa.y + xb.y) * (1.0f / 512.f) - mean * mean, 0.f);
+                rstd = rsqrtf(var + VRD_EPS);
+                nmr = -mean * rstd;
+            }
 #pragma unroll 2
             for (int c = 0; c < 8; ++c) {
                 if ((c & 1) == 0) {
@@ -504,6 +511,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int i = 0; i < CHUNK; ++i) v[i] += s_corr[n + i];
                 }
+                if (do_ln) {
 #pragma unroll
                 for (int i = 0; i < CHUNK / 4; ++i) {
                     const float4 gi = lds128_ro(s_bias_u + (uint32_t)(512 + n + 4 * i) * 4);
@@ -512,6 +520,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     v[4 * i + 1] = fmaf(fmaf(v[4 * i + 1], rstd, nmr), gi.y, be.y);
                     v[4 * i + 2] = fmaf(fmaf(v[4 * i + 2], rstd, nmr), gi.z, be.z);
                     v[4 * i + 3] = fmaf(fmaf(v[4 * i + 3], rstd, nmr), gi.w, be.w);
+                }
                 }
                 if (e.ln_relu) {
 #pragma unroll
@@ -794,8 +803,11 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
         snprintf(g_err, sizeof g_err, "gemm_tcgen05: the LayerNorm epilogue needs N = 512, a bf16 output, no residual and no activation");
         return 1;
     }
+    // experiment (gemm_spec = 3): plain bf16 512 -> 512 GEMMs on 512-column tiles through the EPI_LN kernel without the LayerNorm
+    const bool wide512 = !ln && vrd_options().gemm_spec == 3 && g.N == 512 && g.out_dtype == VRD_BF16 && !has_res && g.act == 0 &&
+                         g.corr == nullptr && !split;
     int block_n;
-    if (ln) {
+    if (ln || wide512) {
         block_n = 512;
     } else if (has_res) {   // two 32-column chunks per epilogue warp (both residual boxes prefetched), four when K is long enough to hide
         if (g.N % 256 == 0 && g.taps * g.K >= 1024 && g.res2 == nullptr) block_n = 256;   // a second residual doubles the staging boxes
@@ -823,7 +835,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     const long long kk = (long long)g.taps * g.K * (split ? 2 : 1);
     if (!make_map(&map_a, g.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, split ? 2 * g.K : g.K, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     // EPI_LN: two boxes of block_n / (2 cg) W rows per stage (output channels [0, 256) and [256, 512))
-    if (!make_map(&map_w, g.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, kk, kk, ln ? block_n / (2 * cg) : block_n / cg, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (!make_map(&map_w, g.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, kk, kk, (ln || wide512) ? block_n / (2 * cg) : block_n / cg, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (g.out_dtype == VRD_BF16) {
         if (!make_map(&map_out, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     } else {
@@ -831,7 +843,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     }
     if (has_res) {
         if (!make_map(&map_res, g.res1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldr1, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    } else if ((wide_ok || ln) && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) {
+    } else if ((wide_ok || ln || wide512) && g.out_dtype == VRD_BF16 && (block_n / (2 * CHUNK)) % 2 == 0) {
         // no residual: the slot carries the [32 rows x 64 cols] box map of the wide bf16 epilogue
         if (!make_map(&map_res, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, 2 * CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     } else {
@@ -844,7 +856,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     }
     const int stage_bytes = A_STAGE_BYTES + (block_n / cg) * BLOCK_K * 2;
     // alignment slack, staging, barriers, bias + corr (EPI_LN: one box per epilogue warp, + the statistics exchange buffer)
-    const int fixed = ln ? 1024 + STAGING_TOTAL / 2 + 1024 + 2 * MAX_N * 4 + 4096
+    const int fixed = (ln || wide512) ? 1024 + STAGING_TOTAL / 2 + 1024 + 2 * MAX_N * 4 + 4096
                          : 1024 + (g.res2 != nullptr ? 2 : 1) * STAGING_TOTAL + 1024 + 2 * MAX_N * 4;
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -867,7 +879,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     // specialised epilogues for the shapes that carry the forward (q / k / v and other bf16 projections, the GELU MLP-up GEMMs, the
     // fp32 residual projections); everything else (ReLU, pad correction, second residual, narrow tiles, experiments) stays generic
     int mode = EPI_GENERIC, bn_ct = 0;
-    if (ln) {
+    if (ln || wide512) {
         mode = EPI_LN; bn_ct = 512;
     } else if (spec_ok && dbg == 0 && g.corr == nullptr && g.res2 == nullptr) {
         if (wide && block_n == 256 && g.act == 0) { mode = EPI_BF16; bn_ct = 256; }

@@ -53,6 +53,8 @@ def parse():
     p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     p.add_argument("--set-videos", type=int, default=10, help="videos in the cfg2 set (one step = one pass over the set)")
     p.add_argument("--set-seed", type=int, default=0)
+    p.add_argument("--extra-seeds", default="", help="comma-separated set seeds: `value` (HBM-resident, pipelined loop) is also measured on "
+                                                      "the cfg2 sets drawn with these seeds and reported under `seeds` (SURVEY 8d: seeds {0,1,2})")
     p.add_argument("--tracklets", type=int, default=None, help="fixed-shape workload: tracklets per video (with --frames)")
     p.add_argument("--frames", type=int, default=None)
     p.add_argument("--videos", type=int, default=2, help="fixed-shape workload: distinct videos per step")
@@ -480,6 +482,40 @@ def main():
                                      "ms_per_step": ms_net / args.steps, "clocks": net_clocks}
         log(f"[bench] network only: {out_extra['network_only']}")
 
+    # other draws of the cfg2 set (different videos, pair counts and lengths), same loop, per-step wall times kept
+    seeds_out = None
+    if args.extra_seeds and args.tracklets is None and args.frames is None:
+        seeds_out = {str(args.set_seed): {"value": pairs / (ms * 1e-3), "pairs_per_step": int(sum(n_pairs)), "ms_per_step": ms / args.steps,
+                                          "step_wall_ms": steps_value}}
+        for sd in [int(x) for x in args.extra_seeds.split(",") if x.strip() != ""]:
+            if sd == args.set_seed:
+                continue
+            vids = []
+            for s_, nf, nt in synth.cfg2_video_set(args.set_videos, sd):
+                vids.append(to_device(synth.synthetic_video(cfg, s_, n_tracklets=nt, n_frames=nf), dev))
+            n_sd = sum(len(v["sids"]) for v in vids)
+            warm(vids, passes=2)
+            sync_all()
+            step_ms.clear()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tw = time.perf_counter()
+            for i, out_v in enumerate(runner.run_videos(model, (vids[j % len(vids)] for j in range(args.steps * len(vids))))):
+                del out_v
+                if (i + 1) % len(vids) == 0:
+                    step_ms.append(round(1e3 * (time.perf_counter() - tw), 1))
+                    tw = time.perf_counter()
+            e1.record()
+            sync_all()
+            ms_sd = reduce_max(e0.elapsed_time(e1))
+            seeds_out[str(sd)] = {"value": world * args.steps * n_sd / (ms_sd * 1e-3), "pairs_per_step": int(n_sd),
+                                  "ms_per_step": ms_sd / args.steps, "step_wall_ms": list(step_ms)}
+            del vids
+            torch.cuda.empty_cache()
+        vals = sorted(v["value"] for v in seeds_out.values())
+        seeds_out["median_value"] = vals[len(vals) // 2]
+        log(f"[bench] seeds: {seeds_out}")
+
     # roofline pass: a CUDA-event pair around every launch (the per-operator Python schedule: same kernels, same order)
     sustained, burst, hbm, src = peaks()
     model.use_native = False
@@ -551,6 +587,8 @@ def main():
            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
            "valid_frames_per_s": world * args.steps * sum(frames) / (ms * 1e-3)}
     out.update(out_extra)
+    if seeds_out is not None:
+        out["seeds"] = seeds_out
     if sweep is not None:
         out["sweep"] = sweep
     if parity is not None:

@@ -286,3 +286,14 @@ def test_full_attention_tcgen05_long_and_ragged(ops, scale):
     out2 = torch.full_like(out, 5.0)
     ops.full_attn(q.cuda(), k.cuda(), v.cuda(), out2, lg.levels[0], 8)
     assert torch.equal(out, out2)
+
+
+def test_launcher_options_roundtrip(ops):
+    """vrd_set_option / vrd_get_option: the experiment switches of the launchers; unknown names fail loudly."""
+    for name in ("pdl", "dw_cfg", "gemm_spec", "embed_ln"):
+        cur = ops.get_option(name)
+        assert ops.set_option(name, cur) == cur and ops.get_option(name) == cur
+    with pytest.raises(ValueError):
+        ops.set_option("no_such_option", 1)
+    with pytest.raises(ValueError):
+        ops.get_option("no_such_option")

@@ -22,6 +22,11 @@
 //                                     so the epilogue warps never issue row-strided global accesses (those cost one L1
 //                                     wavefront per row and bounded the old epilogue).  Overlapped with the next tile's
 //                                     MMAs through the second TMEM stage.
+// Template parameters: CG (1 | 2 CTAs per tile), MODE (the epilogue's feature flags at run time -- EPI_GENERIC -- or fixed at
+// compile time: EPI_BF16, EPI_BF16_GELU, EPI_F32_RES), BN (tile width when fixed).  EPI_LN is the odd one: a 512-column tile whose
+// accumulator fills the tensor memory (one stage: main loop and epilogue alternate) so that the epilogue owns whole rows and applies
+// the channel LayerNorm (+ ReLU) of the embedding convs; see the enum below.  Every kernel starts with griddepcontrol.wait after its
+// prologue (programmatic dependent launch, common.cuh).
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>

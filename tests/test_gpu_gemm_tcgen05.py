@@ -34,6 +34,8 @@ def rnd(shape, seed, scale=1.0):
     (1, 2, 0, False, 256, 256, torch.bfloat16),
     (1, 2, 0, False, 1024, 256, torch.bfloat16),
     (1, 0, 0, False, 256, 512, torch.float32),
+    (1, 2, 0, False, 512, 1024, torch.bfloat16),     # 512-column tile (K >= 1024, bf16 out): GELU
+    (1, 0, 0, False, 512, 1024, torch.bfloat16),
 ])
 def test_gemm_bf16_tcgen05(ops, taps, act, res, corr, N, K, odt):
     lg, lc = PackLayout(LENS, TPADS, 4, "cuda"), PackLayout(LENS, TPADS, 4, "cpu")

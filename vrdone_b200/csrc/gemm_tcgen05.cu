@@ -535,10 +535,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int i = 0; i < CHUNK; ++i) v[i] = 0.f;
                 }
+                if (e.act == 2) {                            // GELU (plain wide-tile GEMMs only; gelu(0) = 0 keeps invalid rows zero)
+#pragma unroll
+                    for (int j = 0; j < CHUNK / 8; ++j)
+                        sts128(box_u + lane * 128 + (((j + 4 * (c & 1)) ^ (lane & 7)) << 4), gelu_pair_bf16(v[8 * j], v[8 * j + 1]),
+                               gelu_pair_bf16(v[8 * j + 2], v[8 * j + 3]), gelu_pair_bf16(v[8 * j + 4], v[8 * j + 5]),
+                               gelu_pair_bf16(v[8 * j + 6], v[8 * j + 7]));
+                } else {
 #pragma unroll
                 for (int j = 0; j < CHUNK / 8; ++j)          // 128-byte rows: chunk jj of row r stored at chunk jj ^ (r & 7) (TMA SWIZZLE_128B)
                     sts128(box_u + lane * 128 + (((j + 4 * (c & 1)) ^ (lane & 7)) << 4), pack2(v[8 * j], v[8 * j + 1]),
                            pack2(v[8 * j + 2], v[8 * j + 3]), pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+                }
                 if ((c & 1) == 1) {
                     fence_async_smem();
                     __syncwarp();
@@ -808,9 +816,11 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
         snprintf(g_err, sizeof g_err, "gemm_tcgen05: the LayerNorm epilogue needs N = 512, a bf16 output, no residual and no activation");
         return 1;
     }
-    // experiment (gemm_spec = 3): plain bf16 512 -> 512 GEMMs on 512-column tiles through the EPI_LN kernel without the LayerNorm
-    const bool wide512 = !ln && vrd_options().gemm_spec == 3 && g.N == 512 && g.out_dtype == VRD_BF16 && !has_res && g.act == 0 &&
-                         g.corr == nullptr && !split;
+    // experiment (gemm_spec = 3): bf16 (optionally GELU) GEMMs with N = 512 on 512-column tiles through the EPI_LN kernel without the
+    // LayerNorm (A is read once).  Measured slower than the 256-column double-buffered tiles: 1007 vs 1029 TFLOP/s at K = 512, 1081 vs
+    // 1136 at K = 1024 (GELU) -- only the K >= 1536 embedding convs, which also lose a whole LayerNorm launch, gain from the wide tile.
+    const bool wide512 = !ln && vrd_options().gemm_spec == 3 && g.N == 512 && g.out_dtype == VRD_BF16 && !has_res &&
+                         (g.act == 0 || g.act == 2) && g.corr == nullptr && !split && dbg == 0;
     int block_n;
     if (ln || wide512) {
         block_n = 512;

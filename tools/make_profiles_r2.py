@@ -122,6 +122,13 @@ def bench_table():
         t = last_json("r2_bench_2gpu.json")
         out += ["", f"Two GPUs (`gpurun --gpus 2`, torchrun, --steps 3 --warmup 2, same build): value {t['value']:,.0f}, e2e {t['e2e']['value']:,.0f}, "
                 f"tracklet api {t['e2e']['tracklet_api_value']:,.0f} pairs/s; sweep {json.dumps(t.get('sweep'))}"]
+    eight = os.path.join(G, "r2_bench_8gpu.json")
+    if os.path.exists(eight):
+        t = last_json("r2_bench_8gpu.json")
+        out += ["", f"Eight GPUs (`gpurun --gpus 8`, torchrun, --steps 3 --warmup 2, `tools/gpu_r2b_8.sh 8`): value {t['value']:,.0f} "
+                f"({t['value'] / d['value']:.2f} x the one-GPU value), e2e with host pair features {t['e2e']['value']:,.0f} (host memory bandwidth: eight copy "
+                f"engines read 11.19 GB per step each out of one host), tracklet api {t['e2e']['tracklet_api_value']:,.0f} pairs/s; sweep {json.dumps(t.get('sweep'))}"]
+        json.dump(t, open(os.path.join(P, "r2_bench_8gpu.json"), "w"), indent=1)
     gs = r.get("gemm_by_shape")
     open(os.path.join(P, "r2_bench_configs.md"), "w").write("\n".join(out) + "\n")
     json.dump(d, open(os.path.join(P, "r2_bench_default.json"), "w"), indent=1)

@@ -87,6 +87,14 @@ int vrd_gemm(const void* A, int a_dtype, int64_t lda, const void* W, const float
              int M, int N, int K, int taps, int act, const float* res1, int64_t ldr1, const float* res2, int64_t ldr2,
              const float* corr, const int32_t* row_seq, const int32_t* seqinfo, int R, vrd_stream_t stream);
 
+/* a7: the attention output projection of an encoder block with the residual and the LayerNorm that feeds the MLP
+ * (blocks.py:1070-1076): out[M, 512] (fp32) = (A * W^T + bias + res) * row validity -- the new residual stream -- and
+ * ln_out[M, 512] (bf16) = LayerNorm_channels(out) * row validity, from one pass over the accumulator row.  bf16 operands.  With
+ * "proj_ln" = 0 (or N != 512) the call runs the projection and the LayerNorm as two launches. */
+int vrd_gemm_res_ln(const void* A, int64_t lda, const void* W, const float* bias, const float* res, int64_t ldr, const float* gamma,
+                    const float* beta, float* out, int64_t ldo, void* ln_out, int64_t ld_ln, int M, int N, int K,
+                    const int32_t* row_seq, const int32_t* seqinfo, int R, vrd_stream_t stream);
+
 /* k1 + k6 fused -- the embedding convs followed by their channel LayerNorm and ReLU (backbones.py:184-197 with blocks.py:143-158):
  * out[M, 512] (bf16) = [relu](LN_channels(A * W^T + bias [+ corr on the last row of padded pairs])) * row validity.  bf16 operands
  * only (tcgen05 path), N must be 512: the tile spans the row, the statistics are taken on the fp32 accumulator in tensor memory and

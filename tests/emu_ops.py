@@ -108,6 +108,21 @@ class EmuOps:
             y = y * self._valid_rows(lay, streams)[:, None]
         out.copy_(y.to(out.dtype))
 
+    def gemm_res_ln(self, a, w, out, ln_out, ln, bias=None, res1=None, lay=None, streams=1):
+        """Projection + residual (fp32 out) and the LayerNorm of the sum (bf16 ln_out)."""
+        self.calls.append("gemm_res_ln")
+        acc = a.float() @ w.float().t()
+        if bias is not None:
+            acc = acc + bias
+        acc = acc + res1
+        if lay is not None:
+            acc = acc * self._valid_rows(lay, streams)[:, None]
+        out.copy_(acc)
+        y = _ln_rows(acc, ln[0], ln[1])
+        if lay is not None:
+            y = y * self._valid_rows(lay, streams)[:, None]
+        ln_out.copy_(y.to(ln_out.dtype))
+
     def layernorm(self, x, g, b, out, relu=False, lay=None, streams=1):
         self.calls.append("layernorm")
         y = _ln_rows(x, g, b)

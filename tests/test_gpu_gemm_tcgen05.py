@@ -137,3 +137,32 @@ def test_gemm_layernorm_epilogue(ops, taps, K, relu, corr, big):
     # separator rows are written as zeros
     sep = (lc.levels[0].row_seq < 0).repeat(streams)
     assert float(out.float().cpu()[sep].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("big", [False, True])
+def test_gemm_residual_layernorm_epilogue(ops, big):
+    """Attention output projection + residual (fp32) and the LayerNorm of the sum (bf16) from one call; ``big``: enough rows for the
+    fused CTA-pair kernel (M >= 16384), otherwise the call runs the two launches itself."""
+    lens = LENS * 12 if big else LENS
+    tpads = TPADS * 12 if big else TPADS
+    lg, lc = PackLayout(lens, tpads, 4, "cuda"), PackLayout(lens, tpads, 4, "cpu")
+    streams, N, K = 2, 512, 512
+    M = streams * lc.levels[0].R
+    a = rnd((M, K), 1).to(torch.bfloat16)
+    a[(lc.levels[0].row_seq < 0).repeat(streams)] = 0
+    w = rnd((N, K), 2, K ** -0.5).to(torch.bfloat16)
+    bias, gm, be = rnd((N,), 3), rnd((N,), 7) * 0.2 + 1, rnd((N,), 8)
+    res = rnd((M, N), 4)
+    ref, ref_ln = torch.empty(M, N), torch.empty(M, N, dtype=torch.bfloat16)
+    EmuOps().gemm_res_ln(a, w, ref, ref_ln, (gm, be), bias=bias, res1=res, lay=lc.levels[0], streams=streams)
+    out = torch.full((M, N), 3.0, device="cuda")
+    out_ln = torch.full((M, N), 3.0, dtype=torch.bfloat16, device="cuda")
+    ops.gemm_res_ln(a.cuda(), w.cuda(), out, out_ln, (gm.cuda(), be.cuda()), bias=bias.cuda(), res1=res.cuda(), lay=lg.levels[0],
+                    streams=streams)
+    torch.cuda.synchronize()
+    err = float((out.cpu() - ref).abs().max())
+    assert err <= 2e-3 * float(ref.abs().max()), f"sum: max abs err {err:.3e}"
+    err = float((out_ln.float().cpu() - ref_ln.float()).abs().max())
+    assert err <= 2e-2 * float(ref_ln.float().abs().max()), f"LayerNorm: max abs err {err:.3e}"
+    sep = (lc.levels[0].row_seq < 0).repeat(streams)
+    assert float(out.cpu()[sep].abs().max()) == 0.0 and float(out_ln.float().cpu()[sep].abs().max()) == 0.0

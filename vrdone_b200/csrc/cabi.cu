@@ -36,6 +36,7 @@ VrdOptions& vrd_options() {
         d.dw_cfg = getenv("VRD_DW_CFG") != nullptr ? atoi(getenv("VRD_DW_CFG")) : 2;
         d.gemm_spec = getenv("VRD_GEMM_SPEC") != nullptr ? atoi(getenv("VRD_GEMM_SPEC")) : 1;
         d.embed_ln = (getenv("VRD_EMBED_LN") != nullptr && atoi(getenv("VRD_EMBED_LN")) == 0) ? 0 : 1;
+        d.proj_ln = (getenv("VRD_PROJ_LN") != nullptr && atoi(getenv("VRD_PROJ_LN")) == 0) ? 0 : 1;
         return d;
     }();
     return o;
@@ -52,6 +53,7 @@ static int* option_slot(const char* name) {
     if (strcmp(name, "dw_cfg") == 0) return &o.dw_cfg;
     if (strcmp(name, "gemm_spec") == 0) return &o.gemm_spec;
     if (strcmp(name, "embed_ln") == 0) return &o.embed_ln;
+    if (strcmp(name, "proj_ln") == 0) return &o.proj_ln;
     return nullptr;
 }
 
@@ -165,6 +167,27 @@ int vrd_gemm_ln(const void* A, int64_t lda, const void* W, const float* bias, co
     g.ln_gamma = gamma; g.ln_beta = beta; g.ln_relu = relu;
     if (vrd::gemm_tcgen05_bf16(g, (cudaStream_t)stream) != 0) return fail(vrd::gemm_tcgen05_error());
     return check_launch("vrd_gemm_ln");
+}
+
+int vrd_gemm_res_ln(const void* A, int64_t lda, const void* W, const float* bias, const float* res, int64_t ldr, const float* gamma,
+                    const float* beta, float* out, int64_t ldo, void* ln_out, int64_t ld_ln, int M, int N, int K,
+                    const int32_t* row_seq, const int32_t* seqinfo, int R, vrd_stream_t stream) {
+    if (gamma == nullptr || beta == nullptr || res == nullptr || ln_out == nullptr) return fail("vrd_gemm_res_ln: null argument");
+    vrd::GemmArgs g;
+    g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.out = out; g.out_dtype = VRD_F32; g.ldo = ldo;
+    g.M = M; g.N = N; g.K = K; g.taps = 1; g.act = 0;
+    g.res1 = res; g.ldr1 = ldr; g.res2 = nullptr; g.ldr2 = 0; g.corr = nullptr;
+    g.row_seq = row_seq; g.seqinfo = reinterpret_cast<const int4*>(seqinfo); g.R = R;
+    if (vrd::gemm_res_ln_fused_ok(g)) {
+        g.ln_gamma = gamma; g.ln_beta = beta; g.ln_relu = 0; g.ln_out = ln_out; g.ld_ln = ld_ln;
+        if (vrd::gemm_tcgen05_bf16(g, (cudaStream_t)stream) != 0) return fail(vrd::gemm_tcgen05_error());
+        return check_launch("vrd_gemm_res_ln");
+    }
+    // switched off, or another row width: two launches
+    if (vrd::gemm_tcgen05_bf16(g, (cudaStream_t)stream) != 0) return fail(vrd::gemm_tcgen05_error());
+    if (vrd::layernorm(out, VRD_F32, ldo, gamma, beta, ln_out, VRD_BF16, ld_ln, M, N, 0, row_seq, R, (cudaStream_t)stream))
+        return fail("vrd_gemm_res_ln: unsupported width for the LayerNorm");
+    return check_launch("vrd_gemm_res_ln");
 }
 
 int vrd_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,

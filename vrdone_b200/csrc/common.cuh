@@ -54,6 +54,7 @@ struct VrdOptions {
     int dw_cfg;     // dwconv_ln_tile variant (see rows.cu)
     int gemm_spec;  // 1: specialised tcgen05 GEMM epilogues (default), 0: the generic run-time-flag epilogue for every launch
     int embed_ln;   // 1: LayerNorm + ReLU of the embedding convs as the GEMM's epilogue on the bf16 path (default), 0: separate launch
+    int proj_ln;    // 1: encoder blocks: attention projection + residual + LayerNorm (MLP input) as one launch (default), 0: two
 };
 VrdOptions& vrd_options();
 inline bool pdl_enabled() { return vrd_options().pdl != 0; }

@@ -80,7 +80,7 @@ struct Run {
     // out = act(a * W^T + bias [+corr]) + res1 + res2 with the layout of level l (or none when l < 0)
     void gemm(const Mat& a, const std::string& wname, const Mat& out, int l, int taps = 1, int act = 0, const Mat* res1 = nullptr,
               const Mat* res2 = nullptr, const float* corr = nullptr, const float* ln_g = nullptr, const float* ln_b = nullptr,
-              int ln_relu = 0) {
+              int ln_relu = 0, const Mat* ln_out = nullptr) {
         const Weight* W = find(wname + ".W");
         if (fail || dry()) return;
         vrd::GemmArgs g;
@@ -91,6 +91,7 @@ struct Run {
         g.res2 = res2 ? (const float*)res2->p : nullptr; g.ldr2 = res2 ? res2->ld : 0;
         g.corr = corr;
         g.ln_gamma = ln_g; g.ln_beta = ln_b; g.ln_relu = ln_relu;
+        if (ln_out != nullptr) { g.ln_out = ln_out->p; g.ld_ln = ln_out->ld; }
         if (l >= 0) { g.row_seq = L[l].row_seq; g.seqinfo = reinterpret_cast<const int4*>(L[l].seqinfo); g.R = L[l].R; }
         else { g.row_seq = nullptr; g.seqinfo = nullptr; g.R = 0; }
         if (W->cols != taps * a.cols || out.rows != a.rows || out.cols != W->rows) { error("gemm shape mismatch", wname); return; }
@@ -161,9 +162,19 @@ struct Run {
             }
         }
         Mat y = A->alloc(rows, C, VRD_F32);
-        gemm(a, p + ".attn.proj", y, lout, 1, 0, &skip);
         Mat h = A->alloc(rows, C, adt);
-        layernorm(y, p + ".ln2", h, false, lout);
+        // bf16 path: projection + residual + the LayerNorm that feeds the MLP as ONE launch
+        bool fused = false;
+        if (adt == VRD_BF16 && C == 512 && !fail && !dry()) {
+            vrd::GemmArgs t;
+            t.M = (int)rows; t.N = C; t.K = C; t.taps = 1; t.act = 0; t.res1 = (const float*)skip.p; t.res2 = nullptr; t.corr = nullptr;
+            fused = vrd::gemm_res_ln_fused_ok(t);
+        }
+        if (fused) gemm(a, p + ".attn.proj", y, lout, 1, 0, &skip, nullptr, nullptr, F(p + ".ln2.g"), F(p + ".ln2.be"), 0, &h);
+        else {
+            gemm(a, p + ".attn.proj", y, lout, 1, 0, &skip);
+            layernorm(y, p + ".ln2", h, false, lout);
+        }
         Mat h2 = A->alloc(rows, 4 * C, adt);
         gemm(h, p + ".mlp.0", h2, lout, 1, VRD_ACT_GELU);
         gemm(h2, p + ".mlp.3", out, lout, 1, 0, &y);

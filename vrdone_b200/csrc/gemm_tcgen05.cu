@@ -157,6 +157,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
@@ -263,7 +274,10 @@ struct EpiArgs {
 // conv output never reaches HBM and the standalone layernorm launch disappears.  The accumulator takes all 512 TMEM columns (two
 // N = 256 instructions per K step), so main loop and epilogue of a CTA alternate instead of overlapping -- these GEMMs have K = 1536
 // or 3072, the epilogue is ~5-10 % of a tile.
-enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_F32_RES = 3, EPI_LN = 4 };
+// EPI_LN_RES: the attention output projection of an encoder block (blocks.py:1070-1076): y = acc + bias + residual is the new
+// residual stream (fp32, written through TMA boxes like the residual arrives) AND h = LayerNorm(y) (bf16) is the MLP's input --
+// both from one pass over the accumulator row; y is parked in tensor memory between the statistics pass and the normalisation.
+enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_F32_RES = 3, EPI_LN = 4, EPI_LN_RES = 5 };
 
 template <int CG, int MODE, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -282,9 +296,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint8_t* smem_w = smem + stages * A_STAGE_BYTES;
     uint8_t* staging = smem_w + stages * w_stage_bytes;          // 1024-aligned: every stage size is a multiple of 1024
     uint8_t* staging2 = staging + STAGING_TOTAL;                 // second-residual boxes (only carved when there is one)
-    constexpr bool LNM = MODE == EPI_LN;                         // one staging box per epilogue warp, the 512-column accumulator
+    constexpr bool LNM = MODE == EPI_LN || MODE == EPI_LN_RES;   // the 512-column accumulator, one stage
+    constexpr bool LNR = MODE == EPI_LN_RES;                     // ... with an fp32 residual in and the fp32 sum out
     static_assert(!LNM || BN == 512, "EPI_LN needs the full row in one tile");
-    uint64_t* bars = (uint64_t*)(staging + (LNM ? STAGING_TOTAL / 2 : (e.res2 != nullptr ? 2 : 1) * STAGING_TOTAL));
+    // EPI_LN: one staging box per epilogue warp; EPI_LN_RES: two (residual in / fp32 out, then the bf16 boxes)
+    uint64_t* bars = (uint64_t*)(staging + (MODE == EPI_LN ? STAGING_TOTAL / 2 : (e.res2 != nullptr ? 2 : 1) * STAGING_TOTAL));
     uint64_t* full = bars;                           // [MAX_STAGES]
     uint64_t* empty = bars + MAX_STAGES;             // [MAX_STAGES]
     uint64_t* tfull = bars + 2 * MAX_STAGES;         // [2]
@@ -293,7 +309,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t* tmem_slot = (uint32_t*)(resbar + 2 * EPI_WARPS);
     float* s_bias = (float*)(tmem_slot + 4);         // [MAX_N]
     float* s_corr = s_bias + MAX_N;                  // [MAX_N]
-    float* s_xch = s_corr + MAX_N;                   // EPI_LN: [2 tile parities][2 column halves][128 rows][sum, sum of squares]
+    float* s_xch = s_corr + MAX_N / 2;               // EPI_LN (N = 512 <= MAX_N / 2): [2 tile parities][2 column halves][128 rows][sum, sum of squares]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_n = e.N / block_n;
@@ -414,6 +430,152 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if constexpr (CG == 2) umma_commit_cg2(&tfull[as]); else umma_commit(&tfull[as]);   // accumulator stage complete
             }
         }
+    } else if (warp >= EPI_WARP0 && LNR) {
+        // ---- EPI_LN_RES.  Pass 1 per 32-column chunk: residual box (TMA, two boxes per warp in flight) + accumulator + bias = y;
+        // statistics; y goes back into tensor memory (tcgen05.st) and, through the same box, to HBM (fp32).  Pass 2: y from tensor
+        // memory -> LayerNorm -> bf16 -> [32 x 64] boxes (the two boxes alternate).
+        const int ew = warp - EPI_WARP0;
+        const int wq = warp & 3;
+        const int half = ew >> 2;
+        const uint32_t s_bias_u = smem_u32(s_bias);
+        uint8_t* my_stage = staging + ew * 2 * STAGING_BYTES;
+        uint64_t* my_resbar = resbar + 2 * ew;
+        uint32_t res_cnt[2] = {0u, 0u};                      // fills of each box so far: the barrier phases
+        int it = 0;
+        for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+            const int m0 = tile * (BLOCK_M * CG) + cta_rank * BLOCK_M;
+            const int row0 = m0 + wq * 32, row = row0 + lane;
+            const int col0 = half * 256;
+            bool valid = row < e.M;
+            if (e.row_seq != nullptr && valid) valid = e.row_seq[row % e.R] >= 0;
+            if (lane == 0) {                                 // the residual boxes of chunks 0 and 1 travel while the MMAs of this tile run
+                bulk_wait_read<0>();                         // the previous tile's bf16 stores have read both boxes
+                for (int b = 0; b < 2; ++b) {
+                    mbar_expect_tx(&my_resbar[b], STAGING_BYTES);
+                    tma_load_2d(my_stage + b * STAGING_BYTES, &map_res, &my_resbar[b], col0 + b * CHUNK, row0);
+                }
+            }
+            __syncwarp();
+            mbar_wait(&tfull[0], it & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + half * 256;
+            uint32_t acc[CHUNK];
+            float s1 = 0.f, s2 = 0.f;
+            tmem_ld32(taddr, acc);
+#pragma unroll 2
+            for (int c = 0; c < 8; ++c) {
+                const int b = c & 1;
+                const uint32_t box_u = smem_u32(my_stage + b * STAGING_BYTES);
+                mbar_wait(&my_resbar[b], res_cnt[b] & 1);
+                ++res_cnt[b];
+                tmem_ld_wait();
+                const int n = col0 + c * CHUNK;
+                float v[CHUNK];
+#pragma unroll
+                for (int i = 0; i < CHUNK / 4; ++i) {
+                    const float4 bi = lds128_ro(s_bias_u + (uint32_t)(n + 4 * i) * 4);
+                    const float4 r = lds128(box_u + lane * 128 + ((i ^ (lane & 7)) << 4));
+                    v[4 * i + 0] = (__uint_as_float(acc[4 * i + 0]) + bi.x) + r.x;
+                    v[4 * i + 1] = (__uint_as_float(acc[4 * i + 1]) + bi.y) + r.y;
+                    v[4 * i + 2] = (__uint_as_float(acc[4 * i + 2]) + bi.z) + r.z;
+                    v[4 * i + 3] = (__uint_as_float(acc[4 * i + 3]) + bi.w) + r.w;
+                }
+                if (c + 1 < 8) tmem_ld32(taddr + (c + 1) * CHUNK, acc);
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < CHUNK; ++i) v[i] = 0.f;
+                }
+                float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < CHUNK; i += 2) {
+                    a0 += v[i]; a1 += v[i + 1];
+                    q0 = fmaf(v[i], v[i], q0); q1 = fmaf(v[i + 1], v[i + 1], q1);
+                }
+                s1 += a0 + a1;
+                s2 += q0 + q1;
+                {   // y back into the accumulator columns it came from (read again in pass 2)
+                    uint32_t vb[CHUNK];
+#pragma unroll
+                    for (int i = 0; i < CHUNK; ++i) vb[i] = __float_as_uint(v[i]);
+                    tmem_st32(taddr + c * CHUNK, vb);
+                }
+#pragma unroll
+                for (int j = 0; j < CHUNK / 4; ++j)
+                    sts128(box_u + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&map_out, box_u, n, row0);
+                    bulk_commit();
+                    if (c + 2 < 8) {                         // refill this box with the residual of chunk c + 2
+                        bulk_wait_read<0>();
+                        mbar_expect_tx(&my_resbar[b], STAGING_BYTES);
+                        tma_load_2d(my_stage + b * STAGING_BYTES, &map_res, &my_resbar[b], col0 + (c + 2) * CHUNK, row0);
+                    }
+                }
+            }
+            tmem_st_wait();
+            float* xs = s_xch + (it & 1) * 512;
+            *reinterpret_cast<float2*>(xs + (half * 128 + wq * 32 + lane) * 2) = make_float2(s1, s2);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
+            const float2 xa = *reinterpret_cast<const float2*>(xs + (wq * 32 + lane) * 2);
+            const float2 xb = *reinterpret_cast<const float2*>(xs + (128 + wq * 32 + lane) * 2);
+            const float mean = (xa.x + xb.x) * (1.0f / 512.f);
+            const float var = fmaxf((xa.y + xb.y) * (1.0f / 512.f) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + VRD_EPS);
+            const float nmr = -mean * rstd;
+            tmem_ld32(taddr, acc);
+#pragma unroll 2
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t box_u = smem_u32(my_stage + ((c >> 1) & 1) * STAGING_BYTES);
+                if ((c & 1) == 0) {
+                    if (lane == 0) { if (c < 4) bulk_wait_read<0>(); else bulk_wait_read<1>(); }   // pass-1 stores / the store two boxes ago
+                    __syncwarp();
+                }
+                tmem_ld_wait();
+                const int n = col0 + c * CHUNK;
+                float v[CHUNK];
+#pragma unroll
+                for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(acc[i]);
+                if (c + 1 < 8) {
+                    tmem_ld32(taddr + (c + 1) * CHUNK, acc);
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[0]), 0));
+                        else mbar_arrive(&tempty[0]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CHUNK / 4; ++i) {
+                    const float4 gi = lds128_ro(s_bias_u + (uint32_t)(512 + n + 4 * i) * 4);
+                    const float4 be = lds128_ro(s_bias_u + (uint32_t)(1024 + n + 4 * i) * 4);
+                    v[4 * i + 0] = fmaf(fmaf(v[4 * i + 0], rstd, nmr), gi.x, be.x);
+                    v[4 * i + 1] = fmaf(fmaf(v[4 * i + 1], rstd, nmr), gi.y, be.y);
+                    v[4 * i + 2] = fmaf(fmaf(v[4 * i + 2], rstd, nmr), gi.z, be.z);
+                    v[4 * i + 3] = fmaf(fmaf(v[4 * i + 3], rstd, nmr), gi.w, be.w);
+                }
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < CHUNK; ++i) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < CHUNK / 8; ++j)
+                    sts128(box_u + lane * 128 + (((j + 4 * (c & 1)) ^ (lane & 7)) << 4), pack2(v[8 * j], v[8 * j + 1]),
+                           pack2(v[8 * j + 2], v[8 * j + 3]), pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+                if ((c & 1) == 1) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_res2, box_u, n - CHUNK, row0);   // map_res2 carries the [32 x 64] bf16 box map of the LayerNorm output
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all();
     } else if (warp >= EPI_WARP0 && LNM) {
         // ---- EPI_LN: thread = row; the two warps of a TMEM lane quarter own 256 columns each.  Pass 1: sum and sum of squares of
         // v = acc + bias (+ pad correction) over the warp's columns, exchanged with the partner warp through shared memory behind a
@@ -752,6 +914,7 @@ GemmKernel pick_kernel(int cg, int mode, int bn) {
     if (mode == EPI_F32_RES && bn == 128) return VRD_PICK(EPI_F32_RES, 128);
     if (mode == EPI_F32_RES && bn == 256) return VRD_PICK(EPI_F32_RES, 256);
     if (mode == EPI_LN && bn == 512) return VRD_PICK(EPI_LN, 512);
+    if (mode == EPI_LN_RES && bn == 512) return cg == 2 ? (GemmKernel)gemm_tcgen05_kernel<2, EPI_LN_RES, 512> : nullptr;
 #undef VRD_PICK
     return nullptr;
 }
@@ -812,8 +975,15 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     const bool has_res = g.res1 != nullptr;
     if (g.res2 != nullptr && !has_res) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: res2 without res1"); return 1; }
     const bool ln = g.ln_gamma != nullptr;
-    if (ln && (g.N != 512 || g.out_dtype != VRD_BF16 || has_res || g.act != 0 || g.ln_beta == nullptr || split)) {
-        snprintf(g_err, sizeof g_err, "gemm_tcgen05: the LayerNorm epilogue needs N = 512, a bf16 output, no residual and no activation");
+    const bool ln_res = ln && has_res;      // y = acc + bias + res (fp32, g.out) and LayerNorm(y) (bf16, g.ln_out)
+    if (ln && !ln_res && (g.N != 512 || g.out_dtype != VRD_BF16 || g.act != 0 || g.ln_beta == nullptr || split)) {
+        snprintf(g_err, sizeof g_err, "gemm_tcgen05: the LayerNorm epilogue needs N = 512, a bf16 output and no activation");
+        return 1;
+    }
+    if (ln_res && (g.N != 512 || g.out_dtype != VRD_F32 || g.act != 0 || g.ln_beta == nullptr || split || g.res2 != nullptr ||
+                   g.corr != nullptr || g.ln_out == nullptr || (g.ld_ln * 2) % 16 != 0 || ((uintptr_t)g.ln_out & 15) != 0)) {
+        snprintf(g_err, sizeof g_err, "gemm_tcgen05: the residual + LayerNorm epilogue needs N = 512, an fp32 output, one residual, "
+                 "no activation and a 16-byte aligned bf16 LayerNorm output");
         return 1;
     }
     // experiment (gemm_spec = 3): bf16 (optionally GELU) GEMMs with N = 512 on 512-column tiles through the EPI_LN kernel without the
@@ -823,7 +993,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
                          (g.act == 0 || g.act == 2) && g.corr == nullptr && !split && dbg == 0;
     int block_n;
     if (ln || wide512) {
-        block_n = 512;
+        block_n = 512;          // (ln_res included)
     } else if (has_res) {   // two 32-column chunks per epilogue warp (both residual boxes prefetched), four when K is long enough to hide
         if (g.N % 256 == 0 && g.taps * g.K >= 1024 && g.res2 == nullptr) block_n = 256;   // a second residual doubles the staging boxes
         else if (g.N % 128 == 0) block_n = 128;
@@ -845,7 +1015,8 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     if (has_res && g.out_dtype != VRD_F32) { snprintf(g_err, sizeof g_err, "gemm_tcgen05: residual needs an fp32 output"); return 1; }
     // CTA pairs whenever there are enough rows to keep every pair busy (the small query-decoder GEMMs keep one CTA per tile):
     // measured +6..10 % on the long-K GEMMs, +4..9 % on the K = 512 ones, neutral on the HBM-bound residual projections
-    const int cg = force_cg == 1 ? 1 : ((force_cg == 2 || g.M >= 128 * 2 * 64) ? 2 : 1);
+    // (the residual + LayerNorm kernel exists for CTA pairs only and is used for every M: results must not depend on the chunking)
+    const int cg = ln_res ? 2 : (force_cg == 1 ? 1 : ((force_cg == 2 || g.M >= 128 * 2 * 64) ? 2 : 1));
     CUtensorMap map_a, map_w, map_out, map_res, map_res2;
     const long long kk = (long long)g.taps * g.K * (split ? 2 : 1);
     if (!make_map(&map_a, g.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, split ? 2 * g.K : g.K, g.lda, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
@@ -864,14 +1035,18 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     } else {
         map_res = map_out;
     }
-    if (g.res2 != nullptr) {
+    if (ln_res) {   // the slot carries the [32 rows x 64 cols] bf16 box map of the LayerNorm output
+        if (!make_map(&map_res2, g.ln_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ld_ln, 32, 2 * CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    } else if (g.res2 != nullptr) {
         if (!make_map(&map_res2, g.res2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldr2, 32, CHUNK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     } else {
         map_res2 = map_res;
     }
     const int stage_bytes = A_STAGE_BYTES + (block_n / cg) * BLOCK_K * 2;
-    // alignment slack, staging, barriers, bias + corr (EPI_LN: one box per epilogue warp, + the statistics exchange buffer)
-    const int fixed = (ln || wide512) ? 1024 + STAGING_TOTAL / 2 + 1024 + 2 * MAX_N * 4 + 4096
+    // alignment slack, staging, barriers, bias + corr (EPI_LN: one box per epilogue warp; the statistics exchange buffer sits in the
+    // unused half of the correction vector's slot)
+    const int fixed = ln_res ? 1024 + STAGING_TOTAL + 1024 + 2 * MAX_N * 4
+                     : (ln || wide512) ? 1024 + STAGING_TOTAL / 2 + 1024 + 2 * MAX_N * 4
                          : 1024 + (g.res2 != nullptr ? 2 : 1) * STAGING_TOTAL + 1024 + 2 * MAX_N * 4;
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -879,7 +1054,7 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     const int smem = fixed + stages * stage_bytes;
     if (attr_once.first()) {
         for (int c = 1; c <= 2; ++c)
-            for (int m = 0; m < 5; ++m)
+            for (int m = 0; m < 6; ++m)
                 for (int bn = 0; bn <= 512; bn += 128) {
                     GemmKernel k = pick_kernel(c, m, bn);
                     if (k != nullptr && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
@@ -894,7 +1069,9 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
     // specialised epilogues for the shapes that carry the forward (q / k / v and other bf16 projections, the GELU MLP-up GEMMs, the
     // fp32 residual projections); everything else (ReLU, pad correction, second residual, narrow tiles, experiments) stays generic
     int mode = EPI_GENERIC, bn_ct = 0;
-    if (ln || wide512) {
+    if (ln_res) {
+        mode = EPI_LN_RES; bn_ct = 512;
+    } else if (ln || wide512) {
         mode = EPI_LN; bn_ct = 512;
     } else if (spec_ok && dbg == 0 && g.corr == nullptr && g.res2 == nullptr) {
         if (wide && block_n == 256 && g.act == 0) { mode = EPI_BF16; bn_ct = 256; }
@@ -937,6 +1114,11 @@ static int gemm_tcgen05_launch(const GemmArgs& g, cudaStream_t st, int split) {
 }
 
 int gemm_tcgen05_bf16(const GemmArgs& g, cudaStream_t st) { return gemm_tcgen05_launch(g, st, 0); }
+
+bool gemm_res_ln_fused_ok(const GemmArgs& g) {
+    return vrd_options().proj_ln != 0 && g.N == 512 && g.M % BLOCK_M == 0 && g.K % BLOCK_K == 0 && g.taps == 1 && g.res1 != nullptr &&
+           g.res2 == nullptr && g.corr == nullptr && g.act == 0;
+}
 
 // ---- fp32 operands on the tensor cores: 3 x bf16 split -------------------------------------------------------------------
 namespace {

@@ -15,6 +15,11 @@ struct DwBranches {
     long long ldo[3];
 };
 
+struct GemmArgs;
+// true when gemm_tcgen05_bf16 takes the residual + LayerNorm epilogue for this problem (N = 512; any number of rows, so that results
+// do not depend on how a video is chunked)
+bool gemm_res_ln_fused_ok(const GemmArgs& g);
+
 struct GemmArgs {
     const void* A; long long lda;      // [M, K] activations (row r, tap d reads row r + d - 1 when taps == 3)
     const void* W;                     // [N, taps*K], K contiguous
@@ -27,6 +32,8 @@ struct GemmArgs {
     const int* row_seq; const int4* seqinfo; int R;   // optional layout: separator rows are written as zeros
     // optional channel LayerNorm (+ ReLU) of the N = 512 outputs in the epilogue (tcgen05 bf16 path only; bf16 output, no residual)
     const float* ln_gamma = nullptr; const float* ln_beta = nullptr; int ln_relu = 0;
+    // with a residual (res1): out = fp32 sum (the residual stream), ln_out = bf16 LayerNorm of it
+    void* ln_out = nullptr; long long ld_ln = 0;
 };
 
 void pack_pairs(const void* ptrs, const long long* strides, Lay lay, int nv, int nc, int nbs, int nbe, void* vis, void* clip,

@@ -33,6 +33,7 @@ _SIGNATURES = {
     "vrd_gemm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp,
                  _vp, _i32, _vp],
     "vrd_gemm_ln": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
+    "vrd_gemm_res_ln": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "vrd_layernorm": [_vp, _i32, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _vp],
     "vrd_small_conv": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp],
     "vrd_dwconv_ln": [_vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
@@ -146,7 +147,7 @@ def _f32(t: Optional[torch.Tensor]):
     return _p(t)
 
 
-_OP_NAMES = frozenset(["pack_pairs", "gemm", "gemm_ln", "layernorm", "small_conv", "dwconv_ln", "window_attn", "full_attn", "maxpool_skip",
+_OP_NAMES = frozenset(["pack_pairs", "gemm", "gemm_ln", "gemm_res_ln", "layernorm", "small_conv", "dwconv_ln", "window_attn", "full_attn", "maxpool_skip",
                        "fpn_top", "fpn_level", "mask_features", "query_ln", "query_self_attn", "query_cross_attn", "mask_logits",
                        "softmax_topk"])
 
@@ -198,7 +199,7 @@ class CudaOps:
                 r = _fn(*a, **k)
                 e1.record()
                 # the GEMM with the LayerNorm epilogue is the same kernel: it is accounted with the GEMMs
-                self._timing.append(("vrd_" + ("gemm" if _name == "gemm_ln" else _name), e0, e1, self._last_flops, self._last_tag,
+                self._timing.append(("vrd_" + ("gemm" if _name in ("gemm_ln", "gemm_res_ln") else _name), e0, e1, self._last_flops, self._last_tag,
                                      self._last_bytes))
                 return r
             setattr(self, name, timed)
@@ -330,6 +331,29 @@ class CudaOps:
         self._last_tag = f"{'big' if M >= 16384 else 'small'} M, {taps}x{K}->{N} bf16 +ln"
         self._check(self.lib.vrd_gemm_ln(ap, lda, _p(w), _f32(bias), _f32(corr), _f32(ln[0]), _f32(ln[1]), int(relu), op, ldo, M, N, K,
                                          taps, rs, si, R, self._stream()), "vrd_gemm_ln")
+
+    def gemm_res_ln(self, a, w, out, ln_out, ln, bias=None, res1=None, lay=None, streams=1):
+        """out (fp32) = a @ w.T + bias + res1 (the residual stream) and ln_out (bf16) = LayerNorm_channels(out): the attention
+        output projection of an encoder block together with the LayerNorm that feeds its MLP."""
+        ap, lda = _mat(a)
+        op, ldo = _mat(out)
+        lp, ldl = _mat(ln_out)
+        rp, ldr = _mat(res1)
+        M, K = a.shape
+        N = w.shape[0]
+        assert a.dtype == torch.bfloat16 and w.dtype == a.dtype and out.dtype == torch.float32 and ln_out.dtype == torch.bfloat16
+        assert w.is_contiguous() and w.shape[1] == K and out.shape == (M, N) and ln_out.shape == (M, N) and res1.shape == (M, N)
+        if lay is not None:
+            assert M == streams * lay.R
+            rs, si, R = self._lay(lay)
+        else:
+            rs, si, R = None, None, 0
+        valid_rows = streams * int(lay.len.sum()) if lay is not None else M
+        self._last_flops = 2.0 * valid_rows * N * K
+        self._last_bytes = valid_rows * (2.0 * K + 4.0 * N + 4.0 * N + 2.0 * N) + w.numel() * 2.0
+        self._last_tag = f"{'big' if M >= 16384 else 'small'} M, 1x{K}->{N} f32 +res +ln"
+        self._check(self.lib.vrd_gemm_res_ln(ap, lda, _p(w), _f32(bias), rp, ldr, _f32(ln[0]), _f32(ln[1]), op, ldo, lp, ldl, M, N, K,
+                                             rs, si, R, self._stream()), "vrd_gemm_res_ln")
 
     def layernorm(self, x, g, b, out, relu=False, lay=None, streams=1):
         xp, ldx = _mat(x)

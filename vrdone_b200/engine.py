@@ -222,9 +222,15 @@ class Engine:
         else:
             skip = self._buf(rows, C, torch.float32)
             ops.maxpool_skip(x, lay_in, lay_out, skip)
-        y = self._gemm(a, p + ".attn.proj", self._buf(rows, C, torch.float32), lay_out, streams, res1=skip)
+        y = self._buf(rows, C, torch.float32)
         h = self._buf(rows, C, self.adt)
-        ops.layernorm(y, self._W(p + ".ln2.g"), self._W(p + ".ln2.be"), h, relu=False, lay=lay_out, streams=streams)
+        if self.adt == torch.bfloat16 and C == 512 and hasattr(ops, "gemm_res_ln"):
+            # bf16 path: projection + residual + the LayerNorm that feeds the MLP in one launch
+            ops.gemm_res_ln(a, self._W(p + ".attn.proj.W"), y, h, (self._W(p + ".ln2.g"), self._W(p + ".ln2.be")),
+                            bias=self._b(p + ".attn.proj.b"), res1=skip, lay=lay_out, streams=streams)
+        else:
+            self._gemm(a, p + ".attn.proj", y, lay_out, streams, res1=skip)
+            ops.layernorm(y, self._W(p + ".ln2.g"), self._W(p + ".ln2.be"), h, relu=False, lay=lay_out, streams=streams)
         h2 = self._gemm(h, p + ".mlp.0", self._buf(rows, 4 * C, self.adt), lay_out, streams, act=ACT_GELU)
         return self._gemm(h2, p + ".mlp.3", self._buf(rows, C, torch.float32), lay_out, streams, res1=y)
 

@@ -37,11 +37,13 @@ int vrd_abi_version(void);
 const char* vrd_last_error(void);
 /* compute capability major*10+minor of the current device (100 on B200); <0 on error */
 int vrd_device_arch(void);
-/* experiment switches of the launchers ("pdl": programmatic dependent launch on / off, "dw_cfg": dwconv_ln_tile variant); the
- * defaults come from the environment (VRD_PDL, VRD_DW_CFG).  Returns the previous value, <0 for an unknown name.  No reference
- * counterpart: it exists so that one process can A/B a switch on the same inputs. */
+/* experiment switches of the launchers -- "pdl": programmatic dependent launch on / off, "dw_cfg": dwconv_ln_tile variant,
+ * "gemm_spec": tcgen05 GEMM epilogue modes, "embed_ln" / "proj_ln": LayerNorm as the epilogue of the embedding convs / of the encoder
+ * blocks' attention projection; the defaults come from the environment (VRD_PDL, VRD_DW_CFG, VRD_GEMM_SPEC, VRD_EMBED_LN,
+ * VRD_PROJ_LN).  vrd_set_option returns the previous value, vrd_get_option the current one, <0 for an unknown
+ * name.  No reference counterpart: they exist so that one process can A/B a switch on the same inputs. */
 int vrd_set_option(const char* name, int value);
-int vrd_get_option(const char* name);   /* current value, <0 for an unknown name; also "gemm_spec", "embed_ln" */
+int vrd_get_option(const char* name);
 
 /* a0 -- replaces utils.dict_to_device for the pair features (eval.py:144, utils/misc.py:98-112): n asynchronous
  * host->device copies on `stream` (the copy engine; src[i] HOST pointers, pinned for true asynchrony) of bytes[i] bytes to

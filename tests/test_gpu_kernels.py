@@ -290,7 +290,7 @@ def test_full_attention_tcgen05_long_and_ragged(ops, scale):
 
 def test_launcher_options_roundtrip(ops):
     """vrd_set_option / vrd_get_option: the experiment switches of the launchers; unknown names fail loudly."""
-    for name in ("pdl", "dw_cfg", "gemm_spec", "embed_ln"):
+    for name in ("pdl", "dw_cfg", "gemm_spec", "embed_ln", "proj_ln"):
         cur = ops.get_option(name)
         assert ops.set_option(name, cur) == cur and ops.get_option(name) == cur
     with pytest.raises(ValueError):

@@ -59,3 +59,25 @@ def test_layout_invariants():
     lens = [600] + [10] * 199 + [900]
     tp = reference_padded_lengths(lens, mc)
     assert tp[0] == 640 and tp[1] == 512 and tp[200] == 960
+
+
+def test_emulated_bf16_schedule_uses_fused_layernorm_epilogues():
+    """The bf16 schedule routes the embedding convs through gemm_ln and the encoder blocks' attention projection through gemm_res_ln
+    (LayerNorm as the GEMM's epilogue); with the CPU emulation of those ops it still reproduces the reference within bf16 accuracy."""
+    fix = H.network_fixture("vidor")
+    cfg, model, sd = H.seeded_model("vidor", fix["wseed"])
+    mc = cfg["model_config"]
+    feats = synth.pair_features(mc, fix["lens"], fix["xseed"])
+    idx = [1, 3]
+    lens = [fix["lens"][i] for i in idx]
+    tpads = [fix["tpads"][i] for i in idx]
+    lay = PackLayout(lens, tpads, 4, "cpu")
+    ops = EmuOps()
+    eng = Engine(PackedWeights(sd, mc, "cpu", torch.bfloat16), ops)
+    with torch.no_grad():
+        out = eng.forward_packed(lay, [feats[i] for i in idx], None, cfg["inference_config"]["topk"], want_masks=True)
+    n_conv, n_stem, n_branch = mc["backbone_arch"]
+    assert ops.calls.count("gemm_ln") == n_conv                      # one stream of embedding convs (no clip features in vidor)
+    assert ops.calls.count("gemm_res_ln") == n_stem + n_branch       # one per encoder block
+    for j, i in enumerate(idx):
+        assert H.rel_err(out["logits"][j], fix["pred_logits"][i]) < 4e-2
